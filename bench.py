@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the tokengeex_b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+A "step" is one encode_batch pass over one batch of synthetic input (BASELINE.json
+configs[1]: 1 GB synthetic multi-language code corpus, 131k Unigram vocab, crlf processor,
+token ids bit-exact).  With N > 1 (torchrun, one rank per GPU) every rank encodes its own
+1 GB shard of the code+Chinese mix (configs[2]); samples are independent, so there is no
+data-path collective and scaling is weak.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOCAB_SIZE = 131072
+MAX_TOKEN_LEN = 16
+VOCAB_SAMPLE_BYTES = 96_000_000
+METRIC = "encode_input_throughput"
+UNIT = "MB/s"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_vocab(synth):
+    """Identical on every rank: built from a fixed common sample (seed 2)."""
+    blob, off = synth.corpus(synth.KIND_MULTILANG, 2, VOCAB_SAMPLE_BYTES)
+    toks, sc, kp = synth.vocab(blob, off, 2, VOCAB_SIZE, MAX_TOKEN_LEN, 0.05)
+    return toks, sc, kp
+
+
+def workload(synth, n_gpus, rank, nbytes, out=None):
+    if n_gpus == 1:
+        kind, seed, name = synth.KIND_MULTILANG, 2, "encode_batch 1GB multi-language code, 131k vocab (configs[1])"
+    else:
+        kind, seed, name = synth.KIND_CODE_CJK, 3 + 1000 * rank, "encode 1GB/GPU shard of code+Chinese mix, 131k vocab (configs[2])"
+    blob, off = synth.corpus(kind, seed, nbytes, out=out)
+    return blob, off, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, restated (oracle port; the Rust
+    crate cannot be built in this image), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from tokengeex_b200 import synth
+    threads = synth.n_threads()
+    toks, sc, kp = build_vocab(synth)
+    om = O.OracleModel(toks, sc)
+    blob, off, name = workload(synth, args.gpus, 0, min(args.bytes, 256_000_000))
+    # calibrate: ~8 MB, then size one step to ~8 s
+    k = int(np.searchsorted(off, 8_000_000))
+    t = time.perf_counter()
+    om.encode_batch(blob, off[:k + 1], crlf=True, threads=threads)
+    rate = int(off[k]) / (time.perf_counter() - t)
+    step_bytes = int(min(int(off[-1]), max(8_000_000, rate * 8.0)))
+    k = int(np.searchsorted(off, step_bytes))
+    o = off[:k + 1]
+    nb = int(o[-1])
+    for _ in range(args.warmup):
+        om.encode_batch(blob, o, crlf=True, threads=threads)
+    times, tokens = [], 0
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        r = om.encode_batch(blob, o, crlf=True, threads=threads)
+        times.append(time.perf_counter() - t)
+        tokens = int(r[1][-1])
+    dt = sum(times)
+    mbps = nb * args.steps / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": mbps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 scores / u32 ids",
+            "data": "synthetic", "tokens_per_s": tokens * args.steps / dt,
+            "config": {"workload": name, "vocab": len(toks), "max_token_len": MAX_TOKEN_LEN, "processor": "crlf",
+                       "sample_bytes_per_step": nb},
+            "cpu_baseline": {"value": mbps, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"first {nb} bytes ({k} samples) of the workload per step, oracle "
+                                       "encode_batch (C++ restatement of the Rust rayon path)"},
+            "e2e": {"value": mbps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--bytes", type=int, default=1_000_000_000, help="input bytes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--g-short", type=int, default=0)
+    ap.add_argument("--long-threshold", type=int, default=0)
+    args = ap.parse_args()
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tokengeex_b200 import _native as N
+    from tokengeex_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the native arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    toks, sc, kp = build_vocab(synth)
+    model = N.Model(toks, sc, device=local)
+    if args.g_short:
+        model.set_option(0, args.g_short)
+    if args.long_threshold:
+        model.set_option(1, args.long_threshold)
+    info = model.info()
+
+    # pinned host input (also the source of the e2e H2D copies)
+    h_text = N.pinned_empty(args.bytes)
+    blob, off, wname = workload(synth, world, rank, args.bytes, out=h_text)
+    S, NB = len(off) - 1, int(off[-1])
+
+    d_text = torch.from_numpy(blob).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_ids = torch.empty(NB + 4, dtype=torch.int32, device="cuda")
+    d_id_off = torch.empty(S + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_dev():
+        tot, rc, bad = model.encode_batch_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, True, d_ids.data_ptr(),
+                                              NB + 4, d_id_off.data_ptr())
+        assert rc == 0, "NoPath in benchmark corpus"
+        return tot
+
+    for _ in range(max(args.warmup, 3)):
+        tokens = step_dev()
+    launches = int(model.stat(0))
+    torch.cuda.synchronize()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dev_ms, vit_ms = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tokens = step_dev()
+        dev_ms.append(model.stat(4))
+        vit_ms.append(model.stat(1))
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+
+    # max over ranks of the device time of the K steps
+    tsum = torch.tensor([sum(dev_ms), wall, float(NB), float(tokens), sum(vit_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tsum.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ttot = tsum.clone()
+        dist.all_reduce(ttot, op=dist.ReduceOp.SUM)
+        dev_total_ms, wall_max = float(tmax[0]), float(tmax[1])
+        bytes_all, tokens_all = float(ttot[2]), float(ttot[3])
+    else:
+        dev_total_ms, wall_max, bytes_all, tokens_all = sum(dev_ms), wall, float(NB), float(tokens)
+    ms_per_step = dev_total_ms / args.steps
+    value = bytes_all / (ms_per_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (the Viterbi kernel launches), this rank
+    peak, peak_src = measured_peak()
+    alg_bytes = NB + 4 * tokens + 16 * (S + 1)
+    vit = float(np.mean(vit_ms)) * 1e-3
+    achieved = alg_bytes / vit / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("viterbi_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # e2e: the C-ABI host call, pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_ids = N.pinned_empty(4 * (NB // 2 + 16)).view(np.uint32)
+        for _ in range(2):
+            r = model.encode_batch(blob, off, crlf=True, ids_out=h_ids)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = model.encode_batch(blob, off, crlf=True, ids_out=h_ids)
+        torch.cuda.synchronize()
+        barrier()
+        e_wall = time.perf_counter() - t0
+        ew = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ew, op=dist.ReduceOp.MAX)
+        e2e = {"value": bytes_all * args.steps / float(ew[0]) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": NB + 8 * (S + 1),
+               "d2h_bytes_per_step": int(4 * r[0].size + 8 * (S + 1) + 12 * S),
+               "ms_per_step": 1e3 * float(ew[0]) / args.steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = synth.n_threads()
+        om = O.OracleModel(toks, sc)
+        k = int(np.searchsorted(off, 8_000_000))
+        t = time.perf_counter()
+        om.encode_batch(blob, off[:k + 1], crlf=True, threads=threads)
+        rate = int(off[k]) / (time.perf_counter() - t)
+        k = int(np.searchsorted(off, min(NB, max(8_000_000, rate * 12.0))))
+        o = off[:k + 1]
+        t = time.perf_counter()
+        r = om.encode_batch(blob, o, crlf=True, threads=threads)
+        dt = time.perf_counter() - t
+        # parity on the sample, while we are here
+        ok = bool(np.array_equal(r[0], d_ids[:int(r[1][-1])].cpu().numpy().view(np.uint32)))
+        cpu = {"value": int(o[-1]) / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {int(o[-1])} bytes ({k} samples) of the same corpus, oracle encode_batch "
+                         "(C++ restatement of the Rust rayon path)", "ids_match_gpu": ok}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64 scores / u32 ids", "data": "synthetic",
+                "tokens_per_s": tokens_all / (ms_per_step * 1e-3),
+                "wall_ms_per_step": 1e3 * wall_max / args.steps,
+                "config": {"workload": wname, "vocab": len(toks), "max_token_len": MAX_TOKEN_LEN,
+                           "processor": "crlf", "bytes_per_gpu": NB, "samples_per_gpu": S,
+                           "l2": "inputs (1 GB/GPU) larger than L2; no flush needed",
+                           "trie_slots": int(info.trie_slots), "parallelism": f"sample-sharded x{world}, no collective"},
+                "gpu_launches": launches * args.steps,
+                "clocks": clk,
+                "e2e": e2e,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "viterbi_kernel<32> + viterbi_kernel<G>", "algorithmic_bytes": alg_bytes,
+                             "kernel_ms": vit * 1e3},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

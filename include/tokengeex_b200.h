@@ -1,0 +1,139 @@
+/* tokengeex_b200 — C ABI of the B200-native TokenGeeX hot path.
+ *
+ * Drop-in boundary for the data-parallel hot path of rojas-diego/tokengeex: UnigramLM
+ * Viterbi segmentation (encode / encode_batch) and the forward-backward expected-count
+ * pass + token-frequency pass that drive EM vocabulary pruning.  The reference is a
+ * pure-Rust crate with no FFI of its own; these entry points are what a Rust `extern
+ * "C"` shim inside the crate would bind (INTEGRATION.md shows that shim).  Each function
+ * cites the reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain pointers + sizes; no exceptions cross the boundary; every function returns a
+ *    tgx_status (0 = ok) and tgx_last_error() describes the last failure on this thread.
+ *  - "blob + offsets" layout for ragged data: item i occupies blob[off[i] .. off[i+1]),
+ *    off has count+1 entries, off[0] == 0.
+ *  - token ids are uint32 (TokenID = u32, src/lib.rs:19); id == index in the vocab array.
+ *  - `_dev` variants take DEVICE pointers (text 16-byte aligned) and leave results in
+ *    device memory; the others take HOST pointers and perform the H2D / D2H copies.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    TGX_ERR_NO_DEVICE.
+ */
+#ifndef TOKENGEEX_B200_H
+#define TOKENGEEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tgx_model tgx_model; /* opaque; replaces tokengeex::Model (src/model.rs:8-13) */
+
+typedef enum tgx_status {
+  TGX_OK = 0,
+  TGX_ERR_INVALID = 1,     /* bad argument */
+  TGX_ERR_UNSUPPORTED = 2, /* vocab beyond device limits (token > 64 B, >= 2^24 tokens/slots) */
+  TGX_ERR_NO_DEVICE = 3,   /* no CUDA device / model created host-only */
+  TGX_ERR_CUDA = 4,        /* CUDA runtime failure (message in tgx_last_error) */
+  TGX_ERR_CAPACITY = 5,    /* output buffer too small; required size reported */
+  TGX_ERR_NO_PATH = 6,     /* Error::NoPath(pos,len) (src/lib.rs:219-224,243-245) */
+  TGX_ERR_BAD_Z = 7        /* E-step: normalisation constant not "normal" (src/prune.rs:90-96) */
+} tgx_status;
+
+/* flags */
+#define TGX_FLAG_CRLF 1u /* apply CrlfProcessor::preprocess (src/processor.rs:47-49) per sample */
+
+typedef struct tgx_model_info {
+  uint64_t vocab_size;
+  uint32_t max_token_len;
+  uint32_t trie_nodes;
+  uint32_t trie_slots; /* 16-byte slots of the device double-array */
+  uint32_t trie_terminals;
+  int32_t device; /* -1 = host-only */
+} tgx_model_info;
+
+/* Last error message of the calling thread ("" if none). */
+const char* tgx_last_error(void);
+
+/* Model::from(vocab) (src/model.rs:16-30): builds the vocabulary trie — here an XOR
+ * double-array — and uploads it to `device`.  Duplicate byte strings keep the LAST id
+ * (src/trie.rs:19); the empty token never matches (src/trie.rs:51-63).
+ * device >= 0: CUDA ordinal.  device == -1: host-only model (trie queries only). */
+int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                     uint64_t vocab_size, int device, tgx_model** out);
+void tgx_model_destroy(tgx_model* m);
+int tgx_model_get_info(const tgx_model* m, tgx_model_info* info);
+
+/* Model::common_prefix_search (src/model.rs:132-138 over src/trie.rs:22-63): ids and
+ * lengths of every vocab token that prefixes text, ascending length.  Host-side walk of
+ * the same double-array.  Writes min(count, cap) entries, returns the count in *count. */
+int tgx_model_common_prefix_search(const tgx_model* m, const uint8_t* text, uint64_t n, uint32_t* ids,
+                                   uint32_t* lens, uint64_t cap, uint64_t* count);
+
+/* CrlfProcessor::preprocess over a batch (src/processor.rs:47-49; applied per sample as in
+ * Tokenizer::encode_ordinary src/tokenizer.rs:92-99 and load_sources src/cli.rs:279-285).
+ * out_text needs off[S] bytes; out_off S+1 entries. */
+int tgx_crlf_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint8_t* out_text,
+                   uint64_t* out_off);
+
+/* Tokenizer::encode_ordinary_batch(inputs, dropout = 0.0) (src/tokenizer.rs:114-123) =
+ * per sample: processors (crlf if TGX_FLAG_CRLF) then Model::encode (src/model.rs:59-129).
+ *  ids      [ids_cap]  concatenated token ids, input order; ids_cap >= off[S] always suffices
+ *  id_off   [S+1]      offsets into ids
+ *  status   [S]        0 ok, TGX_ERR_NO_PATH for NoPath (may be NULL)
+ *  proc_len [S]        length after the processors — the `len` of NoPath(len,len) (may be NULL)
+ * Returns TGX_OK, or TGX_ERR_NO_PATH when any sample failed (*first_bad = lowest failing
+ * index, as `collect::<Result<_>>` surfaces one error; other samples are still encoded),
+ * or TGX_ERR_CAPACITY (id_off[S] holds the required capacity). */
+int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                     uint32_t* ids, uint64_t ids_cap, uint64_t* id_off, int32_t* status, uint64_t* proc_len,
+                     int64_t* first_bad);
+/* Same with device-resident inputs and outputs.  n_bytes = off[S].  *total_ids (host)
+ * receives id_off[S]. */
+int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                         uint64_t n_bytes, uint32_t flags, uint32_t* d_ids, uint64_t ids_cap,
+                         uint64_t* d_id_off, int32_t* d_status, uint64_t* d_proc_len, uint64_t* total_ids,
+                         int64_t* first_bad);
+
+/* ModelVocabularyPruner::run_e_step (src/prune.rs:64-120): forward-backward expected
+ * counts (Lattice::populate_marginal, src/lattice.rs:245-312, over Model::populate_nodes
+ * src/model.rs:34-55) summed over all snippets of at most snippet_len bytes
+ * (MAX_SAMPLE_LENGTH = 81920, src/prune.rs:75).  expected[V] is OVERWRITTEN with this
+ * batch's sum (f64).  Returns TGX_ERR_BAD_Z if some snippet's z is not normal
+ * (*bad_sample = lowest such sample, *bad_z its z); expected is then undefined. */
+int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S,
+                        uint64_t snippet_len, double* expected, int64_t* bad_sample, double* bad_z);
+/* Device variant: d_expected[V] is ACCUMULATED into (+=) so a caller can sum shards /
+ * chunks in place (and all-reduce the same buffer across GPUs). */
+int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                            uint64_t n_bytes, uint64_t snippet_len, double* d_expected, int64_t* bad_sample,
+                            double* bad_z);
+
+/* Frequency pass of prune_vocab (src/prune.rs:205-246): freq[id] += 1 over
+ * Model::encode(sample, 0.0) of WHOLE samples.  freq[V] is overwritten (host variant) /
+ * accumulated (device variant).  TGX_ERR_NO_PATH as for encode. */
+int tgx_token_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                          uint64_t* freq, int64_t* first_bad, uint64_t* bad_len);
+int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                              uint64_t n_bytes, uint32_t flags, uint64_t* d_freq, int64_t* first_bad,
+                              uint64_t* bad_len);
+
+/* Pinned host memory for callers that want asynchronous H2D/D2H (cudaHostAlloc). */
+int tgx_host_alloc(void** p, uint64_t bytes);
+int tgx_host_free(void* p);
+
+/* Counters of the last compute call on this model (for bench.py): number of kernels
+ * launched and device milliseconds of the dominant kernel(s), measured with CUDA events
+ * on the model's stream.  what: 0 = kernels launched, 1 = viterbi ms, 2 = fb-forward ms,
+ * 3 = fb-backward ms, 4 = whole call device ms. */
+double tgx_model_last_stat(const tgx_model* m, int what);
+
+/* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units (1,2,4,8,16,32),
+ * 1 = byte threshold from which a unit is processed by a full warp (G = 32),
+ * 2 = lanes per snippet in the E-step. */
+int tgx_model_set_option(tgx_model* m, int key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,199 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): token ids bit-exact; token frequencies exact;
+expected counts within 1e-9 relative.  All tests need a CUDA device.
+"""
+import math
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import rand_samples, rand_vocab, split_ids, synth_setup
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9  # north_star: "expected counts within 1e-9 relative"
+
+
+@pytest.fixture(scope="module")
+def N():
+    from tokengeex_b200 import _native
+    return _native
+
+
+def both(N, toks, scores):
+    return N.Model(toks, scores, device=0), O.OracleModel(toks, scores)
+
+
+def gpu_encode(N, m, samples, crlf=False):
+    blob, off = N.pack(samples)
+    ids, id_off, status, plen, rc, bad = m.encode_batch(blob, off, crlf=crlf)
+    return split_ids(ids, id_off), status.tolist(), plen.tolist(), rc, bad
+
+
+# ----------------------------------------------------------------------------- goldens
+def test_reference_goldens_encode(N):
+    # /root/reference/src/model.rs:209-215
+    m = N.Model([b"a", b"b", b"c", b"ab"], [-3.0, -3.0, -3.0, -4.0])
+    assert gpu_encode(N, m, [b"abc"])[0] == [[3, 2]]
+    # src/model.rs:218-236 with dropout 0.0
+    m = N.Model([b"a", b"b", b"c", b"d", b"e", b"f", b"ab", b"abc", b"abcd", b"abcde", b"abcdef"],
+                [-3.0] * 6 + [-4.0, -5.0, -6.0, -7.0, -8.0])
+    assert gpu_encode(N, m, [b"abcdef"])[0] == [[10]]
+    # src/model.rs:243-252: 256-byte default vocab, Chinese text
+    toks = [bytes([i]) for i in range(256)]
+    m = N.Model(toks, [1.0 / 256.0] * 256)
+    text = "你好，我叫罗杰斯".encode()
+    ids = gpu_encode(N, m, [text])[0][0]
+    assert len(ids) == len(text) and bytes(ids) == text
+    # tie rule: smallest start wins
+    m = N.Model([b"a", b"b", b"c", b"ab", b"bc"], [-3.0, -3.0, -3.0, -4.0, -4.0])
+    assert gpu_encode(N, m, [b"abc"])[0] == [[0, 4]]
+
+
+def test_empty_nopath_duplicates(N):
+    m = N.Model([b"a", b"ab"], [-1.0, -1.5])
+    ids, status, plen, rc, bad = gpu_encode(N, m, [b"", b"ab", b"abx", b"a", b"", b"xx"])
+    assert ids == [[], [1], [], [0], [], []]
+    assert status == [0, 0, N.TGX_ERR_NO_PATH, 0, 0, N.TGX_ERR_NO_PATH]
+    assert rc == N.TGX_ERR_NO_PATH and bad == 2 and plen[2] == 3  # NoPath(3,3)
+    m = N.Model([b"ab", b"a", b"b", b"ab"], [-1.0, -5.0, -5.0, -2.0])  # last duplicate wins
+    assert gpu_encode(N, m, [b"ab"])[0] == [[3]]
+    # empty batch
+    ids, id_off, status, plen, rc, bad = m.encode_batch(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
+    assert ids.size == 0 and rc == 0
+
+
+@pytest.mark.parametrize("g,thr", [(1, 1 << 30), (2, 1 << 30), (4, 40), (8, 1 << 30), (16, 25), (32, 1), (8, 30)])
+def test_random_small_vs_oracle(N, g, thr):
+    rng = random.Random(100 + g)
+    for it in range(25):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 40), max_len=rng.randrange(1, 9),
+                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
+        gm, om = both(N, toks, scores)
+        gm.set_option(0, g)
+        gm.set_option(1, thr)
+        samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 90)
+        got, status, plen, rc, bad = gpu_encode(N, gm, samples)
+        for i, s in enumerate(samples):
+            try:
+                want = om.encode(s)
+                assert status[i] == 0 and got[i] == want, (it, i, s, toks, scores)
+            except O.NoPath as e:
+                assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
+
+
+def test_crlf_batch_vs_oracle(N):
+    m = N.Model([b"a"], [-1.0])
+    rng = random.Random(7)
+    samples = [b"a\r\nb", b"\r\r\n", b"\r", b"\n", b"x\r", b"\ny", b"", b"\r\n\r\n\r", b"\r\n"]
+    samples += [bytes(rng.choice(b"\r\nab") for _ in range(rng.randrange(0, 9000))) for _ in range(60)]
+    blob, off = N.pack(samples)
+    out, out_off = m.crlf_batch(blob, off)
+    for i, s in enumerate(samples):
+        assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == O.crlf(s) == s.replace(b"\r\n", b"\n"), i
+
+
+def test_synth_corpus_bit_exact_with_crlf(N):
+    blob, off, toks, sc, kp = synth_setup(1, 11, 6_000_000, 32768, 16)
+    gm, om = both(N, toks, sc)
+    for g, thr in [(8, 32768), (4, 4096), (1, 2048)]:
+        gm.set_option(0, g)
+        gm.set_option(1, thr)
+        ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
+        wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=True, threads=8)
+        assert rc == 0 and wbad == 0
+        assert np.array_equal(id_off, wid_off)
+        assert np.array_equal(ids, wids)
+        assert np.array_equal(plen, wplen)
+    # property (ii): decode(encode(x)) == crlf(x)
+    lens = np.array([len(t) for t in toks])
+    assert int(lens[ids].sum()) == int(plen.sum())
+    s0 = blob[int(off[3]):int(off[4])].tobytes()
+    dec = b"".join(toks[i] for i in ids[int(id_off[3]):int(id_off[4])])
+    assert dec == s0.replace(b"\r\n", b"\n")
+
+
+def test_token_frequencies_exact(N):
+    blob, off, toks, sc, kp = synth_setup(2, 12, 3_000_000, 20000, 16)
+    gm, om = both(N, toks, sc)
+    fr, rc, bad, blen = gm.token_frequencies(blob, off)
+    want = om.token_frequencies(blob, off, threads=8)
+    assert rc == 0 and np.array_equal(fr, want)
+    lens = np.array([len(t) for t in toks], dtype=np.uint64)
+    assert int((fr * lens).sum()) == int(off[-1])  # invariant (iv)
+    # NoPath surfaces like src/prune.rs:218-221
+    gm2 = N.Model([b"a"], [-1.0])
+    b2, o2 = N.pack([b"aaa", b"aba"])
+    fr, rc, bad, blen = gm2.token_frequencies(b2, o2)
+    assert rc == N.TGX_ERR_NO_PATH and bad == 1 and blen == 3
+
+
+# ----------------------------------------------------------------------------- E-step
+LATTICE_VOCAB = [(b"<", -3.0), (b" value", -6.0), (b">", -3.0), (b"DC value", -8.0), (b"<DC", -4.0),
+                 (b"<DC value>", -12.0)]
+
+
+@pytest.mark.parametrize("g", [1, 8, 32])
+def test_reference_lattice_marginals(N, g):
+    toks = [t for t, _ in LATTICE_VOCAB]
+    sc = [s for _, s in LATTICE_VOCAB]
+    m = N.Model(toks, sc)
+    m.set_option(2, g)
+    blob, off = N.pack([b"<DC value>"])
+    ex, rc, bad, badz = m.expected_counts(blob, off)
+    want = {b"<DC value>": 0.665241, b">": 0.334759, b"<DC": 0.244728, b" value": 0.244728, b"<": 0.090031,
+            b"DC value": 0.090031}  # /root/reference/src/lattice.rs:447-452
+    assert rc == 0
+    for t, e in zip(toks, ex):
+        assert abs(e - want[t]) < 5e-7
+    # Q7: positions nothing ends at keep log 1
+    m = N.Model([b"ab", b"c", b"bc"], [-1.0, -2.0, -3.0])
+    m.set_option(2, g)
+    blob, off = N.pack([b"abc"])
+    ex, rc, bad, badz = m.expected_counts(blob, off)
+    assert rc == 0 and np.allclose(ex, [0.5, 0.5, 0.5], rtol=1e-12)
+
+
+@pytest.mark.parametrize("g", [1, 4, 32])
+def test_expected_counts_random_vs_oracle(N, g):
+    rng = random.Random(200 + g)
+    for it in range(20):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(5, 40), max_len=rng.randrange(1, 8),
+                                  complete=True)
+        gm, om = both(N, toks, scores)
+        gm.set_option(2, g)
+        samples = rand_samples(rng, b"abcd", rng.randrange(1, 60), 1, 300)
+        blob, off = N.pack(samples)
+        snip = rng.choice([7, 64, 81920])
+        ex, rc, bad, badz = gm.expected_counts(blob, off, snippet_len=snip)
+        want, wrc, wbad, _ = om.run_e_step(blob, off, threads=1, literal=True, max_sample_length=snip)
+        assert rc == 0 and wrc == 0
+        assert np.allclose(ex, want, rtol=REL_TOL, atol=0), np.max(np.abs(ex - want) / np.maximum(want, 1e-300))
+        tot = sum(e * len(t) for e, t in zip(ex, toks))
+        assert abs(tot - int(off[-1])) < 1e-9 * int(off[-1])  # invariant (i)
+
+
+def test_expected_counts_bad_z(N):
+    m = N.Model([b"a"], [-1.0])
+    blob, off = N.pack([b"aa", b"ab", b"a"])
+    ex, rc, bad, badz = m.expected_counts(blob, off)
+    assert rc == N.TGX_ERR_BAD_Z and bad == 1 and badz == 0.0  # Q11: z == 0.0 is not normal
+
+
+def test_expected_counts_synth_vs_oracle(N):
+    blob, off, toks, sc, kp = synth_setup(2, 13, 2_000_000, 30000, 16)
+    gm, om = both(N, toks, sc)
+    for g in (1, 8):
+        gm.set_option(2, g)
+        ex, rc, bad, badz = gm.expected_counts(blob, off)
+        want, wrc, wbad, _ = om.run_e_step(blob, off, threads=8, literal=False)
+        assert rc == 0 and wrc == 0
+        nz = want > 0
+        rel = np.abs(ex[nz] - want[nz]) / want[nz]
+        assert rel.max() < REL_TOL, rel.max()
+        assert np.all(ex[~nz] == 0)
+        lens = np.array([len(t) for t in toks], dtype=np.float64)
+        assert abs(float((ex * lens).sum()) - int(off[-1])) < 1e-9 * int(off[-1])

@@ -1,0 +1,37 @@
+"""Shared helpers for the test-suite (seeded vocabularies / corpora)."""
+import functools
+import random
+
+import numpy as np
+
+
+def rand_vocab(rng, alphabet=b"abc", n_tok=12, max_len=4, complete=True, int_scores=False):
+    toks = set()
+    if complete:
+        toks |= {bytes([c]) for c in alphabet}
+    while len(toks) < n_tok:
+        toks.add(bytes(rng.choice(alphabet) for _ in range(rng.randrange(1, max_len + 1))))
+    toks = sorted(toks)
+    rng.shuffle(toks)
+    if int_scores:  # many exact ties
+        scores = [-float(rng.randrange(2, 6)) for _ in toks]
+    else:
+        scores = [-(rng.random() * 6 + 0.5) for _ in toks]
+    return toks, scores
+
+
+def rand_samples(rng, alphabet, n, lo, hi):
+    return [bytes(rng.choice(alphabet) for _ in range(rng.randrange(lo, hi))) for _ in range(n)]
+
+
+@functools.lru_cache(maxsize=4)
+def synth_setup(kind: int, seed: int, nbytes: int, vocab_size: int, max_len: int):
+    """(blob, off, tokens, scores, keep) — cached per session."""
+    from tokengeex_b200 import synth
+    blob, off = synth.corpus(kind, seed, nbytes)
+    toks, sc, kp = synth.vocab(blob, off, seed, vocab_size, max_len, 0.05)
+    return blob, off, toks, sc, kp
+
+
+def split_ids(ids: np.ndarray, id_off: np.ndarray):
+    return [ids[int(id_off[i]):int(id_off[i + 1])].tolist() for i in range(len(id_off) - 1)]

@@ -1,0 +1,254 @@
+"""ctypes binding of libtokengeex_b200.so (the C ABI in include/tokengeex_b200.h).
+
+The library is built in-tree by ``make -C tokengeex_b200/csrc`` (or
+``__graft_entry__.build()``).  There is no Python or CPU fallback: if the shared
+library is missing, importing this module raises, and every compute entry point
+fails with TGX_ERR_NO_DEVICE when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtokengeex_b200.so")
+
+TGX_OK, TGX_ERR_INVALID, TGX_ERR_UNSUPPORTED, TGX_ERR_NO_DEVICE = 0, 1, 2, 3
+TGX_ERR_CUDA, TGX_ERR_CAPACITY, TGX_ERR_NO_PATH, TGX_ERR_BAD_Z = 4, 5, 6, 7
+TGX_FLAG_CRLF = 1
+SNIPPET_LEN = 8192 * 10  # MAX_SAMPLE_LENGTH, /root/reference/src/prune.rs:75
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("vocab_size", C.c_uint64), ("max_token_len", C.c_uint32), ("trie_nodes", C.c_uint32),
+                ("trie_slots", C.c_uint32), ("trie_terminals", C.c_uint32), ("device", C.c_int32)]
+
+
+# every symbol include/tokengeex_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("tgx_last_error", C.c_char_p, []),
+    ("tgx_model_create", C.c_int, [u8p, u64p, f64p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    ("tgx_model_destroy", None, [C.c_void_p]),
+    ("tgx_model_get_info", C.c_int, [C.c_void_p, C.POINTER(ModelInfo)]),
+    ("tgx_model_common_prefix_search", C.c_int, [C.c_void_p, u8p, C.c_uint64, u32p, u32p, C.c_uint64, u64p]),
+    ("tgx_crlf_batch", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, u8p, u64p]),
+    ("tgx_encode_batch", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u32p, C.c_uint64, u64p, i32p,
+                                   u64p, i64p]),
+    ("tgx_encode_batch_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, u64p, i64p]),
+    ("tgx_expected_counts", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, f64p, i64p, f64p]),
+    ("tgx_expected_counts_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_void_p, i64p, f64p]),
+    ("tgx_token_frequencies", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u64p, i64p, u64p]),
+    ("tgx_token_frequencies_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                            C.c_void_p, i64p, u64p]),
+    ("tgx_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    ("tgx_host_free", C.c_int, [C.c_void_p]),
+    ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
+    ("tgx_model_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C tokengeex_b200/csrc` "
+                "(there is no Python / CPU fallback for the tokengeex_b200 hot path)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class TgxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[tgx {code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _check(rc: int, ok: Sequence[int] = (TGX_OK,)) -> int:
+    if rc not in ok:
+        raise TgxError(rc, lib().tgx_last_error().decode(errors="replace"))
+    return rc
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def pack(items: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """blob u8[] (>= 1 element) + offsets u64[len+1]."""
+    lens = np.fromiter((len(t) for t in items), dtype=np.uint64, count=len(items))
+    off = np.zeros(len(items) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    joined = b"".join(items)
+    blob = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, np.uint8)
+    return blob, off
+
+
+class Model:
+    """Device-resident vocabulary: Model::from(vocab) (/root/reference/src/model.rs:16-30)."""
+
+    def __init__(self, tokens: Sequence[bytes], scores, device: Optional[int] = 0):
+        L = lib()
+        blob, off = pack(tokens)
+        sc = np.ascontiguousarray(scores, dtype=np.float64)
+        if sc.size == 0:
+            sc = np.zeros(1, np.float64)
+        h = C.c_void_p()
+        _check(L.tgx_model_create(_p(blob, u8p), _p(off, u64p), _p(sc, f64p), len(tokens),
+                                  -1 if device is None else int(device), C.byref(h)))
+        self._h = h
+        self.V = len(tokens)
+        self.device = -1 if device is None else int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().tgx_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- info / options --------------------------------------------------------------
+    def info(self) -> ModelInfo:
+        inf = ModelInfo()
+        _check(lib().tgx_model_get_info(self._h, C.byref(inf)))
+        return inf
+
+    def set_option(self, key: int, value: int):
+        _check(lib().tgx_model_set_option(self._h, key, value))
+
+    def stat(self, what: int) -> float:
+        return float(lib().tgx_model_last_stat(self._h, what))
+
+    def common_prefix_search(self, text: bytes):
+        n = len(text)
+        a = np.frombuffer(text, np.uint8) if n else np.zeros(1, np.uint8)
+        cap = max(n, 1)
+        ids = np.zeros(cap, np.uint32)
+        lens = np.zeros(cap, np.uint32)
+        cnt = C.c_uint64(0)
+        _check(lib().tgx_model_common_prefix_search(self._h, _p(a, u8p), n, _p(ids, u32p), _p(lens, u32p), cap,
+                                                    C.byref(cnt)))
+        k = int(cnt.value)
+        return ids[:k].tolist(), lens[:k].tolist()
+
+    # ---- host-buffer API ---------------------------------------------------------------
+    def crlf_batch(self, blob: np.ndarray, off: np.ndarray):
+        S = len(off) - 1
+        out = np.zeros(max(int(off[-1]), 1), np.uint8)
+        out_off = np.zeros(S + 1, np.uint64)
+        _check(lib().tgx_crlf_batch(self._h, _p(blob, u8p), _p(off, u64p), S, _p(out, u8p), _p(out_off, u64p)))
+        return out[:int(out_off[S])], out_off
+
+    def encode_batch(self, blob: np.ndarray, off: np.ndarray, crlf: bool = False, ids_out: np.ndarray = None):
+        """→ (ids u32[T], id_off u64[S+1], status i32[S], proc_len u64[S], rc, first_bad)"""
+        S = len(off) - 1
+        N = int(off[-1])
+        ids = ids_out if ids_out is not None else np.empty(max(N, 1), np.uint32)
+        id_off = np.zeros(S + 1, np.uint64)
+        status = np.zeros(max(S, 1), np.int32)
+        plen = np.zeros(max(S, 1), np.uint64)
+        bad = C.c_int64(-1)
+        rc = lib().tgx_encode_batch(self._h, _p(blob, u8p), _p(off, u64p), S, TGX_FLAG_CRLF if crlf else 0,
+                                    _p(ids, u32p), ids.size, _p(id_off, u64p), _p(status, i32p), _p(plen, u64p),
+                                    C.byref(bad))
+        _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
+        return ids[:int(id_off[S])], id_off, status[:S], plen[:S], rc, int(bad.value)
+
+    def expected_counts(self, blob: np.ndarray, off: np.ndarray, snippet_len: int = SNIPPET_LEN):
+        """→ (expected f64[V], rc, bad_sample, bad_z)"""
+        S = len(off) - 1
+        ex = np.zeros(max(self.V, 1), np.float64)
+        bad = C.c_int64(-1)
+        badz = C.c_double(0.0)
+        rc = lib().tgx_expected_counts(self._h, _p(blob, u8p), _p(off, u64p), S, snippet_len, _p(ex, f64p),
+                                       C.byref(bad), C.byref(badz))
+        _check(rc, (TGX_OK, TGX_ERR_BAD_Z))
+        return ex[:self.V], rc, int(bad.value), float(badz.value)
+
+    def token_frequencies(self, blob: np.ndarray, off: np.ndarray, crlf: bool = False):
+        """→ (freq u64[V], rc, first_bad, bad_len)"""
+        S = len(off) - 1
+        fr = np.zeros(max(self.V, 1), np.uint64)
+        bad = C.c_int64(-1)
+        blen = C.c_uint64(0)
+        rc = lib().tgx_token_frequencies(self._h, _p(blob, u8p), _p(off, u64p), S, TGX_FLAG_CRLF if crlf else 0,
+                                         _p(fr, u64p), C.byref(bad), C.byref(blen))
+        _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
+        return fr[:self.V], rc, int(bad.value), int(blen.value)
+
+    # ---- device-pointer API (torch tensors' data_ptr()) ---------------------------------
+    def encode_batch_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, crlf: bool, d_ids: int, ids_cap: int,
+                         d_id_off: int, d_status: int = 0, d_proc_len: int = 0):
+        tot = C.c_uint64(0)
+        bad = C.c_int64(-1)
+        rc = lib().tgx_encode_batch_dev(self._h, d_text, d_off, S, n_bytes, TGX_FLAG_CRLF if crlf else 0, d_ids,
+                                        ids_cap, d_id_off, d_status or None, d_proc_len or None, C.byref(tot),
+                                        C.byref(bad))
+        _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
+        return int(tot.value), rc, int(bad.value)
+
+    def expected_counts_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, d_expected: int,
+                            snippet_len: int = SNIPPET_LEN):
+        bad = C.c_int64(-1)
+        badz = C.c_double(0.0)
+        rc = lib().tgx_expected_counts_dev(self._h, d_text, d_off, S, n_bytes, snippet_len, d_expected,
+                                           C.byref(bad), C.byref(badz))
+        _check(rc, (TGX_OK, TGX_ERR_BAD_Z))
+        return rc, int(bad.value), float(badz.value)
+
+    def token_frequencies_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, crlf: bool, d_freq: int):
+        bad = C.c_int64(-1)
+        blen = C.c_uint64(0)
+        rc = lib().tgx_token_frequencies_dev(self._h, d_text, d_off, S, n_bytes, TGX_FLAG_CRLF if crlf else 0,
+                                             d_freq, C.byref(bad), C.byref(blen))
+        _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
+        return rc, int(bad.value), int(blen.value)
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """uint8 numpy array over cudaHostAlloc'd memory (freed when the array is collected)."""
+    p = C.c_void_p()
+    _check(lib().tgx_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().tgx_host_free(self.ptr)
+            except Exception:
+                pass
+
+    arr = arr[:nbytes]
+    _OWNERS[arr.ctypes.data] = _Owner(p)
+    return arr
+
+
+_OWNERS = {}

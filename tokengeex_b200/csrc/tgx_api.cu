@@ -1,0 +1,880 @@
+// C ABI of the B200-native TokenGeeX hot path (include/tokengeex_b200.h) and the helper
+// kernels around the Viterbi / forward-backward kernels of tgx_kernels.cuh.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
+// (--fmad=false: every f64 sum on the score path must round exactly like the
+// reference's separate add instructions.)
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tokengeex_b200.h"
+#include "tgx_kernels.cuh"
+#include "trie_build.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(TGX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+// Growable device buffer (never shrinks; reused across calls).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Stats {
+  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0;
+};
+
+}  // namespace
+
+struct tgx_model {
+  tgx::DoubleArray da;
+  uint64_t V = 0;
+  int device = -1;
+  uint4* d_trie = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::recursive_mutex mu;
+  Stats stats;
+  // options
+  int g_short = 8;
+  int64_t long_threshold = 32768;
+  int g_estep = 1;
+  // workspace
+  DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, ntok,
+      idoff, status, A, expected, freq, ids, small, scount;
+};
+
+// =========================================================================================
+// helper kernels
+// =========================================================================================
+namespace tgxk {
+
+constexpr int CRLF_BLOCK = 256;               // threads
+constexpr int CRLF_PER_THREAD = 16;           // bytes
+constexpr int CRLF_TILE = CRLF_BLOCK * CRLF_PER_THREAD;
+
+// K1a: one bit per byte position that starts a sample (so "\r" | "\n" across a sample
+// boundary is not merged: the processor runs per sample, src/tokenizer.rs:92-99).
+__global__ void crlf_mark_starts(const uint64_t* __restrict__ off, uint64_t S, uint32_t* __restrict__ bitmap) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0 || s >= S) return;
+  uint64_t p = off[s];
+  atomicOr(bitmap + (p >> 5), 1u << (p & 31));
+}
+
+// removed(p): text[p] == '\r' followed, inside the same sample, by '\n'
+// (str::replace("\r\n", "\n"), src/processor.rs:47-49: left-to-right, non-overlapping —
+// "\r\n" occurrences never overlap each other, so the predicate is position-local).
+__device__ __forceinline__ uint32_t crlf_removed_mask(const uint8_t* __restrict__ text, uint64_t N,
+                                                      const uint32_t* __restrict__ bitmap, uint64_t base,
+                                                      uint8_t (&b)[CRLF_PER_THREAD + 1]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i <= CRLF_PER_THREAD; i++) b[i] = (base + i < N) ? text[base + i] : 0;
+#pragma unroll
+  for (int i = 0; i < CRLF_PER_THREAD; i++) {
+    uint64_t q = base + i + 1;
+    if (b[i] == '\r' && q < N && b[i + 1] == '\n') {
+      bool boundary = (bitmap[q >> 5] >> (q & 31)) & 1u;
+      if (!boundary) m |= 1u << i;
+    }
+  }
+  return m;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+      if (lane >= o) w += y;
+    }
+    if (lane < (int)(blockDim.x >> 5)) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  uint32_t before = warp ? warp_sums[warp - 1] : 0;
+  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  return before + x - v;
+}
+
+// K1b: removed bytes per 4096-byte tile.
+__global__ void __launch_bounds__(CRLF_BLOCK) crlf_count(const uint8_t* __restrict__ text, uint64_t N,
+                                                         const uint32_t* __restrict__ bitmap,
+                                                         unsigned long long* __restrict__ blk_removed) {
+  __shared__ uint32_t ws[CRLF_BLOCK / 32];
+  uint64_t base = (uint64_t)blockIdx.x * CRLF_TILE + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
+  uint8_t b[CRLF_PER_THREAD + 1];
+  uint32_t m = crlf_removed_mask(text, N, bitmap, base, b);
+  uint32_t total;
+  block_exclusive_scan(__popc(m), ws, &total);
+  if (threadIdx.x == 0) blk_removed[blockIdx.x] = total;
+}
+
+// K1c: scatter kept bytes.  blk_prefix = exclusive scan of blk_removed.
+__global__ void __launch_bounds__(CRLF_BLOCK) crlf_scatter(const uint8_t* __restrict__ text, uint64_t N,
+                                                           const uint32_t* __restrict__ bitmap,
+                                                           const unsigned long long* __restrict__ blk_prefix,
+                                                           uint8_t* __restrict__ out) {
+  __shared__ uint32_t ws[CRLF_BLOCK / 32];
+  uint64_t base = (uint64_t)blockIdx.x * CRLF_TILE + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
+  uint8_t b[CRLF_PER_THREAD + 1];
+  uint32_t m = crlf_removed_mask(text, N, bitmap, base, b);
+  uint32_t before = block_exclusive_scan(__popc(m), ws, nullptr);
+  uint64_t o = base - blk_prefix[blockIdx.x] - before;
+#pragma unroll
+  for (int i = 0; i < CRLF_PER_THREAD; i++) {
+    if (base + i < N && !((m >> i) & 1u)) out[o++] = b[i];
+  }
+}
+
+// K1d: new sample offsets: off[s] - removed_before(off[s]).
+__global__ void crlf_offsets(const uint8_t* __restrict__ text, uint64_t N, const uint64_t* __restrict__ off,
+                             uint64_t S, const uint32_t* __restrict__ bitmap,
+                             const unsigned long long* __restrict__ blk_prefix, uint64_t n_tiles,
+                             uint64_t* __restrict__ new_off) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > S) return;
+  uint64_t p = off[s];
+  uint64_t tile = p / CRLF_TILE;
+  unsigned long long removed;
+  uint64_t q;
+  if (tile >= n_tiles) {  // p == N on a tile boundary: everything before
+    removed = n_tiles ? blk_prefix[n_tiles] : 0;
+    q = p;
+  } else {
+    removed = blk_prefix[tile];
+    q = tile * CRLF_TILE;
+  }
+  for (; q < p; q++) {
+    if (text[q] == '\r' && q + 1 < N && text[q + 1] == '\n' && !((bitmap[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u))
+      removed++;
+  }
+  new_off[s] = p - removed;
+}
+
+// units = samples
+__global__ void units_from_samples(const uint64_t* __restrict__ off, uint64_t S, uint64_t* __restrict__ ustart,
+                                   uint32_t* __restrict__ ulen, uint32_t* __restrict__ idx,
+                                   uint64_t* __restrict__ proc_len) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  uint64_t a = off[s], b = off[s + 1];
+  ustart[s] = a;
+  ulen[s] = (uint32_t)(b - a);
+  idx[s] = (uint32_t)s;
+  if (proc_len) proc_len[s] = b - a;
+}
+
+// units = snippets: sample.as_bytes().chunks(snippet_len)  (src/prune.rs:83)
+__global__ void snippet_counts(const uint64_t* __restrict__ off, uint64_t S, uint64_t snip,
+                               unsigned long long* __restrict__ cnt) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  uint64_t n = off[s + 1] - off[s];
+  cnt[s] = (n + snip - 1) / snip;
+}
+__global__ void units_from_snippets(const uint64_t* __restrict__ off, uint64_t S, uint64_t snip,
+                                    const unsigned long long* __restrict__ first_unit,
+                                    uint64_t* __restrict__ ustart, uint32_t* __restrict__ ulen,
+                                    uint32_t* __restrict__ idx, uint32_t* __restrict__ unit_sample) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  uint64_t a = off[s], n = off[s + 1] - a;
+  unsigned long long u = first_unit[s];
+  for (uint64_t o = 0; o < n; o += snip, u++) {
+    ustart[u] = a + o;
+    ulen[u] = (uint32_t)min((unsigned long long)snip, (unsigned long long)(n - o));
+    idx[u] = (uint32_t)u;
+    unit_sample[u] = (uint32_t)s;
+  }
+}
+
+// counts[0] = #units with len >= long_threshold, counts[1] = #units with len >= 1
+__global__ void split_sorted(const uint32_t* __restrict__ sorted_len, uint32_t U, uint32_t long_threshold,
+                             uint32_t* __restrict__ counts) {
+  if (threadIdx.x || blockIdx.x) return;
+  auto first_below = [&](uint32_t thr) {  // descending order: first index with len < thr
+    uint32_t lo = 0, hi = U;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (sorted_len[mid] >= thr) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  counts[0] = first_below(long_threshold);
+  counts[1] = first_below(1);
+}
+
+// lowest unit index with non-zero status (and its payload)
+__global__ void first_bad_unit(const int32_t* __restrict__ status, uint32_t U, unsigned long long* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < U && status[i] != 0) atomicMin(out, (unsigned long long)i);
+}
+
+__global__ void add_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+}  // namespace tgxk
+
+// =========================================================================================
+// host side
+// =========================================================================================
+namespace {
+
+using namespace tgxk;
+
+struct Timer {
+  cudaEvent_t a, b;
+};
+
+template <int G>
+cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
+  if (!p.u.count) return cudaSuccess;
+  size_t smem = warp_smem_bytes(p.u.rows, p.u.W, G) * WPB;
+  cudaError_t e = cudaFuncSetAttribute(viterbi_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  uint32_t per_block = WPB * (32 / G);
+  uint32_t blocks = (p.u.count + per_block - 1) / per_block;
+  viterbi_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
+  m->stats.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
+  switch (G) {
+    case 1: return launch_viterbi<1>(m, p);
+    case 2: return launch_viterbi<2>(m, p);
+    case 4: return launch_viterbi<4>(m, p);
+    case 8: return launch_viterbi<8>(m, p);
+    case 16: return launch_viterbi<16>(m, p);
+    default: return launch_viterbi<32>(m, p);
+  }
+}
+
+template <int G>
+cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward) {
+  if (!p.u.count) return cudaSuccess;
+  size_t smem = warp_smem_bytes(p.u.rows, p.u.W, G) * WPB;
+  cudaError_t e;
+  uint32_t per_block = WPB * (32 / G);
+  uint32_t blocks = (p.u.count + per_block - 1) / per_block;
+  if (!backward) {
+    e = cudaFuncSetAttribute(fb_forward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fb_forward_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(fb_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fb_backward_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
+  }
+  m->stats.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fb_g(tgx_model* m, int G, const FbParams& p, bool backward) {
+  switch (G) {
+    case 1: return launch_fb<1>(m, p, backward);
+    case 2: return launch_fb<2>(m, p, backward);
+    case 4: return launch_fb<4>(m, p, backward);
+    case 8: return launch_fb<8>(m, p, backward);
+    case 16: return launch_fb<16>(m, p, backward);
+    default: return launch_fb<32>(m, p, backward);
+  }
+}
+
+inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
+
+int check_model(tgx_model* m) {
+  if (!m) return fail(TGX_ERR_INVALID, "null model");
+  if (m->device < 0)
+    return fail(TGX_ERR_NO_DEVICE, "model was created host-only (device = -1); there is no CPU compute path");
+  CU(cudaSetDevice(m->device));
+  return TGX_OK;
+}
+
+// crlf on device: (d_text,d_off) -> (m->text2, m->off2).  N = total bytes.
+int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N) {
+  cudaStream_t st = m->stream;
+  uint64_t n_tiles = (N + CRLF_TILE - 1) / CRLF_TILE;
+  CU(m->text2.reserve(N + 16));
+  CU(m->off2.reserve((S + 1) * 8));
+  CU(m->bitmap.reserve((N / 32 + 2) * 4));
+  CU(m->blk.reserve((n_tiles + 1) * 8 * 2));
+  CU(cudaMemsetAsync(m->bitmap.p, 0, (N / 32 + 2) * 4, st));
+  if (S > 1) {
+    crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->bitmap.as<uint32_t>());
+    m->stats.launches += 1;
+  }
+  unsigned long long* removed = m->blk.as<unsigned long long>();
+  unsigned long long* prefix = removed + n_tiles + 1;
+  CU(cudaMemsetAsync(removed, 0, (n_tiles + 1) * 8, st));
+  if (n_tiles) {
+    crlf_count<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->bitmap.as<uint32_t>(), removed);
+    m->stats.launches += 1;
+  }
+  size_t tmp = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, removed, prefix, (int)(n_tiles + 1), st));
+  CU(m->cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, removed, prefix, (int)(n_tiles + 1), st));
+  m->stats.launches += 2;
+  if (n_tiles) {
+    crlf_scatter<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->bitmap.as<uint32_t>(), prefix,
+                                                          m->text2.as<uint8_t>());
+    m->stats.launches += 1;
+  }
+  crlf_offsets<<<nblk(S + 1, 128), 128, 0, st>>>(d_text, N, d_off, S, m->bitmap.as<uint32_t>(), prefix, n_tiles,
+                                               m->off2.as<uint64_t>());
+  m->stats.launches += 1;
+  CU(cudaGetLastError());
+  return TGX_OK;
+}
+
+// sort unit indices by length, descending: keys in m->ulen, values in m->vals_in -> m->vals_out
+int sort_units(tgx_model* m, uint32_t U) {
+  CU(m->keys_out.reserve((size_t)U * 4 + 4));
+  CU(m->vals_out.reserve((size_t)U * 4 + 4));
+  size_t tmp = 0;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, m->ulen.as<uint32_t>(), m->keys_out.as<uint32_t>(),
+                                               m->vals_in.as<uint32_t>(), m->vals_out.as<uint32_t>(), (int)U, 0, 32,
+                                               m->stream));
+  CU(m->cubtmp.reserve(tmp));
+  CU(cub::DeviceRadixSort::SortPairsDescending(m->cubtmp.p, tmp, m->ulen.as<uint32_t>(), m->keys_out.as<uint32_t>(),
+                                               m->vals_in.as<uint32_t>(), m->vals_out.as<uint32_t>(), (int)U, 0, 32,
+                                               m->stream));
+  m->stats.launches += 4;
+  return TGX_OK;
+}
+
+// Viterbi over all samples.  On return m->bp holds right-aligned ids, m->ntok token
+// counts, m->status per-sample status.  d_freq optional.
+int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
+                uint64_t* d_proc_len, unsigned long long* d_freq, bool emit) {
+  cudaStream_t st = m->stream;
+  if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
+  uint32_t U = (uint32_t)S;
+  CU(m->ustart.reserve((size_t)U * 8 + 8));
+  CU(m->ulen.reserve((size_t)U * 4 + 4));
+  CU(m->vals_in.reserve((size_t)U * 4 + 4));
+  CU(m->bp.reserve((N + 4) * 4));
+  CU(m->ntok.reserve(((size_t)U + 1) * 8));
+  CU(m->status.reserve((size_t)U * 4 + 4));
+  CU(m->small.reserve(64));
+  units_from_samples<<<nblk(U, 256), 256, 0, st>>>(d_off, S, m->ustart.as<uint64_t>(), m->ulen.as<uint32_t>(),
+                                                  m->vals_in.as<uint32_t>(), d_proc_len);
+  m->stats.launches += 1;
+  int rc = sort_units(m, U);
+  if (rc) return rc;
+  uint32_t* counts = m->small.as<uint32_t>();
+  uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
+  split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, counts);
+  m->stats.launches += 1;
+  uint32_t h[2];
+  CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemsetAsync(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
+  CU(cudaMemsetAsync(m->status.p, 0, (size_t)U * 4 + 4, st));
+  CU(cudaStreamSynchronize(st));
+  uint32_t n_long = h[0], n_nonempty = h[1];
+
+  ViterbiParams p;
+  p.u.text = d_text;
+  p.u.unit_start = m->ustart.as<uint64_t>();
+  p.u.unit_len = m->ulen.as<uint32_t>();
+  p.u.order = m->vals_out.as<uint32_t>();
+  p.u.trie = m->d_trie;
+  p.u.root_base = m->da.root_base;
+  p.u.rows = std::max<uint32_t>(1, m->da.max_token_len);
+  p.u.W = p.u.rows + 1;
+  p.bp = m->bp.as<uint32_t>();
+  p.n_tokens = m->ntok.as<unsigned long long>();
+  p.status = m->status.as<int32_t>();
+  p.freq = d_freq;
+  p.emit = emit ? 1 : 0;
+
+  CU(cudaEventRecord(m->ev[0], st));
+  p.u.first = 0;
+  p.u.count = n_long;
+  CU(launch_viterbi_g(m, 32, p));
+  p.u.first = n_long;
+  p.u.count = n_nonempty - n_long;
+  CU(launch_viterbi_g(m, m->g_short, p));
+  CU(cudaEventRecord(m->ev[1], st));
+  return TGX_OK;
+}
+
+int first_bad(tgx_model* m, uint32_t U, int64_t* out_idx) {
+  unsigned long long* d = m->small.as<unsigned long long>() + 2;
+  CU(cudaMemsetAsync(d, 0xFF, 8, m->stream));
+  if (U) {
+    first_bad_unit<<<nblk(U, 256), 256, 0, m->stream>>>(m->status.as<int32_t>(), U, d);
+    m->stats.launches += 1;
+  }
+  unsigned long long h;
+  CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  *out_idx = (h == ~0ull) ? -1 : (int64_t)h;
+  return TGX_OK;
+}
+
+void finish_stats(tgx_model* m, int which) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) {
+    if (which == 1) m->stats.viterbi_ms = ms;
+    if (which == 2) m->stats.fwd_ms = ms;
+  }
+  if (which == 2 && cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->stats.bwd_ms = ms;
+  if (cudaEventElapsedTime(&ms, m->ev[6], m->ev[7]) == cudaSuccess) m->stats.total_ms = ms;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* tgx_last_error(void) { return g_err.c_str(); }
+
+int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                     uint64_t vocab_size, int device, tgx_model** out) {
+  if (!out || !token_offsets || (!token_bytes && vocab_size && token_offsets[vocab_size]) || (!scores && vocab_size))
+    return fail(TGX_ERR_INVALID, "null argument");
+  std::unique_ptr<tgx_model> m(new tgx_model());
+  std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &m->da);
+  if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);
+  m->V = vocab_size;
+  m->device = device;
+  if (device >= 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n)
+      return fail(TGX_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto& e : m->ev) CU(cudaEventCreate(&e));
+    size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
+    CU(cudaMalloc(&m->d_trie, bytes));
+    CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+  }
+  *out = m.release();
+  return TGX_OK;
+}
+
+void tgx_model_destroy(tgx_model* m) {
+  if (!m) return;
+  if (m->device >= 0) {
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    DevBuf* bufs[] = {&m->text, &m->off, &m->text2, &m->off2, &m->bitmap, &m->blk, &m->ustart, &m->ulen,
+                      &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->ntok, &m->idoff,
+                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount};
+    for (auto* b : bufs) b->release();
+    if (m->d_trie) cudaFree(m->d_trie);
+    for (auto& e : m->ev)
+      if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+  }
+  delete m;
+}
+
+int tgx_model_get_info(const tgx_model* m, tgx_model_info* info) {
+  if (!m || !info) return fail(TGX_ERR_INVALID, "null argument");
+  info->vocab_size = m->V;
+  info->max_token_len = m->da.max_token_len;
+  info->trie_nodes = m->da.n_nodes;
+  info->trie_slots = (uint32_t)m->da.slots.size();
+  info->trie_terminals = m->da.n_terminals;
+  info->device = m->device;
+  return TGX_OK;
+}
+
+int tgx_model_common_prefix_search(const tgx_model* m, const uint8_t* text, uint64_t n, uint32_t* ids,
+                                   uint32_t* lens, uint64_t cap, uint64_t* count) {
+  if (!m || (!text && n) || !count) return fail(TGX_ERR_INVALID, "null argument");
+  uint64_t k = 0;
+  tgx::da_common_prefix_search(m->da, text, (size_t)n, [&](uint32_t id, uint32_t len) {
+    if (k < cap) {
+      if (ids) ids[k] = id;
+      if (lens) lens[k] = len;
+    }
+    k++;
+  });
+  *count = k;
+  return TGX_OK;
+}
+
+int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
+  if (!m) return fail(TGX_ERR_INVALID, "null model");
+  auto okg = [](int64_t g) { return g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32; };
+  switch (key) {
+    case 0: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per sample must be 1,2,4,8,16,32"); m->g_short = (int)value; break;
+    case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
+    case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
+    default: return fail(TGX_ERR_INVALID, "unknown option");
+  }
+  return TGX_OK;
+}
+
+double tgx_model_last_stat(const tgx_model* m, int what) {
+  if (!m) return 0;
+  switch (what) {
+    case 0: return m->stats.launches;
+    case 1: return m->stats.viterbi_ms;
+    case 2: return m->stats.fwd_ms;
+    case 3: return m->stats.bwd_ms;
+    case 4: return m->stats.total_ms;
+  }
+  return 0;
+}
+
+int tgx_host_alloc(void** p, uint64_t bytes) {
+  if (!p) return fail(TGX_ERR_INVALID, "null argument");
+  CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return TGX_OK;
+}
+int tgx_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return TGX_OK;
+}
+
+// ---------------------------------------------------------------------------- crlf
+int tgx_crlf_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint8_t* out_text,
+                   uint64_t* out_off) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!off || !out_off || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  m->stats = Stats();
+  uint64_t N = off[S];
+  CU(m->text.reserve(N + 16));
+  CU(m->off.reserve((S + 1) * 8));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+  rc = run_crlf(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out_off, m->off2.p, (S + 1) * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaMemcpyAsync(out_text, m->text2.p, out_off[S], cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return TGX_OK;
+}
+
+// ---------------------------------------------------------------------------- encode
+int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                         uint64_t n_bytes, uint32_t flags, uint32_t* d_ids, uint64_t ids_cap,
+                         uint64_t* d_id_off, int32_t* d_status, uint64_t* d_proc_len, uint64_t* total_ids,
+                         int64_t* first_bad_out) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!d_off || !d_id_off || (!d_ids && ids_cap)) return fail(TGX_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  m->stats = Stats();
+  cudaStream_t st = m->stream;
+  if (first_bad_out) *first_bad_out = -1;
+  if (total_ids) *total_ids = 0;
+  if (S == 0) {
+    CU(cudaMemsetAsync(d_id_off, 0, 8, st));
+    CU(cudaStreamSynchronize(st));
+    return TGX_OK;
+  }
+  CU(cudaEventRecord(m->ev[6], st));
+  const uint8_t* text = d_text;
+  const uint64_t* off = d_off;
+  if (flags & TGX_FLAG_CRLF) {
+    rc = run_crlf(m, d_text, d_off, S, n_bytes);
+    if (rc) return rc;
+    text = m->text2.as<uint8_t>();
+    off = m->off2.as<uint64_t>();
+  }
+  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len, nullptr, true);
+  if (rc) return rc;
+  // id offsets = exclusive scan of token counts (S+1 entries; ntok[S] was zeroed)
+  size_t tmp = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, m->ntok.as<unsigned long long>(),
+                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
+  CU(m->cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, m->ntok.as<unsigned long long>(),
+                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
+  m->stats.launches += 2;
+  if (S) {
+    gather_ids_kernel<<<nblk(S * 32, 256), 256, 0, st>>>(m->bp.as<uint32_t>(), m->ustart.as<uint64_t>(),
+                                                        m->ulen.as<uint32_t>(),
+                                                        reinterpret_cast<unsigned long long*>(d_id_off),
+                                                        (uint32_t)S, d_ids, ids_cap);
+    m->stats.launches += 1;
+  }
+  if (d_status) CU(cudaMemcpyAsync(d_status, m->status.p, S * 4, cudaMemcpyDeviceToDevice, st));
+  uint64_t tot = 0;
+  CU(cudaMemcpyAsync(&tot, d_id_off + S, 8, cudaMemcpyDeviceToHost, st));
+  int64_t bad = -1;
+  rc = first_bad(m, (uint32_t)S, &bad);
+  if (rc) return rc;
+  CU(cudaEventRecord(m->ev[7], st));
+  CU(cudaStreamSynchronize(st));
+  finish_stats(m, 1);
+  if (total_ids) *total_ids = tot;
+  if (first_bad_out) *first_bad_out = bad;
+  if (tot > ids_cap) return fail(TGX_ERR_CAPACITY, "ids capacity too small: need " + std::to_string(tot));
+  if (bad >= 0) return fail(TGX_ERR_NO_PATH, "no path for sample " + std::to_string(bad));
+  return TGX_OK;
+}
+
+int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                     uint32_t* ids, uint64_t ids_cap, uint64_t* id_off, int32_t* status, uint64_t* proc_len,
+                     int64_t* first_bad_out) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!off || !id_off || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  uint64_t N = off[S];
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  CU(m->text.reserve(N + 16));
+  CU(m->off.reserve((S + 1) * 8));
+  CU(m->ids.reserve((N + 4) * 4));
+  CU(m->idoff.reserve((S + 1) * 8));
+  CU(m->scount.reserve((S + 1) * 12 + 32));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+  int32_t* d_status = m->scount.as<int32_t>();
+  uint64_t* d_plen = reinterpret_cast<uint64_t*>(m->scount.as<unsigned char>() + ((S * 4 + 15) & ~15ull));
+  uint64_t tot = 0;
+  int64_t bad = -1;
+  rc = tgx_encode_batch_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, m->ids.as<uint32_t>(), N + 4,
+                            m->idoff.as<uint64_t>(), d_status, d_plen, &tot, &bad);
+  if (first_bad_out) *first_bad_out = bad;
+  if (rc != TGX_OK && rc != TGX_ERR_NO_PATH) return rc;
+  std::string keep_err = g_err;
+  CU(cudaMemcpyAsync(id_off, m->idoff.p, (S + 1) * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (status) CU(cudaMemcpyAsync(status, d_status, S * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (proc_len) CU(cudaMemcpyAsync(proc_len, d_plen, S * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (tot <= ids_cap && tot) CU(cudaMemcpyAsync(ids, m->ids.p, tot * 4, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (tot > ids_cap) return fail(TGX_ERR_CAPACITY, "ids capacity too small: need " + std::to_string(tot));
+  if (rc == TGX_ERR_NO_PATH) return fail(rc, keep_err);
+  return TGX_OK;
+}
+
+// ---------------------------------------------------------------------------- frequency pass
+int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                              uint64_t n_bytes, uint32_t flags, uint64_t* d_freq, int64_t* first_bad_out,
+                              uint64_t* bad_len) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!d_off || !d_freq) return fail(TGX_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  m->stats = Stats();
+  cudaStream_t st = m->stream;
+  if (first_bad_out) *first_bad_out = -1;
+  if (S == 0) return TGX_OK;
+  CU(cudaEventRecord(m->ev[6], st));
+  const uint8_t* text = d_text;
+  const uint64_t* off = d_off;
+  if (flags & TGX_FLAG_CRLF) {
+    rc = run_crlf(m, d_text, d_off, S, n_bytes);
+    if (rc) return rc;
+    text = m->text2.as<uint8_t>();
+    off = m->off2.as<uint64_t>();
+  }
+  rc = run_viterbi(m, text, off, S, n_bytes, nullptr, reinterpret_cast<unsigned long long*>(d_freq), false);
+  if (rc) return rc;
+  int64_t bad = -1;
+  rc = first_bad(m, (uint32_t)S, &bad);
+  if (rc) return rc;
+  CU(cudaEventRecord(m->ev[7], st));
+  CU(cudaStreamSynchronize(st));
+  finish_stats(m, 1);
+  if (first_bad_out) *first_bad_out = bad;
+  if (bad >= 0) {
+    uint32_t l = 0;
+    CU(cudaMemcpy(&l, m->ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    if (bad_len) *bad_len = l;
+    return fail(TGX_ERR_NO_PATH, "no path to position " + std::to_string(l) + "/" + std::to_string(l));
+  }
+  return TGX_OK;
+}
+
+int tgx_token_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                          uint64_t* freq, int64_t* first_bad_out, uint64_t* bad_len) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!off || !freq || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  uint64_t N = off[S];
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  CU(m->text.reserve(N + 16));
+  CU(m->off.reserve((S + 1) * 8));
+  CU(m->freq.reserve(m->V * 8 + 8));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemsetAsync(m->freq.p, 0, m->V * 8 + 8, m->stream));
+  rc = tgx_token_frequencies_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, m->freq.as<uint64_t>(),
+                                 first_bad_out, bad_len);
+  if (rc) return rc;
+  CU(cudaMemcpy(freq, m->freq.p, m->V * 8, cudaMemcpyDeviceToHost));
+  return TGX_OK;
+}
+
+// ---------------------------------------------------------------------------- E-step
+int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                            uint64_t n_bytes, uint64_t snippet_len, double* d_expected, int64_t* bad_sample,
+                            double* bad_z) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!d_off || !d_expected || snippet_len == 0) return fail(TGX_ERR_INVALID, "bad argument");
+  if (snippet_len >= (1ull << 31)) return fail(TGX_ERR_INVALID, "snippet_len must be < 2^31");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  m->stats = Stats();
+  cudaStream_t st = m->stream;
+  CU(cudaEventRecord(m->ev[6], st));
+  if (bad_sample) *bad_sample = -1;
+  if (bad_z) *bad_z = 0.0;
+  // 1. snippet table
+  CU(m->ntok.reserve((S + 2) * 16));
+  unsigned long long* cnt = m->ntok.as<unsigned long long>();
+  unsigned long long* first_unit = cnt + S + 1;
+  CU(cudaMemsetAsync(cnt, 0, (S + 1) * 8, st));
+  if (S) {
+    snippet_counts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, cnt);
+    m->stats.launches += 1;
+  }
+  size_t tmp = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, first_unit, (int)(S + 1), st));
+  CU(m->cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, cnt, first_unit, (int)(S + 1), st));
+  m->stats.launches += 2;
+  unsigned long long U64 = 0;
+  CU(cudaMemcpyAsync(&U64, first_unit + S, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (U64 >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many snippets in one call (< 2^32)");
+  uint32_t U = (uint32_t)U64;
+  if (U == 0) {
+    CU(cudaEventRecord(m->ev[7], st));
+    CU(cudaStreamSynchronize(st));
+    return TGX_OK;
+  }
+  CU(m->ustart.reserve((size_t)U * 8 + 8));
+  CU(m->ulen.reserve((size_t)U * 4 + 4));
+  CU(m->vals_in.reserve((size_t)U * 4 + 4));
+  CU(m->status.reserve((size_t)U * 4 + 4));
+  CU(m->idoff.reserve((size_t)U * 4 + 4));  // unit -> sample
+  CU(m->A.reserve((n_bytes + U + 2) * 8));
+  CU(m->small.reserve(64));
+  units_from_snippets<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, first_unit, m->ustart.as<uint64_t>(),
+                                                   m->ulen.as<uint32_t>(), m->vals_in.as<uint32_t>(),
+                                                   m->idoff.as<uint32_t>());
+  m->stats.launches += 1;
+  rc = sort_units(m, U);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(m->status.p, 0, (size_t)U * 4 + 4, st));
+
+  FbParams p;
+  p.u.text = d_text;
+  p.u.unit_start = m->ustart.as<uint64_t>();
+  p.u.unit_len = m->ulen.as<uint32_t>();
+  p.u.order = m->vals_out.as<uint32_t>();
+  p.u.first = 0;
+  p.u.count = U;
+  p.u.trie = m->d_trie;
+  p.u.root_base = m->da.root_base;
+  p.u.rows = std::max<uint32_t>(1, m->da.max_token_len);
+  p.u.W = p.u.rows + 1;
+  p.A = m->A.as<double>();
+  p.status = m->status.as<int32_t>();
+  p.expected = d_expected;
+
+  CU(cudaEventRecord(m->ev[0], st));
+  CU(launch_fb_g(m, m->g_estep, p, false));
+  CU(cudaEventRecord(m->ev[1], st));
+  CU(cudaEventRecord(m->ev[2], st));
+  CU(launch_fb_g(m, m->g_estep, p, true));
+  CU(cudaEventRecord(m->ev[3], st));
+  int64_t bad = -1;
+  rc = first_bad(m, U, &bad);
+  if (rc) return rc;
+  CU(cudaEventRecord(m->ev[7], st));
+  CU(cudaStreamSynchronize(st));
+  finish_stats(m, 2);
+  if (bad >= 0) {
+    uint32_t smp = 0, l = 0;
+    uint64_t us = 0;
+    CU(cudaMemcpy(&smp, m->idoff.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&l, m->ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&us, m->ustart.as<uint64_t>() + bad, 8, cudaMemcpyDeviceToHost));
+    double z = 0;
+    CU(cudaMemcpy(&z, m->A.as<double>() + us + bad + l, 8, cudaMemcpyDeviceToHost));
+    if (bad_sample) *bad_sample = smp;
+    if (bad_z) *bad_z = z;
+    char buf[160];
+    snprintf(buf, sizeof buf, "normalization constant is f64::NaN (z=%g, sample=%u)", z, smp);
+    return fail(TGX_ERR_BAD_Z, buf);
+  }
+  return TGX_OK;
+}
+
+int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S,
+                        uint64_t snippet_len, double* expected, int64_t* bad_sample, double* bad_z) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!off || !expected || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  uint64_t N = off[S];
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  CU(m->text.reserve(N + 16));
+  CU(m->off.reserve((S + 1) * 8));
+  CU(m->expected.reserve(m->V * 8 + 8));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemsetAsync(m->expected.p, 0, m->V * 8 + 8, m->stream));
+  rc = tgx_expected_counts_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, snippet_len,
+                               m->expected.as<double>(), bad_sample, bad_z);
+  if (rc) return rc;
+  CU(cudaMemcpy(expected, m->expected.p, m->V * 8, cudaMemcpyDeviceToHost));
+  return TGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// sm_100a kernels of the TokenGeeX hot path (see DESIGN.md for the data layout).
+//
+// Work unit = one sample (encode / frequency pass) or one <= 81920-byte snippet (E-step).
+// Units are sorted by length (descending) and handed to groups of G lanes (G = 1..32):
+// a warp runs 32/G units side by side.  Each group alternates two phases over tiles of
+// G positions:
+//   phase A (parallel)  lane i walks the double-array trie from position p0+i and parks
+//                       every match (score, len, id) in the warp's shared-memory buffer;
+//   phase B (ordered)   positions p0 .. p0+G-1 are finalised one after the other; the
+//                       matches of the current position are relaxed by the lanes of the
+//                       group in parallel (distinct lengths -> distinct targets) against a
+//                       rolling window of the next max_token_len positions in shared memory.
+// Phase B replays the reference's evaluation order exactly (ascending start position,
+// strict '>' on f64 sums built left to right), which is what makes ids bit-exact.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tgxk {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t F_OCC = 1u << 24, F_TERM = 2u << 24, F_HASCH = 4u << 24, ID_MASK = 0x00FFFFFFu;
+constexpr int ROW_STRIDE = 33;  // padded row of the match buffer: conflict-free column reads
+constexpr int WPB = 4;          // warps per block
+
+struct UnitParams {
+  const uint8_t* text;         // blob
+  const uint64_t* unit_start;  // [U] absolute byte offset of the unit in text
+  const uint32_t* unit_len;    // [U]
+  const uint32_t* order;       // sorted unit indices; this launch handles order[first .. first+count)
+  uint32_t first, count;
+  const uint4* trie;
+  uint32_t root_base;
+  uint32_t rows;  // match-buffer rows = max token length
+  uint32_t W;     // window slots = rows + 1
+};
+
+struct ViterbiParams {
+  UnitParams u;
+  uint32_t* bp;                  // [N] back-pointers (len << 24 | id) per end position; later ids, right-aligned
+  unsigned long long* n_tokens;  // [U]
+  int32_t* status;               // [U] 0 ok / 6 NoPath
+  unsigned long long* freq;      // optional [V]: frequency pass
+  int emit;                      // write ids in place (encode) or not (frequency pass only)
+};
+
+struct FbParams {
+  UnitParams u;
+  double* A;          // [N + U] forward log-probabilities: unit k owns A[start_k + k .. + n_k]
+  int32_t* status;    // [U] 0 ok / 7 bad z
+  double* expected;   // [V]
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t rows, uint32_t W, int G) {
+  size_t ng = 32 / G;
+  size_t b = (size_t)rows * ROW_STRIDE * 8;  // mscore
+  b += (size_t)ng * W * 8;                   // window f64
+  b += (size_t)rows * ROW_STRIDE * 4;        // mpack
+  b += (size_t)ng * W * 4;                   // window u32
+  b += 32 * 4;                               // mcnt
+  return (b + 15) & ~(size_t)15;
+}
+
+struct WarpSmem {
+  double* mscore;
+  double* wf;       // window f64 [ng][W]
+  uint32_t* mpack;
+  uint32_t* wu;     // window u32 [ng][W]
+  uint32_t* mcnt;
+};
+
+__device__ inline WarpSmem carve(unsigned char* base, uint32_t rows, uint32_t W, int G) {
+  WarpSmem s;
+  size_t ng = 32 / G;
+  s.mscore = reinterpret_cast<double*>(base);
+  s.wf = s.mscore + (size_t)rows * ROW_STRIDE;
+  s.mpack = reinterpret_cast<uint32_t*>(s.wf + ng * W);
+  s.wu = s.mpack + (size_t)rows * ROW_STRIDE;
+  s.mcnt = s.wu + ng * W;
+  return s;
+}
+
+// Phase A: common_prefix_search from `pos` (src/trie.rs:51-63 restated on the double-array):
+// one 16-byte load per byte walked; stops at the first missing edge.
+__device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint8_t* text, uint32_t pos,
+                                                 uint32_t n, const WarpSmem& s, int lane) {
+  uint32_t cnt = 0;
+  if (pos < n) {
+    uint32_t base = u.root_base;
+    uint32_t d = 0;
+    uint32_t maxd = min(n - pos, u.rows);
+    while (d < maxd) {
+      uint32_t c = __ldg(text + pos + d);
+      uint4 e = __ldg(u.trie + (base ^ c));
+      if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) break;
+      d++;
+      if (e.y & F_TERM) {
+        s.mscore[cnt * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
+        s.mpack[cnt * ROW_STRIDE + lane] = (d << 24) | (e.y & ID_MASK);
+        cnt++;
+      }
+      if (!(e.y & F_HASCH)) break;
+      base = e.x >> 8;
+    }
+  }
+  return cnt;
+}
+
+// -----------------------------------------------------------------------------------------
+// K2/K3  Viterbi forward + in-kernel backtrack.  Model::encode, src/model.rs:59-129.
+// -----------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NG = 32 / G;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane & (G - 1), gid = lane / G;
+  const uint32_t W = u.W;
+  WarpSmem s = carve(smem + (size_t)warp * warp_smem_bytes(u.rows, W, G), u.rows, W, G);
+  double* wbest = s.wf + (size_t)gid * W;
+  uint32_t* wbp = s.wu + (size_t)gid * W;
+
+  const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
+  const bool has = gidx < u.count;
+  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  const uint32_t n = has ? u.unit_len[unit] : 0;
+  const uint64_t start = has ? u.unit_start[unit] : 0;
+  const uint8_t* text = u.text + start;
+
+  for (uint32_t i = lig; i < W; i += G) wbp[i] = NONE;
+  uint32_t nmax = n;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+  __syncwarp();
+
+  // positions 0..n are visited (position n only emits its back-pointer)
+  const uint32_t tiles = nmax / G + 1;
+  uint32_t slot0 = 0;  // (tile * G) % W
+  for (uint32_t tile = 0; tile < tiles; tile++) {
+    const uint32_t p0 = tile * G;
+    // ---- phase A
+    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    __syncwarp();
+    // ---- phase B
+    uint32_t my_bp = NONE;  // back-pointer of end position p0 + lig
+    uint32_t sl = slot0;
+#pragma unroll 1
+    for (int j = 0; j < G; j++) {
+      const uint32_t pp = p0 + j;
+      const int src = gid * G + j;
+      double best;
+      uint32_t pk;
+      bool reached;
+      if (pp == 0) {  // dp[0].start = Some(0), score 0.0   (src/model.rs:72-81)
+        best = 0.0; pk = 0; reached = true;
+      } else {
+        best = wbest[sl]; pk = wbp[sl]; reached = pk != NONE;
+      }
+      if (lig == j) my_bp = pk;
+      __syncwarp();
+      if (lig == 0) wbp[sl] = NONE;  // the slot now stands for position pp + W
+      const uint32_t c = (pp < n) ? s.mcnt[src] : 0;
+      if (reached) {  // unreachable positions are skipped (src/model.rs:85-87)
+        for (uint32_t k = lig; k < c; k += G) {
+          const double sc = s.mscore[k * ROW_STRIDE + src];
+          const uint32_t mp = s.mpack[k * ROW_STRIDE + src];
+          const double cand = __dadd_rn(best, sc);  // dp[pos].score + vocab[id].score  (:98)
+          uint32_t ts = sl + (mp >> 24);
+          if (ts >= W) ts -= W;
+          const uint32_t opk = wbp[ts];
+          if (opk == NONE || cand > wbest[ts]) {  // node.start.is_none() || score > node.score  (:100-101)
+            wbest[ts] = cand;
+            wbp[ts] = mp;
+          }
+        }
+      }
+      __syncwarp();
+      if (++sl == W) sl = 0;
+    }
+    const uint32_t e = p0 + lig;
+    if (has && e >= 1 && e <= n) p.bp[start + e - 1] = my_bp;
+    slot0 += G;
+    while (slot0 >= W) slot0 -= W;
+  }
+  __syncwarp();
+
+  // ---- backtrack (src/model.rs:113-126): ids are written right-aligned into the unit's own
+  // back-pointer region: token k from the end lands at index n-1-k >= the index just read.
+  if (has && lig == 0) {
+    unsigned long long k = 0;
+    int st = 0;
+    if (n > 0) {
+      if (p.bp[start + n - 1] == NONE) {
+        st = 6;  // Error::NoPath(n, n)
+      } else {
+        uint32_t pos = n;
+        while (pos > 0) {
+          const uint32_t v = p.bp[start + pos - 1];
+          const uint32_t id = v & ID_MASK;
+          if ((v >> 24) == 0 || (v >> 24) > pos) { st = 99; break; }  // corrupt chain: never loop forever
+          if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
+          if (p.emit) p.bp[start + n - 1 - k] = id;
+          pos -= v >> 24;
+          k++;
+        }
+      }
+    }
+    p.n_tokens[unit] = st ? 0 : k;
+    p.status[unit] = st;
+  }
+}
+
+// K3b: compact the right-aligned ids into the caller's id array (input order).
+__global__ void gather_ids_kernel(const uint32_t* __restrict__ bp, const uint64_t* __restrict__ unit_start,
+                                  const uint32_t* __restrict__ unit_len,
+                                  const unsigned long long* __restrict__ id_off, uint32_t U,
+                                  uint32_t* __restrict__ out, unsigned long long cap) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U) return;
+  const unsigned long long o = id_off[warp], T = id_off[warp + 1] - o;
+  if (o + T > cap) return;
+  const uint32_t* src = bp + unit_start[warp] + unit_len[warp] - T;
+  for (unsigned long long i = lane; i < T; i += 32) out[o + i] = src[i];
+}
+
+// -----------------------------------------------------------------------------------------
+// log_sum_exp, src/lattice.rs:321-333 (init_mode handled by the callers)
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ double tgx_exp(double x) { return exp(x); }
+__device__ __forceinline__ double tgx_log(double x) { return log(x); }
+
+__device__ __forceinline__ double log_sum_exp(double x, double y) {
+  double vmin, vmax;
+  if (x > y) { vmin = y; vmax = x; } else { vmin = x; vmax = y; }
+  if (vmax > __dadd_rn(vmin, 50.0)) return vmax;
+  return __dadd_rn(vmax, tgx_log(__dadd_rn(tgx_exp(__dadd_rn(vmin, -vmax)), 1.0)));
+}
+
+// -----------------------------------------------------------------------------------------
+// K4  forward pass: A[e] = fold over tokens ending at e, ascending start, of
+//     log_sum_exp(., score + A[start]); first term assigns; nothing ends at e -> 0.0.
+//     Lattice::populate_marginal alpha loop, src/lattice.rs:259-272 (per-position form).
+// -----------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NG = 32 / G;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane & (G - 1), gid = lane / G;
+  const uint32_t W = u.W;
+  WarpSmem s = carve(smem + (size_t)warp * warp_smem_bytes(u.rows, W, G), u.rows, W, G);
+  double* wacc = s.wf + (size_t)gid * W;
+  uint32_t* wseen = s.wu + (size_t)gid * W;
+
+  const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
+  const bool has = gidx < u.count;
+  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  const uint32_t n = has ? u.unit_len[unit] : 0;
+  const uint64_t start = has ? u.unit_start[unit] : 0;
+  const uint8_t* text = u.text + start;
+  double* A = p.A + start + unit;
+
+  for (uint32_t i = lig; i < W; i += G) wseen[i] = 0;
+  uint32_t nmax = n;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+  __syncwarp();
+
+  const uint32_t tiles = nmax / G + 1;
+  uint32_t slot0 = 0;
+  for (uint32_t tile = 0; tile < tiles; tile++) {
+    const uint32_t p0 = tile * G;
+    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    __syncwarp();
+    double my_a = 0.0;
+    uint32_t sl = slot0;
+#pragma unroll 1
+    for (int j = 0; j < G; j++) {
+      const uint32_t pp = p0 + j;
+      const int src = gid * G + j;
+      // alpha of every right node at pp; 0.0 when nothing ends here (src/lattice.rs:255, Q7)
+      double a = 0.0;
+      if (pp != 0 && wseen[sl]) a = wacc[sl];
+      if (lig == j) my_a = a;
+      __syncwarp();
+      if (lig == 0) wseen[sl] = 0;
+      const uint32_t c = (pp < n) ? s.mcnt[src] : 0;
+      for (uint32_t k = lig; k < c; k += G) {
+        const double y = __dadd_rn(s.mscore[k * ROW_STRIDE + src], a);  // nodes[lid].score + alpha[lid]
+        uint32_t ts = sl + (s.mpack[k * ROW_STRIDE + src] >> 24);
+        if (ts >= W) ts -= W;
+        if (!wseen[ts]) {  // lid == end_nodes[pos][0]  -> init_mode
+          wacc[ts] = y;
+          wseen[ts] = 1;
+        } else {
+          wacc[ts] = log_sum_exp(wacc[ts], y);
+        }
+      }
+      __syncwarp();
+      if (++sl == W) sl = 0;
+    }
+    const uint32_t e = p0 + lig;
+    if (has && e <= n) A[e] = my_a;
+    slot0 += G;
+    while (slot0 >= W) slot0 -= W;
+  }
+  __syncwarp();
+  if (has && lig == 0) {
+    const double z = A[n];  // alpha[eos]  (src/lattice.rs:290-291)
+    const double az = fabs(z);
+    const bool normal = (az >= 2.2250738585072014e-308) && (az <= 1.7976931348623157e308);  // f64::is_normal
+    p.status[unit] = normal ? 0 : 7;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// K5  backward pass + expected counts.  B[p] = fold over tokens starting at p, ascending
+//     length, of log_sum_exp(., score + B[p+len]) (src/lattice.rs:275-287); contribution
+//     exp(A[p] + score + B[p+len] - z) added to expected[id] (:295-309).
+// -----------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NG = 32 / G;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane & (G - 1), gid = lane / G;
+  const uint32_t W = u.W;
+  WarpSmem s = carve(smem + (size_t)warp * warp_smem_bytes(u.rows, W, G), u.rows, W, G);
+  double* wB = s.wf + (size_t)gid * W;
+
+  const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
+  bool has = gidx < u.count;
+  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  if (has && p.status[unit] != 0) has = false;  // bad z: the reference panics; nothing is added
+  const uint32_t n = has ? u.unit_len[unit] : 0;
+  const uint64_t start = has ? u.unit_start[unit] : 0;
+  const uint8_t* text = u.text + start;
+  const double* A = p.A + start + unit;
+  const double z = has ? A[n] : 0.0;
+
+  uint32_t nmax = n;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+  if (nmax == 0) return;
+  // window slot of position q is q % W; beta at the end of the sentence is 0.0 (EOS)
+  if (lig == 0) wB[n % W] = 0.0;
+  __syncwarp();
+
+  const uint32_t tiles = (nmax + G - 1) / G;
+  for (uint32_t tile = tiles; tile-- > 0;) {
+    const uint32_t p0 = tile * G;
+    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    const double a_mine = (has && p0 + lig < n) ? A[p0 + lig] : 0.0;
+    __syncwarp();
+    uint32_t sl = (p0 + G - 1) % W;  // slot of the tile's last position
+#pragma unroll 1
+    for (int j = G - 1; j >= 0; j--) {
+      const uint32_t pp = p0 + j;
+      const int src = gid * G + j;
+      const double a = __shfl_sync(0xFFFFFFFFu, a_mine, src);
+      const uint32_t c = (pp < n) ? s.mcnt[src] : 0;
+      double b = 0.0;  // stays 0.0 when nothing begins at pp (Q7)
+      for (uint32_t k = 0; k < c; k++) {  // ascending length = begin_nodes[pos] order
+        const double sc = s.mscore[k * ROW_STRIDE + src];
+        uint32_t ts = sl + (s.mpack[k * ROW_STRIDE + src] >> 24);
+        if (ts >= W) ts -= W;
+        const double y = __dadd_rn(sc, wB[ts]);  // nodes[rid].score + beta[rid]
+        b = (k == 0) ? y : log_sum_exp(b, y);
+      }
+      for (uint32_t k = lig; k < c; k += G) {
+        const double sc = s.mscore[k * ROW_STRIDE + src];
+        const uint32_t mp = s.mpack[k * ROW_STRIDE + src];
+        uint32_t ts = sl + (mp >> 24);
+        if (ts >= W) ts -= W;
+        // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), wB[ts]), -z);
+        atomicAdd(p.expected + (mp & ID_MASK), tgx_exp(total));
+      }
+      __syncwarp();
+      if (pp < n && lig == 0) wB[sl] = b;
+      __syncwarp();
+      sl = sl == 0 ? W - 1 : sl - 1;
+    }
+  }
+}
+
+}  // namespace tgxk
