@@ -73,6 +73,7 @@ def test_random_small_vs_oracle(N, g, thr):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 40), max_len=rng.randrange(1, 9),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = both(N, toks, scores)
+        gm.set_option(3, 1)  # lane-group kernels
         gm.set_option(0, g)
         gm.set_option(1, thr)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 90)
@@ -83,6 +84,39 @@ def test_random_small_vs_oracle(N, g, thr):
                 assert status[i] == 0 and got[i] == want, (it, i, s, toks, scores)
             except O.NoPath as e:
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
+
+
+@pytest.mark.parametrize("producers", [1, 2, 3, 4, 7])
+def test_random_small_vs_oracle_cta(N, producers):
+    """CTA-cooperative producer/consumer kernel (the default path)."""
+    rng = random.Random(300 + producers)
+    for it in range(25):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 12),
+                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 0)
+        gm.set_option(4, producers)
+        samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 400)
+        got, status, plen, rc, bad = gpu_encode(N, gm, samples)
+        for i, s in enumerate(samples):
+            try:
+                want = om.encode(s)
+                assert status[i] == 0 and got[i] == want, (it, i, s, toks, scores)
+            except O.NoPath as e:
+                assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
+
+
+def test_long_tokens_fall_back_to_group_kernels(N):
+    """max_token_len > 31 cannot use the 32-cell register window; the lane-group kernels take over."""
+    rng = random.Random(77)
+    toks = [bytes([c]) for c in b"ab"] + [b"ab" * 20, b"a" * 33, b"b" * 64, b"ba" * 7]
+    scores = [-3.0, -3.0, -9.0, -8.0, -20.0, -5.0]
+    gm, om = both(N, toks, scores)
+    samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 0, 300)
+    got, status, plen, rc, bad = gpu_encode(N, gm, samples)
+    assert rc == 0
+    for i, s in enumerate(samples):
+        assert got[i] == om.encode(s)
 
 
 def test_crlf_batch_vs_oracle(N):
@@ -99,11 +133,12 @@ def test_crlf_batch_vs_oracle(N):
 def test_synth_corpus_bit_exact_with_crlf(N):
     blob, off, toks, sc, kp = synth_setup(1, 11, 6_000_000, 32768, 16)
     gm, om = both(N, toks, sc)
-    for g, thr in [(8, 32768), (4, 4096), (1, 2048)]:
+    wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=True, threads=8)
+    for algo, g, thr in [(0, 8, 32768), (1, 8, 32768), (1, 4, 4096), (1, 1, 2048)]:
+        gm.set_option(3, algo)
         gm.set_option(0, g)
         gm.set_option(1, thr)
         ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
-        wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=True, threads=8)
         assert rc == 0 and wbad == 0
         assert np.array_equal(id_off, wid_off)
         assert np.array_equal(ids, wids)

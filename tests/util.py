@@ -6,6 +6,8 @@ import numpy as np
 
 
 def rand_vocab(rng, alphabet=b"abc", n_tok=12, max_len=4, complete=True, int_scores=False):
+    n_possible = sum(len(alphabet) ** l for l in range(1, max_len + 1))
+    n_tok = min(n_tok, n_possible)
     toks = set()
     if complete:
         toks |= {bytes([c]) for c in alphabet}

@@ -76,6 +76,9 @@ struct tgx_model {
   int g_short = 8;
   int64_t long_threshold = 32768;
   int g_estep = 1;
+  int algo = 0;        // 0 = CTA-cooperative Viterbi (max_token_len <= 31), 1 = lane-group kernels
+  int producers = 3;   // producer warps per CTA
+  int num_sms = 148;
   // workspace
   DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, ntok,
       idoff, status, A, expected, freq, ids, small, scount;
@@ -289,6 +292,33 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
   return cudaGetLastError();
 }
 
+template <int P>
+cudaError_t launch_viterbi_cta(tgx_model* m, ViterbiParams p, uint64_t N, unsigned int* counter) {
+  if (!p.u.count) return cudaSuccess;
+  size_t smem = std::max<size_t>(2 * P * cta_stage_bytes(p.u.rows), 8192);
+  cudaError_t e = cudaFuncSetAttribute(viterbi_cta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_cta_kernel<P>, 32 * (P + 1), smem);
+  if (e != cudaSuccess) return e;
+  uint32_t grid = (uint32_t)std::min<uint64_t>(p.u.count, (uint64_t)std::max(1, per_sm) * m->num_sms);
+  e = cudaMemsetAsync(counter, 0, 4, m->stream);
+  if (e != cudaSuccess) return e;
+  viterbi_cta_kernel<P><<<grid, 32 * (P + 1), smem, m->stream>>>(p, counter, p.u.text + N, (uint32_t)(smem / 4));
+  m->stats.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi_cta_p(tgx_model* m, int P, const ViterbiParams& p, uint64_t N, unsigned int* counter) {
+  switch (P) {
+    case 1: return launch_viterbi_cta<1>(m, p, N, counter);
+    case 2: return launch_viterbi_cta<2>(m, p, N, counter);
+    case 4: return launch_viterbi_cta<4>(m, p, N, counter);
+    case 7: return launch_viterbi_cta<7>(m, p, N, counter);
+    default: return launch_viterbi_cta<3>(m, p, N, counter);
+  }
+}
+
 cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
   switch (G) {
     case 1: return launch_viterbi<1>(m, p);
@@ -440,12 +470,18 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   p.emit = emit ? 1 : 0;
 
   CU(cudaEventRecord(m->ev[0], st));
-  p.u.first = 0;
-  p.u.count = n_long;
-  CU(launch_viterbi_g(m, 32, p));
-  p.u.first = n_long;
-  p.u.count = n_nonempty - n_long;
-  CU(launch_viterbi_g(m, m->g_short, p));
+  if (m->algo == 0 && p.u.rows <= 31) {
+    p.u.first = 0;
+    p.u.count = n_nonempty;
+    CU(launch_viterbi_cta_p(m, m->producers, p, N, m->small.as<unsigned int>() + 8));
+  } else {
+    p.u.first = 0;
+    p.u.count = n_long;
+    CU(launch_viterbi_g(m, 32, p));
+    p.u.first = n_long;
+    p.u.count = n_nonempty - n_long;
+    CU(launch_viterbi_g(m, m->g_short, p));
+  }
   CU(cudaEventRecord(m->ev[1], st));
   return TGX_OK;
 }
@@ -497,6 +533,7 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n)
       return fail(TGX_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
     CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     for (auto& e : m->ev) CU(cudaEventCreate(&e));
     size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
@@ -558,6 +595,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 0: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per sample must be 1,2,4,8,16,32"); m->g_short = (int)value; break;
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
+    case 3: if (value != 0 && value != 1) return fail(TGX_ERR_INVALID, "algo must be 0 or 1"); m->algo = (int)value; break;
+    case 4: if (value != 1 && value != 2 && value != 3 && value != 4 && value != 7) return fail(TGX_ERR_INVALID, "producers must be 1,2,3,4,7"); m->producers = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
   return TGX_OK;

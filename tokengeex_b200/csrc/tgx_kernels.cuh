@@ -211,6 +211,213 @@ __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// K2c  CTA-cooperative Viterbi: one sample per CTA, producer/consumer.
+//
+// The per-sample critical path is the ordered relax chain (position p must be final before
+// its matches are pushed), so the kernel is built around its latency, not its width:
+//   * P producer warps run phase A (trie walks) one 32-position tile each, writing a DENSE
+//     table  mpack[depth][column] / mscore[depth][column]  (0 = no token of that length);
+//   * ONE consumer warp runs phase B entirely in registers: lane l owns the dp cell of
+//     every position q with q % 32 == l (max_token_len <= 31), so finalising position p is
+//     a shuffle-broadcast of lane p%32's (score, back-pointer) and the relax of the match
+//     of length len is a predicated compare in lane (p+len)%32 — no shared-memory
+//     round trip and no barrier inside the chain.
+// Rounds of P tiles are double-buffered and separated by one __syncthreads().
+// CTAs fetch samples from a global counter in length-descending order (LPT).
+// -----------------------------------------------------------------------------------------
+struct CtaStage {
+  uint32_t* mpack;   // [rows][ROW_STRIDE]
+  double* mscore;    // [rows][ROW_STRIDE]
+};
+
+__host__ __device__ inline size_t cta_stage_bytes(uint32_t rows) {
+  return ((size_t)rows * ROW_STRIDE * 12 + 15) & ~(size_t)15;
+}
+
+// 24-byte text window starting at the 8-byte aligned address at or below `ptr`
+// (w[0] bits 8*sh.. hold *ptr).  Never reads at or beyond blob_end.
+__device__ __forceinline__ void load_window(const uint8_t* ptr, const uint8_t* blob_end, unsigned long long (&w)[3],
+                                            uint32_t& sh) {
+  const unsigned long long a = reinterpret_cast<unsigned long long>(ptr) & ~7ull;
+  sh = (uint32_t)(reinterpret_cast<unsigned long long>(ptr) & 7ull);
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a);
+  if (reinterpret_cast<const uint8_t*>(q + 3) <= blob_end) {
+    w[0] = __ldg(q); w[1] = __ldg(q + 1); w[2] = __ldg(q + 2);
+  } else {  // last bytes of the blob
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(q);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      unsigned long long v = 0;
+      for (int k = 0; k < 8; k++) {
+        const uint8_t* bp_ = b + i * 8 + k;
+        const unsigned long long byte = (bp_ >= ptr && bp_ < blob_end) ? (unsigned long long)__ldg(bp_) : 0ull;
+        v |= byte << (8 * k);
+      }
+      w[i] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void produce_tile(const UnitParams& u, const uint8_t* text, const uint8_t* blob_end,
+                                             uint32_t pos, uint32_t n, uint32_t* mpack, double* mscore, int lane) {
+  const uint32_t rows = u.rows;
+  for (uint32_t d = 0; d < rows; d++) mpack[d * ROW_STRIDE + lane] = 0;
+  if (pos >= n) return;
+  const uint32_t maxd = min(n - pos, rows);
+  uint32_t base = u.root_base;
+  bool alive = true;
+  for (uint32_t d0 = 0; d0 < maxd && alive; d0 += 16) {
+    unsigned long long w[3];
+    uint32_t sh;
+    load_window(text + pos + d0, blob_end, w, sh);
+    const uint32_t lim = min(16u, maxd - d0);
+    for (uint32_t dd = 0; dd < lim; dd++) {
+      const uint32_t idx = sh + dd;
+      const unsigned long long word = idx < 8 ? w[0] : (idx < 16 ? w[1] : w[2]);
+      const uint32_t c = (uint32_t)(word >> ((idx & 7) * 8)) & 0xFFu;
+      const uint4 e = __ldg(u.trie + (base ^ c));
+      if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) { alive = false; break; }
+      const uint32_t d = d0 + dd;
+      if (e.y & F_TERM) {
+        mscore[d * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
+        mpack[d * ROW_STRIDE + lane] = ((d + 1) << 24) | (e.y & ID_MASK);
+      }
+      if (!(e.y & F_HASCH)) { alive = false; break; }
+      base = e.x >> 8;
+    }
+  }
+}
+
+// Phase B over one 32-position tile, in registers.  best/pk: this lane's dp cell.
+__device__ __forceinline__ uint32_t consume_tile(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
+                                                 uint32_t rows, int lane, double& best, uint32_t& pk) {
+  uint32_t my_bp = NONE;
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 8) {
+    uint32_t mp[8];
+    double sc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {  // independent of the dp chain: issued ahead of it
+      const int j = j0 + jj;
+      const uint32_t len = (uint32_t)(lane - j) & 31u;
+      mp[jj] = 0;
+      sc[jj] = 0.0;
+      if (len >= 1 && len <= rows) {
+        mp[jj] = mpack[(len - 1) * ROW_STRIDE + j];
+        if (mp[jj]) sc[jj] = mscore[(len - 1) * ROW_STRIDE + j];
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = j0 + jj;
+      const double bsrc = __shfl_sync(0xFFFFFFFFu, best, j);
+      const uint32_t ksrc = __shfl_sync(0xFFFFFFFFu, pk, j);
+      if (lane == j) { my_bp = pk; pk = NONE; }  // this cell now stands for position p + 32
+      if (mp[jj] != 0 && ksrc != NONE) {          // unreachable positions push nothing (src/model.rs:85-87)
+        const double cand = __dadd_rn(bsrc, sc[jj]);  // dp[pos].score + vocab[id].score  (:98)
+        if (pk == NONE || cand > best) {            // node.start.is_none() || score > node.score  (:100-101)
+          best = cand;
+          pk = mp[jj];
+        }
+      }
+    }
+  }
+  return my_bp;
+}
+
+template <int P>
+__global__ void __launch_bounds__(32 * (P + 1)) viterbi_cta_kernel(ViterbiParams p, unsigned int* work_counter,
+                                                                   const uint8_t* blob_end, uint32_t chunk_cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t s_unit, s_pos, s_endpk;
+  __shared__ unsigned long long s_k;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t rows = u.rows;
+  const size_t stage_b = cta_stage_bytes(rows);
+  uint32_t* chunk = reinterpret_cast<uint32_t*>(smem);
+
+  for (;;) {
+    if (threadIdx.x == 0) s_unit = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t r = s_unit;
+    if (r >= u.count) break;
+    const uint32_t unit = u.order[u.first + r];
+    const uint32_t n = u.unit_len[unit];
+    const uint64_t start = u.unit_start[unit];
+    const uint8_t* text = u.text + start;
+    const uint32_t ntiles = n / 32 + 1;  // positions 0..n
+    const uint32_t rounds = (ntiles + P - 1) / P;
+    double best = 0.0;
+    uint32_t pk = (lane == 0) ? 0u : NONE;  // dp[0].start = Some(0)  (src/model.rs:81)
+    uint32_t last_bp = NONE;
+    for (uint32_t round = 0; round <= rounds; round++) {
+      if (warp > 0) {
+        const uint32_t t = round * P + (warp - 1);
+        if (round < rounds && t < ntiles) {
+          unsigned char* st = smem + ((size_t)(round & 1) * P + (warp - 1)) * stage_b;
+          double* ms = reinterpret_cast<double*>(st);
+          uint32_t* mp = reinterpret_cast<uint32_t*>(st + (size_t)rows * ROW_STRIDE * 8);
+          produce_tile(u, text, blob_end, t * 32 + lane, n, mp, ms, lane);
+        }
+      } else if (round > 0) {
+        for (int k = 0; k < P; k++) {
+          const uint32_t t = (round - 1) * P + k;
+          if (t >= ntiles) break;
+          const unsigned char* st = smem + ((size_t)((round - 1) & 1) * P + k) * stage_b;
+          const double* ms = reinterpret_cast<const double*>(st);
+          const uint32_t* mp = reinterpret_cast<const uint32_t*>(st + (size_t)rows * ROW_STRIDE * 8);
+          const uint32_t my_bp = consume_tile(mp, ms, rows, lane, best, pk);
+          const uint32_t e = t * 32 + lane;
+          if (e >= 1 && e <= n) p.bp[start + e - 1] = my_bp;
+          if (e == n) last_bp = my_bp;
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0 && lane == (int)(n & 31u)) s_endpk = (n == 0) ? 0u : last_bp;
+    if (threadIdx.x == 0) { s_pos = n; s_k = 0; }
+    __syncthreads();
+    // ---- backtrack (src/model.rs:113-126) through shared-memory chunks of the back-pointers
+    int st_code = 0;
+    if (n > 0 && s_endpk == NONE) {
+      st_code = 6;  // Error::NoPath(n, n)
+    } else {
+      uint32_t pos = n;
+      while (pos > 0) {
+        const uint32_t lo = pos > chunk_cap ? pos - chunk_cap : 0;
+        for (uint32_t i = threadIdx.x; i < pos - lo; i += blockDim.x) chunk[i] = p.bp[start + lo + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned long long k = s_k;
+          uint32_t q = pos;
+          while (q > lo) {
+            const uint32_t v = chunk[q - 1 - lo];
+            const uint32_t len = v >> 24;
+            if (len == 0 || len > q) { q = 0; k = ~0ull; break; }  // corrupt chain: never loop forever
+            const uint32_t id = v & ID_MASK;
+            if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
+            if (p.emit) p.bp[start + n - 1 - k] = id;
+            q -= len;
+            k++;
+          }
+          s_pos = q;
+          s_k = k;
+        }
+        __syncthreads();
+        pos = s_pos;
+      }
+      if (s_k == ~0ull) st_code = 99;
+    }
+    if (threadIdx.x == 0) {
+      p.n_tokens[unit] = st_code ? 0ull : s_k;
+      p.status[unit] = st_code;
+    }
+    __syncthreads();
+  }
+}
+
 // K3b: compact the right-aligned ids into the caller's id array (input order).
 __global__ void gather_ids_kernel(const uint32_t* __restrict__ bp, const uint64_t* __restrict__ unit_start,
                                   const uint32_t* __restrict__ unit_len,

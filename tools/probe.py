@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Developer probe: times encode / frequency pass / E-step variants on one GPU (not the bench contract)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bytes", type=int, default=100_000_000)
+    ap.add_argument("--vocab", type=int, default=131072)
+    ap.add_argument("--kind", type=int, default=1)
+    ap.add_argument("--what", default="encode,estep")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    from tokengeex_b200 import _native as N, synth
+    vb, vo = synth.corpus(synth.KIND_MULTILANG, 2, 96_000_000)
+    toks, sc, kp = synth.vocab(vb, vo, 2, args.vocab, 16, 0.05)
+    m = N.Model(toks, sc, device=0)
+    blob, off = synth.corpus(args.kind, 2, args.bytes)
+    S, NB = len(off) - 1, int(off[-1])
+    d_text = torch.from_numpy(blob).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_ids = torch.empty(NB + 4, dtype=torch.int32, device="cuda")
+    d_id_off = torch.empty(S + 1, dtype=torch.int64, device="cuda")
+    d_ex = torch.zeros(len(toks), dtype=torch.float64, device="cuda")
+    d_fr = torch.zeros(len(toks), dtype=torch.int64, device="cuda")
+    print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
+    what = args.what.split(",")
+    if "encode" in what:
+        for algo, opts in [(0, {4: 3}), (0, {4: 2}), (0, {4: 4}), (0, {4: 7}), (1, {0: 8, 1: 4096})]:
+            m.set_option(3, algo)
+            for k, v in opts.items():
+                m.set_option(k, v)
+            best = 1e9
+            for _ in range(args.reps + 1):
+                tot, rc, bad = m.encode_batch_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, True, d_ids.data_ptr(),
+                                                  NB + 4, d_id_off.data_ptr())
+                best = min(best, m.stat(4))
+            print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  viterbi {m.stat(1):.2f} ms "
+                  f"tokens={tot}", flush=True)
+        m.set_option(3, 0)
+        m.set_option(4, 3)
+    if "freq" in what:
+        for _ in range(args.reps):
+            d_fr.zero_()
+            rc, bad, bl = m.token_frequencies_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, False, d_fr.data_ptr())
+            print(f"freq: {m.stat(4):.2f} ms  {NB / m.stat(4) / 1e6:.2f} GB/s sum={int(d_fr.sum())}", flush=True)
+    if "estep" in what:
+        for g in [1, 4, 8, 32]:
+            m.set_option(2, g)
+            for _ in range(args.reps):
+                d_ex.zero_()
+                rc, bad, bz = m.expected_counts_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, d_ex.data_ptr())
+            print(f"estep G={g}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
+                  f"{NB / m.stat(4) / 1e6:.3f} GB/s sum={float(d_ex.sum()):.3f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
