@@ -295,7 +295,7 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
 template <int P>
 cudaError_t launch_viterbi_cta(tgx_model* m, ViterbiParams p, uint64_t N, unsigned int* counter) {
   if (!p.u.count) return cudaSuccess;
-  size_t smem = std::max<size_t>(2 * P * cta_stage_bytes(p.u.rows), 8192);
+  size_t smem = std::max<size_t>(2 * P * cta_stage_bytes(p.u.rows), 8192 + 4 * BT_STAGE);
   cudaError_t e = cudaFuncSetAttribute(viterbi_cta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -304,7 +304,8 @@ cudaError_t launch_viterbi_cta(tgx_model* m, ViterbiParams p, uint64_t N, unsign
   uint32_t grid = (uint32_t)std::min<uint64_t>(p.u.count, (uint64_t)std::max(1, per_sm) * m->num_sms);
   e = cudaMemsetAsync(counter, 0, 4, m->stream);
   if (e != cudaSuccess) return e;
-  viterbi_cta_kernel<P><<<grid, 32 * (P + 1), smem, m->stream>>>(p, counter, p.u.text + N, (uint32_t)(smem / 4));
+  viterbi_cta_kernel<P><<<grid, 32 * (P + 1), smem, m->stream>>>(p, counter, p.u.text + N,
+                                                                  (uint32_t)(smem / 4 - BT_STAGE));
   m->stats.launches += 1;
   return cudaGetLastError();
 }

@@ -22,6 +22,7 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t F_OCC = 1u << 24, F_TERM = 2u << 24, F_HASCH = 4u << 24, ID_MASK = 0x00FFFFFFu;
 constexpr int ROW_STRIDE = 33;  // padded row of the match buffer: conflict-free column reads
 constexpr int WPB = 4;          // warps per block
+constexpr uint32_t BT_STAGE = 1024;  // tokens parked per backtrack flush (CTA kernel)
 
 struct UnitParams {
   const uint8_t* text;         // blob
@@ -290,35 +291,43 @@ __device__ __forceinline__ void produce_tile(const UnitParams& u, const uint8_t*
 }
 
 // Phase B over one 32-position tile, in registers.  best/pk: this lane's dp cell.
+// The (mp, sc) operands of 8 positions are fetched branch-free and one sub-tile ahead of
+// the ordered chain, so the only latency left on the chain is shuffle -> DADD -> compare.
+__device__ __forceinline__ void load_sub(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
+                                         uint32_t rows, int lane, int j0, uint32_t (&mp)[8], double (&sc)[8]) {
+#pragma unroll
+  for (int jj = 0; jj < 8; jj++) {
+    const int j = j0 + jj;
+    const uint32_t len = (uint32_t)(lane - j) & 31u;
+    const bool valid = len >= 1 && len <= rows;
+    const uint32_t row = valid ? len - 1 : 0;
+    const uint32_t m = mpack[row * ROW_STRIDE + j];
+    sc[jj] = mscore[row * ROW_STRIDE + j];  // garbage when m == 0: never used
+    mp[jj] = valid ? m : 0u;
+  }
+}
+
 __device__ __forceinline__ uint32_t consume_tile(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
                                                  uint32_t rows, int lane, double& best, uint32_t& pk) {
   uint32_t my_bp = NONE;
+  uint32_t mp[2][8];
+  double sc[2][8];
+  load_sub(mpack, mscore, rows, lane, 0, mp[0], sc[0]);
 #pragma unroll
-  for (int j0 = 0; j0 < 32; j0 += 8) {
-    uint32_t mp[8];
-    double sc[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {  // independent of the dp chain: issued ahead of it
-      const int j = j0 + jj;
-      const uint32_t len = (uint32_t)(lane - j) & 31u;
-      mp[jj] = 0;
-      sc[jj] = 0.0;
-      if (len >= 1 && len <= rows) {
-        mp[jj] = mpack[(len - 1) * ROW_STRIDE + j];
-        if (mp[jj]) sc[jj] = mscore[(len - 1) * ROW_STRIDE + j];
-      }
-    }
+  for (int s8 = 0; s8 < 4; s8++) {
+    if (s8 + 1 < 4) load_sub(mpack, mscore, rows, lane, (s8 + 1) * 8, mp[(s8 + 1) & 1], sc[(s8 + 1) & 1]);
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
-      const int j = j0 + jj;
+      const int j = s8 * 8 + jj;
       const double bsrc = __shfl_sync(0xFFFFFFFFu, best, j);
       const uint32_t ksrc = __shfl_sync(0xFFFFFFFFu, pk, j);
-      if (lane == j) { my_bp = pk; pk = NONE; }  // this cell now stands for position p + 32
-      if (mp[jj] != 0 && ksrc != NONE) {          // unreachable positions push nothing (src/model.rs:85-87)
-        const double cand = __dadd_rn(bsrc, sc[jj]);  // dp[pos].score + vocab[id].score  (:98)
-        if (pk == NONE || cand > best) {            // node.start.is_none() || score > node.score  (:100-101)
+      if (lane == j) { my_bp = pk; pk = NONE; }     // this cell now stands for position p + 32
+      const uint32_t m = mp[s8 & 1][jj];
+      if (m != 0 && ksrc != NONE) {                  // unreachable positions push nothing (src/model.rs:85-87)
+        const double cand = __dadd_rn(bsrc, sc[s8 & 1][jj]);  // dp[pos].score + vocab[id].score  (:98)
+        if (pk == NONE || cand > best) {              // node.start.is_none() || score > node.score  (:100-101)
           best = cand;
-          pk = mp[jj];
+          pk = m;
         }
       }
     }
@@ -379,36 +388,52 @@ __global__ void __launch_bounds__(32 * (P + 1)) viterbi_cta_kernel(ViterbiParams
     if (warp == 0 && lane == (int)(n & 31u)) s_endpk = (n == 0) ? 0u : last_bp;
     if (threadIdx.x == 0) { s_pos = n; s_k = 0; }
     __syncthreads();
-    // ---- backtrack (src/model.rs:113-126) through shared-memory chunks of the back-pointers
+    // ---- backtrack (src/model.rs:113-126).  Back-pointers are staged in shared memory a chunk
+    // at a time; one thread follows the chain (a pure LDS -> subtract dependency) and parks the
+    // visited entries in a second buffer, which all threads then flush: ids go right-aligned
+    // into the sample's own back-pointer region (token k from the end at index n-1-k, always
+    // >= any index still to be read), frequencies through atomics.
     int st_code = 0;
     if (n > 0 && s_endpk == NONE) {
       st_code = 6;  // Error::NoPath(n, n)
     } else {
+      uint32_t* stage = chunk + chunk_cap;  // [BT_STAGE]
       uint32_t pos = n;
+      unsigned long long kbase = 0;
       while (pos > 0) {
         const uint32_t lo = pos > chunk_cap ? pos - chunk_cap : 0;
         for (uint32_t i = threadIdx.x; i < pos - lo; i += blockDim.x) chunk[i] = p.bp[start + lo + i];
         __syncthreads();
-        if (threadIdx.x == 0) {
-          unsigned long long k = s_k;
-          uint32_t q = pos;
-          while (q > lo) {
-            const uint32_t v = chunk[q - 1 - lo];
-            const uint32_t len = v >> 24;
-            if (len == 0 || len > q) { q = 0; k = ~0ull; break; }  // corrupt chain: never loop forever
-            const uint32_t id = v & ID_MASK;
-            if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
-            if (p.emit) p.bp[start + n - 1 - k] = id;
-            q -= len;
-            k++;
+        uint32_t q = pos;
+        while (q > lo) {  // uniform: q is re-read from shared memory after every stage
+          if (threadIdx.x == 0) {
+            uint32_t qq = q, cnt = 0;
+            while (qq > lo && cnt < BT_STAGE) {
+              const uint32_t v = chunk[qq - 1 - lo];
+              const uint32_t len = v >> 24;
+              if (len == 0 || len > qq) { qq = 0xFFFFFFFFu; break; }  // corrupt chain: abort, never spin
+              stage[cnt++] = v;
+              qq -= len;
+            }
+            s_pos = qq;
+            s_k = cnt;
           }
-          s_pos = q;
-          s_k = k;
+          __syncthreads();
+          const uint32_t cnt = (uint32_t)s_k;
+          for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t id = stage[i] & ID_MASK;
+            if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
+            if (p.emit) p.bp[start + n - 1 - (kbase + i)] = id;
+          }
+          kbase += cnt;
+          q = s_pos;
+          __syncthreads();
+          if (q == 0xFFFFFFFFu) break;
         }
-        __syncthreads();
-        pos = s_pos;
+        if (q == 0xFFFFFFFFu) { st_code = 99; break; }
+        pos = q;
       }
-      if (s_k == ~0ull) st_code = 99;
+      if (threadIdx.x == 0) s_k = kbase;
     }
     if (threadIdx.x == 0) {
       p.n_tokens[unit] = st_code ? 0ull : s_k;
