@@ -77,7 +77,7 @@ struct tgx_model {
   int64_t long_threshold = 32768;
   int g_estep = 1;
   int algo = 0;        // 0 = CTA-cooperative Viterbi (max_token_len <= 31), 1 = lane-group kernels
-  int producers = 3;   // producer warps per CTA
+  int producers = 2;   // producer warps per CTA
   int num_sms = 148;
   // workspace
   DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, ntok,

@@ -260,83 +260,97 @@ __device__ __forceinline__ void load_window(const uint8_t* ptr, const uint8_t* b
   }
 }
 
+// Eight text bytes starting at ptr + 8*g, assembled from the 24-byte window.
+__device__ __forceinline__ unsigned long long window_bytes(const unsigned long long (&w)[3], uint32_t sh, int g) {
+  // g in {0,1}: bytes [8g, 8g+8) relative to ptr  =  (w[g] >> 8sh) | (w[g+1] << (64 - 8sh))
+  const unsigned long long lo = w[g], hi = w[g + 1];
+  return sh ? ((lo >> (8 * sh)) | (hi << (64 - 8 * sh))) : lo;
+}
+
+// Phase A for one 32-position tile.  Dense table per stage: row d (token length d+1), column =
+// start position within the tile; empty entries hold score -inf (their mpack is never read).
 __device__ __forceinline__ void produce_tile(const UnitParams& u, const uint8_t* text, const uint8_t* blob_end,
                                              uint32_t pos, uint32_t n, uint32_t* mpack, double* mscore, int lane) {
   const uint32_t rows = u.rows;
-  for (uint32_t d = 0; d < rows; d++) mpack[d * ROW_STRIDE + lane] = 0;
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
+  {
+    double* r = mscore + lane;
+    for (uint32_t d = 0; d < rows; d++, r += ROW_STRIDE) *r = ninf;
+  }
   if (pos >= n) return;
   const uint32_t maxd = min(n - pos, rows);
   uint32_t base = u.root_base;
-  bool alive = true;
-  for (uint32_t d0 = 0; d0 < maxd && alive; d0 += 16) {
+  double* ms = mscore + lane;
+  uint32_t* mp = mpack + lane;
+  uint32_t dpk = 1u << 24;  // (depth + 1) << 24
+  for (uint32_t d0 = 0; d0 < maxd; d0 += 16) {
     unsigned long long w[3];
     uint32_t sh;
     load_window(text + pos + d0, blob_end, w, sh);
-    const uint32_t lim = min(16u, maxd - d0);
-    for (uint32_t dd = 0; dd < lim; dd++) {
-      const uint32_t idx = sh + dd;
-      const unsigned long long word = idx < 8 ? w[0] : (idx < 16 ? w[1] : w[2]);
-      const uint32_t c = (uint32_t)(word >> ((idx & 7) * 8)) & 0xFFu;
-      const uint4 e = __ldg(u.trie + (base ^ c));
-      if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) { alive = false; break; }
-      const uint32_t d = d0 + dd;
-      if (e.y & F_TERM) {
-        mscore[d * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
-        mpack[d * ROW_STRIDE + lane] = ((d + 1) << 24) | (e.y & ID_MASK);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const unsigned long long a = window_bytes(w, sh, g);
+      const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (d0 + g * 8 + k >= maxd) return;
+        const uint32_t c = __byte_perm(k < 4 ? alo : ahi, 0, 0x4440 + (k & 3));
+        const uint4 e = __ldg(u.trie + (base ^ c));
+        if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) return;
+        if (e.y & F_TERM) {
+          *ms = __hiloint2double((int)e.w, (int)e.z);
+          *mp = dpk | (e.y & ID_MASK);
+        }
+        if (!(e.y & F_HASCH)) return;
+        base = e.x >> 8;
+        ms += ROW_STRIDE;
+        mp += ROW_STRIDE;
+        dpk += 1u << 24;
       }
-      if (!(e.y & F_HASCH)) { alive = false; break; }
-      base = e.x >> 8;
     }
   }
 }
 
-// Phase B over one 32-position tile, in registers.  best/pk: this lane's dp cell.
-// The (mp, sc) operands of 8 positions are fetched branch-free and one sub-tile ahead of
-// the ordered chain, so the only latency left on the chain is shuffle -> DADD -> compare.
-__device__ __forceinline__ void load_sub(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
-                                         uint32_t rows, int lane, int j0, uint32_t (&mp)[8], double (&sc)[8]) {
-#pragma unroll
-  for (int jj = 0; jj < 8; jj++) {
-    const int j = j0 + jj;
-    const uint32_t len = (uint32_t)(lane - j) & 31u;
-    const bool valid = len >= 1 && len <= rows;
-    const uint32_t row = valid ? len - 1 : 0;
-    const uint32_t m = mpack[row * ROW_STRIDE + j];
-    sc[jj] = mscore[row * ROW_STRIDE + j];  // garbage when m == 0: never used
-    mp[jj] = valid ? m : 0u;
-  }
+// Phase B over one 32-position tile, in registers.  Lane l owns the dp cell (best, pk) of
+// every position q with q % 32 == l; "unreached" is best == -inf (scores are finite, so a
+// candidate built on an unreached position is -inf and can never win, and the first finite
+// candidate always replaces -inf — the reference's `start.is_none() ||` test, src/model.rs:100).
+// Operands (score, packed len|id) are fetched three positions ahead of the ordered chain,
+// which is then only  shuffle -> DADD -> compare -> select.
+__device__ __forceinline__ void load_operand(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
+                                             uint32_t rows, int lane, int j, uint32_t& mp, double& sc) {
+  const uint32_t len = (uint32_t)(lane - j) & 31u;
+  const bool valid = (len - 1u) < rows;
+  const uint32_t row = valid ? len - 1u : 0u;
+  mp = mpack[row * ROW_STRIDE + j];
+  const double v = mscore[row * ROW_STRIDE + j];
+  sc = valid ? v : __longlong_as_double(0xFFF0000000000000ll);
 }
 
 __device__ __forceinline__ uint32_t consume_tile(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
                                                  uint32_t rows, int lane, double& best, uint32_t& pk) {
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
   uint32_t my_bp = NONE;
-  uint32_t mp[2][8];
-  double sc[2][8];
-  load_sub(mpack, mscore, rows, lane, 0, mp[0], sc[0]);
+  uint32_t mp[4];
+  double sc[4];
 #pragma unroll
-  for (int s8 = 0; s8 < 4; s8++) {
-    if (s8 + 1 < 4) load_sub(mpack, mscore, rows, lane, (s8 + 1) * 8, mp[(s8 + 1) & 1], sc[(s8 + 1) & 1]);
+  for (int j = 0; j < 3; j++) load_operand(mpack, mscore, rows, lane, j, mp[j], sc[j]);
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int j = s8 * 8 + jj;
-      const double bsrc = __shfl_sync(0xFFFFFFFFu, best, j);
-      const uint32_t ksrc = __shfl_sync(0xFFFFFFFFu, pk, j);
-      if (lane == j) { my_bp = pk; pk = NONE; }     // this cell now stands for position p + 32
-      const uint32_t m = mp[s8 & 1][jj];
-      if (m != 0 && ksrc != NONE) {                  // unreachable positions push nothing (src/model.rs:85-87)
-        const double cand = __dadd_rn(bsrc, sc[s8 & 1][jj]);  // dp[pos].score + vocab[id].score  (:98)
-        if (pk == NONE || cand > best) {              // node.start.is_none() || score > node.score  (:100-101)
-          best = cand;
-          pk = m;
-        }
-      }
+  for (int j = 0; j < 32; j++) {
+    if (j + 3 < 32) load_operand(mpack, mscore, rows, lane, j + 3, mp[(j + 3) & 3], sc[(j + 3) & 3]);
+    const double bsrc = __shfl_sync(0xFFFFFFFFu, best, j);
+    if (lane == j) { my_bp = pk; pk = NONE; best = ninf; }  // the cell now stands for position p + 32
+    const double cand = __dadd_rn(bsrc, sc[j & 3]);           // dp[pos].score + vocab[id].score  (src/model.rs:98)
+    if (cand > best) {                                        // (:100-101)
+      best = cand;
+      pk = mp[j & 3];
     }
   }
   return my_bp;
 }
 
 template <int P>
-__global__ void __launch_bounds__(32 * (P + 1)) viterbi_cta_kernel(ViterbiParams p, unsigned int* work_counter,
+__global__ void __launch_bounds__(32 * (P + 1), (P <= 2 ? 8 : 4)) viterbi_cta_kernel(ViterbiParams p, unsigned int* work_counter,
                                                                    const uint8_t* blob_end, uint32_t chunk_cap) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t s_unit, s_pos, s_endpk;
@@ -358,8 +372,9 @@ __global__ void __launch_bounds__(32 * (P + 1)) viterbi_cta_kernel(ViterbiParams
     const uint8_t* text = u.text + start;
     const uint32_t ntiles = n / 32 + 1;  // positions 0..n
     const uint32_t rounds = (ntiles + P - 1) / P;
-    double best = 0.0;
-    uint32_t pk = (lane == 0) ? 0u : NONE;  // dp[0].start = Some(0)  (src/model.rs:81)
+    // dp[0] = { score 0.0, start Some(0) }  (src/model.rs:72-81); every other cell unreached
+    double best = (lane == 0) ? 0.0 : __longlong_as_double(0xFFF0000000000000ll);
+    uint32_t pk = (lane == 0) ? 0u : NONE;
     uint32_t last_bp = NONE;
     for (uint32_t round = 0; round <= rounds; round++) {
       if (warp > 0) {
