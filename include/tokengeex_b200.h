@@ -132,7 +132,8 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  * 1 = byte threshold from which a unit is processed by a full warp (G = 32),
  * 2 = lanes per snippet in the E-step, 3 = Viterbi algorithm (0 = CTA-cooperative
  * producer/consumer kernel, the default when max_token_len <= 31; 1 = lane-group kernels),
- * 4 = producer warps per CTA of the CTA-cooperative kernel (1,2,3,4,7). */
+ * 4 = producer warps per CTA of the CTA-cooperative kernel (1,2,3,4,7),
+ * 5 = E-step byte threshold from which a snippet gets a full warp. */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

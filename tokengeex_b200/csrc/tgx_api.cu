@@ -69,13 +69,16 @@ struct tgx_model {
   int device = -1;
   uint4* d_trie = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // long units run beside the short ones
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::recursive_mutex mu;
   Stats stats;
   // options
   int g_short = 8;
   int64_t long_threshold = 32768;
   int g_estep = 1;
+  int64_t estep_long_threshold = 8192;  // snippets at least this long get a full warp (G = 32)
   int algo = 0;        // 0 = CTA-cooperative Viterbi (max_token_len <= 31), 1 = lane-group kernels
   int producers = 2;   // producer warps per CTA
   int num_sms = 148;
@@ -332,7 +335,7 @@ cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
 }
 
 template <int G>
-cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward) {
+cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward, cudaStream_t st) {
   if (!p.u.count) return cudaSuccess;
   size_t smem = warp_smem_bytes(p.u.rows, p.u.W, G) * WPB;
   cudaError_t e;
@@ -341,24 +344,24 @@ cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward) {
   if (!backward) {
     e = cudaFuncSetAttribute(fb_forward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fb_forward_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
+    fb_forward_kernel<G><<<blocks, WPB * 32, smem, st>>>(p);
   } else {
     e = cudaFuncSetAttribute(fb_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fb_backward_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
+    fb_backward_kernel<G><<<blocks, WPB * 32, smem, st>>>(p);
   }
   m->stats.launches += 1;
   return cudaGetLastError();
 }
 
-cudaError_t launch_fb_g(tgx_model* m, int G, const FbParams& p, bool backward) {
+cudaError_t launch_fb_g(tgx_model* m, int G, const FbParams& p, bool backward, cudaStream_t st) {
   switch (G) {
-    case 1: return launch_fb<1>(m, p, backward);
-    case 2: return launch_fb<2>(m, p, backward);
-    case 4: return launch_fb<4>(m, p, backward);
-    case 8: return launch_fb<8>(m, p, backward);
-    case 16: return launch_fb<16>(m, p, backward);
-    default: return launch_fb<32>(m, p, backward);
+    case 1: return launch_fb<1>(m, p, backward, st);
+    case 2: return launch_fb<2>(m, p, backward, st);
+    case 4: return launch_fb<4>(m, p, backward, st);
+    case 8: return launch_fb<8>(m, p, backward, st);
+    case 16: return launch_fb<16>(m, p, backward, st);
+    default: return launch_fb<32>(m, p, backward, st);
   }
 }
 
@@ -535,7 +538,14 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
       return fail(TGX_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaMemcpyToSymbol(tgxk::c_exp_hdr, TGX_EXP_HDR, sizeof(TGX_EXP_HDR)));
+    CU(cudaMemcpyToSymbol(tgxk::c_log_hdr, TGX_LOG_HDR, sizeof(TGX_LOG_HDR)));
+    CU(cudaMemcpyToSymbol(tgxk::c_exp_tab, TGX_EXP_TAB, sizeof(TGX_EXP_TAB)));
+    CU(cudaMemcpyToSymbol(tgxk::c_log_tab, TGX_LOG_TAB, sizeof(TGX_LOG_TAB)));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     for (auto& e : m->ev) CU(cudaEventCreate(&e));
     size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
     CU(cudaMalloc(&m->d_trie, bytes));
@@ -559,6 +569,9 @@ void tgx_model_destroy(tgx_model* m) {
     for (auto& e : m->ev)
       if (e) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
   }
   delete m;
 }
@@ -596,6 +609,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 0: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per sample must be 1,2,4,8,16,32"); m->g_short = (int)value; break;
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
+    case 5: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->estep_long_threshold = value; break;
     case 3: if (value != 0 && value != 1) return fail(TGX_ERR_INVALID, "algo must be 0 or 1"); m->algo = (int)value; break;
     case 4: if (value != 1 && value != 2 && value != 3 && value != 4 && value != 7) return fail(TGX_ERR_INVALID, "producers must be 1,2,3,4,7"); m->producers = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
@@ -868,12 +882,36 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.status = m->status.as<int32_t>();
   p.expected = d_expected;
 
+  // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second
+  // stream; the many short ones run lane-per-snippet beside them.
+  uint32_t n_long = 0;
+  if (m->g_estep != 32) {
+    uint32_t* counts = m->small.as<uint32_t>();
+    uint32_t thr = (uint32_t)std::min<int64_t>(m->estep_long_threshold, 0x7FFFFFFF);
+    split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, counts);
+    m->stats.launches += 1;
+    uint32_t h[2];
+    CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_long = h[0];
+  }
+  CU(cudaEventRecord(m->ev_fork, st));
+  CU(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+  FbParams pl = p, ps = p;
+  pl.u.first = 0;
+  pl.u.count = n_long;
+  ps.u.first = n_long;
+  ps.u.count = U - n_long;
   CU(cudaEventRecord(m->ev[0], st));
-  CU(launch_fb_g(m, m->g_estep, p, false));
+  CU(launch_fb_g(m, 32, pl, false, m->stream2));
+  CU(launch_fb_g(m, m->g_estep, ps, false, st));
   CU(cudaEventRecord(m->ev[1], st));
   CU(cudaEventRecord(m->ev[2], st));
-  CU(launch_fb_g(m, m->g_estep, p, true));
+  CU(launch_fb_g(m, 32, pl, true, m->stream2));
+  CU(launch_fb_g(m, m->g_estep, ps, true, st));
   CU(cudaEventRecord(m->ev[3], st));
+  CU(cudaEventRecord(m->ev_join, m->stream2));
+  CU(cudaStreamWaitEvent(st, m->ev_join, 0));
   int64_t bad = -1;
   rc = first_bad(m, U, &bad);
   if (rc) return rc;

@@ -16,6 +16,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "tgx_libm.h"
+#include "tgx_libm_tables.h"
+
 namespace tgxk {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
@@ -475,14 +478,42 @@ __global__ void gather_ids_kernel(const uint32_t* __restrict__ bp, const uint64_
 // -----------------------------------------------------------------------------------------
 // log_sum_exp, src/lattice.rs:321-333 (init_mode handled by the callers)
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ double tgx_exp(double x) { return exp(x); }
-__device__ __forceinline__ double tgx_log(double x) { return log(x); }
+// exp / ln: glibc's algorithm restated bit for bit (tgx_libm.h), coefficients broadcast from
+// constant memory, the two 2 KB lookup tables staged in shared memory by every block.
+__constant__ unsigned long long c_exp_hdr[8];
+__constant__ unsigned long long c_log_hdr[18];
+__constant__ unsigned long long c_exp_tab[256];
+__constant__ unsigned long long c_log_tab[256];
 
-__device__ __forceinline__ double log_sum_exp(double x, double y) {
+struct LibmTabs {
+  const uint64_t* et;  // shared
+  const double* lt;    // shared
+};
+
+__device__ __forceinline__ LibmTabs stage_libm_tables(unsigned long long* s_et, double* s_lt) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_et[i] = c_exp_tab[i];
+    s_lt[i] = __longlong_as_double((long long)c_log_tab[i]);
+  }
+  __syncthreads();
+  LibmTabs t;
+  t.et = reinterpret_cast<const uint64_t*>(s_et);
+  t.lt = s_lt;
+  return t;
+}
+
+__device__ __forceinline__ double tgx_exp(double x, const LibmTabs& t) {
+  return tgx_exp_impl(x, reinterpret_cast<const double*>(c_exp_hdr), t.et);
+}
+__device__ __forceinline__ double tgx_log(double x, const LibmTabs& t) {
+  return tgx_log_impl(x, reinterpret_cast<const double*>(c_log_hdr), t.lt);
+}
+
+__device__ __forceinline__ double log_sum_exp(double x, double y, const LibmTabs& t) {
   double vmin, vmax;
   if (x > y) { vmin = y; vmax = x; } else { vmin = x; vmax = y; }
   if (vmax > __dadd_rn(vmin, 50.0)) return vmax;
-  return __dadd_rn(vmax, tgx_log(__dadd_rn(tgx_exp(__dadd_rn(vmin, -vmax)), 1.0)));
+  return __dadd_rn(vmax, tgx_log(__dadd_rn(tgx_exp(__dadd_rn(vmin, -vmax), t), 1.0), t));
 }
 
 // -----------------------------------------------------------------------------------------
@@ -501,6 +532,9 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
   WarpSmem s = carve(smem + (size_t)warp * warp_smem_bytes(u.rows, W, G), u.rows, W, G);
   double* wacc = s.wf + (size_t)gid * W;
   uint32_t* wseen = s.wu + (size_t)gid * W;
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
 
   const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
   const bool has = gidx < u.count;
@@ -543,7 +577,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
           wacc[ts] = y;
           wseen[ts] = 1;
         } else {
-          wacc[ts] = log_sum_exp(wacc[ts], y);
+          wacc[ts] = log_sum_exp(wacc[ts], y, lt);
         }
       }
       __syncwarp();
@@ -578,6 +612,9 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
   const uint32_t W = u.W;
   WarpSmem s = carve(smem + (size_t)warp * warp_smem_bytes(u.rows, W, G), u.rows, W, G);
   double* wB = s.wf + (size_t)gid * W;
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
 
   const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
   bool has = gidx < u.count;
@@ -616,7 +653,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
         uint32_t ts = sl + (s.mpack[k * ROW_STRIDE + src] >> 24);
         if (ts >= W) ts -= W;
         const double y = __dadd_rn(sc, wB[ts]);  // nodes[rid].score + beta[rid]
-        b = (k == 0) ? y : log_sum_exp(b, y);
+        b = (k == 0) ? y : log_sum_exp(b, y, lt);
       }
       for (uint32_t k = lig; k < c; k += G) {
         const double sc = s.mscore[k * ROW_STRIDE + src];
@@ -625,7 +662,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
         if (ts >= W) ts -= W;
         // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), wB[ts]), -z);
-        atomicAdd(p.expected + (mp & ID_MASK), tgx_exp(total));
+        atomicAdd(p.expected + (mp & ID_MASK), tgx_exp(total, lt));
       }
       __syncwarp();
       if (pp < n && lig == 0) wB[sl] = b;
