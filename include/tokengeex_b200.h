@@ -118,6 +118,21 @@ int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_
                               uint64_t n_bytes, uint32_t flags, uint64_t* d_freq, int64_t* first_bad,
                               uint64_t* bad_len);
 
+/* ---- host half of the EM pruning loop (no device work; see tokengeex_b200/csrc/prune_host.cpp) ----
+ * ModelVocabularyPruner::run_m_step (src/prune.rs:124-170, digamma :322-335).  kept[i] = 1 iff
+ * token i survives (expected[i] >= 0.5 || keep[i]); new_scores[i] = digamma(max(expected[i],
+ * 0.5)) - digamma(sum over survivors).  TGX_ERR_INVALID if a score is NaN/inf (reference panics). */
+int tgx_m_step(const double* expected, const uint8_t* keep, uint64_t vocab_size, uint8_t* kept,
+               double* new_scores, uint64_t* n_kept);
+/* ModelVocabularyPruner::prune_vocab (src/prune.rs:173-319) given the token frequencies of its
+ * frequency pass (tgx_token_frequencies): n-best alternatives per token (Lattice::nbest(2),
+ * src/lattice.rs:152-238), loss ranking, cut at max(floor(V*shrink), target).  out_ids[*out_n] =
+ * indices of the surviving tokens in their final (score-descending) order.  audit[8] optional. */
+int tgx_prune_select(const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                     const uint8_t* keep, uint64_t vocab_size, const uint64_t* freq, uint64_t n_samples,
+                     uint64_t target_vocab_size, double shrink_factor, int threads, uint32_t* out_ids,
+                     uint64_t* out_n, double* audit);
+
 /* Pinned host memory for callers that want asynchronous H2D/D2H (cudaHostAlloc). */
 int tgx_host_alloc(void** p, uint64_t bytes);
 int tgx_host_free(void* p);

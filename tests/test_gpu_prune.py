@@ -1,0 +1,30 @@
+"""Full EM pruning schedule on the GPU path vs the oracle's restatement of prune.rs:23-57:
+the final vocabulary must be set-identical (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import synth_setup
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_prune(blob, off, toks, sc, kp, target, shrink, subiters):
+    om = O.OracleModel(toks, sc, kp)
+    m2, iters = om.prune(blob, off, vocab_size=target, shrink=shrink, em_subiters=subiters, threads=8)
+    return m2.export(), iters
+
+
+@pytest.mark.parametrize("kind,seed,nbytes,v0,target,subiters", [(2, 21, 1_500_000, 4000, 2000, 2),
+                                                                 (1, 22, 1_000_000, 2500, 1800, 1)])
+def test_full_prune_set_identical(kind, seed, nbytes, v0, target, subiters):
+    from tokengeex_b200.prune import ModelVocabularyPruner, Vocab
+    blob, off, toks, sc, kp = synth_setup(kind, seed, nbytes, v0, 16)
+    (wt, ws, wk), witers = oracle_prune(blob, off, toks, sc, kp, target, 0.8, subiters)
+    pruner = ModelVocabularyPruner(target, shrink_factor=0.8, em_subiters=subiters, dropout=0.0)
+    vocab, report = pruner.prune(Vocab(list(toks), np.array(sc), np.array(kp)), blob, off)
+    assert report.vocab_sizes == witers                      # same size after every E/M and prune step
+    assert set(vocab.tokens) == set(wt)                       # the north-star bar: set-identical
+    assert vocab.tokens == wt                                 # and in fact the same order
+    assert np.allclose(vocab.scores, ws, rtol=1e-9, atol=0)   # scores through digamma of counts within 1e-9
+    assert np.array_equal(vocab.keep, wk)

@@ -52,6 +52,9 @@ SYMBOLS = [
     ("tgx_token_frequencies", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u64p, i64p, u64p]),
     ("tgx_token_frequencies_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                             C.c_void_p, i64p, u64p]),
+    ("tgx_m_step", C.c_int, [f64p, u8p, C.c_uint64, u8p, f64p, u64p]),
+    ("tgx_prune_select", C.c_int, [u8p, u64p, f64p, u8p, C.c_uint64, u64p, C.c_uint64, C.c_uint64, C.c_double,
+                                   C.c_int, u32p, u64p, f64p]),
     ("tgx_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("tgx_host_free", C.c_int, [C.c_void_p]),
     ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
@@ -252,3 +255,38 @@ def pinned_empty(nbytes: int) -> np.ndarray:
 
 
 _OWNERS = {}
+
+
+# ---- host half of the EM pruning loop (tokengeex_b200/csrc/prune_host.cpp) -------------------------
+def m_step(expected: np.ndarray, keep: np.ndarray):
+    """run_m_step → (kept mask u8[V], new_scores f64[V]); raises on NaN/inf scores."""
+    V = len(expected)
+    ex = np.ascontiguousarray(expected, np.float64)
+    kp = np.ascontiguousarray(keep, np.uint8)
+    kept = np.zeros(max(V, 1), np.uint8)
+    ns = np.zeros(max(V, 1), np.float64)
+    nk = C.c_uint64(0)
+    rc = lib().tgx_m_step(_p(ex, f64p), _p(kp, u8p), V, _p(kept, u8p), _p(ns, f64p), C.byref(nk))
+    if rc:
+        raise TgxError(rc, "M-step: alternative vocabulary contains invalid frequency")
+    return kept[:V], ns[:V]
+
+
+def prune_select(tokens: Sequence[bytes], scores, keep, freq, n_samples: int, target: int, shrink: float,
+                 threads: int = 0):
+    """prune_vocab minus its frequency pass → (ids of survivors in final order u32[], audit f64[8])."""
+    V = len(tokens)
+    blob, off = pack(tokens)
+    sc = np.ascontiguousarray(scores, np.float64)
+    kp = np.ascontiguousarray(keep, np.uint8)
+    fr = np.ascontiguousarray(freq, np.uint64)
+    out = np.zeros(max(V, 1), np.uint32)
+    n = C.c_uint64(0)
+    audit = np.zeros(8, np.float64)
+    if threads <= 0:
+        threads = max(1, len(os.sched_getaffinity(0)))
+    rc = lib().tgx_prune_select(_p(blob, u8p), _p(off, u64p), _p(sc, f64p), _p(kp, u8p), V, _p(fr, u64p), n_samples,
+                                target, shrink, threads, _p(out, u32p), C.byref(n), _p(audit, f64p))
+    if rc:
+        raise TgxError(rc, "prune_vocab failed (loss is not normal, or vocabulary unsupported)")
+    return out[:int(n.value)].copy(), audit

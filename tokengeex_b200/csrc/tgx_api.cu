@@ -77,14 +77,14 @@ struct tgx_model {
   // options
   int g_short = 8;
   int64_t long_threshold = 32768;
-  int g_estep = 1;
-  int64_t estep_long_threshold = 8192;  // snippets at least this long get a full warp (G = 32)
+  int g_estep = 8;
+  int64_t estep_long_threshold = 1ll << 40;  // snippets at least this long get a full warp (G = 32); off by default
   int algo = 0;        // 0 = CTA-cooperative Viterbi (max_token_len <= 31), 1 = lane-group kernels
   int producers = 2;   // producer warps per CTA
   int num_sms = 148;
   // workspace
   DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, ntok,
-      idoff, status, A, expected, freq, ids, small, scount;
+      idoff, status, A, expected, freq, ids, small, scount, hot;
 };
 
 // =========================================================================================
@@ -563,7 +563,7 @@ void tgx_model_destroy(tgx_model* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* bufs[] = {&m->text, &m->off, &m->text2, &m->off2, &m->bitmap, &m->blk, &m->ustart, &m->ulen,
                       &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->ntok, &m->idoff,
-                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount};
+                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount, &m->hot};
     for (auto* b : bufs) b->release();
     if (m->d_trie) cudaFree(m->d_trie);
     for (auto& e : m->ev)
@@ -881,6 +881,11 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.A = m->A.as<double>();
   p.status = m->status.as<int32_t>();
   p.expected = d_expected;
+  p.hot_k = (uint32_t)std::min<uint64_t>(m->V, 4096);
+  p.hot_r = 64;
+  CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8));
+  CU(cudaMemsetAsync(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8, st));
+  p.hot = m->hot.as<double>();
 
   // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second
   // stream; the many short ones run lane-per-snippet beside them.
@@ -912,6 +917,10 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   CU(cudaEventRecord(m->ev[3], st));
   CU(cudaEventRecord(m->ev_join, m->stream2));
   CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+  if (p.hot_k) {
+    fold_hot_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot, p.hot_k, p.hot_r, d_expected);
+    m->stats.launches += 1;
+  }
   int64_t bad = -1;
   rc = first_bad(m, U, &bad);
   if (rc) return rc;

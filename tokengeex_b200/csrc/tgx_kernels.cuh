@@ -53,6 +53,11 @@ struct FbParams {
   double* A;          // [N + U] forward log-probabilities: unit k owns A[start_k + k .. + n_k]
   int32_t* status;    // [U] 0 ok / 7 bad z
   double* expected;   // [V]
+  // Hot tokens (small ids: vocabularies are score-sorted) would serialise every SM's atomics
+  // on a handful of L2 addresses, so ids < hot_k accumulate into one of hot_r replicas
+  // (picked per block) that fold_hot_kernel sums into expected[] afterwards.
+  double* hot;        // [hot_r][hot_k]
+  uint32_t hot_k, hot_r;
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t rows, uint32_t W, int G) {
@@ -662,7 +667,9 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
         if (ts >= W) ts -= W;
         // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), wB[ts]), -z);
-        atomicAdd(p.expected + (mp & ID_MASK), tgx_exp(total, lt));
+        const uint32_t id = mp & ID_MASK;
+        double* dst = id < p.hot_k ? p.hot + (size_t)(blockIdx.x % p.hot_r) * p.hot_k + id : p.expected + id;
+        atomicAdd(dst, tgx_exp(total, lt));
       }
       __syncwarp();
       if (pp < n && lig == 0) wB[sl] = b;
@@ -670,6 +677,15 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
       sl = sl == 0 ? W - 1 : sl - 1;
     }
   }
+}
+
+__global__ void fold_hot_kernel(const double* __restrict__ hot, uint32_t hot_k, uint32_t hot_r,
+                                double* __restrict__ expected) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hot_k) return;
+  double s = 0.0;
+  for (uint32_t r = 0; r < hot_r; r++) s += hot[(size_t)r * hot_k + i];
+  expected[i] += s;
 }
 
 }  // namespace tgxk

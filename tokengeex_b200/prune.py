@@ -1,0 +1,132 @@
+"""EM vocabulary pruning driven by the GPU hot path.
+
+Mirrors ``ModelVocabularyPruner`` (/root/reference/src/prune.rs:6-57): the E-step
+(run_e_step, :64-120) and the frequency pass of prune_vocab (:205-246) run on the GPU
+through the C ABI; run_m_step (:124-170) and the rest of prune_vocab (:173-319) run on the
+host in C++ (csrc/prune_host.cpp).  After every step the model is rebuilt from the new
+vocabulary exactly as ``*model = Model::from(vocab)`` does (:48, :53) — here that means a
+new double-array trie uploaded to the device.
+
+With more than one rank (torch.distributed), every rank holds a shard of the samples; the
+expected-count vector and the frequency vector are all-reduced (one collective per E-step
+/ frequency pass) so that every rank runs the identical host steps on identical inputs.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+log = logging.getLogger("tokengeex_b200.prune")
+
+
+@dataclass
+class Vocab:
+    """Vec<ScoredToken> (/root/reference/src/lib.rs:27-31)."""
+    tokens: List[bytes]
+    scores: np.ndarray  # f64[V]
+    keep: np.ndarray    # u8[V]
+
+    def __len__(self):
+        return len(self.tokens)
+
+
+@dataclass
+class PruneReport:
+    vocab_sizes: List[int] = field(default_factory=list)   # after every M-step / prune step
+    e_step_s: List[float] = field(default_factory=list)
+    m_step_s: List[float] = field(default_factory=list)
+    freq_s: List[float] = field(default_factory=list)
+    select_s: List[float] = field(default_factory=list)
+    rebuild_s: List[float] = field(default_factory=list)
+    audits: List[np.ndarray] = field(default_factory=list)
+
+
+class ModelVocabularyPruner:
+    """new(vocab_size, shrink_factor, em_subiters, dropout) — src/prune.rs:13-21.
+
+    dropout must be 0.0: the GPU path is specified for the deterministic setting
+    (the reference's dropout uses an unseeded thread_rng and cannot be reproduced).
+    """
+
+    def __init__(self, vocab_size: int, shrink_factor: float = 0.8, em_subiters: int = 1, dropout: float = 0.0,
+                 device: int = 0, allreduce: Optional[Callable[[np.ndarray], np.ndarray]] = None,
+                 n_samples_global: Optional[int] = None):
+        if dropout != 0.0:
+            raise ValueError("tokengeex_b200 prunes with dropout == 0.0 only")
+        self.vocab_size = vocab_size
+        self.shrink_factor = shrink_factor
+        self.em_subiters = em_subiters
+        self.device = device
+        self.allreduce = allreduce
+        self.n_samples_global = n_samples_global
+
+    # -- steps --------------------------------------------------------------------------------
+    def run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray) -> np.ndarray:
+        ex, rc, bad, badz = model.expected_counts(blob, off)
+        if rc == N.TGX_ERR_BAD_Z:  # the reference panics (src/prune.rs:90-96)
+            raise FloatingPointError(f"normalization constant is f64::NaN (z={badz}, sample={bad})")
+        if self.allreduce is not None:
+            ex = self.allreduce(ex)
+        return ex
+
+    def run_m_step(self, vocab: Vocab, expected: np.ndarray) -> Vocab:
+        kept, ns = N.m_step(expected, vocab.keep)
+        idx = np.flatnonzero(kept)
+        return Vocab([vocab.tokens[i] for i in idx], ns[idx].copy(), vocab.keep[idx].copy())
+
+    def prune_vocab(self, model: N.Model, vocab: Vocab, blob: np.ndarray, off: np.ndarray, report: PruneReport) -> Vocab:
+        t = time.perf_counter()
+        fr, rc, bad, blen = model.token_frequencies(blob, off)
+        if rc == N.TGX_ERR_NO_PATH:
+            raise RuntimeError(f"no path to position {blen}/{blen}")  # Error::NoPath, src/prune.rs:218-221
+        if self.allreduce is not None:
+            fr = self.allreduce(fr)
+        report.freq_s.append(time.perf_counter() - t)
+        t = time.perf_counter()
+        n_samples = self.n_samples_global if self.n_samples_global is not None else len(off) - 1
+        ids, audit = N.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
+                                    self.shrink_factor)
+        report.select_s.append(time.perf_counter() - t)
+        report.audits.append(audit)
+        return Vocab([vocab.tokens[i] for i in ids], vocab.scores[ids].copy(), vocab.keep[ids].copy())
+
+    # -- src/prune.rs:23-57 ------------------------------------------------------------------------
+    def prune(self, vocab: Vocab, blob: np.ndarray, off: np.ndarray) -> (Vocab, PruneReport):
+        report = PruneReport()
+        t = time.perf_counter()
+        model = N.Model(vocab.tokens, vocab.scores, device=self.device)
+        report.rebuild_s.append(time.perf_counter() - t)
+        while len(vocab) > self.vocab_size:
+            for subiter in range(self.em_subiters):
+                log.info("EM subiter %d/%d", subiter + 1, self.em_subiters)
+                t = time.perf_counter()
+                expected = self.run_e_step(model, blob, off)
+                report.e_step_s.append(time.perf_counter() - t)
+                log.info("E-step completed subiter=%d vocab_size=%d", subiter, len(vocab))
+                t = time.perf_counter()
+                new_vocab = self.run_m_step(vocab, expected)
+                report.m_step_s.append(time.perf_counter() - t)
+                log.info("M-step completed subiter=%d vocab_size=%d alternative_vocab_size=%d", subiter, len(vocab),
+                         len(new_vocab))
+                vocab = new_vocab
+                t = time.perf_counter()
+                model.close()
+                model = N.Model(vocab.tokens, vocab.scores, device=self.device)  # *model = Model::from(vocab)
+                report.rebuild_s.append(time.perf_counter() - t)
+                report.vocab_sizes.append(len(vocab))
+            before = len(vocab)
+            vocab = self.prune_vocab(model, vocab, blob, off, report)
+            log.info("Pruning vocabulary from=%d to=%d", before, len(vocab))
+            t = time.perf_counter()
+            model.close()
+            model = N.Model(vocab.tokens, vocab.scores, device=self.device)
+            report.rebuild_s.append(time.perf_counter() - t)
+            report.vocab_sizes.append(len(vocab))
+        model.close()
+        return vocab, report

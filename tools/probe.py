@@ -53,12 +53,14 @@ def main():
             rc, bad, bl = m.token_frequencies_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, False, d_fr.data_ptr())
             print(f"freq: {m.stat(4):.2f} ms  {NB / m.stat(4) / 1e6:.2f} GB/s sum={int(d_fr.sum())}", flush=True)
     if "estep" in what:
-        for g in [1, 4, 8, 32]:
+        for g, thr in [(1, 1 << 30), (2, 1 << 30), (4, 1 << 30), (8, 1 << 30), (16, 1 << 30), (32, 1 << 30), (1, 4096),
+                       (2, 8192), (4, 16384), (8, 32768)]:
             m.set_option(2, g)
+            m.set_option(5, thr)
             for _ in range(args.reps):
                 d_ex.zero_()
                 rc, bad, bz = m.expected_counts_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, d_ex.data_ptr())
-            print(f"estep G={g}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
+            print(f"estep G={g} thr={thr}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
                   f"{NB / m.stat(4) / 1e6:.3f} GB/s sum={float(d_ex.sum()):.3f}", flush=True)
 
 
