@@ -25,6 +25,14 @@ def test_full_prune_set_identical(kind, seed, nbytes, v0, target, subiters):
     vocab, report = pruner.prune(Vocab(list(toks), np.array(sc), np.array(kp)), blob, off)
     assert report.vocab_sizes == witers                      # same size after every E/M and prune step
     assert set(vocab.tokens) == set(wt)                       # the north-star bar: set-identical
-    assert vocab.tokens == wt                                 # and in fact the same order
-    assert np.allclose(vocab.scores, ws, rtol=1e-9, atol=0)   # scores through digamma of counts within 1e-9
-    assert np.array_equal(vocab.keep, wk)
+    # Order: prune_vocab ends with sort_unstable_by(score desc) (src/prune.rs:316).  Scores come from digamma of
+    # f64 sums whose association differs between any two runs (rayon merge order in the reference, atomics here), so
+    # tokens whose scores agree to ~1e-13 may swap places; compare per token, and check the order is a valid sort.
+    got = dict(zip(vocab.tokens, zip(vocab.scores.tolist(), vocab.keep.tolist())))
+    want = dict(zip(wt, zip(np.asarray(ws).tolist(), np.asarray(wk).tolist())))
+    for t, (s, k) in want.items():
+        assert abs(got[t][0] - s) <= 1e-9 * abs(s) and got[t][1] == k
+    assert np.all(np.diff(vocab.scores) <= 0)
+    swapped = [i for i, (a, b) in enumerate(zip(vocab.tokens, wt)) if a != b]
+    for i in swapped:  # a swap is only legitimate between (near-)tied scores
+        assert abs(vocab.scores[i] - ws[i]) <= 1e-9 * abs(ws[i])
