@@ -58,7 +58,7 @@ struct DevBuf {
 };
 
 struct Stats {
-  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0;
+  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0;
 };
 
 }  // namespace
@@ -76,15 +76,17 @@ struct tgx_model {
   Stats stats;
   // options
   int g_short = 8;
-  int64_t long_threshold = 32768;
+  int64_t long_threshold = 512;  // samples at least this long: full warp (lane-group forward kernels, backtrack)
   int g_estep = 8;
   int64_t estep_long_threshold = 1ll << 40;  // snippets at least this long get a full warp (G = 32); off by default
-  int algo = 0;        // 0 = CTA-cooperative Viterbi (max_token_len <= 31), 1 = lane-group kernels
-  int producers = 2;   // producer warps per CTA
+  int algo = 0;        // 0 = pair-CTA Viterbi (max_token_len <= 16), 1 = lane-group kernels
+  int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
   int num_sms = 148;
+  int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
+  int smem_optin = 232448;
   // workspace
-  DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, ntok,
-      idoff, status, A, expected, freq, ids, small, scount, hot;
+  DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt,
+      ntok, idoff, status, A, expected, freq, ids, small, scount, hot;
 };
 
 // =========================================================================================
@@ -295,32 +297,41 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
   return cudaGetLastError();
 }
 
-template <int P>
-cudaError_t launch_viterbi_cta(tgx_model* m, ViterbiParams p, uint64_t N, unsigned int* counter) {
-  if (!p.u.count) return cudaSuccess;
-  size_t smem = std::max<size_t>(2 * P * cta_stage_bytes(p.u.rows), 8192 + 4 * BT_STAGE);
-  cudaError_t e = cudaFuncSetAttribute(viterbi_cta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int R, int HOT>
+cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
+  constexpr int WG = 2 * R + 1;
+  const size_t budget = (size_t)m->smem_optin;
+  uint32_t groups = (uint32_t)std::min<size_t>({(budget - (size_t)p.hot_slots * 16) / pair_group_bytes(R),
+                                                (size_t)(1024 / (32 * WG)), (size_t)15});
+  if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
+  groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
+  p.groups = groups;
+  const size_t smem = pair_smem_bytes(R, groups, p.hot_slots);
+  cudaError_t e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_cta_kernel<P>, 32 * (P + 1), smem);
+  const uint32_t grid =
+      (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
+  e = cudaMemsetAsync(p.counter, 0, 4, m->stream);
   if (e != cudaSuccess) return e;
-  uint32_t grid = (uint32_t)std::min<uint64_t>(p.u.count, (uint64_t)std::max(1, per_sm) * m->num_sms);
-  e = cudaMemsetAsync(counter, 0, 4, m->stream);
-  if (e != cudaSuccess) return e;
-  viterbi_cta_kernel<P><<<grid, 32 * (P + 1), smem, m->stream>>>(p, counter, p.u.text + N,
-                                                                  (uint32_t)(smem / 4 - BT_STAGE));
+  viterbi_pair_kernel<R, HOT><<<grid, groups * WG * 32, smem, m->stream>>>(p);
   m->stats.launches += 1;
   return cudaGetLastError();
 }
 
-cudaError_t launch_viterbi_cta_p(tgx_model* m, int P, const ViterbiParams& p, uint64_t N, unsigned int* counter) {
-  switch (P) {
-    case 1: return launch_viterbi_cta<1>(m, p, N, counter);
-    case 2: return launch_viterbi_cta<2>(m, p, N, counter);
-    case 4: return launch_viterbi_cta<4>(m, p, N, counter);
-    case 7: return launch_viterbi_cta<7>(m, p, N, counter);
-    default: return launch_viterbi_cta<3>(m, p, N, counter);
+template <int R>
+cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p) {
+  // stage as many leading trie levels in shared memory as fit a quarter of it
+  const size_t cap = (size_t)m->smem_optin / 4;
+  if ((size_t)m->da.hot[2] * 16 <= cap) {
+    p.hot_slots = m->da.hot[2];
+    return launch_viterbi_pair<R, 2>(m, p);
   }
+  if ((size_t)m->da.hot[1] * 16 <= cap) {
+    p.hot_slots = m->da.hot[1];
+    return launch_viterbi_pair<R, 1>(m, p);
+  }
+  p.hot_slots = 0;
+  return launch_viterbi_pair<R, 0>(m, p);
 }
 
 cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
@@ -428,17 +439,20 @@ int sort_units(tgx_model* m, uint32_t U) {
   return TGX_OK;
 }
 
-// Viterbi over all samples.  On return m->bp holds right-aligned ids, m->ntok token
-// counts, m->status per-sample status.  d_freq optional.
+// Viterbi over all samples: forward dp (back lengths) + backtrack (token-end marks).  On return
+// m->mark holds the length of the token ending at every marked byte, m->ntok token counts,
+// m->status per-sample status.
 int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
-                uint64_t* d_proc_len, unsigned long long* d_freq, bool emit) {
+                uint64_t* d_proc_len) {
   cudaStream_t st = m->stream;
   if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
   uint32_t U = (uint32_t)S;
+  const uint64_t n_tiles = (N + EM_TILE - 1) / EM_TILE;
   CU(m->ustart.reserve((size_t)U * 8 + 8));
   CU(m->ulen.reserve((size_t)U * 4 + 4));
   CU(m->vals_in.reserve((size_t)U * 4 + 4));
-  CU(m->bp.reserve((N + 4) * 4));
+  CU(m->bp.reserve(N + 64));
+  CU(m->mark.reserve(n_tiles * EM_TILE + 64));
   CU(m->ntok.reserve(((size_t)U + 1) * 8));
   CU(m->status.reserve((size_t)U * 4 + 4));
   CU(m->small.reserve(64));
@@ -455,30 +469,39 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemsetAsync(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
   CU(cudaMemsetAsync(m->status.p, 0, (size_t)U * 4 + 4, st));
+  CU(cudaMemsetAsync(m->mark.p, 0, n_tiles * EM_TILE, st));
   CU(cudaStreamSynchronize(st));
   uint32_t n_long = h[0], n_nonempty = h[1];
 
-  ViterbiParams p;
-  p.u.text = d_text;
-  p.u.unit_start = m->ustart.as<uint64_t>();
-  p.u.unit_len = m->ulen.as<uint32_t>();
-  p.u.order = m->vals_out.as<uint32_t>();
-  p.u.trie = m->d_trie;
-  p.u.root_base = m->da.root_base;
-  p.u.rows = std::max<uint32_t>(1, m->da.max_token_len);
-  p.u.W = p.u.rows + 1;
-  p.bp = m->bp.as<uint32_t>();
-  p.n_tokens = m->ntok.as<unsigned long long>();
-  p.status = m->status.as<int32_t>();
-  p.freq = d_freq;
-  p.emit = emit ? 1 : 0;
+  UnitParams u;
+  u.text = d_text;
+  u.unit_start = m->ustart.as<uint64_t>();
+  u.unit_len = m->ulen.as<uint32_t>();
+  u.order = m->vals_out.as<uint32_t>();
+  u.trie = m->d_trie;
+  u.root_base = m->da.root_base;
+  u.rows = std::max<uint32_t>(1, m->da.max_token_len);
+  u.W = u.rows + 1;
 
   CU(cudaEventRecord(m->ev[0], st));
-  if (m->algo == 0 && p.u.rows <= 31) {
+  if (m->algo == 0 && u.rows <= 16) {
+    PairParams p;
+    p.u = u;
     p.u.first = 0;
     p.u.count = n_nonempty;
-    CU(launch_viterbi_cta_p(m, m->producers, p, N, m->small.as<unsigned int>() + 8));
+    p.blob_end = d_text + N;
+    p.bp = m->bp.as<uint8_t>();
+    p.counter = m->small.as<unsigned int>() + 8;
+    if (!p.u.count) {
+    } else if (m->producers >= 4) {
+      CU(launch_viterbi_pair_r<2>(m, p));
+    } else {
+      CU(launch_viterbi_pair_r<1>(m, p));
+    }
   } else {
+    ViterbiParams p;
+    p.u = u;
+    p.bp = m->bp.as<uint8_t>();
     p.u.first = 0;
     p.u.count = n_long;
     CU(launch_viterbi_g(m, 32, p));
@@ -487,6 +510,62 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     CU(launch_viterbi_g(m, m->g_short, p));
   }
   CU(cudaEventRecord(m->ev[1], st));
+  CU(cudaEventRecord(m->ev[2], st));
+  if (n_nonempty) {
+    BacktrackParams b;
+    b.unit_start = u.unit_start;
+    b.unit_len = u.unit_len;
+    b.order = u.order;
+    b.bp = m->bp.as<uint8_t>();
+    b.mark = m->mark.as<uint8_t>();
+    b.n_tokens = m->ntok.as<unsigned long long>();
+    b.status = m->status.as<int32_t>();
+    // long samples (sorted first): one warp each; short ones: one thread each
+    b.first = 0;
+    b.count = n_long;
+    if (b.count) backtrack_warp_kernel<<<nblk(b.count, BW_WARPS), BW_WARPS * 32, 0, st>>>(b);
+    b.first = n_long;
+    b.count = n_nonempty - n_long;
+    if (b.count) backtrack_thread_kernel<<<nblk(b.count, BT_THREADS), BT_THREADS, 0, st>>>(b);
+    m->stats.launches += 2;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(m->ev[3], st));
+  return TGX_OK;
+}
+
+// Token ids (and/or frequencies) from the marks: count per tile, scan, emit.
+int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, uint64_t ids_cap,
+             unsigned long long* d_freq) {
+  cudaStream_t st = m->stream;
+  const uint64_t n_tiles = (N + EM_TILE - 1) / EM_TILE;
+  CU(cudaEventRecord(m->ev[4], st));
+  if (n_tiles) {
+    CU(m->tilecnt.reserve((n_tiles + 1) * 16));
+    unsigned long long* cnt = m->tilecnt.as<unsigned long long>();
+    unsigned long long* prefix = cnt + n_tiles + 1;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)m->num_sms * 8);
+    mark_count_kernel<<<grid, EM_BLOCK, 0, st>>>(m->mark.as<uint4>(), n_tiles, cnt);
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, prefix, (int)n_tiles, st));
+    CU(m->cubtmp.reserve(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, cnt, prefix, (int)n_tiles, st));
+    EmitParams e;
+    e.mark = m->mark.as<uint4>();
+    e.text = d_text;
+    e.n_tiles = n_tiles;
+    e.tile_prefix = prefix;
+    e.trie = m->d_trie;
+    e.root_base = m->da.root_base;
+    e.ids = d_ids;
+    e.cap = ids_cap;
+    e.freq = d_freq;
+    e.V = (uint32_t)m->V;
+    emit_kernel<<<grid, EM_BLOCK, d_freq ? EM_HOT * 4 : 0, st>>>(e);
+    m->stats.launches += 4;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(m->ev[5], st));
   return TGX_OK;
 }
 
@@ -511,6 +590,8 @@ void finish_stats(tgx_model* m, int which) {
     if (which == 2) m->stats.fwd_ms = ms;
   }
   if (which == 2 && cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->stats.bwd_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->stats.back_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->stats.emit_ms = ms;
   if (cudaEventElapsedTime(&ms, m->ev[6], m->ev[7]) == cudaSuccess) m->stats.total_ms = ms;
 }
 
@@ -538,6 +619,7 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
       return fail(TGX_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaMemcpyToSymbol(tgxk::c_exp_hdr, TGX_EXP_HDR, sizeof(TGX_EXP_HDR)));
     CU(cudaMemcpyToSymbol(tgxk::c_log_hdr, TGX_LOG_HDR, sizeof(TGX_LOG_HDR)));
     CU(cudaMemcpyToSymbol(tgxk::c_exp_tab, TGX_EXP_TAB, sizeof(TGX_EXP_TAB)));
@@ -562,7 +644,7 @@ void tgx_model_destroy(tgx_model* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* bufs[] = {&m->text, &m->off, &m->text2, &m->off2, &m->bitmap, &m->blk, &m->ustart, &m->ulen,
-                      &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->ntok, &m->idoff,
+                      &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->mark, &m->tilecnt, &m->ntok, &m->idoff,
                       &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount, &m->hot};
     for (auto* b : bufs) b->release();
     if (m->d_trie) cudaFree(m->d_trie);
@@ -611,7 +693,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->estep_long_threshold = value; break;
     case 3: if (value != 0 && value != 1) return fail(TGX_ERR_INVALID, "algo must be 0 or 1"); m->algo = (int)value; break;
-    case 4: if (value != 1 && value != 2 && value != 3 && value != 4 && value != 7) return fail(TGX_ERR_INVALID, "producers must be 1,2,3,4,7"); m->producers = (int)value; break;
+    case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
+    case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
   return TGX_OK;
@@ -625,6 +708,8 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
     case 2: return m->stats.fwd_ms;
     case 3: return m->stats.bwd_ms;
     case 4: return m->stats.total_ms;
+    case 5: return m->stats.back_ms;
+    case 6: return m->stats.emit_ms;
   }
   return 0;
 }
@@ -688,7 +773,7 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     text = m->text2.as<uint8_t>();
     off = m->off2.as<uint64_t>();
   }
-  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len, nullptr, true);
+  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len);
   if (rc) return rc;
   // id offsets = exclusive scan of token counts (S+1 entries; ntok[S] was zeroed)
   size_t tmp = 0;
@@ -698,13 +783,8 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, m->ntok.as<unsigned long long>(),
                                    reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
   m->stats.launches += 2;
-  if (S) {
-    gather_ids_kernel<<<nblk(S * 32, 256), 256, 0, st>>>(m->bp.as<uint32_t>(), m->ustart.as<uint64_t>(),
-                                                        m->ulen.as<uint32_t>(),
-                                                        reinterpret_cast<unsigned long long*>(d_id_off),
-                                                        (uint32_t)S, d_ids, ids_cap);
-    m->stats.launches += 1;
-  }
+  rc = run_emit(m, text, n_bytes, d_ids, ids_cap, nullptr);
+  if (rc) return rc;
   if (d_status) CU(cudaMemcpyAsync(d_status, m->status.p, S * 4, cudaMemcpyDeviceToDevice, st));
   uint64_t tot = 0;
   CU(cudaMemcpyAsync(&tot, d_id_off + S, 8, cudaMemcpyDeviceToHost, st));
@@ -776,7 +856,9 @@ int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_
     text = m->text2.as<uint8_t>();
     off = m->off2.as<uint64_t>();
   }
-  rc = run_viterbi(m, text, off, S, n_bytes, nullptr, reinterpret_cast<unsigned long long*>(d_freq), false);
+  rc = run_viterbi(m, text, off, S, n_bytes, nullptr);
+  if (rc) return rc;
+  rc = run_emit(m, text, n_bytes, nullptr, 0, reinterpret_cast<unsigned long long*>(d_freq));
   if (rc) return rc;
   int64_t bad = -1;
   rc = first_bad(m, (uint32_t)S, &bad);

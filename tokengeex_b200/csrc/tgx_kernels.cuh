@@ -22,10 +22,9 @@
 namespace tgxk {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr uint32_t F_OCC = 1u << 24, F_TERM = 2u << 24, F_HASCH = 4u << 24, ID_MASK = 0x00FFFFFFu;
+constexpr uint32_t F_TERM = 2u << 24, F_HASCH = 4u << 24, ID_MASK = 0x00FFFFFFu;  // slot.y; see trie_build.h
 constexpr int ROW_STRIDE = 33;  // padded row of the match buffer: conflict-free column reads
 constexpr int WPB = 4;          // warps per block
-constexpr uint32_t BT_STAGE = 1024;  // tokens parked per backtrack flush (CTA kernel)
 
 struct UnitParams {
   const uint8_t* text;         // blob
@@ -34,18 +33,14 @@ struct UnitParams {
   const uint32_t* order;       // sorted unit indices; this launch handles order[first .. first+count)
   uint32_t first, count;
   const uint4* trie;
-  uint32_t root_base;
+  uint32_t root_base;  // xbase of the root
   uint32_t rows;  // match-buffer rows = max token length
   uint32_t W;     // window slots = rows + 1
 };
 
 struct ViterbiParams {
   UnitParams u;
-  uint32_t* bp;                  // [N] back-pointers (len << 24 | id) per end position; later ids, right-aligned
-  unsigned long long* n_tokens;  // [U]
-  int32_t* status;               // [U] 0 ok / 6 NoPath
-  unsigned long long* freq;      // optional [V]: frequency pass
-  int emit;                      // write ids in place (encode) or not (frequency pass only)
+  uint8_t* bp;  // [N] byte length of the best last token per end position (0 = unreachable)
 };
 
 struct FbParams {
@@ -95,13 +90,13 @@ __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint
                                                  uint32_t n, const WarpSmem& s, int lane) {
   uint32_t cnt = 0;
   if (pos < n) {
-    uint32_t base = u.root_base;
+    uint32_t xb = u.root_base;
     uint32_t d = 0;
     uint32_t maxd = min(n - pos, u.rows);
     while (d < maxd) {
-      uint32_t c = __ldg(text + pos + d);
-      uint4 e = __ldg(u.trie + (base ^ c));
-      if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) break;
+      const uint32_t cw = 0x100u | __ldg(text + pos + d);
+      uint4 e = __ldg(u.trie + (xb ^ cw));
+      if ((e.x ^ cw) & 0x1FFu) break;
       d++;
       if (e.y & F_TERM) {
         s.mscore[cnt * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
@@ -109,14 +104,17 @@ __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint
         cnt++;
       }
       if (!(e.y & F_HASCH)) break;
-      base = e.x >> 8;
+      xb = e.x >> 9;
     }
   }
   return cnt;
 }
 
 // -----------------------------------------------------------------------------------------
-// K2/K3  Viterbi forward + in-kernel backtrack.  Model::encode, src/model.rs:59-129.
+// K2g  Viterbi forward, lane-group form (any max_token_len <= 64; the fallback when the
+//      vocabulary has tokens longer than 16 bytes).  Model::encode forward loop,
+//      src/model.rs:83-110.  Output: bp[start + e - 1] = byte length of the best last token
+//      ending at position e (0 = position unreachable).
 // -----------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
@@ -188,60 +186,60 @@ __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
       if (++sl == W) sl = 0;
     }
     const uint32_t e = p0 + lig;
-    if (has && e >= 1 && e <= n) p.bp[start + e - 1] = my_bp;
+    if (has && e >= 1 && e <= n) p.bp[start + e - 1] = (my_bp == NONE) ? (uint8_t)0 : (uint8_t)(my_bp >> 24);
     slot0 += G;
     while (slot0 >= W) slot0 -= W;
-  }
-  __syncwarp();
-
-  // ---- backtrack (src/model.rs:113-126): ids are written right-aligned into the unit's own
-  // back-pointer region: token k from the end lands at index n-1-k >= the index just read.
-  if (has && lig == 0) {
-    unsigned long long k = 0;
-    int st = 0;
-    if (n > 0) {
-      if (p.bp[start + n - 1] == NONE) {
-        st = 6;  // Error::NoPath(n, n)
-      } else {
-        uint32_t pos = n;
-        while (pos > 0) {
-          const uint32_t v = p.bp[start + pos - 1];
-          const uint32_t id = v & ID_MASK;
-          if ((v >> 24) == 0 || (v >> 24) > pos) { st = 99; break; }  // corrupt chain: never loop forever
-          if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
-          if (p.emit) p.bp[start + n - 1 - k] = id;
-          pos -= v >> 24;
-          k++;
-        }
-      }
-    }
-    p.n_tokens[unit] = st ? 0 : k;
-    p.status[unit] = st;
   }
 }
 
 // -----------------------------------------------------------------------------------------
-// K2c  CTA-cooperative Viterbi: one sample per CTA, producer/consumer.
+// K2  Viterbi forward, pair-CTA form (max_token_len <= 16): the encode hot loop.
 //
-// The per-sample critical path is the ordered relax chain (position p must be final before
-// its matches are pushed), so the kernel is built around its latency, not its width:
-//   * P producer warps run phase A (trie walks) one 32-position tile each, writing a DENSE
-//     table  mpack[depth][column] / mscore[depth][column]  (0 = no token of that length);
-//   * ONE consumer warp runs phase B entirely in registers: lane l owns the dp cell of
-//     every position q with q % 32 == l (max_token_len <= 31), so finalising position p is
-//     a shuffle-broadcast of lane p%32's (score, back-pointer) and the relax of the match
-//     of length len is a predicated compare in lane (p+len)%32 — no shared-memory
-//     round trip and no barrier inside the chain.
-// Rounds of P tiles are double-buffered and separated by one __syncthreads().
-// CTAs fetch samples from a global counter in length-descending order (LPT).
+// The ordered relax chain of a sample (position p must be final before its matches are
+// pushed; src/model.rs:83-110) is one f64 add + compare per position and cannot be split
+// without changing roundings, so the kernel is organised around it:
+//   * a CTA works on TWO samples at a time.  ONE consumer warp owns both chains: lanes
+//     0-15 the first sample, lanes 16-31 the second.  Lane g of a half owns the dp cell of
+//     every position q with q % 16 == g (a token is at most 16 bytes, so the 16 cells
+//     ahead of the current position are exactly the cells in flight).  Finalising position
+//     p is a 16-wide shuffle broadcast of its owner's score; the relax of "token of length
+//     len starting at p" is an add + compare in lane (p + len) % 16.  The cell of p is
+//     re-used for p + 16 by letting its owner take the length-16 candidate unconditionally.
+//   * 2R producer warps walk the double-array trie, one start position per lane, and park
+//     the scores in a dense shared-memory table indexed [start position][target cell]
+//     (row stride 17 doubles: conflict-free for both the row-wise producer and the
+//     column-wise consumer); -inf = no such token.  The dp keeps only the START index of the
+//     best candidate; the back length (1 byte per position, the only HBM output of this
+//     kernel) is derived when the cell is final.  Token ids are recovered later, in
+//     parallel, by emit_kernel.
+//   * rounds of R tiles (32 positions) per sample are double-buffered and separated by one
+//     __syncthreads(); the consumer's half-warp leaders schedule the next round and fetch
+//     new samples from a global counter in length-descending order (LPT).
 // -----------------------------------------------------------------------------------------
-struct CtaStage {
-  uint32_t* mpack;   // [rows][ROW_STRIDE]
-  double* mscore;    // [rows][ROW_STRIDE]
+constexpr int PT_ROW = 17;
+constexpr int PT_TILE = 32 * PT_ROW;  // doubles per (sample slot, tile)
+
+struct __align__(16) PairInfo {
+  unsigned long long start;
+  uint32_t n, tile0, ntiles;
+  int32_t unit;  // < 0: nothing to do
+  uint32_t pad[2];
+};
+static_assert(sizeof(PairInfo) == 32, "PairInfo is 32 bytes");
+
+struct PairParams {
+  UnitParams u;
+  const uint8_t* blob_end;
+  uint8_t* bp;  // [N] back length per end position
+  unsigned int* counter;
+  uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
+  uint32_t groups;     // consumer/producer groups per CTA
 };
 
-__host__ __device__ inline size_t cta_stage_bytes(uint32_t rows) {
-  return ((size_t)rows * ROW_STRIDE * 12 + 15) & ~(size_t)15;
+// shared memory of one CTA: [hot trie prefix][per group: tables 2 x 2 x R tiles | 4 x 2 PairInfo]
+__host__ __device__ inline size_t pair_group_bytes(int R) { return (size_t)2 * 2 * R * PT_TILE * 8 + 8 * 32; }
+__host__ __device__ inline size_t pair_smem_bytes(int R, uint32_t groups, uint32_t hot_slots) {
+  return (size_t)hot_slots * 16 + (size_t)groups * pair_group_bytes(R);
 }
 
 // 24-byte text window starting at the 8-byte aligned address at or below `ptr`
@@ -270,214 +268,458 @@ __device__ __forceinline__ void load_window(const uint8_t* ptr, const uint8_t* b
 
 // Eight text bytes starting at ptr + 8*g, assembled from the 24-byte window.
 __device__ __forceinline__ unsigned long long window_bytes(const unsigned long long (&w)[3], uint32_t sh, int g) {
-  // g in {0,1}: bytes [8g, 8g+8) relative to ptr  =  (w[g] >> 8sh) | (w[g+1] << (64 - 8sh))
   const unsigned long long lo = w[g], hi = w[g + 1];
   return sh ? ((lo >> (8 * sh)) | (hi << (64 - 8 * sh))) : lo;
 }
 
-// Phase A for one 32-position tile.  Dense table per stage: row d (token length d+1), column =
-// start position within the tile; empty entries hold score -inf (their mpack is never read).
-__device__ __forceinline__ void produce_tile(const UnitParams& u, const uint8_t* text, const uint8_t* blob_end,
-                                             uint32_t pos, uint32_t n, uint32_t* mpack, double* mscore, int lane) {
-  const uint32_t rows = u.rows;
+// Phase A for one start position: TrieIterator::next (src/trie.rs:51-63) unrolled over the 16
+// possible depths.  The walk may run past the end of the sample (into the next sample's bytes):
+// such a token lands on a dp cell beyond position n, which is never read.
+template <int HOT>
+__device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, const uint4* __restrict__ hot,
+                                             uint32_t root, const uint8_t* ptr, const uint8_t* blob_end, bool active,
+                                             double* row, int lane) {
   const double ninf = __longlong_as_double(0xFFF0000000000000ll);
-  {
-    double* r = mscore + lane;
-    for (uint32_t d = 0; d < rows; d++, r += ROW_STRIDE) *r = ninf;
-  }
-  if (pos >= n) return;
-  const uint32_t maxd = min(n - pos, rows);
-  uint32_t base = u.root_base;
-  double* ms = mscore + lane;
-  uint32_t* mp = mpack + lane;
-  uint32_t dpk = 1u << 24;  // (depth + 1) << 24
-  for (uint32_t d0 = 0; d0 < maxd; d0 += 16) {
-    unsigned long long w[3];
-    uint32_t sh;
-    load_window(text + pos + d0, blob_end, w, sh);
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-      const unsigned long long a = window_bytes(w, sh, g);
-      const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+  for (int c = 0; c < 16; c++) row[c] = ninf;
+  if (!active) return;
+  unsigned long long w[3];
+  uint32_t sh;
+  load_window(ptr, blob_end, w, sh);
+  unsigned char* rb = reinterpret_cast<unsigned char*>(row);
+  const uint32_t l18 = (uint32_t)(lane + 1) * 8u;
+  uint32_t xb = root;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (d0 + g * 8 + k >= maxd) return;
-        const uint32_t c = __byte_perm(k < 4 ? alo : ahi, 0, 0x4440 + (k & 3));
-        const uint4 e = __ldg(u.trie + (base ^ c));
-        if ((e.x & 0xFFu) != c || !(e.y & F_OCC)) return;
-        if (e.y & F_TERM) {
-          *ms = __hiloint2double((int)e.w, (int)e.z);
-          *mp = dpk | (e.y & ID_MASK);
-        }
-        if (!(e.y & F_HASCH)) return;
-        base = e.x >> 8;
-        ms += ROW_STRIDE;
-        mp += ROW_STRIDE;
-        dpk += 1u << 24;
-      }
+  for (int g = 0; g < 2; g++) {
+    const unsigned long long a = window_bytes(w, sh, g);
+    const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int d = g * 8 + k;
+      const uint32_t cw = __byte_perm(k < 4 ? alo : ahi, 1u, 0x5540 + (k & 3));  // 0x100 | byte
+      // the first HOT levels of the trie live in shared memory (every probe out of a node of
+      // depth < HOT lands in the staged prefix, hit or miss; see trie_build.h)
+      const uint4 e = (d < HOT) ? hot[xb ^ cw] : __ldg(trie + (xb ^ cw));
+      if ((e.x ^ cw) & 0x1FFu) return;
+      if (e.y & F_TERM)  // target cell (start + len) % 16 = (lane + d + 1) % 16
+        *reinterpret_cast<double*>(rb + ((l18 + 8u * d) & 120u)) = __hiloint2double((int)e.w, (int)e.z);
+      if (!(e.y & F_HASCH)) return;
+      xb = e.x >> 9;
     }
   }
 }
 
-// Phase B over one 32-position tile, in registers.  Lane l owns the dp cell (best, pk) of
-// every position q with q % 32 == l; "unreached" is best == -inf (scores are finite, so a
-// candidate built on an unreached position is -inf and can never win, and the first finite
-// candidate always replaces -inf — the reference's `start.is_none() ||` test, src/model.rs:100).
-// Operands (score, packed len|id) are fetched three positions ahead of the ordered chain,
-// which is then only  shuffle -> DADD -> compare -> select.
-__device__ __forceinline__ void load_operand(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
-                                             uint32_t rows, int lane, int j, uint32_t& mp, double& sc) {
-  const uint32_t len = (uint32_t)(lane - j) & 31u;
-  const bool valid = (len - 1u) < rows;
-  const uint32_t row = valid ? len - 1u : 0u;
-  mp = mpack[row * ROW_STRIDE + j];
-  const double v = mscore[row * ROW_STRIDE + j];
-  sc = valid ? v : __longlong_as_double(0xFFF0000000000000ll);
-}
-
-__device__ __forceinline__ uint32_t consume_tile(const uint32_t* __restrict__ mpack, const double* __restrict__ mscore,
-                                                 uint32_t rows, int lane, double& best, uint32_t& pk) {
-  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
-  uint32_t my_bp = NONE;
-  uint32_t mp[4];
+// Phase B over one 32-position tile for both halves of the consumer warp.  tb = this half's
+// table + g, so the operand of step j is tb[j * PT_ROW].  "Unreached" is best == -inf: scores
+// are finite, so a candidate built on an unreached position is -inf and can never win, and the
+// first finite candidate always replaces -inf (the reference's `start.is_none() ||`, src/model.rs:100).
+__device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int g, double& best, uint32_t& ps,
+                                             uint32_t& len0, uint32_t& len1) {
   double sc[4];
-#pragma unroll
-  for (int j = 0; j < 3; j++) load_operand(mpack, mscore, rows, lane, j, mp[j], sc[j]);
+  sc[0] = tb[0];
+  sc[1] = tb[PT_ROW];
+  uint32_t sv_hi = 0, sv_ps = 0;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
-    if (j + 3 < 32) load_operand(mpack, mscore, rows, lane, j + 3, mp[(j + 3) & 3], sc[(j + 3) & 3]);
-    const double bsrc = __shfl_sync(0xFFFFFFFFu, best, j);
-    if (lane == j) { my_bp = pk; pk = NONE; best = ninf; }  // the cell now stands for position p + 32
-    const double cand = __dadd_rn(bsrc, sc[j & 3]);           // dp[pos].score + vocab[id].score  (src/model.rs:98)
-    if (cand > best) {                                        // (:100-101)
+    if (j + 2 < 32) sc[(j + 2) & 3] = tb[(j + 2) * PT_ROW];
+    const double bs = __shfl_sync(0xFFFFFFFFu, best, j & 15, 16);  // dp[pos].score, final
+    const bool own = g == (j & 15);
+    if (own) {  // this lane's cell is position j of the tile: keep its result, the cell moves on to j + 16
+      sv_hi = (uint32_t)__double2hiint(best);
+      sv_ps = ps;
+    }
+    const double cand = __dadd_rn(bs, sc[j & 3]);  // dp[pos].score + vocab[id].score  (src/model.rs:98)
+    if (cand > best || own) {                      // (:100-101); a fresh cell takes its first candidate
       best = cand;
-      pk = mp[j & 3];
+      ps = j;
+    }
+    if ((j & 15) == 15) {
+      const uint32_t l = (sv_hi == 0xFFF00000u) ? 0u : (((uint32_t)(j - 15 + g) - sv_ps) & 31u);
+      if (j == 15) len0 = l; else len1 = l;
     }
   }
-  return my_bp;
 }
 
-template <int P>
-__global__ void __launch_bounds__(32 * (P + 1), (P <= 2 ? 8 : 4)) viterbi_cta_kernel(ViterbiParams p, unsigned int* work_counter,
-                                                                   const uint8_t* blob_end, uint32_t chunk_cap) {
+template <int R, int HOT>
+__global__ void __launch_bounds__(1024, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ uint32_t s_unit, s_pos, s_endpk;
-  __shared__ unsigned long long s_k;
+  constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t rows = u.rows;
-  const size_t stage_b = cta_stage_bytes(rows);
-  uint32_t* chunk = reinterpret_cast<uint32_t*>(smem);
+  const int grp = warp / WG, wg = warp % WG;
+  const int h = lane >> 4, g = lane & 15;
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
 
-  for (;;) {
-    if (threadIdx.x == 0) s_unit = atomicAdd(work_counter, 1u);
-    __syncthreads();
-    const uint32_t r = s_unit;
-    if (r >= u.count) break;
-    const uint32_t unit = u.order[u.first + r];
-    const uint32_t n = u.unit_len[unit];
-    const uint64_t start = u.unit_start[unit];
-    const uint8_t* text = u.text + start;
-    const uint32_t ntiles = n / 32 + 1;  // positions 0..n
-    const uint32_t rounds = (ntiles + P - 1) / P;
-    // dp[0] = { score 0.0, start Some(0) }  (src/model.rs:72-81); every other cell unreached
-    double best = (lane == 0) ? 0.0 : __longlong_as_double(0xFFF0000000000000ll);
-    uint32_t pk = (lane == 0) ? 0u : NONE;
-    uint32_t last_bp = NONE;
-    for (uint32_t round = 0; round <= rounds; round++) {
-      if (warp > 0) {
-        const uint32_t t = round * P + (warp - 1);
-        if (round < rounds && t < ntiles) {
-          unsigned char* st = smem + ((size_t)(round & 1) * P + (warp - 1)) * stage_b;
-          double* ms = reinterpret_cast<double*>(st);
-          uint32_t* mp = reinterpret_cast<uint32_t*>(st + (size_t)rows * ROW_STRIDE * 8);
-          produce_tile(u, text, blob_end, t * 32 + lane, n, mp, ms, lane);
-        }
-      } else if (round > 0) {
-        for (int k = 0; k < P; k++) {
-          const uint32_t t = (round - 1) * P + k;
-          if (t >= ntiles) break;
-          const unsigned char* st = smem + ((size_t)((round - 1) & 1) * P + k) * stage_b;
-          const double* ms = reinterpret_cast<const double*>(st);
-          const uint32_t* mp = reinterpret_cast<const uint32_t*>(st + (size_t)rows * ROW_STRIDE * 8);
-          const uint32_t my_bp = consume_tile(mp, ms, rows, lane, best, pk);
-          const uint32_t e = t * 32 + lane;
-          if (e >= 1 && e <= n) p.bp[start + e - 1] = my_bp;
-          if (e == n) last_bp = my_bp;
-        }
-      }
-      __syncthreads();
-    }
-    if (warp == 0 && lane == (int)(n & 31u)) s_endpk = (n == 0) ? 0u : last_bp;
-    if (threadIdx.x == 0) { s_pos = n; s_k = 0; }
-    __syncthreads();
-    // ---- backtrack (src/model.rs:113-126).  Back-pointers are staged in shared memory a chunk
-    // at a time; one thread follows the chain (a pure LDS -> subtract dependency) and parks the
-    // visited entries in a second buffer, which all threads then flush: ids go right-aligned
-    // into the sample's own back-pointer region (token k from the end at index n-1-k, always
-    // >= any index still to be read), frequencies through atomics.
-    int st_code = 0;
-    if (n > 0 && s_endpk == NONE) {
-      st_code = 6;  // Error::NoPath(n, n)
+  const uint4* hot = reinterpret_cast<const uint4*>(smem);
+  unsigned char* gbase = smem + (size_t)p.hot_slots * 16 + (size_t)grp * pair_group_bytes(R);
+  double* tab = reinterpret_cast<double*>(gbase);  // [2 stages][2 halves][R][PT_TILE]
+  PairInfo* s_info = reinterpret_cast<PairInfo*>(gbase + (size_t)2 * 2 * R * PT_TILE * 8);  // [4][2]
+  if (HOT > 0) {
+    uint4* hw = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = threadIdx.x; i < p.hot_slots; i += blockDim.x) hw[i] = __ldg(u.trie + i);
+  }
+
+  // consumer state: one dp cell per lane
+  double best = ninf;
+  uint32_t ps = 0;
+  // scheduler state (half-warp leaders of the consumer warp)
+  PairInfo cur;
+  cur.unit = -1; cur.start = 0; cur.n = 0; cur.tile0 = 0; cur.ntiles = 0; cur.pad[0] = cur.pad[1] = 0;
+  auto fetch = [&]() {
+    const uint32_t idx = atomicAdd(p.counter, 1u);
+    if (idx < u.count) {
+      cur.unit = (int32_t)u.order[u.first + idx];
+      cur.n = u.unit_len[cur.unit];
+      cur.start = u.unit_start[cur.unit];
+      cur.tile0 = 0;
+      cur.ntiles = cur.n / 32 + 1;  // positions 0..n
     } else {
-      uint32_t* stage = chunk + chunk_cap;  // [BT_STAGE]
-      uint32_t pos = n;
-      unsigned long long kbase = 0;
-      while (pos > 0) {
-        const uint32_t lo = pos > chunk_cap ? pos - chunk_cap : 0;
-        for (uint32_t i = threadIdx.x; i < pos - lo; i += blockDim.x) chunk[i] = p.bp[start + lo + i];
-        __syncthreads();
-        uint32_t q = pos;
-        while (q > lo) {  // uniform: q is re-read from shared memory after every stage
-          if (threadIdx.x == 0) {
-            uint32_t qq = q, cnt = 0;
-            while (qq > lo && cnt < BT_STAGE) {
-              const uint32_t v = chunk[qq - 1 - lo];
-              const uint32_t len = v >> 24;
-              if (len == 0 || len > qq) { qq = 0xFFFFFFFFu; break; }  // corrupt chain: abort, never spin
-              stage[cnt++] = v;
-              qq -= len;
-            }
-            s_pos = qq;
-            s_k = cnt;
-          }
-          __syncthreads();
-          const uint32_t cnt = (uint32_t)s_k;
-          for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t id = stage[i] & ID_MASK;
-            if (p.freq) atomicAdd(p.freq + id, 1ull);  // src/prune.rs:223-225
-            if (p.emit) p.bp[start + n - 1 - (kbase + i)] = id;
-          }
-          kbase += cnt;
-          q = s_pos;
-          __syncthreads();
-          if (q == 0xFFFFFFFFu) break;
-        }
-        if (q == 0xFFFFFFFFu) { st_code = 99; break; }
-        pos = q;
-      }
-      if (threadIdx.x == 0) s_k = kbase;
+      cur.unit = -1;
     }
+  };
+  if (wg == 0 && g == 0) {
+    fetch();
+    s_info[0 * 2 + h] = cur;
+    PairInfo none = cur;
+    none.unit = -1;
+    s_info[3 * 2 + h] = none;
+  }
+  __syncthreads();
+
+  for (uint32_t r = 0;; r++) {
+    if (wg == 0) {
+      if (g == 0) {  // what the producers do in round r + 1
+        if (cur.unit >= 0) {
+          cur.tile0 += R;
+          if (cur.tile0 >= cur.ntiles) fetch();
+        }
+        s_info[((r + 1) & 3) * 2 + h] = cur;
+      }
+      const PairInfo ci = s_info[((r + 3) & 3) * 2 + h];  // what they did in round r - 1
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const uint32_t t = ci.tile0 + k;
+        const bool act = ci.unit >= 0 && t < ci.ntiles;
+        if (act && t == 0) {  // dp[0] = { score 0.0, start Some(0) }  (src/model.rs:72-81); the rest unreached
+          best = (g == 0) ? 0.0 : ninf;
+          ps = 0;
+        }
+        const double* tb = tab + ((size_t)(((r + 1) & 1) * 2 + h) * R + k) * PT_TILE + g;
+        uint32_t len0, len1;
+        pair_consume(tb, g, best, ps, len0, len1);  // both halves always run it (full-warp shuffles)
+        if (act) {
+          const uint32_t e0 = t * 32 + g, e1 = e0 + 16;
+          if (e0 >= 1 && e0 <= ci.n) p.bp[ci.start + e0 - 1] = (uint8_t)len0;
+          if (e1 <= ci.n) p.bp[ci.start + e1 - 1] = (uint8_t)len1;
+        }
+      }
+    } else {
+      const int w = wg - 1;
+      const int ph = w & 1, k = w >> 1;
+      const PairInfo pi = s_info[(r & 3) * 2 + ph];
+      const uint32_t t = pi.tile0 + k;
+      if (pi.unit >= 0 && t < pi.ntiles) {
+        const uint32_t pos = t * 32 + lane;
+        double* row = tab + ((size_t)((r & 1) * 2 + ph) * R + k) * PT_TILE + lane * PT_ROW;
+        pair_produce<HOT>(u.trie, hot, u.root_base, u.text + pi.start + pos, p.blob_end, pos < pi.n, row, lane);
+      }
+    }
+    // group barrier: the groups of a CTA only share the read-only hot trie
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(WG * 32) : "memory");
+    const bool more = s_info[(r & 3) * 2 + 0].unit >= 0 || s_info[(r & 3) * 2 + 1].unit >= 0 ||
+                      s_info[((r + 1) & 3) * 2 + 0].unit >= 0 || s_info[((r + 1) & 3) * 2 + 1].unit >= 0;
+    if (!more) break;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// K3a  backtrack (src/model.rs:113-123): one thread per sample follows the back lengths from
+//      position n and marks every token END with the token's length (mark[] is zeroed by the
+//      caller and separate from bp[], so the chain's loads stay L1 hits).
+// -----------------------------------------------------------------------------------------
+struct BacktrackParams {
+  const uint64_t* unit_start;
+  const uint32_t* unit_len;
+  const uint32_t* order;
+  uint32_t first, count;
+  const uint8_t* bp;
+  uint8_t* mark;                 // [N]
+  unsigned long long* n_tokens;  // [U]
+  int32_t* status;               // [U] 0 ok / 6 NoPath
+};
+
+// Short samples: one thread per sample follows the chain with plain dependent loads.
+constexpr int BT_THREADS = 128;
+
+__global__ void __launch_bounds__(BT_THREADS) backtrack_thread_kernel(BacktrackParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.count) return;
+  const uint32_t unit = p.order[p.first + i];
+  const uint32_t n = p.unit_len[unit];
+  const uint64_t start = p.unit_start[unit];
+  const uint8_t* b = p.bp + start;
+  uint8_t* mk = p.mark + start;
+  unsigned long long k = 0;
+  int st = 0;
+  if (n > 0) {
+    if (__ldg(b + n - 1) == 0) {
+      st = 6;  // Error::NoPath(n, n)  (src/model.rs:119)
+    } else {
+      uint32_t pos = n;
+      while (pos > 0) {
+        const uint32_t l = __ldg(b + pos - 1);
+        if (l == 0 || l > pos) { st = 99; break; }  // corrupt chain: never loop forever
+        mk[pos - 1] = (uint8_t)l;
+        pos -= l;
+        k++;
+      }
+    }
+  }
+  p.n_tokens[unit] = st ? 0ull : k;
+  p.status[unit] = st;
+}
+
+// Long samples: one WARP per sample, 1024 positions at a time, so that the serial part of the
+// chain pos -> pos - len[pos] shrinks from one dependent step per token to one per 32 positions:
+//   phase 1  lane s owns the 32-position segment s of the chunk and computes, for EVERY position
+//            x of its segment, where the chain starting at x leaves the segment (exit[x] =
+//            exit[x - len[x]] unless x - len[x] is already below the segment): 32 short,
+//            lane-private steps, all lanes in parallel;
+//   phase 2  the true chain enters the top segment at the chunk's top position; hopping
+//            segment to segment through exit[] (one shared-memory load per segment) yields the
+//            entry position of every segment;
+//   phase 3  lane s re-walks its own segment from its entry and marks the token ends.
+// Tokens are at most 64 bytes (tgx::MAX_TOKEN_LEN), so a hop lands at most two segments down
+// and the next chunk's top at most 63 bytes below this chunk.  The back lengths of the next
+// chunk are prefetched into registers by the whole warp (warp-uniform, so the per-warp
+// scoreboard costs nothing).
+constexpr int BW_WARPS = 8;
+constexpr int BW_CHUNK = 1024;
+constexpr int BW_VECS = 72;                 // staged 16-byte vectors: window [wbase, wbase + 1152)
+constexpr int BW_SEG_STRIDE = 34;           // int16 per segment row (bank skew)
+
+__global__ void __launch_bounds__(BW_WARPS * 32) backtrack_warp_kernel(BacktrackParams p) {
+  __shared__ __align__(16) uint8_t s_len[BW_WARPS][BW_VECS * 16];
+  __shared__ int16_t s_exit[BW_WARPS][32 * BW_SEG_STRIDE];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * BW_WARPS + w;
+  if (i >= p.count) return;
+  const uint32_t unit = p.order[p.first + i];
+  const uint32_t n = p.unit_len[unit];
+  const uint64_t start = p.unit_start[unit];
+  const uint4* b16 = reinterpret_cast<const uint4*>(p.bp);
+  uint8_t* sl = s_len[w];
+  int16_t* ex = s_exit[w] + lane * BW_SEG_STRIDE;  // this lane's segment row, indices 1..32
+  unsigned long long k = 0;
+  int st = 0;
+  if (n == 0) {  // (not scheduled: empty samples are filtered by the caller)
+    if (lane == 0) { p.n_tokens[unit] = 0; p.status[unit] = 0; }
+    return;
+  }
+  uint64_t gtop = start + n - 1;                                           // last byte of the current token
+  uint64_t gbase = (gtop - start >= BW_CHUNK) ? gtop - (BW_CHUNK - 1) : start;  // first byte of the chunk
+  uint64_t wbase = gbase & ~15ull;                                         // staged window
+  uint4 v[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const uint32_t vi = lane + 32 * j;
+    v[j] = (vi < BW_VECS && wbase + 16ull * vi <= gtop) ? __ldg(b16 + (wbase >> 4) + vi) : make_uint4(0, 0, 0, 0);
+  }
+  for (;;) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const uint32_t vi = lane + 32 * j;
+      if (vi < BW_VECS) reinterpret_cast<uint4*>(sl)[vi] = v[j];
+    }
+    __syncwarp();
+    const uint32_t C = (uint32_t)(gtop - gbase) + 1;   // positions x = 1..C <-> byte gbase + x - 1
+    const uint32_t off = (uint32_t)(gbase - wbase);    // sl[off + x - 1] = back length of position x
+    if (gtop == start + n - 1 && sl[off + C - 1] == 0) { st = 6; break; }  // Error::NoPath(n, n)  (src/model.rs:119)
+    // prefetch the next chunk's window: its top is at most 63 bytes below gbase
+    const bool last = gbase == start;
+    const uint64_t nwbase = (gbase >= 1087 ? gbase - 1087 : 0) & ~15ull;
+    if (!last) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const uint32_t vi = lane + 32 * j;
+        v[j] = (vi < BW_VECS && nwbase + 16ull * vi < gbase) ? __ldg(b16 + (nwbase >> 4) + vi) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    // ---- phase 1
+    const int lo = 32 * lane;
+#pragma unroll 4
+    for (int q = 1; q <= 32; q++) {
+      const int x = lo + q;
+      if (x > (int)C) break;
+      const int l = sl[off + x - 1];
+      const int t = x - l;
+      int e;
+      if (l == 0) e = x;            // unreachable position: never on the chain
+      else if (t <= lo) e = t;      // leaves the segment (may be <= 0: leaves the chunk)
+      else e = ex[t - lo];
+      ex[q] = (int16_t)e;
+    }
+    __syncwarp();
+    // ---- phase 2 (every lane follows the same hops; broadcast loads)
+    int cur = (int)C, myent = 0;
+    while (cur >= 1) {
+      const int s = (cur - 1) >> 5;
+      if (s == lane) myent = cur;
+      const int nxt = (int)s_exit[w][s * BW_SEG_STRIDE + (cur - 32 * s)];
+      if (nxt >= cur) { cur = -32768; break; }  // corrupt chain: never loop forever
+      cur = nxt;
+    }
+    // ---- phase 3
+    if (cur != -32768) {
+      int x = myent;
+      while (x > lo) {
+        const int l = sl[off + x - 1];
+        if (l == 0) break;
+        p.mark[gbase + x - 1] = (uint8_t)l;
+        k++;
+        x -= l;
+      }
+    }
+    __syncwarp();
+    // cur <= 0 is where the chain left the chunk; as a sample position: (gbase - start) + cur
+    const long long pe = (long long)(gbase - start) + cur;
+    if (cur == -32768 || cur > 0 || pe < 0) { st = 99; break; }  // corrupt chain
+    if (pe == 0) break;                                           // reached position 0: done
+    gtop = gbase + cur - 1;  // the end of the first token that ends below this chunk
+    gbase = (gtop - start >= BW_CHUNK) ? gtop - (BW_CHUNK - 1) : start;
+    wbase = nwbase;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
+  if (lane == 0) {
+    p.n_tokens[unit] = st ? 0ull : k;
+    p.status[unit] = st;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// K3b/K3c  emit: stream-compact the marked token ends (in blob order = output order, since
+//      samples are contiguous and in input order) and recover each token's id by walking the
+//      trie over its bytes — thousands of independent walks instead of one id per dp relax.
+//      With freq != nullptr it is the frequency pass of prune_vocab (src/prune.rs:223-225).
+// -----------------------------------------------------------------------------------------
+constexpr int EM_BLOCK = 256;
+constexpr int EM_PER_THREAD = 16;
+constexpr int EM_TILE = EM_BLOCK * EM_PER_THREAD;
+constexpr uint32_t EM_HOT = 4096;  // ids below this are counted in shared memory first (frequency pass)
+
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) {  // 0x80 in every non-zero byte
+  return (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;
+}
+
+__device__ __forceinline__ uint32_t em_block_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  uint32_t before = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < EM_BLOCK / 32; i++) {
+    const uint32_t ws = warp_sums[i];
+    if (i < warp) before += ws;
+    tot += ws;
+  }
+  total = tot;
+  return before + x - v;
+}
+
+// mark is padded with zeros to a multiple of EM_TILE bytes.
+__global__ void __launch_bounds__(EM_BLOCK) mark_count_kernel(const uint4* __restrict__ mark, uint64_t n_tiles,
+                                                              unsigned long long* __restrict__ tile_cnt) {
+  __shared__ uint32_t ws[EM_BLOCK / 32];
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint4 v = mark[tile * EM_BLOCK + threadIdx.x];
+    uint32_t c = __popc(nonzero_bytes(v.x)) + __popc(nonzero_bytes(v.y)) + __popc(nonzero_bytes(v.z)) +
+                 __popc(nonzero_bytes(v.w));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
     if (threadIdx.x == 0) {
-      p.n_tokens[unit] = st_code ? 0ull : s_k;
-      p.status[unit] = st_code;
+      uint32_t t = 0;
+#pragma unroll
+      for (int i = 0; i < EM_BLOCK / 32; i++) t += ws[i];
+      tile_cnt[tile] = t;
     }
     __syncthreads();
   }
 }
 
-// K3b: compact the right-aligned ids into the caller's id array (input order).
-__global__ void gather_ids_kernel(const uint32_t* __restrict__ bp, const uint64_t* __restrict__ unit_start,
-                                  const uint32_t* __restrict__ unit_len,
-                                  const unsigned long long* __restrict__ id_off, uint32_t U,
-                                  uint32_t* __restrict__ out, unsigned long long cap) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= U) return;
-  const unsigned long long o = id_off[warp], T = id_off[warp + 1] - o;
-  if (o + T > cap) return;
-  const uint32_t* src = bp + unit_start[warp] + unit_len[warp] - T;
-  for (unsigned long long i = lane; i < T; i += 32) out[o + i] = src[i];
+struct EmitParams {
+  const uint4* mark;
+  const uint8_t* text;
+  uint64_t n_tiles;
+  const unsigned long long* tile_prefix;  // exclusive scan of tile_cnt
+  const uint4* trie;
+  uint32_t root_base;  // xbase of the root
+  uint32_t* ids;             // may be null
+  unsigned long long cap;
+  unsigned long long* freq;  // may be null
+  uint32_t V;
+};
+
+__global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
+  __shared__ uint32_t ws[EM_BLOCK / 32];
+  __shared__ uint32_t s_tok[EM_TILE];  // (len << 16) | offset of the token's last byte in the tile
+  extern __shared__ uint32_t s_hot[];  // [EM_HOT] when freq
+  if (p.freq) {
+    for (uint32_t i = threadIdx.x; i < EM_HOT; i += EM_BLOCK) s_hot[i] = 0;
+    __syncthreads();
+  }
+  for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const uint4 v = p.mark[tile * EM_BLOCK + threadIdx.x];
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c += __popc(nonzero_bytes(wv[i]));
+    uint32_t total;
+    uint32_t o = em_block_scan(c, ws, total);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const uint32_t l = (wv[i] >> (8 * b)) & 0xFFu;
+        if (l) s_tok[o++] = (l << 16) | (uint32_t)(threadIdx.x * EM_PER_THREAD + i * 4 + b);
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = p.tile_prefix[tile];
+    const uint8_t* tt = p.text + tile * EM_TILE;
+    for (uint32_t k = threadIdx.x; k < total; k += EM_BLOCK) {
+      const uint32_t tk = s_tok[k];
+      const uint32_t len = tk >> 16;
+      const uint8_t* q = tt + (tk & 0xFFFFu) + 1 - len;  // first byte of the token (may lie in an earlier tile)
+      uint32_t xb = p.root_base;
+      uint4 e = make_uint4(0, 0, 0, 0);
+      for (uint32_t d = 0; d < len; d++) {  // the token is in the vocabulary: no checks needed
+        e = __ldg(p.trie + (xb ^ (0x100u | __ldg(q + d))));
+        xb = e.x >> 9;
+      }
+      const uint32_t id = e.y & ID_MASK;
+      if (p.ids && base + k < p.cap) p.ids[base + k] = id;
+      if (p.freq) {
+        if (id < EM_HOT) atomicAdd(s_hot + id, 1u);
+        else atomicAdd(p.freq + id, 1ull);
+      }
+    }
+    __syncthreads();
+  }
+  if (p.freq) {
+    for (uint32_t i = threadIdx.x; i < EM_HOT && i < p.V; i += EM_BLOCK) {
+      const uint32_t c = s_hot[i];
+      if (c) atomicAdd(p.freq + i, (unsigned long long)c);
+    }
+  }
 }
 
 // -----------------------------------------------------------------------------------------

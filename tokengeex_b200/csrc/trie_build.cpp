@@ -106,9 +106,12 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   std::vector<uint32_t> bfs;
   bfs.reserve(nodes.size());
   bfs.push_back(0);
-  std::vector<uint32_t> depth_end;  // bfs index where each depth ends
+  std::vector<uint8_t> depth(nodes.size(), 0);
   for (size_t i = 0; i < bfs.size(); i++)
-    for (uint32_t c = nodes[bfs[i]].first_child; c; c = nodes[c].next_sibling) bfs.push_back(c);
+    for (uint32_t c = nodes[bfs[i]].first_child; c; c = nodes[c].next_sibling) {
+      depth[c] = (uint8_t)std::min<uint32_t>(depth[bfs[i]] + 1u, 255u);
+      bfs.push_back(c);
+    }
 
   // 4. slot allocation
   FreeList fl;
@@ -152,12 +155,16 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     if (base == FreeList::END) {
       // open a fresh block: any base inside it works (all slots free, no base used)
       uint32_t lo = fl.size();
-      if (lo + 256 > MAX_SLOTS) return "trie too large (slot index must fit 24 bits)";
+      if (lo + 256 > MAX_SLOTS) return "trie too large (slot index must fit 23 bits)";
       fl.add_block();
       base = lo;
     }
     fl.base_used[base] = 1;
     base_of[nidx] = base;
+    if (depth[nidx] < 2) {  // every probe out of this node stays inside base's 256-slot block
+      uint32_t end = (base | 255u) + 1u;
+      for (int d = depth[nidx] + 1; d <= 2; d++) out->hot[d] = std::max(out->hot[d], end);
+    }
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) {
       uint32_t s = base ^ nodes[c].label;
       fl.take(s);
@@ -170,8 +177,9 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   for (size_t i = 0; i < nodes.size(); i++) {
     const Node& nd = nodes[i];
     Slot s{0, 0, 0, 0};
-    s.x = (base_of[i] << 8) | nd.label;
-    uint32_t flags = i == 0 ? 0 : SLOT_OCC;  // the root is never a transition target
+    // the root is never a transition target: it stays "empty" (bit 8 clear)
+    s.x = ((base_of[i] ^ 0x100u) << 9) | (i == 0 ? 0u : SLOT_OCC) | nd.label;
+    uint32_t flags = 0;
     if (nd.first_child) flags |= SLOT_HASCH;
     if (nd.term_id >= 0 && i != 0) {
       flags |= SLOT_TERM;
@@ -184,11 +192,11 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     s.y |= flags;
     out->slots[nd.slot] = s;
   }
-  out->root_base = base_of[0];
+  out->root_base = base_of[0] ^ 0x100u;
   out->max_token_len = max_len;
   out->n_nodes = (uint32_t)nodes.size();
   out->n_terminals = n_term;
-  out->hot_slots = 0;
+  for (int d = 1; d <= 2; d++) out->hot[d] = std::min<uint32_t>(std::max(out->hot[d], 256u), (uint32_t)fl.size());
   return "";
 }
 

@@ -5,12 +5,15 @@
 // XOR double-array laid out for the GPU: one 16-byte slot per trie node, so that one
 // 128-bit load performs the transition, the terminal test and the score fetch.
 //
-//   slot.x = (base << 8) | label      base: children of this node live at base ^ byte
-//   slot.y = id | flags << 24         id: token id (24 bit), flags: OCC | TERM | HASCH
+//   slot.x = (xbase << 9) | 0x100 | label   occupied slots carry bit 8; an empty slot is all zero.
+//                                      xbase = base ^ 0x100: with cw = 0x100 | byte the children of
+//                                      this node live at xbase ^ cw (= base ^ byte)
+//   slot.y = id | flags << 24         id: token id (24 bit), flags: TERM | HASCH
 //   slot.zw = f64 score bits          score of vocab[id] (valid when TERM)
 //
-// A transition s --c--> t is valid iff t = base(s) ^ c is occupied and label(t) == c.
-// Bases are unique per parent, which makes the one-byte label a sufficient check
+// A transition s --c--> t is valid iff t = xbase(s) ^ cw satisfies (slot[t].x ^ cw) & 0x1FF == 0,
+// i.e. t is occupied and label(t) == c: ONE masked compare on the word that also carries the
+// next base.  Bases are unique per parent, which makes the one-byte label a sufficient check
 // (two parents reaching the same slot with the same label would share a base).
 // Semantics kept from the reference: duplicate byte strings keep the LAST id
 // (src/trie.rs:19); the empty token is never matched (src/trie.rs:51-63).
@@ -21,13 +24,13 @@
 
 namespace tgx {
 
-constexpr uint32_t SLOT_OCC = 1u << 24;
-constexpr uint32_t SLOT_TERM = 2u << 24;
+constexpr uint32_t SLOT_OCC = 0x100u;         // in slot.x
+constexpr uint32_t SLOT_TERM = 2u << 24;      // in slot.y
 constexpr uint32_t SLOT_HASCH = 4u << 24;
 constexpr uint32_t SLOT_ID_MASK = 0x00FFFFFFu;
 constexpr uint32_t MAX_TOKEN_LEN = 64;        // rows of the per-lane match buffer
 constexpr uint32_t MAX_VOCAB = 1u << 24;      // 24-bit ids inside slots / back-pointers
-constexpr uint32_t MAX_SLOTS = 1u << 24;      // 24-bit bases
+constexpr uint32_t MAX_SLOTS = 1u << 23;      // 23-bit bases
 
 struct Slot {
   uint32_t x, y, z, w;
@@ -35,11 +38,15 @@ struct Slot {
 
 struct DoubleArray {
   std::vector<Slot> slots;   // slot 0 is the root (never a transition target)
-  uint32_t root_base = 0;
+  uint32_t root_base = 0;    // xbase of the root (see above)
   uint32_t max_token_len = 0;
   uint32_t n_nodes = 0;      // trie nodes incl. root
   uint32_t n_terminals = 0;  // distinct token byte strings
-  uint32_t hot_slots = 0;    // slots [0, hot_slots) hold the BFS-first (shallow) nodes
+  // Slots are handed out in BFS order, so shallow nodes sit at the front: every transition out of
+  // a node of depth < d (hit or miss: base ^ byte stays inside base's 256-slot block) lands in
+  // [0, hot[d]).  hot[1] covers the root's children, hot[2] also their children.  The kernels
+  // stage that prefix in shared memory.
+  uint32_t hot[3] = {0, 0, 0};
 };
 
 // Returns "" on success, else an error message.
@@ -49,16 +56,16 @@ std::string build_double_array(const uint8_t* token_bytes, const uint64_t* token
 // Host walk (used by Tokenizer::common_prefix_search, src/model.rs:132-138).
 template <class F>
 inline void da_common_prefix_search(const DoubleArray& da, const uint8_t* s, size_t n, F&& f) {
-  uint32_t base = da.root_base;
+  uint32_t xbase = da.root_base;
   for (size_t d = 0; d < n; d++) {
-    uint32_t c = s[d];
-    uint32_t t = base ^ c;
+    uint32_t cw = 0x100u | s[d];
+    uint32_t t = xbase ^ cw;
     if (t >= da.slots.size()) return;
     const Slot& e = da.slots[t];
-    if ((e.x & 0xFFu) != c || !(e.y & SLOT_OCC)) return;
+    if ((e.x ^ cw) & 0x1FFu) return;
     if (e.y & SLOT_TERM) f(e.y & SLOT_ID_MASK, (uint32_t)d + 1);
     if (!(e.y & SLOT_HASCH)) return;
-    base = e.x >> 8;
+    xbase = e.x >> 9;
   }
 }
 

@@ -34,7 +34,8 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        for algo, opts in [(0, {4: 3}), (0, {4: 2}), (0, {4: 4}), (0, {4: 7}), (1, {0: 8, 1: 4096})]:
+        for algo, opts in [(0, {4: 2, 6: 0}), (0, {4: 2, 6: 8}), (0, {4: 2, 6: 6}), (0, {4: 4, 6: 0}), (0, {4: 4, 6: 5}),
+                           (0, {4: 4, 6: 4}), (0, {4: 4, 6: 3})]:
             m.set_option(3, algo)
             for k, v in opts.items():
                 m.set_option(k, v)
@@ -43,10 +44,11 @@ def main():
                 tot, rc, bad = m.encode_batch_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, True, d_ids.data_ptr(),
                                                   NB + 4, d_id_off.data_ptr())
                 best = min(best, m.stat(4))
-            print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  viterbi {m.stat(1):.2f} ms "
-                  f"tokens={tot}", flush=True)
+            print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  forward {m.stat(1):.2f} ms "
+                  f"backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot}", flush=True)
         m.set_option(3, 0)
-        m.set_option(4, 3)
+        m.set_option(4, 2)
+        m.set_option(6, 0)
     if "freq" in what:
         for _ in range(args.reps):
             d_fr.zero_()
