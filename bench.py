@@ -224,12 +224,14 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    dev_ms, vit_ms = [], []
+    dev_ms, vit_ms, back_ms, emit_ms = [], [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tokens = step_dev()
         dev_ms.append(model.stat(4))
         vit_ms.append(model.stat(1))
+        back_ms.append(model.stat(5))
+        emit_ms.append(model.stat(6))
     torch.cuda.synchronize()
     barrier()
     wall = time.perf_counter() - t0
@@ -319,8 +321,12 @@ def main():
                 "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "viterbi_kernel<32> + viterbi_kernel<G>", "algorithmic_bytes": alg_bytes,
-                             "kernel_ms": vit * 1e3},
+                             "kernel": "viterbi_pair_kernel (forward dp; one launch per step)",
+                             "algorithmic_bytes": alg_bytes, "kernel_ms": vit * 1e3,
+                             "step_breakdown_ms": {"forward": vit * 1e3, "backtrack": float(np.mean(back_ms)),
+                                                   "emit": float(np.mean(emit_ms)),
+                                                   "crlf_sort_scan_other": ms_per_step - vit * 1e3 -
+                                                   float(np.mean(back_ms)) - float(np.mean(emit_ms))}},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

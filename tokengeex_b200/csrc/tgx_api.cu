@@ -302,7 +302,7 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   constexpr int WG = 2 * R + 1;
   const size_t budget = (size_t)m->smem_optin;
   uint32_t groups = (uint32_t)std::min<size_t>({(budget - (size_t)p.hot_slots * 16) / pair_group_bytes(R),
-                                                (size_t)(1024 / (32 * WG)), (size_t)15});
+                                                (size_t)((R == 1 ? 960 : 800) / (32 * WG)), (size_t)15});
   if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
   groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
   p.groups = groups;

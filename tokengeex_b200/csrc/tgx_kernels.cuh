@@ -277,15 +277,12 @@ __device__ __forceinline__ unsigned long long window_bytes(const unsigned long l
 // such a token lands on a dp cell beyond position n, which is never read.
 template <int HOT>
 __device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, const uint4* __restrict__ hot,
-                                             uint32_t root, const uint8_t* ptr, const uint8_t* blob_end, bool active,
+                                             uint32_t root, const unsigned long long (&w)[3], uint32_t sh, bool active,
                                              double* row, int lane) {
   const double ninf = __longlong_as_double(0xFFF0000000000000ll);
 #pragma unroll
   for (int c = 0; c < 16; c++) row[c] = ninf;
   if (!active) return;
-  unsigned long long w[3];
-  uint32_t sh;
-  load_window(ptr, blob_end, w, sh);
   unsigned char* rb = reinterpret_cast<unsigned char*>(row);
   const uint32_t l18 = (uint32_t)(lane + 1) * 8u;
   uint32_t xb = root;
@@ -341,7 +338,7 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
 }
 
 template <int R, int HOT>
-__global__ void __launch_bounds__(1024, 1) viterbi_pair_kernel(PairParams p) {
+__global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
@@ -362,6 +359,10 @@ __global__ void __launch_bounds__(1024, 1) viterbi_pair_kernel(PairParams p) {
   // consumer state: one dp cell per lane
   double best = ninf;
   uint32_t ps = 0;
+  // producer state: text window prefetched for the next round
+  unsigned long long pw[3] = {0, 0, 0};
+  uint32_t psh = 0, pf_tile = 0;
+  int32_t pf_unit = -1;
   // scheduler state (half-warp leaders of the consumer warp)
   PairInfo cur;
   cur.unit = -1; cur.start = 0; cur.n = 0; cur.tile0 = 0; cur.ntiles = 0; cur.pad[0] = cur.pad[1] = 0;
@@ -421,7 +422,19 @@ __global__ void __launch_bounds__(1024, 1) viterbi_pair_kernel(PairParams p) {
       if (pi.unit >= 0 && t < pi.ntiles) {
         const uint32_t pos = t * 32 + lane;
         double* row = tab + ((size_t)((r & 1) * 2 + ph) * R + k) * PT_TILE + lane * PT_ROW;
-        pair_produce<HOT>(u.trie, hot, u.root_base, u.text + pi.start + pos, p.blob_end, pos < pi.n, row, lane);
+        const uint8_t* ptr = u.text + pi.start + pos;
+        // the text of this tile was requested a round ago (HBM latency off the round's critical path)
+        if (!(pf_unit == pi.unit && pf_tile == t)) load_window(ptr, p.blob_end, pw, psh);
+        unsigned long long w3[3] = {pw[0], pw[1], pw[2]};
+        const uint32_t sh = psh;
+        if (t + R < pi.ntiles) {
+          load_window(ptr + 32 * R, p.blob_end, pw, psh);
+          pf_unit = pi.unit;
+          pf_tile = t + R;
+        } else {
+          pf_unit = -1;
+        }
+        pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n, row, lane);
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie

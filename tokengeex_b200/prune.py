@@ -10,6 +10,11 @@ new double-array trie uploaded to the device.
 With more than one rank (torch.distributed), every rank holds a shard of the samples; the
 expected-count vector and the frequency vector are all-reduced (one collective per E-step
 / frequency pass) so that every rank runs the identical host steps on identical inputs.
+
+When torch sees a CUDA device the corpus shard is uploaded ONCE and stays resident in HBM for
+the whole schedule (every E-step / frequency pass reads it through the `_dev` entry points);
+the count vectors are accumulated on the device and, under NCCL, all-reduced there before the
+single D2H copy of V values per step.
 """
 from __future__ import annotations
 
@@ -66,8 +71,39 @@ class ModelVocabularyPruner:
         self.allreduce = allreduce
         self.n_samples_global = n_samples_global
 
+    # -- device-resident corpus ------------------------------------------------------------------
+    def _upload(self, blob: np.ndarray, off: np.ndarray):
+        """Corpus shard -> HBM, once per prune() (None when torch has no CUDA device: host-buffer API)."""
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                return None
+        except ImportError:
+            return None
+        dev = torch.device("cuda", self.device)
+        d_text = torch.from_numpy(np.ascontiguousarray(blob)).to(dev)
+        d_off = torch.from_numpy(off.astype(np.uint64).view(np.int64)).to(dev)
+        return {"torch": torch, "dev": dev, "text": d_text, "off": d_off, "S": len(off) - 1, "N": int(off[-1])}
+
+    def _reduce_dev(self, t):
+        """Sum across ranks on the device when the collective runs there (NCCL), else via the host."""
+        coll = self.allreduce
+        if coll is None:
+            return t.cpu().numpy()
+        if hasattr(coll, "allreduce_tensor") and str(getattr(coll, "device", "cpu")).startswith("cuda"):
+            return coll.allreduce_tensor(t).cpu().numpy()
+        return coll(t.cpu().numpy())
+
     # -- steps --------------------------------------------------------------------------------
-    def run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray) -> np.ndarray:
+    def run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray, dev=None) -> np.ndarray:
+        if dev is not None:
+            torch = dev["torch"]
+            d_ex = torch.zeros(max(model.V, 1), dtype=torch.float64, device=dev["dev"])
+            rc, bad, badz = model.expected_counts_dev(dev["text"].data_ptr(), dev["off"].data_ptr(), dev["S"],
+                                                      dev["N"], d_ex.data_ptr())
+            if rc == N.TGX_ERR_BAD_Z:
+                raise FloatingPointError(f"normalization constant is f64::NaN (z={badz}, sample={bad})")
+            return self._reduce_dev(d_ex)[:model.V]
         ex, rc, bad, badz = model.expected_counts(blob, off)
         if rc == N.TGX_ERR_BAD_Z:  # the reference panics (src/prune.rs:90-96)
             raise FloatingPointError(f"normalization constant is f64::NaN (z={badz}, sample={bad})")
@@ -80,13 +116,23 @@ class ModelVocabularyPruner:
         idx = np.flatnonzero(kept)
         return Vocab([vocab.tokens[i] for i in idx], ns[idx].copy(), vocab.keep[idx].copy())
 
-    def prune_vocab(self, model: N.Model, vocab: Vocab, blob: np.ndarray, off: np.ndarray, report: PruneReport) -> Vocab:
+    def prune_vocab(self, model: N.Model, vocab: Vocab, blob: np.ndarray, off: np.ndarray, report: PruneReport,
+                    dev=None) -> Vocab:
         t = time.perf_counter()
-        fr, rc, bad, blen = model.token_frequencies(blob, off)
-        if rc == N.TGX_ERR_NO_PATH:
-            raise RuntimeError(f"no path to position {blen}/{blen}")  # Error::NoPath, src/prune.rs:218-221
-        if self.allreduce is not None:
-            fr = self.allreduce(fr)
+        if dev is not None:
+            torch = dev["torch"]
+            d_fr = torch.zeros(max(model.V, 1), dtype=torch.int64, device=dev["dev"])
+            rc, bad, blen = model.token_frequencies_dev(dev["text"].data_ptr(), dev["off"].data_ptr(), dev["S"],
+                                                        dev["N"], False, d_fr.data_ptr())
+            if rc == N.TGX_ERR_NO_PATH:
+                raise RuntimeError(f"no path to position {blen}/{blen}")
+            fr = self._reduce_dev(d_fr)[:model.V].view(np.uint64)
+        else:
+            fr, rc, bad, blen = model.token_frequencies(blob, off)
+            if rc == N.TGX_ERR_NO_PATH:
+                raise RuntimeError(f"no path to position {blen}/{blen}")  # Error::NoPath, src/prune.rs:218-221
+            if self.allreduce is not None:
+                fr = self.allreduce(fr)
         report.freq_s.append(time.perf_counter() - t)
         t = time.perf_counter()
         n_samples = self.n_samples_global if self.n_samples_global is not None else len(off) - 1
@@ -99,6 +145,7 @@ class ModelVocabularyPruner:
     # -- src/prune.rs:23-57 ------------------------------------------------------------------------
     def prune(self, vocab: Vocab, blob: np.ndarray, off: np.ndarray) -> (Vocab, PruneReport):
         report = PruneReport()
+        dev = self._upload(blob, off)
         t = time.perf_counter()
         model = N.Model(vocab.tokens, vocab.scores, device=self.device)
         report.rebuild_s.append(time.perf_counter() - t)
@@ -106,7 +153,7 @@ class ModelVocabularyPruner:
             for subiter in range(self.em_subiters):
                 log.info("EM subiter %d/%d", subiter + 1, self.em_subiters)
                 t = time.perf_counter()
-                expected = self.run_e_step(model, blob, off)
+                expected = self.run_e_step(model, blob, off, dev)
                 report.e_step_s.append(time.perf_counter() - t)
                 log.info("E-step completed subiter=%d vocab_size=%d", subiter, len(vocab))
                 t = time.perf_counter()
@@ -121,7 +168,7 @@ class ModelVocabularyPruner:
                 report.rebuild_s.append(time.perf_counter() - t)
                 report.vocab_sizes.append(len(vocab))
             before = len(vocab)
-            vocab = self.prune_vocab(model, vocab, blob, off, report)
+            vocab = self.prune_vocab(model, vocab, blob, off, report, dev)
             log.info("Pruning vocabulary from=%d to=%d", before, len(vocab))
             t = time.perf_counter()
             model.close()

@@ -34,8 +34,7 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        for algo, opts in [(0, {4: 2, 6: 0}), (0, {4: 2, 6: 8}), (0, {4: 2, 6: 6}), (0, {4: 4, 6: 0}), (0, {4: 4, 6: 5}),
-                           (0, {4: 4, 6: 4}), (0, {4: 4, 6: 3})]:
+        for algo, opts in [(0, {4: 4, 6: 0}), (0, {4: 2, 6: 0})]:
             m.set_option(3, algo)
             for k, v in opts.items():
                 m.set_option(k, v)
