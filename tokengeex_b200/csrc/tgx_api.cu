@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -110,21 +111,46 @@ __global__ void crlf_mark_starts(const uint64_t* __restrict__ off, uint64_t S, u
 // removed(p): text[p] == '\r' followed, inside the same sample, by '\n'
 // (str::replace("\r\n", "\n"), src/processor.rs:47-49: left-to-right, non-overlapping —
 // "\r\n" occurrences never overlap each other, so the predicate is position-local).
-__device__ __forceinline__ uint32_t crlf_removed_mask(const uint8_t* __restrict__ text, uint64_t N,
-                                                      const uint32_t* __restrict__ bitmap, uint64_t base,
-                                                      uint8_t (&b)[CRLF_PER_THREAD + 1]) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i <= CRLF_PER_THREAD; i++) b[i] = (base + i < N) ? text[base + i] : 0;
-#pragma unroll
-  for (int i = 0; i < CRLF_PER_THREAD; i++) {
-    uint64_t q = base + i + 1;
-    if (b[i] == '\r' && q < N && b[i + 1] == '\n') {
-      bool boundary = (bitmap[q >> 5] >> (q & 31)) & 1u;
-      if (!boundary) m |= 1u << i;
-    }
+// One thread looks at 16 bytes (one aligned 16-byte load when the blob allows it) plus the byte
+// after them.  Returns the 16-bit mask of removed bytes; `starts` receives the sample-start
+// flags of positions base .. base+15; `nvalid` the number of bytes below N.
+__device__ __forceinline__ uint32_t crlf_mask16(const uint8_t* __restrict__ text, uint64_t N,
+                                                const uint32_t* __restrict__ bitmap, uint64_t base, uint4& v,
+                                                uint32_t& starts, uint32_t& nvalid) {
+  if (base >= N) {
+    v = make_uint4(0, 0, 0, 0);
+    starts = 0;
+    nvalid = 0;
+    return 0;
   }
-  return m;
+  nvalid = (uint32_t)min((uint64_t)16, N - base);
+  uint32_t next = 0;
+  if (nvalid == 16) {
+    v = *reinterpret_cast<const uint4*>(text + base);
+    if (base + 16 < N) next = text[base + 16];
+  } else {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < nvalid; i++) w[i >> 2] |= (uint32_t)text[base + i] << (8 * (i & 3));
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // start flags of positions base .. base+16 (bit i <-> position base + i)
+  const uint32_t wi = (uint32_t)(base >> 5);
+  const unsigned long long bits = (unsigned long long)bitmap[wi] | ((unsigned long long)bitmap[wi + 1] << 32);
+  const uint32_t sb = (uint32_t)(bits >> (base & 31)) & 0x1FFFFu;
+  starts = sb & 0xFFFFu;
+  const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+  uint32_t cr = 0, lf = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t c = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    cr |= (uint32_t)(c == '\r') << i;
+    lf |= (uint32_t)(c == '\n') << i;
+  }
+  lf |= (uint32_t)(next == '\n') << 16;
+  // byte i is removed iff it is '\r', byte i+1 exists, is '\n' and does not start a sample
+  uint32_t m = cr & (lf >> 1) & ~(sb >> 1);
+  if (nvalid < 16) m &= (1u << nvalid) - 1u;  // the byte after the last valid one does not exist (next == 0)
+  return m & 0xFFFFu;
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
@@ -137,18 +163,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   }
   if (lane == 31) warp_sums[warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+  uint32_t before = 0, tot = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
-      if (lane >= o) w += y;
-    }
-    if (lane < (int)(blockDim.x >> 5)) warp_sums[lane] = w;
+  for (int i = 0; i < CRLF_BLOCK / 32; i++) {
+    const uint32_t ws = warp_sums[i];
+    if (i < warp) before += ws;
+    tot += ws;
   }
-  __syncthreads();
-  uint32_t before = warp ? warp_sums[warp - 1] : 0;
-  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  if (total) *total = tot;
   return before + x - v;
 }
 
@@ -157,54 +179,101 @@ __global__ void __launch_bounds__(CRLF_BLOCK) crlf_count(const uint8_t* __restri
                                                          const uint32_t* __restrict__ bitmap,
                                                          unsigned long long* __restrict__ blk_removed) {
   __shared__ uint32_t ws[CRLF_BLOCK / 32];
-  uint64_t base = (uint64_t)blockIdx.x * CRLF_TILE + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
-  uint8_t b[CRLF_PER_THREAD + 1];
-  uint32_t m = crlf_removed_mask(text, N, bitmap, base, b);
-  uint32_t total;
-  block_exclusive_scan(__popc(m), ws, &total);
-  if (threadIdx.x == 0) blk_removed[blockIdx.x] = total;
+  const uint64_t base = (uint64_t)blockIdx.x * CRLF_TILE + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
+  uint4 v;
+  uint32_t starts, nvalid;
+  uint32_t c = __popc(crlf_mask16(text, N, bitmap, base, v, starts, nvalid));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < CRLF_BLOCK / 32; i++) t += ws[i];
+    blk_removed[blockIdx.x] = t;
+  }
 }
 
-// K1c: scatter kept bytes.  blk_prefix = exclusive scan of blk_removed.
+// first index s in [0, S] with off[s] >= p
+__device__ __forceinline__ uint64_t lower_bound_off(const uint64_t* __restrict__ off, uint64_t S, uint64_t p) {
+  uint64_t lo = 0, hi = S + 1;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (off[mid] < p) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// K1c: compact every tile through shared memory and write it with aligned 16-byte stores; the
+// thread that sees a sample start also writes that sample's new offset (found by binary search).
+// blk_prefix = exclusive scan of blk_removed (n_tiles + 1 entries).
 __global__ void __launch_bounds__(CRLF_BLOCK) crlf_scatter(const uint8_t* __restrict__ text, uint64_t N,
+                                                           const uint64_t* __restrict__ off, uint64_t S,
                                                            const uint32_t* __restrict__ bitmap,
                                                            const unsigned long long* __restrict__ blk_prefix,
-                                                           uint8_t* __restrict__ out) {
+                                                           uint64_t n_tiles, uint8_t* __restrict__ out,
+                                                           uint64_t* __restrict__ new_off) {
   __shared__ uint32_t ws[CRLF_BLOCK / 32];
-  uint64_t base = (uint64_t)blockIdx.x * CRLF_TILE + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
-  uint8_t b[CRLF_PER_THREAD + 1];
-  uint32_t m = crlf_removed_mask(text, N, bitmap, base, b);
-  uint32_t before = block_exclusive_scan(__popc(m), ws, nullptr);
-  uint64_t o = base - blk_prefix[blockIdx.x] - before;
+  __shared__ __align__(16) uint8_t stage[CRLF_TILE + 32];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * CRLF_TILE;
+  const uint64_t base = tile_base + (uint64_t)threadIdx.x * CRLF_PER_THREAD;
+  uint4 v;
+  uint32_t starts, nvalid;
+  const uint32_t m = crlf_mask16(text, N, bitmap, base, v, starts, nvalid);
+  const uint32_t kept = nvalid - __popc(m);
+  uint32_t total;
+  const uint32_t o = block_exclusive_scan(kept, ws, &total);
+  const uint64_t ob = tile_base - blk_prefix[blockIdx.x];  // blob index (in `out`) of the tile's first kept byte
+  // ---- new offsets of the samples that start inside this thread's 16 bytes
+  uint32_t sb = starts;
+  if (base == 0) sb |= 1u;  // position 0 starts sample 0 (and every empty sample before the first byte)
+  if (nvalid < 16) sb &= (1u << nvalid) - 1u;
+  while (sb) {
+    const int i = __ffs(sb) - 1;
+    sb &= sb - 1;
+    const uint64_t p = base + i;
+    const uint64_t np = ob + o + __popc(~m & ((1u << i) - 1u));
+    for (uint64_t s = lower_bound_off(off, S, p); s <= S && off[s] == p; s++) new_off[s] = np;
+  }
+  if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) {  // samples that start at N (off[S], trailing empties)
+    const uint64_t np = N - blk_prefix[n_tiles];
+    for (uint64_t s = lower_bound_off(off, S, N); s <= S; s++) new_off[s] = np;
+  }
+  // ---- compaction into shared memory
+  const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+  if (m == 0 && nvalid == 16 && (o & 3u) == 0) {
 #pragma unroll
-  for (int i = 0; i < CRLF_PER_THREAD; i++) {
-    if (base + i < N && !((m >> i) & 1u)) out[o++] = b[i];
-  }
-}
-
-// K1d: new sample offsets: off[s] - removed_before(off[s]).
-__global__ void crlf_offsets(const uint8_t* __restrict__ text, uint64_t N, const uint64_t* __restrict__ off,
-                             uint64_t S, const uint32_t* __restrict__ bitmap,
-                             const unsigned long long* __restrict__ blk_prefix, uint64_t n_tiles,
-                             uint64_t* __restrict__ new_off) {
-  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s > S) return;
-  uint64_t p = off[s];
-  uint64_t tile = p / CRLF_TILE;
-  unsigned long long removed;
-  uint64_t q;
-  if (tile >= n_tiles) {  // p == N on a tile boundary: everything before
-    removed = n_tiles ? blk_prefix[n_tiles] : 0;
-    q = p;
+    for (int j = 0; j < 4; j++) *reinterpret_cast<uint32_t*>(stage + o + 4 * j) = wv[j];
   } else {
-    removed = blk_prefix[tile];
-    q = tile * CRLF_TILE;
+    uint32_t q = o;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      if (i < (int)nvalid && !((m >> i) & 1u)) stage[q++] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
   }
-  for (; q < p; q++) {
-    if (text[q] == '\r' && q + 1 < N && text[q + 1] == '\n' && !((bitmap[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u))
-      removed++;
+  __syncthreads();
+  // ---- [ob, ob + total) of `out`: unaligned head and tail by bytes, the rest by 16-byte vectors
+  const uint64_t oe = ob + total;
+  const uint64_t a0 = min((uint64_t)((ob + 15) & ~15ull), oe);
+  const uint32_t head = (uint32_t)(a0 - ob);
+  if (threadIdx.x < head) out[ob + threadIdx.x] = stage[threadIdx.x];
+  const uint32_t nvec = (uint32_t)((oe - a0) >> 4);
+  for (uint32_t c = threadIdx.x; c < nvec; c += CRLF_BLOCK) {
+    const uint32_t so = head + 16 * c;  // source offset in stage (any alignment)
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage + (so & ~3u));
+    const uint32_t sh = 8 * (so & 3u);
+    uint32_t w[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) w[j] = sw[j];
+    uint4 r;
+    r.x = __funnelshift_r(w[0], w[1], sh);
+    r.y = __funnelshift_r(w[1], w[2], sh);
+    r.z = __funnelshift_r(w[2], w[3], sh);
+    r.w = __funnelshift_r(w[3], w[4], sh);
+    *reinterpret_cast<uint4*>(out + a0 + 16ull * c) = r;
   }
-  new_off[s] = p - removed;
+  const uint64_t t0 = a0 + 16ull * nvec;
+  if (threadIdx.x < (uint32_t)(oe - t0)) out[t0 + threadIdx.x] = stage[(uint32_t)(t0 - ob) + threadIdx.x];
 }
 
 // units = samples
@@ -392,9 +461,9 @@ int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_
   uint64_t n_tiles = (N + CRLF_TILE - 1) / CRLF_TILE;
   CU(m->text2.reserve(N + 16));
   CU(m->off2.reserve((S + 1) * 8));
-  CU(m->bitmap.reserve((N / 32 + 2) * 4));
+  CU(m->bitmap.reserve((N / 32 + 4) * 4));
   CU(m->blk.reserve((n_tiles + 1) * 8 * 2));
-  CU(cudaMemsetAsync(m->bitmap.p, 0, (N / 32 + 2) * 4, st));
+  CU(cudaMemsetAsync(m->bitmap.p, 0, (N / 32 + 4) * 4, st));
   if (S > 1) {
     crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->bitmap.as<uint32_t>());
     m->stats.launches += 1;
@@ -412,13 +481,12 @@ int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_
   CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, removed, prefix, (int)(n_tiles + 1), st));
   m->stats.launches += 2;
   if (n_tiles) {
-    crlf_scatter<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->bitmap.as<uint32_t>(), prefix,
-                                                          m->text2.as<uint8_t>());
+    crlf_scatter<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, d_off, S, m->bitmap.as<uint32_t>(), prefix,
+                                                          n_tiles, m->text2.as<uint8_t>(), m->off2.as<uint64_t>());
     m->stats.launches += 1;
+  } else {
+    CU(cudaMemsetAsync(m->off2.p, 0, (S + 1) * 8, st));  // no bytes at all: every sample is empty
   }
-  crlf_offsets<<<nblk(S + 1, 128), 128, 0, st>>>(d_text, N, d_off, S, m->bitmap.as<uint32_t>(), prefix, n_tiles,
-                                               m->off2.as<uint64_t>());
-  m->stats.launches += 1;
   CU(cudaGetLastError());
   return TGX_OK;
 }
@@ -492,6 +560,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.blob_end = d_text + N;
     p.bp = m->bp.as<uint8_t>();
     p.counter = m->small.as<unsigned int>() + 8;
+    p.dbg = getenv("TGX_DBG") ? (uint32_t)atoi(getenv("TGX_DBG")) : 0u;
     if (!p.u.count) {
     } else if (m->producers >= 4) {
       CU(launch_viterbi_pair_r<2>(m, p));

@@ -234,6 +234,7 @@ struct PairParams {
   unsigned int* counter;
   uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
   uint32_t groups;     // consumer/producer groups per CTA
+  uint32_t dbg;        // developer timing experiments (tools/probe.py): 1 = skip walks, 2 = skip the dp
 };
 
 // shared memory of one CTA: [hot trie prefix][per group: tables 2 x 2 x R tiles | 4 x 2 PairInfo]
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
         }
         const double* tb = tab + ((size_t)(((r + 1) & 1) * 2 + h) * R + k) * PT_TILE + g;
         uint32_t len0, len1;
+        if (p.dbg & 2u) { len0 = len1 = 1; } else
         pair_consume(tb, g, best, ps, len0, len1);  // both halves always run it (full-warp shuffles)
         if (act) {
           const uint32_t e0 = t * 32 + g, e1 = e0 + 16;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
         } else {
           pf_unit = -1;
         }
-        pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n, row, lane);
+        pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane);
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--kind", type=int, default=1)
     ap.add_argument("--what", default="encode,estep")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--single", type=int, default=0, help="encode only the N longest samples")
     args = ap.parse_args()
     import torch
     from tokengeex_b200 import _native as N, synth
@@ -24,6 +25,11 @@ def main():
     toks, sc, kp = synth.vocab(vb, vo, 2, args.vocab, 16, 0.05)
     m = N.Model(toks, sc, device=0)
     blob, off = synth.corpus(args.kind, 2, args.bytes)
+    if args.single:
+        lens = np.diff(off.astype(np.int64))
+        idx = np.argsort(-lens)[:args.single]
+        parts = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in idx]
+        blob, off = N.pack(parts)
     S, NB = len(off) - 1, int(off[-1])
     d_text = torch.from_numpy(blob).cuda()
     d_off = torch.from_numpy(off.view(np.int64)).cuda()
