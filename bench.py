@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--bytes", type=int, default=1_000_000_000, help="input bytes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk-bytes", type=int, default=0, help="bytes per chunk of the pipelined host entry point")
     ap.add_argument("--g-short", type=int, default=0)
     ap.add_argument("--long-threshold", type=int, default=0)
     args = ap.parse_args()
@@ -197,6 +198,8 @@ def main():
         model.set_option(0, args.g_short)
     if args.long_threshold:
         model.set_option(1, args.long_threshold)
+    if args.chunk_bytes:
+        model.set_option(7, args.chunk_bytes)
     info = model.info()
 
     # pinned host input (also the source of the e2e H2D copies)

@@ -139,16 +139,18 @@ int tgx_host_free(void* p);
 
 /* Counters of the last compute call on this model (for bench.py): number of kernels
  * launched and device milliseconds of the dominant kernel(s), measured with CUDA events
- * on the model's stream.  what: 0 = kernels launched, 1 = viterbi ms, 2 = fb-forward ms,
- * 3 = fb-backward ms, 4 = whole call device ms. */
+ * on the model's stream.  what: 0 = kernels launched, 1 = Viterbi forward ms, 2 = fb-forward ms,
+ * 3 = fb-backward ms, 4 = whole call device ms, 5 = backtrack ms, 6 = emit ms.  (For the chunked
+ * host entry point these describe the LAST chunk.) */
 double tgx_model_last_stat(const tgx_model* m, int what);
 
-/* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units (1,2,4,8,16,32),
- * 1 = byte threshold from which a unit is processed by a full warp (G = 32),
- * 2 = lanes per snippet in the E-step, 3 = Viterbi algorithm (0 = CTA-cooperative
- * producer/consumer kernel, the default when max_token_len <= 31; 1 = lane-group kernels),
- * 4 = producer warps per CTA of the CTA-cooperative kernel (1,2,3,4,7),
- * 5 = E-step byte threshold from which a snippet gets a full warp. */
+/* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units of the lane-group
+ * kernels (1,2,4,8,16,32), 1 = byte threshold from which a unit gets a full warp (lane-group forward
+ * kernels; warp-cooperative backtrack), 2 = lanes per snippet in the E-step, 3 = Viterbi forward
+ * algorithm (0 = pair-CTA kernel, the default when max_token_len <= 16; 1 = lane-group kernels),
+ * 4 = producer warps per consumer warp of the pair kernel (2 or 4), 5 = E-step byte threshold from
+ * which a snippet gets a full warp, 6 = consumer/producer groups per CTA of the pair kernel (0 = as
+ * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch. */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

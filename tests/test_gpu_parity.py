@@ -148,6 +148,29 @@ def test_long_tokens_fall_back_to_group_kernels(N):
         assert got[i] == om.encode(s)
 
 
+def test_chunked_host_entry_point(N):
+    """tgx_encode_batch splits large inputs into chunks of whole samples and overlaps the copies with the kernels;
+    forcing tiny chunks must not change ids, offsets, statuses, or which sample is reported as the first failure."""
+    blob, off, toks, sc, kp = synth_setup(2, 31, 1_200_000, 6000, 16)
+    gm, om = both(N, toks, sc)
+    wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=True, threads=8)
+    for chunk in (4096, 100_000, 1 << 30):
+        gm.set_option(7, chunk)
+        ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
+        assert rc == 0 and np.array_equal(ids, wids) and np.array_equal(id_off, wid_off)
+        assert np.array_equal(plen, wplen) and not status.any()
+    # a vocabulary without some bytes: NoPath samples in several chunks; the LOWEST index is reported
+    toks2 = [t for t in toks if t not in (b"e", b"{")]
+    sc2 = [s for t, s in zip(toks, sc) if t not in (b"e", b"{")]
+    gm2, om2 = both(N, toks2, sc2)
+    wids, wid_off, wstatus, wplen, wbad = om2.encode_batch(blob, off, crlf=False, threads=8)
+    gm2.set_option(7, 50_000)
+    ids, id_off, status, plen, rc, bad = gm2.encode_batch(blob, off, crlf=False)
+    assert np.array_equal(status != 0, wstatus != 0) and np.array_equal(id_off, wid_off) and np.array_equal(ids, wids)
+    if (wstatus != 0).any():
+        assert rc == N.TGX_ERR_NO_PATH and bad == int(np.flatnonzero(wstatus)[0])
+
+
 def test_crlf_batch_vs_oracle(N):
     m = N.Model([b"a"], [-1.0])
     rng = random.Random(7)

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -71,6 +72,19 @@ struct tgx_model {
   uint4* d_trie = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones
+  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
+  // The compute stream never issues a D2H copy itself: measured on B200 (profiles/r01_ubench_overlap.txt),
+  // once a stream has used the D2H copy engine its next kernels queue behind whatever that engine is
+  // doing — here the bulk D2H of the previous chunk.  Control words are read through this stream.
+  cudaStream_t stream_ctl = nullptr;
+  cudaEvent_t ev_ctl = nullptr;
+  unsigned long long* h_words = nullptr;  // pinned, 8 words
+  cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
+  uint64_t* h_off = nullptr;       // pinned staging for rebased chunk offsets
+  uint64_t h_off_cap = 0;
+  unsigned char* h_out = nullptr;  // pinned staging for the small per-sample outputs (id_off, status, proc_len)
+  uint64_t h_out_cap = 0;
+  uint64_t chunk_bytes = 352ull << 20;  // ~3 chunks per GB: below that the longest sample's dp chain dominates a chunk
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::recursive_mutex mu;
@@ -87,7 +101,7 @@ struct tgx_model {
   int smem_optin = 232448;
   // workspace
   DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt,
-      ntok, idoff, status, A, expected, freq, ids, small, scount, hot;
+      ntok, idoff, status, A, expected, freq, ids, small, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
 };
 
 // =========================================================================================
@@ -335,6 +349,26 @@ __global__ void first_bad_unit(const int32_t* __restrict__ status, uint32_t U, u
   if (i < U && status[i] != 0) atomicMin(out, (unsigned long long)i);
 }
 
+// Device memory is cleared by a kernel, not by cudaMemsetAsync: a memset may be scheduled on a copy
+// engine, where it queues behind the bulk D2H copy of the previous chunk (tgx_encode_batch).
+__global__ void fill_bytes_kernel(unsigned char* __restrict__ p, unsigned long long n, unsigned int byte) {
+  const unsigned int w = byte * 0x01010101u;
+  const unsigned long long head = min(n, (unsigned long long)((16 - (reinterpret_cast<unsigned long long>(p) & 15)) & 15));
+  const unsigned long long nvec = (n - head) >> 4;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+  uint4* v = reinterpret_cast<uint4*>(p + head);
+  for (unsigned long long i = tid; i < nvec; i += nthr) v[i] = make_uint4(w, w, w, w);
+  const unsigned long long tail0 = head + (nvec << 4);
+  for (unsigned long long i = tid; i < head; i += nthr) p[i] = (unsigned char)byte;
+  for (unsigned long long i = tail0 + tid; i < n; i += nthr) p[i] = (unsigned char)byte;
+}
+
+__global__ void copy_u32(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 __global__ void add_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
@@ -352,6 +386,13 @@ using namespace tgxk;
 struct Timer {
   cudaEvent_t a, b;
 };
+
+cudaError_t dev_fill(void* p, int byte, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  const uint32_t blocks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, (n + 4095) / 4096), 148 * 8);
+  fill_bytes_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<unsigned char*>(p), (unsigned long long)n, (unsigned int)byte & 0xFFu);
+  return cudaGetLastError();
+}
 
 template <int G>
 cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
@@ -380,7 +421,7 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   if (e != cudaSuccess) return e;
   const uint32_t grid =
       (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
-  e = cudaMemsetAsync(p.counter, 0, 4, m->stream);
+  e = dev_fill(p.counter, 0, 4, m->stream);
   if (e != cudaSuccess) return e;
   viterbi_pair_kernel<R, HOT><<<grid, groups * WG * 32, smem, m->stream>>>(p);
   m->stats.launches += 1;
@@ -447,11 +488,13 @@ cudaError_t launch_fb_g(tgx_model* m, int G, const FbParams& p, bool backward, c
 
 inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
 
+
 int check_model(tgx_model* m) {
   if (!m) return fail(TGX_ERR_INVALID, "null model");
   if (m->device < 0)
     return fail(TGX_ERR_NO_DEVICE, "model was created host-only (device = -1); there is no CPU compute path");
   CU(cudaSetDevice(m->device));
+  (void)cudaGetLastError();  // a stale non-sticky error of an earlier call must not fail this one
   return TGX_OK;
 }
 
@@ -463,14 +506,14 @@ int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_
   CU(m->off2.reserve((S + 1) * 8));
   CU(m->bitmap.reserve((N / 32 + 4) * 4));
   CU(m->blk.reserve((n_tiles + 1) * 8 * 2));
-  CU(cudaMemsetAsync(m->bitmap.p, 0, (N / 32 + 4) * 4, st));
+  CU(dev_fill(m->bitmap.p, 0, (N / 32 + 4) * 4, st));
   if (S > 1) {
     crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->bitmap.as<uint32_t>());
     m->stats.launches += 1;
   }
   unsigned long long* removed = m->blk.as<unsigned long long>();
   unsigned long long* prefix = removed + n_tiles + 1;
-  CU(cudaMemsetAsync(removed, 0, (n_tiles + 1) * 8, st));
+  CU(dev_fill(removed, 0, (n_tiles + 1) * 8, st));
   if (n_tiles) {
     crlf_count<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->bitmap.as<uint32_t>(), removed);
     m->stats.launches += 1;
@@ -485,7 +528,7 @@ int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_
                                                           n_tiles, m->text2.as<uint8_t>(), m->off2.as<uint64_t>());
     m->stats.launches += 1;
   } else {
-    CU(cudaMemsetAsync(m->off2.p, 0, (S + 1) * 8, st));  // no bytes at all: every sample is empty
+    CU(dev_fill(m->off2.p, 0, (S + 1) * 8, st));  // no bytes at all: every sample is empty
   }
   CU(cudaGetLastError());
   return TGX_OK;
@@ -533,13 +576,10 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
   split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, counts);
   m->stats.launches += 1;
-  uint32_t h[2];
-  CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemsetAsync(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
-  CU(cudaMemsetAsync(m->status.p, 0, (size_t)U * 4 + 4, st));
-  CU(cudaMemsetAsync(m->mark.p, 0, n_tiles * EM_TILE, st));
-  CU(cudaStreamSynchronize(st));
-  uint32_t n_long = h[0], n_nonempty = h[1];
+  CU(dev_fill(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
+  CU(dev_fill(m->status.p, 0, (size_t)U * 4 + 4, st));
+  CU(dev_fill(m->mark.p, 0, n_tiles * EM_TILE, st));
+  // (no host synchronisation here: every kernel below reads its unit range from `counts`)
 
   UnitParams u;
   u.text = d_text;
@@ -550,13 +590,15 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.root_base = m->da.root_base;
   u.rows = std::max<uint32_t>(1, m->da.max_token_len);
   u.W = u.rows + 1;
+  u.counts = counts;
+  u.first = 0;
+  u.count = U;  // upper bound for the grids
 
   CU(cudaEventRecord(m->ev[0], st));
   if (m->algo == 0 && u.rows <= 16) {
     PairParams p;
     p.u = u;
-    p.u.first = 0;
-    p.u.count = n_nonempty;
+    p.u.part = 0;
     p.blob_end = d_text + N;
     p.bp = m->bp.as<uint8_t>();
     p.counter = m->small.as<unsigned int>() + 8;
@@ -571,31 +613,30 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     ViterbiParams p;
     p.u = u;
     p.bp = m->bp.as<uint8_t>();
-    p.u.first = 0;
-    p.u.count = n_long;
+    p.u.part = 1;
     CU(launch_viterbi_g(m, 32, p));
-    p.u.first = n_long;
-    p.u.count = n_nonempty - n_long;
+    p.u.part = 2;
     CU(launch_viterbi_g(m, m->g_short, p));
   }
   CU(cudaEventRecord(m->ev[1], st));
   CU(cudaEventRecord(m->ev[2], st));
-  if (n_nonempty) {
+  if (U) {
     BacktrackParams b;
     b.unit_start = u.unit_start;
     b.unit_len = u.unit_len;
     b.order = u.order;
+    b.counts = counts;
+    b.first = 0;
+    b.count = U;
     b.bp = m->bp.as<uint8_t>();
     b.mark = m->mark.as<uint8_t>();
     b.n_tokens = m->ntok.as<unsigned long long>();
     b.status = m->status.as<int32_t>();
     // long samples (sorted first): one warp each; short ones: one thread each
-    b.first = 0;
-    b.count = n_long;
-    if (b.count) backtrack_warp_kernel<<<nblk(b.count, BW_WARPS), BW_WARPS * 32, 0, st>>>(b);
-    b.first = n_long;
-    b.count = n_nonempty - n_long;
-    if (b.count) backtrack_thread_kernel<<<nblk(b.count, BT_THREADS), BT_THREADS, 0, st>>>(b);
+    b.part = 1;
+    backtrack_warp_kernel<<<nblk(U, BW_WARPS), BW_WARPS * 32, 0, st>>>(b);
+    b.part = 2;
+    backtrack_thread_kernel<<<nblk(U, BT_THREADS), BT_THREADS, 0, st>>>(b);
     m->stats.launches += 2;
     CU(cudaGetLastError());
   }
@@ -638,16 +679,29 @@ int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, u
   return TGX_OK;
 }
 
-int first_bad(tgx_model* m, uint32_t U, int64_t* out_idx) {
+// Reads up to two device words once everything queued on the compute stream has finished, through
+// the control stream (see tgx_model::stream_ctl); returns with both streams idle.
+int read_words(tgx_model* m, const void* d0, const void* d1, unsigned long long* o0, unsigned long long* o1) {
+  CU(cudaEventRecord(m->ev_ctl, m->stream));
+  CU(cudaStreamWaitEvent(m->stream_ctl, m->ev_ctl, 0));
+  if (d0) CU(cudaMemcpyAsync(m->h_words, d0, 8, cudaMemcpyDeviceToHost, m->stream_ctl));
+  if (d1) CU(cudaMemcpyAsync(m->h_words + 1, d1, 8, cudaMemcpyDeviceToHost, m->stream_ctl));
+  CU(cudaStreamSynchronize(m->stream_ctl));
+  if (d0 && o0) *o0 = m->h_words[0];
+  if (d1 && o1) *o1 = m->h_words[1];
+  return TGX_OK;
+}
+
+int first_bad(tgx_model* m, uint32_t U, int64_t* out_idx, const void* extra = nullptr, unsigned long long* extra_out = nullptr) {
   unsigned long long* d = m->small.as<unsigned long long>() + 2;
-  CU(cudaMemsetAsync(d, 0xFF, 8, m->stream));
+  CU(dev_fill(d, 0xFF, 8, m->stream));
   if (U) {
     first_bad_unit<<<nblk(U, 256), 256, 0, m->stream>>>(m->status.as<int32_t>(), U, d);
     m->stats.launches += 1;
   }
-  unsigned long long h;
-  CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, m->stream));
-  CU(cudaStreamSynchronize(m->stream));
+  unsigned long long h = ~0ull;
+  int rc = read_words(m, d, extra, &h, extra_out);
+  if (rc) return rc;
   *out_idx = (h == ~0ull) ? -1 : (int64_t)h;
   return TGX_OK;
 }
@@ -695,6 +749,15 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     CU(cudaMemcpyToSymbol(tgxk::c_log_tab, TGX_LOG_TAB, sizeof(TGX_LOG_TAB)));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream_ctl, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->ev_ctl, cudaEventDisableTiming));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&m->h_words), 64, cudaHostAllocDefault));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     for (auto& e : m->ev) CU(cudaEventCreate(&e));
@@ -714,15 +777,28 @@ void tgx_model_destroy(tgx_model* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* bufs[] = {&m->text, &m->off, &m->text2, &m->off2, &m->bitmap, &m->blk, &m->ustart, &m->ulen,
                       &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->mark, &m->tilecnt, &m->ntok, &m->idoff,
-                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount, &m->hot};
+                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount, &m->hot,
+                      &m->text_b, &m->off_b, &m->ids_b, &m->idoff_b, &m->scount_b};
     for (auto* b : bufs) b->release();
     if (m->d_trie) cudaFree(m->d_trie);
     for (auto& e : m->ev)
       if (e) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
+    if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
+    if (m->stream_ctl) cudaStreamDestroy(m->stream_ctl);
+    if (m->ev_ctl) cudaEventDestroy(m->ev_ctl);
+    if (m->h_words) cudaFreeHost(m->h_words);
+    for (int i = 0; i < 2; i++) {
+      if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+      if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
+    }
+    if (m->h_off) cudaFreeHost(m->h_off);
+    if (m->h_out) cudaFreeHost(m->h_out);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    (void)cudaGetLastError();  // nothing above is allowed to leak an error into the next call
   }
   delete m;
 }
@@ -763,6 +839,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->estep_long_threshold = value; break;
     case 3: if (value != 0 && value != 1) return fail(TGX_ERR_INVALID, "algo must be 0 or 1"); m->algo = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
+    case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -829,7 +906,7 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   if (first_bad_out) *first_bad_out = -1;
   if (total_ids) *total_ids = 0;
   if (S == 0) {
-    CU(cudaMemsetAsync(d_id_off, 0, 8, st));
+    CU(dev_fill(d_id_off, 0, 8, st));
     CU(cudaStreamSynchronize(st));
     return TGX_OK;
   }
@@ -854,11 +931,14 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   m->stats.launches += 2;
   rc = run_emit(m, text, n_bytes, d_ids, ids_cap, nullptr);
   if (rc) return rc;
-  if (d_status) CU(cudaMemcpyAsync(d_status, m->status.p, S * 4, cudaMemcpyDeviceToDevice, st));
-  uint64_t tot = 0;
-  CU(cudaMemcpyAsync(&tot, d_id_off + S, 8, cudaMemcpyDeviceToHost, st));
+  if (d_status) {  // (a kernel, not a D2D memcpy: keep the compute stream off the copy engines)
+    copy_u32<<<nblk(S, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(m->status.p),
+                                           reinterpret_cast<uint32_t*>(d_status), S);
+    m->stats.launches += 1;
+  }
+  unsigned long long tot = 0;
   int64_t bad = -1;
-  rc = first_bad(m, (uint32_t)S, &bad);
+  rc = first_bad(m, (uint32_t)S, &bad, d_id_off + S, &tot);  // waits for the whole chunk
   if (rc) return rc;
   CU(cudaEventRecord(m->ev[7], st));
   CU(cudaStreamSynchronize(st));
@@ -876,31 +956,166 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
   int rc = check_model(m);
   if (rc) return rc;
   if (!off || !id_off || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
-  uint64_t N = off[S];
+  const uint64_t N = off[S];
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  CU(m->text.reserve(N + 16));
-  CU(m->off.reserve((S + 1) * 8));
-  CU(m->ids.reserve((N + 4) * 4));
-  CU(m->idoff.reserve((S + 1) * 8));
-  CU(m->scount.reserve((S + 1) * 12 + 32));
-  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
-  int32_t* d_status = m->scount.as<int32_t>();
-  uint64_t* d_plen = reinterpret_cast<uint64_t*>(m->scount.as<unsigned char>() + ((S * 4 + 15) & ~15ull));
-  uint64_t tot = 0;
-  int64_t bad = -1;
-  rc = tgx_encode_batch_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, m->ids.as<uint32_t>(), N + 4,
-                            m->idoff.as<uint64_t>(), d_status, d_plen, &tot, &bad);
-  if (first_bad_out) *first_bad_out = bad;
-  if (rc != TGX_OK && rc != TGX_ERR_NO_PATH) return rc;
-  std::string keep_err = g_err;
-  CU(cudaMemcpyAsync(id_off, m->idoff.p, (S + 1) * 8, cudaMemcpyDeviceToHost, m->stream));
-  if (status) CU(cudaMemcpyAsync(status, d_status, S * 4, cudaMemcpyDeviceToHost, m->stream));
-  if (proc_len) CU(cudaMemcpyAsync(proc_len, d_plen, S * 8, cudaMemcpyDeviceToHost, m->stream));
-  if (tot <= ids_cap && tot) CU(cudaMemcpyAsync(ids, m->ids.p, tot * 4, cudaMemcpyDeviceToHost, m->stream));
-  CU(cudaStreamSynchronize(m->stream));
-  if (tot > ids_cap) return fail(TGX_ERR_CAPACITY, "ids capacity too small: need " + std::to_string(tot));
-  if (rc == TGX_ERR_NO_PATH) return fail(rc, keep_err);
+  if (first_bad_out) *first_bad_out = -1;
+  if (S == 0) {
+    id_off[0] = 0;
+    return TGX_OK;
+  }
+  // Chunks of whole samples (~chunk_bytes each): the H2D copy of chunk k+1 and the D2H copy of
+  // chunk k-1 run on their own streams beside the kernels of chunk k (two buffer sets).
+  const uint64_t K = std::max<uint64_t>(1, std::min<uint64_t>(16, (N + m->chunk_bytes - 1) / m->chunk_bytes));
+  std::vector<uint64_t> cut(K + 1, 0);
+  cut[K] = S;
+  for (uint64_t k = 1; k < K; k++) {
+    const uint64_t target = N / K * k;
+    uint64_t i = (uint64_t)(std::lower_bound(off, off + S + 1, target) - off);
+    cut[k] = std::min<uint64_t>(std::max<uint64_t>(i, cut[k - 1]), S);
+  }
+  uint64_t max_b = 0, max_s = 0;
+  for (uint64_t k = 0; k < K; k++) {
+    max_b = std::max(max_b, off[cut[k + 1]] - off[cut[k]]);
+    max_s = std::max(max_s, cut[k + 1] - cut[k]);
+  }
+  DevBuf* d_text[2] = {&m->text, &m->text_b};
+  DevBuf* d_off[2] = {&m->off, &m->off_b};
+  DevBuf* d_ids[2] = {&m->ids, &m->ids_b};
+  DevBuf* d_idoff[2] = {&m->idoff, &m->idoff_b};
+  DevBuf* d_sc[2] = {&m->scount, &m->scount_b};
+  const int nset = K > 1 ? 2 : 1;
+  for (int i = 0; i < nset; i++) {
+    CU(d_text[i]->reserve(max_b + 16));
+    CU(d_off[i]->reserve((max_s + 1) * 8));
+    CU(d_ids[i]->reserve((max_b + 4) * 4));
+    CU(d_idoff[i]->reserve((max_s + 1) * 8));
+    CU(d_sc[i]->reserve((max_s + 1) * 12 + 32));
+  }
+  // rebased offsets travel through pinned staging (one slice per chunk, alive until the end)
+  if (m->h_off_cap < S + K + 1) {
+    if (m->h_off) cudaFreeHost(m->h_off);
+    if (m->h_out) cudaFreeHost(m->h_out);
+    m->h_off = nullptr;
+    m->h_off_cap = 0;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&m->h_off), (S + K + 1) * 8, cudaHostAllocDefault));
+    m->h_off_cap = S + K + 1;
+  }
+  const uint64_t so_idoff = 0, so_status = (S + K + 1) * 8, so_plen = so_status + ((S * 4 + 15) & ~15ull);
+  const uint64_t out_bytes = so_plen + S * 8 + 16;
+  if (m->h_out_cap < out_bytes) {
+    if (m->h_out) cudaFreeHost(m->h_out);
+    m->h_out = nullptr;
+    m->h_out_cap = 0;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&m->h_out), out_bytes, cudaHostAllocDefault));
+    m->h_out_cap = out_bytes;
+  }
+  uint64_t* st_idoff = reinterpret_cast<uint64_t*>(m->h_out + so_idoff);  // chunk k's S_k + 1 entries at [s0 + k ..]
+  int32_t* st_status = reinterpret_cast<int32_t*>(m->h_out + so_status);
+  uint64_t* st_plen = reinterpret_cast<uint64_t*>(m->h_out + so_plen);
+  std::vector<cudaEvent_t> tev;  // trace: [base, per chunk: h2d0,h2d1,c0,c1,d2h0,d2h1]
+  auto h2d = [&](uint64_t k) -> int {
+    const int b = (int)(k & 1);
+    const uint64_t s0 = cut[k], s1 = cut[k + 1], b0 = off[s0], nb = off[s1] - b0;
+    uint64_t* ho = m->h_off + s0 + k;
+    for (uint64_t i = 0; i <= s1 - s0; i++) ho[i] = off[s0 + i] - b0;
+    cudaStream_t st = K > 1 ? m->stream_h2d : m->stream;
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 0], st);
+    if (nb) CU(cudaMemcpyAsync(d_text[b]->p, text + b0, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_off[b]->p, ho, (s1 - s0 + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 1], st);
+    if (K > 1) CU(cudaEventRecord(m->ev_h2d[b], st));
+    return TGX_OK;
+  };
+  const bool trace = getenv("TGX_TRACE") != nullptr;
+  auto now_ms = [] {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  const double t_begin = now_ms();
+  if (trace) {
+    tev.resize(1 + 6 * K);
+    for (auto& e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[0], m->stream);
+  }
+  rc = h2d(0);
+  if (rc) return rc;
+  uint64_t base = 0;  // ids emitted by earlier chunks
+  std::vector<uint64_t> bases(K, 0);
+  int64_t bad_all = -1;
+  bool overflow = false;
+  std::string keep_err;
+  int final_rc = TGX_OK;
+  for (uint64_t k = 0; k < K; k++) {
+    const int b = (int)(k & 1);
+    const uint64_t s0 = cut[k], s1 = cut[k + 1], Sk = s1 - s0, nb = off[s1] - off[s0];
+    const double t_i0 = now_ms();
+    if (k + 1 < K) {
+      rc = h2d(k + 1);
+      if (rc) return rc;
+    }
+    if (trace) fprintf(stderr, "[tgx] chunk %llu: iteration starts at %.2f ms, next H2D enqueued by %.2f ms\n",
+                       (unsigned long long)k, t_i0 - t_begin, now_ms() - t_begin);
+    if (K > 1) {
+      CU(cudaStreamWaitEvent(m->stream, m->ev_h2d[b], 0));
+      if (k >= 2) CU(cudaStreamWaitEvent(m->stream, m->ev_d2h[b], 0));  // the set's previous results left the device
+    }
+    int32_t* dst = d_sc[b]->as<int32_t>();
+    uint64_t* dpl = reinterpret_cast<uint64_t*>(d_sc[b]->as<unsigned char>() + ((Sk * 4 + 15) & ~15ull));
+    uint64_t tot = 0;
+    int64_t bad = -1;
+    const double t_c0 = now_ms();
+    if (trace) cudaEventRecord(tev[1 + 6 * k + 2], m->stream);
+    rc = tgx_encode_batch_dev(m, d_text[b]->as<uint8_t>(), d_off[b]->as<uint64_t>(), Sk, nb, flags,
+                              d_ids[b]->as<uint32_t>(), nb + 4, d_idoff[b]->as<uint64_t>(), dst, dpl, &tot, &bad);
+    if (rc != TGX_OK && rc != TGX_ERR_NO_PATH) return rc;
+    if (trace)
+      fprintf(stderr, "[tgx] chunk %llu/%llu: %llu bytes, enqueue at %.2f ms, kernels done at %.2f ms (device %.2f ms)\n",
+              (unsigned long long)k, (unsigned long long)K, (unsigned long long)nb, t_c0 - t_begin, now_ms() - t_begin,
+              m->stats.total_ms);
+    if (rc == TGX_ERR_NO_PATH && bad_all < 0) {
+      bad_all = (int64_t)s0 + bad;
+      keep_err = "no path for sample " + std::to_string(bad_all);
+      final_rc = rc;
+    }
+    if (trace) cudaEventRecord(tev[1 + 6 * k + 3], m->stream);
+    cudaStream_t st = K > 1 ? m->stream_d2h : m->stream;  // tgx_encode_batch_dev returned synchronised
+    if (trace) cudaEventRecord(tev[1 + 6 * k + 4], st);
+    CU(cudaMemcpyAsync(st_idoff + s0 + k, d_idoff[b]->p, (Sk + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (status && Sk) CU(cudaMemcpyAsync(st_status + s0, dst, Sk * 4, cudaMemcpyDeviceToHost, st));
+    if (proc_len && Sk) CU(cudaMemcpyAsync(st_plen + s0, dpl, Sk * 8, cudaMemcpyDeviceToHost, st));
+    if (base + tot > ids_cap) overflow = true;
+    if (!overflow && tot) CU(cudaMemcpyAsync(ids + base, d_ids[b]->p, tot * 4, cudaMemcpyDeviceToHost, st));
+    if (K > 1) CU(cudaEventRecord(m->ev_d2h[b], st));
+    if (trace) cudaEventRecord(tev[1 + 6 * k + 5], st);
+    if (trace) fprintf(stderr, "[tgx] chunk %llu: D2H enqueued by %.2f ms\n", (unsigned long long)k, now_ms() - t_begin);
+    bases[k] = base;
+    base += tot;
+  }
+  CU(cudaStreamSynchronize(K > 1 ? m->stream_d2h : m->stream));
+  if (trace) {
+    fprintf(stderr, "[tgx] all copies done at %.2f ms\n", now_ms() - t_begin);
+    cudaDeviceSynchronize();
+    for (uint64_t k = 0; k < K; k++) {
+      float t[6];
+      for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 6 * k + j]);
+      fprintf(stderr, "[tgx] device timeline chunk %llu: H2D %.2f-%.2f  kernels %.2f-%.2f  D2H %.2f-%.2f ms\n",
+              (unsigned long long)k, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
+  // chunk-relative id offsets -> global; small outputs leave the pinned staging
+  for (uint64_t k = 0; k < K; k++) {
+    const uint64_t add = bases[k];
+    const uint64_t* src = st_idoff + cut[k] + k;
+    for (uint64_t s = cut[k]; s < cut[k + 1]; s++) id_off[s] = src[s - cut[k]] + add;
+  }
+  id_off[S] = base;
+  if (status) std::memcpy(status, st_status, S * 4);
+  if (proc_len) std::memcpy(proc_len, st_plen, S * 8);
+  if (first_bad_out) *first_bad_out = bad_all;
+  if (overflow) return fail(TGX_ERR_CAPACITY, "ids capacity too small: need " + std::to_string(base));
+  if (final_rc == TGX_ERR_NO_PATH) return fail(final_rc, keep_err);
   return TGX_OK;
 }
 
@@ -957,7 +1172,7 @@ int tgx_token_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off
   CU(m->freq.reserve(m->V * 8 + 8));
   CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
   CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemsetAsync(m->freq.p, 0, m->V * 8 + 8, m->stream));
+  CU(dev_fill(m->freq.p, 0, m->V * 8 + 8, m->stream));
   rc = tgx_token_frequencies_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, m->freq.as<uint64_t>(),
                                  first_bad_out, bad_len);
   if (rc) return rc;
@@ -983,7 +1198,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   CU(m->ntok.reserve((S + 2) * 16));
   unsigned long long* cnt = m->ntok.as<unsigned long long>();
   unsigned long long* first_unit = cnt + S + 1;
-  CU(cudaMemsetAsync(cnt, 0, (S + 1) * 8, st));
+  CU(dev_fill(cnt, 0, (S + 1) * 8, st));
   if (S) {
     snippet_counts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, cnt);
     m->stats.launches += 1;
@@ -1016,7 +1231,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   m->stats.launches += 1;
   rc = sort_units(m, U);
   if (rc) return rc;
-  CU(cudaMemsetAsync(m->status.p, 0, (size_t)U * 4 + 4, st));
+  CU(dev_fill(m->status.p, 0, (size_t)U * 4 + 4, st));
 
   FbParams p;
   p.u.text = d_text;
@@ -1025,6 +1240,8 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.u.order = m->vals_out.as<uint32_t>();
   p.u.first = 0;
   p.u.count = U;
+  p.u.counts = nullptr;
+  p.u.part = 0;
   p.u.trie = m->d_trie;
   p.u.root_base = m->da.root_base;
   p.u.rows = std::max<uint32_t>(1, m->da.max_token_len);
@@ -1035,7 +1252,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.hot_k = (uint32_t)std::min<uint64_t>(m->V, 4096);
   p.hot_r = 64;
   CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8));
-  CU(cudaMemsetAsync(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8, st));
+  CU(dev_fill(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8, st));
   p.hot = m->hot.as<double>();
 
   // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second
@@ -1107,7 +1324,7 @@ int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, 
   CU(m->expected.reserve(m->V * 8 + 8));
   CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
   CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemsetAsync(m->expected.p, 0, m->V * 8 + 8, m->stream));
+  CU(dev_fill(m->expected.p, 0, m->V * 8 + 8, m->stream));
   rc = tgx_expected_counts_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, snippet_len,
                                m->expected.as<double>(), bad_sample, bad_z);
   if (rc) return rc;
@@ -1116,3 +1333,4 @@ int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, 
 }
 
 }  // extern "C"
+

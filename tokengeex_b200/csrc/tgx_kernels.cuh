@@ -30,8 +30,15 @@ struct UnitParams {
   const uint8_t* text;         // blob
   const uint64_t* unit_start;  // [U] absolute byte offset of the unit in text
   const uint32_t* unit_len;    // [U]
-  const uint32_t* order;       // sorted unit indices; this launch handles order[first .. first+count)
+  const uint32_t* order;       // sorted unit indices (length-descending)
+  // This launch handles order[first .. first+count).  When `counts` is set the range is read on the
+  // device (counts[0] = #units at least as long as the "long" threshold, counts[1] = #non-empty
+  // units), so that the host never has to wait for the sort in the middle of a call:
+  // part 0 = every non-empty unit, 1 = the long ones, 2 = the short ones.  `count` is then only
+  // the upper bound the grid was sized for.
   uint32_t first, count;
+  const uint32_t* counts;
+  int part;
   const uint4* trie;
   uint32_t root_base;  // xbase of the root
   uint32_t rows;  // match-buffer rows = max token length
@@ -54,6 +61,14 @@ struct FbParams {
   double* hot;        // [hot_r][hot_k]
   uint32_t hot_k, hot_r;
 };
+
+__device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uint32_t& first, uint32_t& count) {
+  if (!counts) return;
+  const uint32_t nl = counts[0], nn = counts[1];
+  if (part == 1) { first = 0; count = nl; }
+  else if (part == 2) { first = nl; count = nn - nl; }
+  else { first = 0; count = nn; }
+}
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t rows, uint32_t W, int G) {
   size_t ng = 32 / G;
@@ -129,8 +144,10 @@ __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
   uint32_t* wbp = s.wu + (size_t)gid * W;
 
   const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
-  const bool has = gidx < u.count;
-  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  uint32_t ufirst = u.first, ucount = u.count;
+  unit_range(u.counts, u.part, ufirst, ucount);
+  const bool has = gidx < ucount;
+  const uint32_t unit = has ? u.order[ufirst + gidx] : 0;
   const uint32_t n = has ? u.unit_len[unit] : 0;
   const uint64_t start = has ? u.unit_start[unit] : 0;
   const uint8_t* text = u.text + start;
@@ -367,10 +384,12 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
   // scheduler state (half-warp leaders of the consumer warp)
   PairInfo cur;
   cur.unit = -1; cur.start = 0; cur.n = 0; cur.tile0 = 0; cur.ntiles = 0; cur.pad[0] = cur.pad[1] = 0;
+  uint32_t ufirst = u.first, ucount = u.count;
+  unit_range(u.counts, u.part, ufirst, ucount);
   auto fetch = [&]() {
     const uint32_t idx = atomicAdd(p.counter, 1u);
-    if (idx < u.count) {
-      cur.unit = (int32_t)u.order[u.first + idx];
+    if (idx < ucount) {
+      cur.unit = (int32_t)u.order[ufirst + idx];
       cur.n = u.unit_len[cur.unit];
       cur.start = u.unit_start[cur.unit];
       cur.tile0 = 0;
@@ -456,7 +475,9 @@ struct BacktrackParams {
   const uint64_t* unit_start;
   const uint32_t* unit_len;
   const uint32_t* order;
-  uint32_t first, count;
+  uint32_t first, count;   // see UnitParams
+  const uint32_t* counts;
+  int part;
   const uint8_t* bp;
   uint8_t* mark;                 // [N]
   unsigned long long* n_tokens;  // [U]
@@ -468,8 +489,10 @@ constexpr int BT_THREADS = 128;
 
 __global__ void __launch_bounds__(BT_THREADS) backtrack_thread_kernel(BacktrackParams p) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.count) return;
-  const uint32_t unit = p.order[p.first + i];
+  uint32_t pfirst = p.first, pcount = p.count;
+  unit_range(p.counts, p.part, pfirst, pcount);
+  if (i >= pcount) return;
+  const uint32_t unit = p.order[pfirst + i];
   const uint32_t n = p.unit_len[unit];
   const uint64_t start = p.unit_start[unit];
   const uint8_t* b = p.bp + start;
@@ -518,8 +541,10 @@ __global__ void __launch_bounds__(BW_WARPS * 32) backtrack_warp_kernel(Backtrack
   __shared__ int16_t s_exit[BW_WARPS][32 * BW_SEG_STRIDE];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t i = blockIdx.x * BW_WARPS + w;
-  if (i >= p.count) return;
-  const uint32_t unit = p.order[p.first + i];
+  uint32_t pfirst = p.first, pcount = p.count;
+  unit_range(p.counts, p.part, pfirst, pcount);
+  if (i >= pcount) return;
+  const uint32_t unit = p.order[pfirst + i];
   const uint32_t n = p.unit_len[unit];
   const uint64_t start = p.unit_start[unit];
   const uint4* b16 = reinterpret_cast<const uint4*>(p.bp);
@@ -799,8 +824,10 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
   const LibmTabs lt = stage_libm_tables(s_et, s_lt);
 
   const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
-  const bool has = gidx < u.count;
-  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  uint32_t ufirst = u.first, ucount = u.count;
+  unit_range(u.counts, u.part, ufirst, ucount);
+  const bool has = gidx < ucount;
+  const uint32_t unit = has ? u.order[ufirst + gidx] : 0;
   const uint32_t n = has ? u.unit_len[unit] : 0;
   const uint64_t start = has ? u.unit_start[unit] : 0;
   const uint8_t* text = u.text + start;
@@ -879,8 +906,10 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
   const LibmTabs lt = stage_libm_tables(s_et, s_lt);
 
   const uint64_t gidx = ((uint64_t)blockIdx.x * WPB + warp) * NG + gid;
-  bool has = gidx < u.count;
-  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  uint32_t ufirst = u.first, ucount = u.count;
+  unit_range(u.counts, u.part, ufirst, ucount);
+  bool has = gidx < ucount;
+  const uint32_t unit = has ? u.order[ufirst + gidx] : 0;
   if (has && p.status[unit] != 0) has = false;  // bad z: the reference panics; nothing is added
   const uint32_t n = has ? u.unit_len[unit] : 0;
   const uint64_t start = has ? u.unit_start[unit] : 0;
