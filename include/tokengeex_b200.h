@@ -147,10 +147,13 @@ double tgx_model_last_stat(const tgx_model* m, int what);
 /* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units of the lane-group
  * kernels (1,2,4,8,16,32), 1 = byte threshold from which a unit gets a full warp (lane-group forward
  * kernels; warp-cooperative backtrack), 2 = lanes per snippet in the E-step, 3 = Viterbi forward
- * algorithm (0 = pair-CTA kernel, the default when max_token_len <= 16; 1 = lane-group kernels),
+ * algorithm when max_token_len <= 16 (0 = pair-CTA kernel, the default; 1 = lane-group kernels; 2 = thread-per-sample
+ * lane kernel; 3 = hybrid of 0 and 2),
  * 4 = producer warps per consumer warp of the pair kernel (2 or 4), 5 = E-step byte threshold from
  * which a snippet gets a full warp, 6 = consumer/producer groups per CTA of the pair kernel (0 = as
- * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch. */
+ * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch, 8 = byte threshold from which a sample
+ * goes to the pair body of the hybrid kernel, 9 = warps per CTA of the lane kernel (1..16), 10 = CTAs of the hybrid
+ * kernel that start on the long samples. */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

@@ -98,7 +98,7 @@ def test_random_small_vs_oracle_cta(N, producers):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 12),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 0)
+        gm.set_option(3, 0)  # pair-CTA kernel
         gm.set_option(4, producers)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 400)
         got, status, plen, rc, bad = gpu_encode(N, gm, samples)
@@ -122,7 +122,7 @@ def test_pair_kernel_full_window(N, producers):
         toks = list(toks) + [alphabet[:1] * 16, alphabet[1:2] * 16, (alphabet[:2] * 8)]
         scores = list(scores) + [-2.5, -30.0, -4.0]
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 0)
+        gm.set_option(3, 0)  # pair-CTA kernel
         gm.set_option(4, producers)
         samples = rand_samples(rng, alphabet, rng.randrange(3, 40), 0, 5000)
         samples += [alphabet[:1] * rng.randrange(1, 700), alphabet[1:2] * 333, alphabet[:2] * 517, b""]
@@ -135,17 +135,83 @@ def test_pair_kernel_full_window(N, producers):
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
 
 
-def test_long_tokens_fall_back_to_group_kernels(N):
-    """max_token_len > 16 cannot use the 16-cell register window of the pair kernel; the lane-group kernels take over."""
-    rng = random.Random(77)
-    toks = [bytes([c]) for c in b"ab"] + [b"ab" * 20, b"a" * 33, b"b" * 64, b"ba" * 7]
-    scores = [-3.0, -3.0, -9.0, -8.0, -20.0, -5.0]
-    gm, om = both(N, toks, scores)
-    samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 0, 300)
+def check_against_oracle(N, gm, om, samples, ctx=None):
     got, status, plen, rc, bad = gpu_encode(N, gm, samples)
-    assert rc == 0
+    first_bad = -1
     for i, s in enumerate(samples):
-        assert got[i] == om.encode(s)
+        try:
+            want = om.encode(s)
+            assert status[i] == 0 and got[i] == want, (ctx, i, len(s))
+        except O.NoPath as e:
+            assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length, (ctx, i)
+            if first_bad < 0:
+                first_bad = i
+    assert bad == first_bad and (rc == 0) == (first_bad < 0), (ctx, rc, bad, first_bad)
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+def test_long_tokens(N, algo):
+    """max_token_len > 16 cannot use the 16-cell windows of the pair / lane kernels: whatever forward algorithm is
+    selected, the lane-group kernels take over."""
+    rng = random.Random(77)
+    for toks, scores in [
+        ([bytes([c]) for c in b"ab"] + [b"ab" * 20, b"a" * 33, b"b" * 64, b"ba" * 7], [-3.0, -3.0, -9.0, -8.0, -20.0, -5.0]),
+        ([bytes([c]) for c in b"ab"] + [b"ab" * 10, b"a" * 17, b"b" * 32, b"ba" * 7], [-3.0, -3.0, -9.0, -8.0, -20.0, -5.0]),
+    ]:
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, algo)
+        samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 0, 300)
+        check_against_oracle(N, gm, om, samples)
+
+
+@pytest.mark.parametrize("warps", [1, 4, 12])
+def test_lane_kernel_random_vs_oracle(N, warps):
+    """Thread-per-sample lane kernel alone (algo 2): random vocabularies incl. incomplete ones (NoPath, positions
+    without any match), exact ties, every sample alignment, more samples than lanes (work fetch)."""
+    rng = random.Random(500 + warps)
+    for it in range(20):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 17),
+                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 2)
+        gm.set_option(9, warps)
+        samples = rand_samples(rng, b"abcd", rng.randrange(1, 300), 0, 400)
+        check_against_oracle(N, gm, om, samples, it)
+
+
+def test_lane_kernel_full_window(N):
+    """Tokens of every length 1..16 (length 16 lands on the cell that was just recycled), long samples (many packed
+    8-byte back-length stores, head/tail byte stores at every alignment), unreachable stretches."""
+    rng = random.Random(901)
+    for it in range(10):
+        alphabet = b"ab" if it % 2 == 0 else b"abc"
+        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(30, 400), max_len=16,
+                                  complete=(it % 3 != 0), int_scores=(it % 2 == 1))
+        toks = list(toks) + [alphabet[:1] * 16, alphabet[1:2] * 16, (alphabet[:2] * 8)]
+        scores = list(scores) + [-2.5, -30.0, -4.0]
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 2)
+        samples = rand_samples(rng, alphabet, rng.randrange(3, 40), 0, 5000)
+        samples += [alphabet[:1] * k for k in range(1, 20)] + [alphabet[1:2] * 333, alphabet[:2] * 517, b""]
+        check_against_oracle(N, gm, om, samples, it)
+
+
+@pytest.mark.parametrize("thr,pair_ctas", [(1, 148), (200, 64), (200, 1), (1 << 30, 64), (300, 0)])
+def test_hybrid_kernel_vs_oracle(N, thr, pair_ctas):
+    """Hybrid forward kernel (algo 3): the first pair_ctas CTAs run the pair-CTA body over the samples of at least `thr`
+    bytes and then join the lane body; every split of the samples between the two bodies gives the same ids."""
+    rng = random.Random(1300 + pair_ctas)
+    for it in range(8):
+        alphabet = b"ab" if it % 2 == 0 else b"abcd"
+        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(20, 300), max_len=rng.randrange(2, 17),
+                                  complete=(it % 3 != 0), int_scores=(it % 2 == 1))
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 3)
+        gm.set_option(8, thr)
+        gm.set_option(10, pair_ctas)
+        samples = rand_samples(rng, alphabet, rng.randrange(3, 400), 0, 600) + rand_samples(rng, alphabet, 5, 1000, 9000)
+        rng.shuffle(samples)
+        check_against_oracle(N, gm, om, samples, it)
 
 
 def test_chunked_host_entry_point(N):

@@ -20,6 +20,7 @@
 
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
+#include "tgx_lane_kernel.cuh"
 #include "trie_build.h"
 
 namespace {
@@ -94,7 +95,16 @@ struct tgx_model {
   int64_t long_threshold = 512;  // samples at least this long: full warp (lane-group forward kernels, backtrack)
   int g_estep = 8;
   int64_t estep_long_threshold = 1ll << 40;  // snippets at least this long get a full warp (G = 32); off by default
-  int algo = 0;        // 0 = pair-CTA Viterbi (max_token_len <= 16), 1 = lane-group kernels
+  // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
+  // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
+  // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
+  // Measured on B200 (profiles/r01_probe_lane_kernel.txt): a lane advances one position per ~6800 cycles however
+  // many warps share the SM, so 2 and 3 lose to 0 on every corpus with samples beyond a few KB; they stay as
+  // tested alternatives.
+  int algo = 0;
+  int64_t lane_threshold = 24576;
+  int lane_warps = 12;  // warps per CTA of the lane kernel
+  int pair_ctas = 64;   // CTAs that start on the long samples in the hybrid kernel
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
   int num_sms = 148;
   int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
@@ -327,9 +337,10 @@ __global__ void units_from_snippets(const uint64_t* __restrict__ off, uint64_t S
   }
 }
 
-// counts[0] = #units with len >= long_threshold, counts[1] = #units with len >= 1
+// counts[0] = #units with len >= long_threshold, counts[1] = #units with len >= 1,
+// counts[2] = #units with len >= lane_threshold
 __global__ void split_sorted(const uint32_t* __restrict__ sorted_len, uint32_t U, uint32_t long_threshold,
-                             uint32_t* __restrict__ counts) {
+                             uint32_t lane_threshold, uint32_t* __restrict__ counts) {
   if (threadIdx.x || blockIdx.x) return;
   auto first_below = [&](uint32_t thr) {  // descending order: first index with len < thr
     uint32_t lo = 0, hi = U;
@@ -341,6 +352,7 @@ __global__ void split_sorted(const uint32_t* __restrict__ sorted_len, uint32_t U
   };
   counts[0] = first_below(long_threshold);
   counts[1] = first_below(1);
+  counts[2] = first_below(lane_threshold);
 }
 
 // lowest unit index with non-zero status (and its payload)
@@ -442,6 +454,71 @@ cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p) {
   }
   p.hot_slots = 0;
   return launch_viterbi_pair<R, 0>(m, p);
+}
+
+constexpr int LANE_KW = 3, LANE_KC = 2;
+
+// hot trie prefix for the lane / hybrid kernels: as many leading levels as fit `cap` bytes
+uint32_t pick_hot(const tgx_model* m, size_t cap, int* levels) {
+  for (int l = 2; l >= 1; l--)
+    if ((size_t)m->da.hot[l] * 16 <= cap) {
+      if (levels) *levels = l;
+      return m->da.hot[l];
+    }
+  if (levels) *levels = 0;
+  return 0;
+}
+
+template <int CELLS>
+cudaError_t launch_viterbi_lane(tgx_model* m, LaneParams p) {
+  if (!p.u.count) return cudaSuccess;
+  p.hot_slots = pick_hot(m, (size_t)m->smem_optin / 4, nullptr);
+  const size_t per_warp = lane_warp_bytes<CELLS>();
+  uint32_t warps = (uint32_t)std::min<size_t>((size_t)m->lane_warps, ((size_t)m->smem_optin - (size_t)p.hot_slots * 16) / per_warp);
+  warps = std::max<uint32_t>(1, std::min<uint32_t>(warps, (p.u.count + 31) / 32));
+  const size_t smem = (size_t)p.hot_slots * 16 + warps * per_warp;
+  cudaError_t e = cudaFuncSetAttribute(viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 32 * warps - 1) / (32 * warps), (uint64_t)m->num_sms);
+  e = dev_fill(p.counter, 0, 4, m->stream);
+  if (e != cudaSuccess) return e;
+  viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC><<<grid, warps * 32, smem, m->stream>>>(p);
+  m->stats.launches += 1;
+  return cudaGetLastError();
+}
+
+template <int HOT>
+cudaError_t launch_viterbi_hybrid_h(tgx_model* m, HybridParams p, uint32_t hot_slots) {
+  constexpr int R = 2, WG = 2 * R + 1;
+  p.pair.hot_slots = p.lane.hot_slots = hot_slots;
+  const size_t budget = (size_t)m->smem_optin - (size_t)hot_slots * 16;
+  uint32_t groups = (uint32_t)std::min<size_t>({budget / pair_group_bytes(R), (size_t)(800 / (32 * WG)), (size_t)15});
+  if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
+  p.pair.groups = std::max<uint32_t>(1, groups);
+  p.lane_warps = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)m->lane_warps, budget / lane_warp_bytes<16>()));
+  const size_t smem = (size_t)hot_slots * 16 + std::max<size_t>(p.pair.groups * pair_group_bytes(R), p.lane_warps * lane_warp_bytes<16>());
+  const uint32_t threads = std::max<uint32_t>(p.pair.groups * WG * 32, p.lane_warps * 32);
+  cudaError_t e = cudaFuncSetAttribute(viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.lane.u.count + 31) / 32, (uint64_t)m->num_sms);
+  p.pair_ctas = std::min<uint32_t>((uint32_t)m->pair_ctas, grid);
+  if (p.pair_ctas == 0) p.lane.u.part = 0;  // nobody runs the pair body: the lanes take every sample
+  e = dev_fill(p.pair.counter, 0, 8, m->stream);  // both counters
+  if (e != cudaSuccess) return e;
+  viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC><<<grid, threads, smem, m->stream>>>(p);
+  m->stats.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi_hybrid(tgx_model* m, const HybridParams& p) {
+  if (!p.lane.u.count) return cudaSuccess;
+  int levels = 0;
+  const uint32_t hot_slots = pick_hot(m, (size_t)m->smem_optin / 4, &levels);
+  if (levels == 2) return launch_viterbi_hybrid_h<2>(m, p, hot_slots);
+  if (levels == 1) return launch_viterbi_hybrid_h<1>(m, p, hot_slots);
+  return launch_viterbi_hybrid_h<0>(m, p, 0);
 }
 
 cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
@@ -574,7 +651,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   if (rc) return rc;
   uint32_t* counts = m->small.as<uint32_t>();
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
-  split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, counts);
+  split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr,
+                                 (uint32_t)std::min<int64_t>(m->lane_threshold, 0x7FFFFFFF), counts);
   m->stats.launches += 1;
   CU(dev_fill(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
   CU(dev_fill(m->status.p, 0, (size_t)U * 4 + 4, st));
@@ -595,7 +673,30 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.count = U;  // upper bound for the grids
 
   CU(cudaEventRecord(m->ev[0], st));
-  if (m->algo == 0 && u.rows <= 16) {
+  if (m->algo == 3 && u.rows <= 16) {
+    HybridParams hp;
+    hp.pair.u = u;
+    hp.pair.u.part = 3;
+    hp.pair.blob_end = d_text + N;
+    hp.pair.bp = m->bp.as<uint8_t>();
+    hp.pair.counter = m->small.as<unsigned int>() + 8;
+    hp.pair.dbg = 0;
+    hp.lane.u = u;
+    hp.lane.u.part = 4;
+    hp.lane.blob_end = d_text + N;
+    hp.lane.bp = m->bp.as<uint8_t>();
+    hp.lane.counter = m->small.as<unsigned int>() + 9;
+    hp.pair_ctas = hp.lane_warps = 0;
+    CU(launch_viterbi_hybrid(m, hp));
+  } else if (m->algo == 2 && u.rows <= 16) {
+    LaneParams p;
+    p.u = u;
+    p.u.part = 0;
+    p.blob_end = d_text + N;
+    p.bp = m->bp.as<uint8_t>();
+    p.counter = m->small.as<unsigned int>() + 9;
+    CU(launch_viterbi_lane<16>(m, p));
+  } else if (m->algo == 0 && u.rows <= 16) {
     PairParams p;
     p.u = u;
     p.u.part = 0;
@@ -837,7 +938,10 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->estep_long_threshold = value; break;
-    case 3: if (value != 0 && value != 1) return fail(TGX_ERR_INVALID, "algo must be 0 or 1"); m->algo = (int)value; break;
+    case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
+    case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
+    case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
+    case 10: if (value < 0 || value > 1024) return fail(TGX_ERR_INVALID, "pair CTAs must be 0..1024"); m->pair_ctas = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
@@ -1261,7 +1365,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   if (m->g_estep != 32) {
     uint32_t* counts = m->small.as<uint32_t>();
     uint32_t thr = (uint32_t)std::min<int64_t>(m->estep_long_threshold, 0x7FFFFFFF);
-    split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, counts);
+    split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, thr, counts);
     m->stats.launches += 1;
     uint32_t h[2];
     CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));

@@ -34,8 +34,9 @@ struct UnitParams {
   // This launch handles order[first .. first+count).  When `counts` is set the range is read on the
   // device (counts[0] = #units at least as long as the "long" threshold, counts[1] = #non-empty
   // units), so that the host never has to wait for the sort in the middle of a call:
-  // part 0 = every non-empty unit, 1 = the long ones, 2 = the short ones.  `count` is then only
-  // the upper bound the grid was sized for.
+  // part 0 = every non-empty unit, 1 = the long ones, 2 = the short ones; 3 / 4 = the same split at
+  // the second threshold (counts[2]: pair-CTA kernel vs lane kernel).  `count` is then only the
+  // upper bound the grid was sized for.
   uint32_t first, count;
   const uint32_t* counts;
   int part;
@@ -67,6 +68,8 @@ __device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uin
   const uint32_t nl = counts[0], nn = counts[1];
   if (part == 1) { first = 0; count = nl; }
   else if (part == 2) { first = nl; count = nn - nl; }
+  else if (part == 3) { first = 0; count = counts[2]; }                    // at least lane_threshold bytes
+  else if (part == 4) { first = counts[2]; count = nn - counts[2]; }       // shorter than that
   else { first = 0; count = nn; }
 }
 
@@ -355,13 +358,15 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
   }
 }
 
+// Body shared by viterbi_pair_kernel and the hybrid kernel; called by every thread of the CTA
+// (warps beyond p.groups * WG only help staging the hot trie prefix).
 template <int R, int HOT>
-__global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(PairParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem) {
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = warp / WG, wg = warp % WG;
+  const bool spare = (uint32_t)grp >= p.groups;
   const int h = lane >> 4, g = lane & 15;
   const double ninf = __longlong_as_double(0xFFF0000000000000ll);
 
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
       cur.unit = -1;
     }
   };
-  if (wg == 0 && g == 0) {
+  if (!spare && wg == 0 && g == 0) {
     fetch();
     s_info[0 * 2 + h] = cur;
     PairInfo none = cur;
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
     s_info[3 * 2 + h] = none;
   }
   __syncthreads();
+  if (spare) return;
 
   for (uint32_t r = 0;; r++) {
     if (wg == 0) {
@@ -464,6 +470,12 @@ __global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(Pai
                       s_info[((r + 1) & 3) * 2 + 0].unit >= 0 || s_info[((r + 1) & 3) * 2 + 1].unit >= 0;
     if (!more) break;
   }
+}
+
+template <int R, int HOT>
+__global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(PairParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pair_body<R, HOT>(p, smem);
 }
 
 // -----------------------------------------------------------------------------------------

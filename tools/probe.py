@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--what", default="encode,estep")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--single", type=int, default=0, help="encode only the N longest samples")
+    ap.add_argument("--algos", default="", help="comma list of forward algos to time (default all)")
     args = ap.parse_args()
     import torch
     from tokengeex_b200 import _native as N, synth
@@ -40,7 +41,11 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        for algo, opts in [(0, {4: 4, 6: 0}), (0, {4: 2, 6: 0})]:
+        cfgs = [(0, {}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
+                (3, {9: 12, 8: 32768, 10: 48}), (3, {9: 8, 8: 24576, 10: 64})]
+        if args.algos:
+            cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
+        for algo, opts in cfgs:
             m.set_option(3, algo)
             for k, v in opts.items():
                 m.set_option(k, v)
@@ -49,11 +54,10 @@ def main():
                 tot, rc, bad = m.encode_batch_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, True, d_ids.data_ptr(),
                                                   NB + 4, d_id_off.data_ptr())
                 best = min(best, m.stat(4))
+            chk = int(d_ids[:tot].to(torch.int64).sum()) if tot else 0
             print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  forward {m.stat(1):.2f} ms "
-                  f"backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot}", flush=True)
+                  f"backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot} idsum={chk} rc={rc}", flush=True)
         m.set_option(3, 0)
-        m.set_option(4, 2)
-        m.set_option(6, 0)
     if "freq" in what:
         for _ in range(args.reps):
             d_fr.zero_()
