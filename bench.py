@@ -45,10 +45,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def build_vocab(synth):
-    """Identical on every rank: built from a fixed common sample (seed 2)."""
-    blob, off = synth.corpus(synth.KIND_MULTILANG, 2, VOCAB_SAMPLE_BYTES)
-    toks, sc, kp = synth.vocab(blob, off, 2, VOCAB_SIZE, MAX_TOKEN_LEN, 0.05)
+def build_vocab(synth, n_gpus=1):
+    """Identical on every rank: built from a fixed common sample of the workload's corpus kind (multi-language code
+    at N = 1, configs[1]; code+Chinese mix at N > 1, configs[2])."""
+    if n_gpus == 1:
+        blob, off = synth.corpus(synth.KIND_MULTILANG, 2, VOCAB_SAMPLE_BYTES)
+        toks, sc, kp = synth.vocab(blob, off, 2, VOCAB_SIZE, MAX_TOKEN_LEN, 0.05)
+    else:
+        blob, off = synth.corpus(synth.KIND_CODE_CJK, 3, VOCAB_SAMPLE_BYTES)
+        toks, sc, kp = synth.vocab(blob, off, 3, VOCAB_SIZE, MAX_TOKEN_LEN, 0.05)
     return toks, sc, kp
 
 
@@ -121,7 +126,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     from tokengeex_b200 import synth
     threads = synth.n_threads()
-    toks, sc, kp = build_vocab(synth)
+    toks, sc, kp = build_vocab(synth, args.gpus)
     om = O.OracleModel(toks, sc)
     blob, off, name = workload(synth, args.gpus, 0, min(args.bytes, 256_000_000))
     # calibrate: ~8 MB, then size one step to ~8 s
@@ -156,6 +161,127 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+PRUNE_VOCAB = 500_000
+PRUNE_VOCAB_SAMPLE_BYTES = 200_000_000
+
+
+def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
+    """One EM iteration of `tokengeex prune` (BASELINE.json configs[3]): E-step (forward-backward expected counts,
+    src/prune.rs:64-120) -> M-step -> model rebuild -> frequency pass -> prune_vocab selection (src/prune.rs:23-57),
+    over a code+Chinese corpus of args.prune_bytes in total, sharded by sample across the ranks, 500k initial
+    vocabulary, one all-reduce of the count vector per pass.  Seconds are wall clock around synchronised regions,
+    max over ranks."""
+    from tokengeex_b200 import prune as P
+    dev = torch.device("cuda", local)
+    # the vocabulary is built once (rank 0) and broadcast: identical on every rank
+    if rank == 0:
+        vb, vo = synth.corpus(synth.KIND_CODE_CJK, 4, PRUNE_VOCAB_SAMPLE_BYTES)
+        toks, sc, kp = synth.vocab(vb, vo, 4, PRUNE_VOCAB, MAX_TOKEN_LEN, 0.05)
+        del vb, vo
+        tb, to = N.pack(toks)
+        hdr = torch.tensor([len(toks), len(tb)], dtype=torch.int64, device=dev)
+    else:
+        hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(hdr, 0)
+    V, nb = int(hdr[0]), int(hdr[1])
+    if rank == 0:
+        t_tb, t_to = torch.from_numpy(tb[:nb].copy()).to(dev), torch.from_numpy(to.view(np.int64).copy()).to(dev)
+        t_sc, t_kp = torch.from_numpy(np.ascontiguousarray(sc)).to(dev), torch.from_numpy(np.ascontiguousarray(kp)).to(dev)
+    else:
+        t_tb = torch.empty(nb, dtype=torch.uint8, device=dev)
+        t_to = torch.empty(V + 1, dtype=torch.int64, device=dev)
+        t_sc = torch.empty(V, dtype=torch.float64, device=dev)
+        t_kp = torch.empty(V, dtype=torch.uint8, device=dev)
+    if world > 1:
+        for t in (t_tb, t_to, t_sc, t_kp):
+            dist.broadcast(t, 0)
+        tb, to = t_tb.cpu().numpy(), t_to.cpu().numpy().view(np.uint64)
+        toks = [tb[int(to[i]):int(to[i + 1])].tobytes() for i in range(V)]
+        sc, kp = t_sc.cpu().numpy(), t_kp.cpu().numpy()
+    del t_tb, t_to, t_sc, t_kp
+    vocab = P.Vocab(list(toks), np.asarray(sc, np.float64), np.asarray(kp, np.uint8))
+
+    per_rank = args.prune_bytes // world
+    blob, off = synth.corpus(synth.KIND_CODE_CJK, 4 + 1000 * rank, per_rank)
+    S, NB = len(off) - 1, int(off[-1])
+    coll = None
+    n_samples = S
+    if world > 1:
+        from tokengeex_b200.dist import Collective
+        coll = Collective(device=f"cuda:{local}")
+        n_samples = coll.sum_int(S)
+    pr = P.ModelVocabularyPruner(65536, 0.8, 2, 0.0, device=local, allreduce=coll, n_samples_global=n_samples)
+    d = pr._upload(blob, off)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn):
+        sync()
+        t = time.perf_counter()
+        r = fn()
+        sync()
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return r, float(dt[0])
+
+    model, t_build0 = timed(lambda: N.Model(vocab.tokens, vocab.scores, device=local))
+    pr.run_e_step(model, blob, off, d)  # warm-up: workspaces are allocated on the first call
+    expected, t_e = timed(lambda: pr.run_e_step(model, blob, off, d))
+    e_dev_ms, fwd_ms, bwd_ms = model.stat(4), model.stat(2), model.stat(3)
+    new_vocab, t_m = timed(lambda: pr.run_m_step(vocab, expected))
+
+    def rebuild():  # *model = Model::from(vocab): new trie, same handle and workspaces
+        model.rebuild(new_vocab.tokens, new_vocab.scores)
+        return model
+    model2, t_rebuild = timed(rebuild)
+    rep = P.PruneReport()
+    pruned, t_prune = timed(lambda: pr.prune_vocab(model2, new_vocab, blob, off, rep, d))
+    t_freq, t_sel = rep.freq_s[-1], rep.select_s[-1]
+    out = {"workload": f"EM prune iteration, {args.prune_bytes} B code+Chinese corpus sharded x{world}, "
+                       f"{len(vocab)} initial vocab, max_token_len {MAX_TOKEN_LEN} (configs[3])",
+           "unit": "s", "iter_s": t_e + t_m + t_rebuild + t_prune,
+           "e_step_s": t_e, "m_step_s": t_m, "model_rebuild_s": t_rebuild, "freq_pass_s": t_freq,
+           "prune_select_s": t_sel, "vocab_after_m_step": len(new_vocab), "vocab_after_prune": len(pruned),
+           "e_step_device_ms": e_dev_ms, "fb_forward_ms": fwd_ms, "fb_backward_ms": bwd_ms,
+           "e_step_input_MBps": args.prune_bytes / t_e / 1e6,
+           "bytes_per_gpu": NB, "samples_per_gpu": S,
+           "roofline": None, "cpu_baseline": None}
+    peak, peak_src = measured_peak()
+    alg = NB + 8 * (S + 1) + 8 * len(vocab)
+    out["roofline"] = {"bound": "hbm", "achieved": alg / (e_dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": alg / (e_dev_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
+                       "kernel": "fb_forward_kernel + fb_backward_kernel (whole E-step, device ms)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = synth.n_threads()
+        om = O.OracleModel(vocab.tokens, vocab.scores)
+        k = int(np.searchsorted(off, 2_000_000))
+        t = time.perf_counter()
+        om.run_e_step(blob, off[:k + 1], threads=threads)
+        rate = int(off[k]) / (time.perf_counter() - t)
+        k = int(np.searchsorted(off, min(NB, max(2_000_000, rate * 10.0))))
+        o = off[:k + 1]
+        t = time.perf_counter()
+        want = om.run_e_step(blob, o, threads=threads)[0]
+        dt = time.perf_counter() - t
+        chk = N.Model(vocab.tokens, vocab.scores, device=local)
+        got = chk.expected_counts(blob[:max(int(o[-1]), 1)], o)[0]
+        chk.close()
+        nz = want > 0
+        rel = float(np.max(np.abs(got[nz] - want[nz]) / want[nz])) if nz.any() else 0.0
+        out["cpu_baseline"] = {"max_rel_diff_vs_gpu": rel, "within_1e-9": bool(rel < 1e-9),"e_step_input_MBps": int(o[-1]) / dt / 1e6, "unit": "MB/s", "cores": threads, "kind": "port",
+                               "sample": f"first {int(o[-1])} bytes ({k} samples) of the same corpus, oracle run_e_step "
+                                         "(C++ restatement of src/prune.rs:64-120, rayon-like chunking)",
+                               "e_step_s_extrapolated": args.prune_bytes / (int(o[-1]) / dt)}
+    model2.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +291,8 @@ def main():
     ap.add_argument("--bytes", type=int, default=1_000_000_000, help="input bytes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prune", action="store_true", help="skip the EM prune-iteration measurement")
+    ap.add_argument("--prune-bytes", type=int, default=4_000_000_000, help="total corpus bytes of the prune iteration")
     ap.add_argument("--chunk-bytes", type=int, default=0, help="bytes per chunk of the pipelined host entry point")
     ap.add_argument("--g-short", type=int, default=0)
     ap.add_argument("--long-threshold", type=int, default=0)
@@ -192,7 +320,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    toks, sc, kp = build_vocab(synth)
+    toks, sc, kp = build_vocab(synth, world)
     model = N.Model(toks, sc, device=local)
     if args.g_short:
         model.set_option(0, args.g_short)
@@ -270,7 +398,7 @@ def main():
     # e2e: the C-ABI host call, pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        h_ids = N.pinned_empty(4 * (NB // 2 + 16)).view(np.uint32)
+        h_ids = N.pinned_empty(4 * (int(tokens) + 16)).view(np.uint32)  # token count known from the device pass
         for _ in range(2):
             r = model.encode_batch(blob, off, crlf=True, ids_out=h_ids)
         torch.cuda.synchronize()
@@ -309,6 +437,15 @@ def main():
                "sample": f"first {int(o[-1])} bytes ({k} samples) of the same corpus, oracle encode_batch "
                          "(C++ restatement of the Rust rayon path)", "ids_match_gpu": ok}
 
+    prune_iter = None
+    if not args.no_prune:
+        del d_text, d_ids, d_id_off, d_off, blob, h_text
+        if not args.no_e2e:
+            del h_ids
+        model.close()
+        torch.cuda.empty_cache()
+        prune_iter = run_prune_iter(args, rank, world, local, torch, dist, N, synth)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -330,7 +467,8 @@ def main():
                                                    "emit": float(np.mean(emit_ms)),
                                                    "crlf_sort_scan_other": ms_per_step - vit * 1e3 -
                                                    float(np.mean(back_ms)) - float(np.mean(emit_ms))}},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu,
+                "prune_iter": prune_iter}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -61,6 +61,12 @@ const char* tgx_last_error(void);
  * device >= 0: CUDA ordinal.  device == -1: host-only model (trie queries only). */
 int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
                      uint64_t vocab_size, int device, tgx_model** out);
+/* `*model = Model::from(vocab)` as the EM loop does after every M-step / prune step (src/prune.rs:48,53), in
+ * place: a new trie for the new vocabulary on the same device; streams and workspaces are kept (a fresh handle
+ * would free and re-allocate GBs of scratch per EM sub-iteration).  On failure the model is unchanged.  Must not
+ * run concurrently with compute calls on the same handle from other threads that still expect the old vocabulary. */
+int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                      uint64_t vocab_size);
 void tgx_model_destroy(tgx_model* m);
 int tgx_model_get_info(const tgx_model* m, tgx_model_info* info);
 

@@ -36,3 +36,32 @@ def test_full_prune_set_identical(kind, seed, nbytes, v0, target, subiters):
     swapped = [i for i, (a, b) in enumerate(zip(vocab.tokens, wt)) if a != b]
     for i in swapped:  # a swap is only legitimate between (near-)tied scores
         assert abs(vocab.scores[i] - ws[i]) <= 1e-9 * abs(ws[i])
+
+
+def test_model_rebuild_in_place():
+    """tgx_model_rebuild = `*model = Model::from(vocab)` (src/prune.rs:48,53) on the same handle: encode and E-step
+    after the rebuild equal a fresh model's / the oracle's for the NEW vocabulary, smaller or larger than the old."""
+    import random
+
+    from oracle import oracle as O
+    from tests.util import rand_samples, rand_vocab
+    from tokengeex_b200 import _native as N
+    rng = random.Random(5)
+    toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=60, max_len=6)
+    gm = N.Model(toks, scores, device=0)
+    samples = rand_samples(rng, b"abcd", 200, 0, 300)
+    blob, off = N.pack(samples)
+    for n_tok, max_len in [(20, 3), (300, 9), (8, 16)]:
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=n_tok, max_len=max_len)
+        gm.rebuild(toks, scores)
+        assert gm.info().vocab_size == len(toks)
+        om = O.OracleModel(toks, scores)
+        ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off)
+        wids, wid_off, wst, wplen, wbad = om.encode_batch(blob, off, threads=4)
+        assert rc == 0 and np.array_equal(ids, wids) and np.array_equal(id_off, wid_off)
+        ex = gm.expected_counts(blob, off)[0]
+        want = om.run_e_step(blob, off, threads=4)[0]
+        nz = want > 0
+        assert float(np.max(np.abs(ex[nz] - want[nz]) / want[nz])) < 1e-9
+        fr = gm.token_frequencies(blob, off)[0]
+        assert np.array_equal(fr, om.token_frequencies(blob, off, threads=4))

@@ -59,6 +59,7 @@ SYMBOLS = [
     ("tgx_host_free", C.c_int, [C.c_void_p]),
     ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
     ("tgx_model_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    ("tgx_model_rebuild", C.c_int, [C.c_void_p, u8p, u64p, f64p, C.c_uint64]),
 ]
 
 _lib = None
@@ -122,6 +123,15 @@ class Model:
         self._h = h
         self.V = len(tokens)
         self.device = -1 if device is None else int(device)
+
+    def rebuild(self, tokens: Sequence[bytes], scores):
+        """`*model = Model::from(vocab)` in place (/root/reference/src/prune.rs:48,53): new trie, same workspaces."""
+        blob, off = pack(tokens)
+        sc = np.ascontiguousarray(scores, dtype=np.float64)
+        if sc.size == 0:
+            sc = np.zeros(1, np.float64)
+        _check(lib().tgx_model_rebuild(self._h, _p(blob, u8p), _p(off, u64p), _p(sc, f64p), len(tokens)))
+        self.V = len(tokens)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -71,6 +71,7 @@ struct tgx_model {
   uint64_t V = 0;
   int device = -1;
   uint4* d_trie = nullptr;
+  size_t trie_cap = 0;  // slots allocated at d_trie
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
@@ -93,8 +94,8 @@ struct tgx_model {
   // options
   int g_short = 8;
   int64_t long_threshold = 512;  // samples at least this long: full warp (lane-group forward kernels, backtrack)
-  int g_estep = 8;
-  int64_t estep_long_threshold = 1ll << 40;  // snippets at least this long get a full warp (G = 32); off by default
+  int g_estep = 4;
+  int64_t estep_long_threshold = 16384;  // snippets at least this long get a full warp (G = 32) on a second stream
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
   // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
@@ -430,6 +431,10 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   p.groups = groups;
   const size_t smem = pair_smem_bytes(R, groups, p.hot_slots);
   cudaError_t e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // whatever the tables leave of the 256 KB L1/shared array caches trie slots beyond the staged prefix
+  e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1));
   if (e != cudaSuccess) return e;
   const uint32_t grid =
       (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
@@ -864,10 +869,37 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     for (auto& e : m->ev) CU(cudaEventCreate(&e));
     size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
     CU(cudaMalloc(&m->d_trie, bytes));
+    m->trie_cap = m->da.slots.size();
     CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->stream));
     CU(cudaStreamSynchronize(m->stream));
   }
   *out = m.release();
+  return TGX_OK;
+}
+
+int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                      uint64_t vocab_size) {
+  if (!m || !token_offsets || (!token_bytes && vocab_size && token_offsets[vocab_size]) || (!scores && vocab_size))
+    return fail(TGX_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  tgx::DoubleArray da;
+  std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da);
+  if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);  // the model is unchanged
+  if (m->device >= 0) {
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    if (da.slots.size() > m->trie_cap) {
+      uint4* p = nullptr;
+      CU(cudaMalloc(&p, da.slots.size() * sizeof(tgx::Slot)));
+      if (m->d_trie) cudaFree(m->d_trie);
+      m->d_trie = p;
+      m->trie_cap = da.slots.size();
+    }
+    CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+  }
+  m->da = std::move(da);
+  m->V = vocab_size;
   return TGX_OK;
 }
 

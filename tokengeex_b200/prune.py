@@ -163,16 +163,14 @@ class ModelVocabularyPruner:
                          len(new_vocab))
                 vocab = new_vocab
                 t = time.perf_counter()
-                model.close()
-                model = N.Model(vocab.tokens, vocab.scores, device=self.device)  # *model = Model::from(vocab)
+                model.rebuild(vocab.tokens, vocab.scores)  # *model = Model::from(vocab)  (src/prune.rs:48)
                 report.rebuild_s.append(time.perf_counter() - t)
                 report.vocab_sizes.append(len(vocab))
             before = len(vocab)
             vocab = self.prune_vocab(model, vocab, blob, off, report, dev)
             log.info("Pruning vocabulary from=%d to=%d", before, len(vocab))
             t = time.perf_counter()
-            model.close()
-            model = N.Model(vocab.tokens, vocab.scores, device=self.device)
+            model.rebuild(vocab.tokens, vocab.scores)  # (src/prune.rs:53)
             report.rebuild_s.append(time.perf_counter() - t)
             report.vocab_sizes.append(len(vocab))
         model.close()
