@@ -66,31 +66,44 @@ struct Stats {
 
 }  // namespace
 
-struct tgx_model {
-  tgx::DoubleArray da;
-  uint64_t V = 0;
-  int device = -1;
-  uint4* d_trie = nullptr;
-  size_t trie_cap = 0;  // slots allocated at d_trie
+// Scratch of one batch in flight: its compute stream, the stream its control words are read through, events and
+// every intermediate buffer.  The model owns two, so that the chunked host entry point can have the kernels of
+// chunk k+1 queued behind chunk k (the tail of a chunk is a handful of long samples on a few SMs).
+struct Workspace {
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // long units run beside the short ones
-  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   // The compute stream never issues a D2H copy itself: measured on B200 (profiles/r01_ubench_overlap.txt),
   // once a stream has used the D2H copy engine its next kernels queue behind whatever that engine is
   // doing — here the bulk D2H of the previous chunk.  Control words are read through this stream.
   cudaStream_t stream_ctl = nullptr;
   cudaEvent_t ev_ctl = nullptr;
   unsigned long long* h_words = nullptr;  // pinned, 8 words
+  cudaEvent_t ev[8] = {};
+  Stats stats;
+  DevBuf text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt, ntok, status,
+      small;
+};
+
+struct tgx_model {
+  tgx::DoubleArray da;
+  uint64_t V = 0;
+  int device = -1;
+  uint4* d_trie = nullptr;
+  size_t trie_cap = 0;  // slots allocated at d_trie
+  Workspace ws[2];
+  int wi = 0;  // workspace the next launches go to
+  Workspace& w() { return ws[wi]; }
+  const Workspace& w() const { return ws[wi]; }
+  Stats last_stats;  // of the last finished call (tgx_model_last_stat)
+  cudaStream_t stream2 = nullptr;  // long units run beside the short ones (E-step)
+  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
   uint64_t* h_off = nullptr;       // pinned staging for rebased chunk offsets
   uint64_t h_off_cap = 0;
   unsigned char* h_out = nullptr;  // pinned staging for the small per-sample outputs (id_off, status, proc_len)
   uint64_t h_out_cap = 0;
   uint64_t chunk_bytes = 352ull << 20;  // ~3 chunks per GB: below that the longest sample's dp chain dominates a chunk
-  cudaEvent_t ev[8] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::recursive_mutex mu;
-  Stats stats;
   // options
   int g_short = 8;
   int64_t long_threshold = 512;  // samples at least this long: full warp (lane-group forward kernels, backtrack)
@@ -110,9 +123,13 @@ struct tgx_model {
   int num_sms = 148;
   int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
   int smem_optin = 232448;
-  // workspace
-  DevBuf text, off, text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt,
-      ntok, idoff, status, A, expected, freq, ids, small, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
+  // Chunked host entry point: queue chunk k+1's kernels (second workspace) before chunk k has finished.  Off by
+  // default: measured on B200 (tools/e2e_trace.py, 1 GB) it LOSES, 75.4 vs 67.6 ms with two chunks — the next
+  // chunk's persistent forward CTAs take every SM the moment the current forward kernel drains, and the current
+  // chunk's backtrack / emit kernels then wait for registers until those CTAs exit.
+  int overlap_chunks = 0;
+  // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
+  DevBuf text, off, idoff, A, expected, freq, ids, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
 };
 
 // =========================================================================================
@@ -415,8 +432,8 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
   if (e != cudaSuccess) return e;
   uint32_t per_block = WPB * (32 / G);
   uint32_t blocks = (p.u.count + per_block - 1) / per_block;
-  viterbi_kernel<G><<<blocks, WPB * 32, smem, m->stream>>>(p);
-  m->stats.launches += 1;
+  viterbi_kernel<G><<<blocks, WPB * 32, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
@@ -438,10 +455,10 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   if (e != cudaSuccess) return e;
   const uint32_t grid =
       (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
-  e = dev_fill(p.counter, 0, 4, m->stream);
+  e = dev_fill(p.counter, 0, 4, m->w().stream);
   if (e != cudaSuccess) return e;
-  viterbi_pair_kernel<R, HOT><<<grid, groups * WG * 32, smem, m->stream>>>(p);
-  m->stats.launches += 1;
+  viterbi_pair_kernel<R, HOT><<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
@@ -486,10 +503,10 @@ cudaError_t launch_viterbi_lane(tgx_model* m, LaneParams p) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 32 * warps - 1) / (32 * warps), (uint64_t)m->num_sms);
-  e = dev_fill(p.counter, 0, 4, m->stream);
+  e = dev_fill(p.counter, 0, 4, m->w().stream);
   if (e != cudaSuccess) return e;
-  viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC><<<grid, warps * 32, smem, m->stream>>>(p);
-  m->stats.launches += 1;
+  viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC><<<grid, warps * 32, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
@@ -510,10 +527,10 @@ cudaError_t launch_viterbi_hybrid_h(tgx_model* m, HybridParams p, uint32_t hot_s
   const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.lane.u.count + 31) / 32, (uint64_t)m->num_sms);
   p.pair_ctas = std::min<uint32_t>((uint32_t)m->pair_ctas, grid);
   if (p.pair_ctas == 0) p.lane.u.part = 0;  // nobody runs the pair body: the lanes take every sample
-  e = dev_fill(p.pair.counter, 0, 8, m->stream);  // both counters
+  e = dev_fill(p.pair.counter, 0, 8, m->w().stream);  // both counters
   if (e != cudaSuccess) return e;
-  viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC><<<grid, threads, smem, m->stream>>>(p);
-  m->stats.launches += 1;
+  viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC><<<grid, threads, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
@@ -553,7 +570,7 @@ cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward, cudaStream_t st) 
     if (e != cudaSuccess) return e;
     fb_backward_kernel<G><<<blocks, WPB * 32, smem, st>>>(p);
   }
-  m->stats.launches += 1;
+  m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
@@ -580,95 +597,95 @@ int check_model(tgx_model* m) {
   return TGX_OK;
 }
 
-// crlf on device: (d_text,d_off) -> (m->text2, m->off2).  N = total bytes.
+// crlf on device: (d_text,d_off) -> (m->w().text2, m->w().off2).  N = total bytes.
 int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N) {
-  cudaStream_t st = m->stream;
+  cudaStream_t st = m->w().stream;
   uint64_t n_tiles = (N + CRLF_TILE - 1) / CRLF_TILE;
-  CU(m->text2.reserve(N + 16));
-  CU(m->off2.reserve((S + 1) * 8));
-  CU(m->bitmap.reserve((N / 32 + 4) * 4));
-  CU(m->blk.reserve((n_tiles + 1) * 8 * 2));
-  CU(dev_fill(m->bitmap.p, 0, (N / 32 + 4) * 4, st));
+  CU(m->w().text2.reserve(N + 16));
+  CU(m->w().off2.reserve((S + 1) * 8));
+  CU(m->w().bitmap.reserve((N / 32 + 4) * 4));
+  CU(m->w().blk.reserve((n_tiles + 1) * 8 * 2));
+  CU(dev_fill(m->w().bitmap.p, 0, (N / 32 + 4) * 4, st));
   if (S > 1) {
-    crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->bitmap.as<uint32_t>());
-    m->stats.launches += 1;
+    crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->w().bitmap.as<uint32_t>());
+    m->w().stats.launches += 1;
   }
-  unsigned long long* removed = m->blk.as<unsigned long long>();
+  unsigned long long* removed = m->w().blk.as<unsigned long long>();
   unsigned long long* prefix = removed + n_tiles + 1;
   CU(dev_fill(removed, 0, (n_tiles + 1) * 8, st));
   if (n_tiles) {
-    crlf_count<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->bitmap.as<uint32_t>(), removed);
-    m->stats.launches += 1;
+    crlf_count<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, m->w().bitmap.as<uint32_t>(), removed);
+    m->w().stats.launches += 1;
   }
   size_t tmp = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, removed, prefix, (int)(n_tiles + 1), st));
-  CU(m->cubtmp.reserve(tmp));
-  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, removed, prefix, (int)(n_tiles + 1), st));
-  m->stats.launches += 2;
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->w().cubtmp.p, tmp, removed, prefix, (int)(n_tiles + 1), st));
+  m->w().stats.launches += 2;
   if (n_tiles) {
-    crlf_scatter<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, d_off, S, m->bitmap.as<uint32_t>(), prefix,
-                                                          n_tiles, m->text2.as<uint8_t>(), m->off2.as<uint64_t>());
-    m->stats.launches += 1;
+    crlf_scatter<<<(uint32_t)n_tiles, CRLF_BLOCK, 0, st>>>(d_text, N, d_off, S, m->w().bitmap.as<uint32_t>(), prefix,
+                                                          n_tiles, m->w().text2.as<uint8_t>(), m->w().off2.as<uint64_t>());
+    m->w().stats.launches += 1;
   } else {
-    CU(dev_fill(m->off2.p, 0, (S + 1) * 8, st));  // no bytes at all: every sample is empty
+    CU(dev_fill(m->w().off2.p, 0, (S + 1) * 8, st));  // no bytes at all: every sample is empty
   }
   CU(cudaGetLastError());
   return TGX_OK;
 }
 
-// sort unit indices by length, descending: keys in m->ulen, values in m->vals_in -> m->vals_out
+// sort unit indices by length, descending: keys in m->w().ulen, values in m->w().vals_in -> m->w().vals_out
 int sort_units(tgx_model* m, uint32_t U) {
-  CU(m->keys_out.reserve((size_t)U * 4 + 4));
-  CU(m->vals_out.reserve((size_t)U * 4 + 4));
+  CU(m->w().keys_out.reserve((size_t)U * 4 + 4));
+  CU(m->w().vals_out.reserve((size_t)U * 4 + 4));
   size_t tmp = 0;
-  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, m->ulen.as<uint32_t>(), m->keys_out.as<uint32_t>(),
-                                               m->vals_in.as<uint32_t>(), m->vals_out.as<uint32_t>(), (int)U, 0, 32,
-                                               m->stream));
-  CU(m->cubtmp.reserve(tmp));
-  CU(cub::DeviceRadixSort::SortPairsDescending(m->cubtmp.p, tmp, m->ulen.as<uint32_t>(), m->keys_out.as<uint32_t>(),
-                                               m->vals_in.as<uint32_t>(), m->vals_out.as<uint32_t>(), (int)U, 0, 32,
-                                               m->stream));
-  m->stats.launches += 4;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, m->w().ulen.as<uint32_t>(), m->w().keys_out.as<uint32_t>(),
+                                               m->w().vals_in.as<uint32_t>(), m->w().vals_out.as<uint32_t>(), (int)U, 0, 32,
+                                               m->w().stream));
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceRadixSort::SortPairsDescending(m->w().cubtmp.p, tmp, m->w().ulen.as<uint32_t>(), m->w().keys_out.as<uint32_t>(),
+                                               m->w().vals_in.as<uint32_t>(), m->w().vals_out.as<uint32_t>(), (int)U, 0, 32,
+                                               m->w().stream));
+  m->w().stats.launches += 4;
   return TGX_OK;
 }
 
 // Viterbi over all samples: forward dp (back lengths) + backtrack (token-end marks).  On return
-// m->mark holds the length of the token ending at every marked byte, m->ntok token counts,
-// m->status per-sample status.
+// m->w().mark holds the length of the token ending at every marked byte, m->w().ntok token counts,
+// m->w().status per-sample status.
 int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
                 uint64_t* d_proc_len) {
-  cudaStream_t st = m->stream;
+  cudaStream_t st = m->w().stream;
   if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
   uint32_t U = (uint32_t)S;
   const uint64_t n_tiles = (N + EM_TILE - 1) / EM_TILE;
-  CU(m->ustart.reserve((size_t)U * 8 + 8));
-  CU(m->ulen.reserve((size_t)U * 4 + 4));
-  CU(m->vals_in.reserve((size_t)U * 4 + 4));
-  CU(m->bp.reserve(N + 64));
-  CU(m->mark.reserve(n_tiles * EM_TILE + 64));
-  CU(m->ntok.reserve(((size_t)U + 1) * 8));
-  CU(m->status.reserve((size_t)U * 4 + 4));
-  CU(m->small.reserve(64));
-  units_from_samples<<<nblk(U, 256), 256, 0, st>>>(d_off, S, m->ustart.as<uint64_t>(), m->ulen.as<uint32_t>(),
-                                                  m->vals_in.as<uint32_t>(), d_proc_len);
-  m->stats.launches += 1;
+  CU(m->w().ustart.reserve((size_t)U * 8 + 8));
+  CU(m->w().ulen.reserve((size_t)U * 4 + 4));
+  CU(m->w().vals_in.reserve((size_t)U * 4 + 4));
+  CU(m->w().bp.reserve(N + 64));
+  CU(m->w().mark.reserve(n_tiles * EM_TILE + 64));
+  CU(m->w().ntok.reserve(((size_t)U + 1) * 8));
+  CU(m->w().status.reserve((size_t)U * 4 + 4));
+  CU(m->w().small.reserve(64));
+  units_from_samples<<<nblk(U, 256), 256, 0, st>>>(d_off, S, m->w().ustart.as<uint64_t>(), m->w().ulen.as<uint32_t>(),
+                                                  m->w().vals_in.as<uint32_t>(), d_proc_len);
+  m->w().stats.launches += 1;
   int rc = sort_units(m, U);
   if (rc) return rc;
-  uint32_t* counts = m->small.as<uint32_t>();
+  uint32_t* counts = m->w().small.as<uint32_t>();
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
-  split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr,
+  split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr,
                                  (uint32_t)std::min<int64_t>(m->lane_threshold, 0x7FFFFFFF), counts);
-  m->stats.launches += 1;
-  CU(dev_fill(m->ntok.p, 0, ((size_t)U + 1) * 8, st));
-  CU(dev_fill(m->status.p, 0, (size_t)U * 4 + 4, st));
-  CU(dev_fill(m->mark.p, 0, n_tiles * EM_TILE, st));
+  m->w().stats.launches += 1;
+  CU(dev_fill(m->w().ntok.p, 0, ((size_t)U + 1) * 8, st));
+  CU(dev_fill(m->w().status.p, 0, (size_t)U * 4 + 4, st));
+  CU(dev_fill(m->w().mark.p, 0, n_tiles * EM_TILE, st));
   // (no host synchronisation here: every kernel below reads its unit range from `counts`)
 
   UnitParams u;
   u.text = d_text;
-  u.unit_start = m->ustart.as<uint64_t>();
-  u.unit_len = m->ulen.as<uint32_t>();
-  u.order = m->vals_out.as<uint32_t>();
+  u.unit_start = m->w().ustart.as<uint64_t>();
+  u.unit_len = m->w().ulen.as<uint32_t>();
+  u.order = m->w().vals_out.as<uint32_t>();
   u.trie = m->d_trie;
   u.root_base = m->da.root_base;
   u.rows = std::max<uint32_t>(1, m->da.max_token_len);
@@ -677,20 +694,20 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.first = 0;
   u.count = U;  // upper bound for the grids
 
-  CU(cudaEventRecord(m->ev[0], st));
+  CU(cudaEventRecord(m->w().ev[0], st));
   if (m->algo == 3 && u.rows <= 16) {
     HybridParams hp;
     hp.pair.u = u;
     hp.pair.u.part = 3;
     hp.pair.blob_end = d_text + N;
-    hp.pair.bp = m->bp.as<uint8_t>();
-    hp.pair.counter = m->small.as<unsigned int>() + 8;
+    hp.pair.bp = m->w().bp.as<uint8_t>();
+    hp.pair.counter = m->w().small.as<unsigned int>() + 8;
     hp.pair.dbg = 0;
     hp.lane.u = u;
     hp.lane.u.part = 4;
     hp.lane.blob_end = d_text + N;
-    hp.lane.bp = m->bp.as<uint8_t>();
-    hp.lane.counter = m->small.as<unsigned int>() + 9;
+    hp.lane.bp = m->w().bp.as<uint8_t>();
+    hp.lane.counter = m->w().small.as<unsigned int>() + 9;
     hp.pair_ctas = hp.lane_warps = 0;
     CU(launch_viterbi_hybrid(m, hp));
   } else if (m->algo == 2 && u.rows <= 16) {
@@ -698,16 +715,16 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.u = u;
     p.u.part = 0;
     p.blob_end = d_text + N;
-    p.bp = m->bp.as<uint8_t>();
-    p.counter = m->small.as<unsigned int>() + 9;
+    p.bp = m->w().bp.as<uint8_t>();
+    p.counter = m->w().small.as<unsigned int>() + 9;
     CU(launch_viterbi_lane<16>(m, p));
   } else if (m->algo == 0 && u.rows <= 16) {
     PairParams p;
     p.u = u;
     p.u.part = 0;
     p.blob_end = d_text + N;
-    p.bp = m->bp.as<uint8_t>();
-    p.counter = m->small.as<unsigned int>() + 8;
+    p.bp = m->w().bp.as<uint8_t>();
+    p.counter = m->w().small.as<unsigned int>() + 8;
     p.dbg = getenv("TGX_DBG") ? (uint32_t)atoi(getenv("TGX_DBG")) : 0u;
     if (!p.u.count) {
     } else if (m->producers >= 4) {
@@ -718,14 +735,14 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   } else {
     ViterbiParams p;
     p.u = u;
-    p.bp = m->bp.as<uint8_t>();
+    p.bp = m->w().bp.as<uint8_t>();
     p.u.part = 1;
     CU(launch_viterbi_g(m, 32, p));
     p.u.part = 2;
     CU(launch_viterbi_g(m, m->g_short, p));
   }
-  CU(cudaEventRecord(m->ev[1], st));
-  CU(cudaEventRecord(m->ev[2], st));
+  CU(cudaEventRecord(m->w().ev[1], st));
+  CU(cudaEventRecord(m->w().ev[2], st));
   if (U) {
     BacktrackParams b;
     b.unit_start = u.unit_start;
@@ -734,40 +751,40 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     b.counts = counts;
     b.first = 0;
     b.count = U;
-    b.bp = m->bp.as<uint8_t>();
-    b.mark = m->mark.as<uint8_t>();
-    b.n_tokens = m->ntok.as<unsigned long long>();
-    b.status = m->status.as<int32_t>();
+    b.bp = m->w().bp.as<uint8_t>();
+    b.mark = m->w().mark.as<uint8_t>();
+    b.n_tokens = m->w().ntok.as<unsigned long long>();
+    b.status = m->w().status.as<int32_t>();
     // long samples (sorted first): one warp each; short ones: one thread each
     b.part = 1;
     backtrack_warp_kernel<<<nblk(U, BW_WARPS), BW_WARPS * 32, 0, st>>>(b);
     b.part = 2;
     backtrack_thread_kernel<<<nblk(U, BT_THREADS), BT_THREADS, 0, st>>>(b);
-    m->stats.launches += 2;
+    m->w().stats.launches += 2;
     CU(cudaGetLastError());
   }
-  CU(cudaEventRecord(m->ev[3], st));
+  CU(cudaEventRecord(m->w().ev[3], st));
   return TGX_OK;
 }
 
 // Token ids (and/or frequencies) from the marks: count per tile, scan, emit.
 int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, uint64_t ids_cap,
              unsigned long long* d_freq) {
-  cudaStream_t st = m->stream;
+  cudaStream_t st = m->w().stream;
   const uint64_t n_tiles = (N + EM_TILE - 1) / EM_TILE;
-  CU(cudaEventRecord(m->ev[4], st));
+  CU(cudaEventRecord(m->w().ev[4], st));
   if (n_tiles) {
-    CU(m->tilecnt.reserve((n_tiles + 1) * 16));
-    unsigned long long* cnt = m->tilecnt.as<unsigned long long>();
+    CU(m->w().tilecnt.reserve((n_tiles + 1) * 16));
+    unsigned long long* cnt = m->w().tilecnt.as<unsigned long long>();
     unsigned long long* prefix = cnt + n_tiles + 1;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)m->num_sms * 8);
-    mark_count_kernel<<<grid, EM_BLOCK, 0, st>>>(m->mark.as<uint4>(), n_tiles, cnt);
+    mark_count_kernel<<<grid, EM_BLOCK, 0, st>>>(m->w().mark.as<uint4>(), n_tiles, cnt);
     size_t tmp = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, prefix, (int)n_tiles, st));
-    CU(m->cubtmp.reserve(tmp));
-    CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, cnt, prefix, (int)n_tiles, st));
+    CU(m->w().cubtmp.reserve(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(m->w().cubtmp.p, tmp, cnt, prefix, (int)n_tiles, st));
     EmitParams e;
-    e.mark = m->mark.as<uint4>();
+    e.mark = m->w().mark.as<uint4>();
     e.text = d_text;
     e.n_tiles = n_tiles;
     e.tile_prefix = prefix;
@@ -778,32 +795,32 @@ int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, u
     e.freq = d_freq;
     e.V = (uint32_t)m->V;
     emit_kernel<<<grid, EM_BLOCK, d_freq ? EM_HOT * 4 : 0, st>>>(e);
-    m->stats.launches += 4;
+    m->w().stats.launches += 4;
     CU(cudaGetLastError());
   }
-  CU(cudaEventRecord(m->ev[5], st));
+  CU(cudaEventRecord(m->w().ev[5], st));
   return TGX_OK;
 }
 
 // Reads up to two device words once everything queued on the compute stream has finished, through
 // the control stream (see tgx_model::stream_ctl); returns with both streams idle.
 int read_words(tgx_model* m, const void* d0, const void* d1, unsigned long long* o0, unsigned long long* o1) {
-  CU(cudaEventRecord(m->ev_ctl, m->stream));
-  CU(cudaStreamWaitEvent(m->stream_ctl, m->ev_ctl, 0));
-  if (d0) CU(cudaMemcpyAsync(m->h_words, d0, 8, cudaMemcpyDeviceToHost, m->stream_ctl));
-  if (d1) CU(cudaMemcpyAsync(m->h_words + 1, d1, 8, cudaMemcpyDeviceToHost, m->stream_ctl));
-  CU(cudaStreamSynchronize(m->stream_ctl));
-  if (d0 && o0) *o0 = m->h_words[0];
-  if (d1 && o1) *o1 = m->h_words[1];
+  CU(cudaEventRecord(m->w().ev_ctl, m->w().stream));
+  CU(cudaStreamWaitEvent(m->w().stream_ctl, m->w().ev_ctl, 0));
+  if (d0) CU(cudaMemcpyAsync(m->w().h_words, d0, 8, cudaMemcpyDeviceToHost, m->w().stream_ctl));
+  if (d1) CU(cudaMemcpyAsync(m->w().h_words + 1, d1, 8, cudaMemcpyDeviceToHost, m->w().stream_ctl));
+  CU(cudaStreamSynchronize(m->w().stream_ctl));
+  if (d0 && o0) *o0 = m->w().h_words[0];
+  if (d1 && o1) *o1 = m->w().h_words[1];
   return TGX_OK;
 }
 
 int first_bad(tgx_model* m, uint32_t U, int64_t* out_idx, const void* extra = nullptr, unsigned long long* extra_out = nullptr) {
-  unsigned long long* d = m->small.as<unsigned long long>() + 2;
-  CU(dev_fill(d, 0xFF, 8, m->stream));
+  unsigned long long* d = m->w().small.as<unsigned long long>() + 2;
+  CU(dev_fill(d, 0xFF, 8, m->w().stream));
   if (U) {
-    first_bad_unit<<<nblk(U, 256), 256, 0, m->stream>>>(m->status.as<int32_t>(), U, d);
-    m->stats.launches += 1;
+    first_bad_unit<<<nblk(U, 256), 256, 0, m->w().stream>>>(m->w().status.as<int32_t>(), U, d);
+    m->w().stats.launches += 1;
   }
   unsigned long long h = ~0ull;
   int rc = read_words(m, d, extra, &h, extra_out);
@@ -814,14 +831,15 @@ int first_bad(tgx_model* m, uint32_t U, int64_t* out_idx, const void* extra = nu
 
 void finish_stats(tgx_model* m, int which) {
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) {
-    if (which == 1) m->stats.viterbi_ms = ms;
-    if (which == 2) m->stats.fwd_ms = ms;
+  if (cudaEventElapsedTime(&ms, m->w().ev[0], m->w().ev[1]) == cudaSuccess) {
+    if (which == 1) m->w().stats.viterbi_ms = ms;
+    if (which == 2) m->w().stats.fwd_ms = ms;
   }
-  if (which == 2 && cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->stats.bwd_ms = ms;
-  if (which == 1 && cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->stats.back_ms = ms;
-  if (which == 1 && cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->stats.emit_ms = ms;
-  if (cudaEventElapsedTime(&ms, m->ev[6], m->ev[7]) == cudaSuccess) m->stats.total_ms = ms;
+  if (which == 2 && cudaEventElapsedTime(&ms, m->w().ev[2], m->w().ev[3]) == cudaSuccess) m->w().stats.bwd_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[2], m->w().ev[3]) == cudaSuccess) m->w().stats.back_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[4], m->w().ev[5]) == cudaSuccess) m->w().stats.emit_ms = ms;
+  if (cudaEventElapsedTime(&ms, m->w().ev[6], m->w().ev[7]) == cudaSuccess) m->w().stats.total_ms = ms;
+  m->last_stats = m->w().stats;
 }
 
 }  // namespace
@@ -853,25 +871,27 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     CU(cudaMemcpyToSymbol(tgxk::c_log_hdr, TGX_LOG_HDR, sizeof(TGX_LOG_HDR)));
     CU(cudaMemcpyToSymbol(tgxk::c_exp_tab, TGX_EXP_TAB, sizeof(TGX_EXP_TAB)));
     CU(cudaMemcpyToSymbol(tgxk::c_log_tab, TGX_LOG_TAB, sizeof(TGX_LOG_TAB)));
-    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto& w : m->ws) {
+      CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&w.stream_ctl, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&w.ev_ctl, cudaEventDisableTiming));
+      CU(cudaHostAlloc(reinterpret_cast<void**>(&w.h_words), 64, cudaHostAllocDefault));
+      for (auto& e : w.ev) CU(cudaEventCreate(&e));
+    }
     CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&m->stream_ctl, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&m->ev_ctl, cudaEventDisableTiming));
-    CU(cudaHostAlloc(reinterpret_cast<void**>(&m->h_words), 64, cudaHostAllocDefault));
     for (int i = 0; i < 2; i++) {
       CU(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-    for (auto& e : m->ev) CU(cudaEventCreate(&e));
     size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
     CU(cudaMalloc(&m->d_trie, bytes));
     m->trie_cap = m->da.slots.size();
-    CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->stream));
-    CU(cudaStreamSynchronize(m->stream));
+    CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->w().stream));
+    CU(cudaStreamSynchronize(m->w().stream));
   }
   *out = m.release();
   return TGX_OK;
@@ -887,7 +907,7 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
   if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);  // the model is unchanged
   if (m->device >= 0) {
     CU(cudaSetDevice(m->device));
-    CU(cudaStreamSynchronize(m->stream));
+    CU(cudaStreamSynchronize(m->w().stream));
     if (da.slots.size() > m->trie_cap) {
       uint4* p = nullptr;
       CU(cudaMalloc(&p, da.slots.size() * sizeof(tgx::Slot)));
@@ -895,8 +915,8 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
       m->d_trie = p;
       m->trie_cap = da.slots.size();
     }
-    CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->stream));
-    CU(cudaStreamSynchronize(m->stream));
+    CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
+    CU(cudaStreamSynchronize(m->w().stream));
   }
   m->da = std::move(da);
   m->V = vocab_size;
@@ -907,22 +927,25 @@ void tgx_model_destroy(tgx_model* m) {
   if (!m) return;
   if (m->device >= 0) {
     cudaSetDevice(m->device);
-    if (m->stream) cudaStreamSynchronize(m->stream);
-    DevBuf* bufs[] = {&m->text, &m->off, &m->text2, &m->off2, &m->bitmap, &m->blk, &m->ustart, &m->ulen,
-                      &m->keys_out, &m->vals_in, &m->vals_out, &m->cubtmp, &m->bp, &m->mark, &m->tilecnt, &m->ntok, &m->idoff,
-                      &m->status, &m->A, &m->expected, &m->freq, &m->ids, &m->small, &m->scount, &m->hot,
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&m->text, &m->off, &m->idoff, &m->A, &m->expected, &m->freq, &m->ids, &m->scount, &m->hot,
                       &m->text_b, &m->off_b, &m->ids_b, &m->idoff_b, &m->scount_b};
     for (auto* b : bufs) b->release();
+    for (auto& w : m->ws) {
+      DevBuf* wb[] = {&w.text2, &w.off2, &w.bitmap, &w.blk, &w.ustart, &w.ulen, &w.keys_out, &w.vals_in, &w.vals_out,
+                      &w.cubtmp, &w.bp, &w.mark, &w.tilecnt, &w.ntok, &w.status, &w.small};
+      for (auto* b : wb) b->release();
+      for (auto& e : w.ev)
+        if (e) cudaEventDestroy(e);
+      if (w.stream) cudaStreamDestroy(w.stream);
+      if (w.stream_ctl) cudaStreamDestroy(w.stream_ctl);
+      if (w.ev_ctl) cudaEventDestroy(w.ev_ctl);
+      if (w.h_words) cudaFreeHost(w.h_words);
+    }
     if (m->d_trie) cudaFree(m->d_trie);
-    for (auto& e : m->ev)
-      if (e) cudaEventDestroy(e);
-    if (m->stream) cudaStreamDestroy(m->stream);
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
     if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
-    if (m->stream_ctl) cudaStreamDestroy(m->stream_ctl);
-    if (m->ev_ctl) cudaEventDestroy(m->ev_ctl);
-    if (m->h_words) cudaFreeHost(m->h_words);
     for (int i = 0; i < 2; i++) {
       if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
       if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
@@ -973,6 +996,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
+    case 11: m->overlap_chunks = value ? 1 : 0; break;
     case 10: if (value < 0 || value > 1024) return fail(TGX_ERR_INVALID, "pair CTAs must be 0..1024"); m->pair_ctas = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
@@ -985,13 +1009,13 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
 double tgx_model_last_stat(const tgx_model* m, int what) {
   if (!m) return 0;
   switch (what) {
-    case 0: return m->stats.launches;
-    case 1: return m->stats.viterbi_ms;
-    case 2: return m->stats.fwd_ms;
-    case 3: return m->stats.bwd_ms;
-    case 4: return m->stats.total_ms;
-    case 5: return m->stats.back_ms;
-    case 6: return m->stats.emit_ms;
+    case 0: return m->last_stats.launches;
+    case 1: return m->last_stats.viterbi_ms;
+    case 2: return m->last_stats.fwd_ms;
+    case 3: return m->last_stats.bwd_ms;
+    case 4: return m->last_stats.total_ms;
+    case 5: return m->last_stats.back_ms;
+    case 6: return m->last_stats.emit_ms;
   }
   return 0;
 }
@@ -1013,22 +1037,83 @@ int tgx_crlf_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uint6
   if (rc) return rc;
   if (!off || !out_off || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  m->stats = Stats();
+  m->w().stats = Stats();
   uint64_t N = off[S];
   CU(m->text.reserve(N + 16));
   CU(m->off.reserve((S + 1) * 8));
-  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->w().stream));
   rc = run_crlf(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(out_off, m->off2.p, (S + 1) * 8, cudaMemcpyDeviceToHost, m->stream));
-  CU(cudaStreamSynchronize(m->stream));
-  CU(cudaMemcpyAsync(out_text, m->text2.p, out_off[S], cudaMemcpyDeviceToHost, m->stream));
-  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaMemcpyAsync(out_off, m->w().off2.p, (S + 1) * 8, cudaMemcpyDeviceToHost, m->w().stream));
+  CU(cudaStreamSynchronize(m->w().stream));
+  CU(cudaMemcpyAsync(out_text, m->w().text2.p, out_off[S], cudaMemcpyDeviceToHost, m->w().stream));
+  CU(cudaStreamSynchronize(m->w().stream));
   return TGX_OK;
 }
 
 // ---------------------------------------------------------------------------- encode
+namespace {
+
+// Queues every kernel of one encode batch on the current workspace; nothing here waits for the device.
+int encode_enqueue(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t n_bytes,
+                   uint32_t flags, uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_id_off, int32_t* d_status,
+                   uint64_t* d_proc_len) {
+  m->w().stats = Stats();
+  cudaStream_t st = m->w().stream;
+  CU(cudaEventRecord(m->w().ev[6], st));
+  const uint8_t* text = d_text;
+  const uint64_t* off = d_off;
+  int rc;
+  if (flags & TGX_FLAG_CRLF) {
+    rc = run_crlf(m, d_text, d_off, S, n_bytes);
+    if (rc) return rc;
+    text = m->w().text2.as<uint8_t>();
+    off = m->w().off2.as<uint64_t>();
+  }
+  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len);
+  if (rc) return rc;
+  // id offsets = exclusive scan of token counts (S+1 entries; ntok[S] was zeroed)
+  size_t tmp = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, m->w().ntok.as<unsigned long long>(),
+                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->w().cubtmp.p, tmp, m->w().ntok.as<unsigned long long>(),
+                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
+  m->w().stats.launches += 2;
+  rc = run_emit(m, text, n_bytes, d_ids, ids_cap, nullptr);
+  if (rc) return rc;
+  if (d_status) {  // (a kernel, not a D2D memcpy: keep the compute stream off the copy engines)
+    copy_u32<<<nblk(S, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(m->w().status.p),
+                                           reinterpret_cast<uint32_t*>(d_status), S);
+    m->w().stats.launches += 1;
+  }
+  // control words: lowest failing sample and the total id count, read through the control stream
+  unsigned long long* d = m->w().small.as<unsigned long long>() + 2;
+  CU(dev_fill(d, 0xFF, 8, st));
+  first_bad_unit<<<nblk(S, 256), 256, 0, st>>>(m->w().status.as<int32_t>(), (uint32_t)S, d);
+  m->w().stats.launches += 1;
+  CU(cudaEventRecord(m->w().ev[7], st));
+  CU(cudaEventRecord(m->w().ev_ctl, st));
+  CU(cudaStreamWaitEvent(m->w().stream_ctl, m->w().ev_ctl, 0));
+  CU(cudaMemcpyAsync(m->w().h_words, d, 8, cudaMemcpyDeviceToHost, m->w().stream_ctl));
+  CU(cudaMemcpyAsync(m->w().h_words + 1, d_id_off + S, 8, cudaMemcpyDeviceToHost, m->w().stream_ctl));
+  return TGX_OK;
+}
+
+// Waits for the batch queued on the current workspace; total id count and lowest failing sample (-1 = none).
+int encode_finish(tgx_model* m, uint64_t* total_ids, int64_t* bad) {
+  CU(cudaStreamSynchronize(m->w().stream_ctl));
+  CU(cudaStreamSynchronize(m->w().stream));
+  finish_stats(m, 1);
+  const unsigned long long h = m->w().h_words[0];
+  *bad = (h == ~0ull) ? -1 : (int64_t)h;
+  *total_ids = m->w().h_words[1];
+  return TGX_OK;
+}
+
+}  // namespace
+
 int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
                          uint64_t n_bytes, uint32_t flags, uint32_t* d_ids, uint64_t ids_cap,
                          uint64_t* d_id_off, int32_t* d_status, uint64_t* d_proc_len, uint64_t* total_ids,
@@ -1037,48 +1122,20 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   if (rc) return rc;
   if (!d_off || !d_id_off || (!d_ids && ids_cap)) return fail(TGX_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  m->stats = Stats();
-  cudaStream_t st = m->stream;
   if (first_bad_out) *first_bad_out = -1;
   if (total_ids) *total_ids = 0;
+  if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
   if (S == 0) {
-    CU(dev_fill(d_id_off, 0, 8, st));
-    CU(cudaStreamSynchronize(st));
+    CU(dev_fill(d_id_off, 0, 8, m->w().stream));
+    CU(cudaStreamSynchronize(m->w().stream));
     return TGX_OK;
   }
-  CU(cudaEventRecord(m->ev[6], st));
-  const uint8_t* text = d_text;
-  const uint64_t* off = d_off;
-  if (flags & TGX_FLAG_CRLF) {
-    rc = run_crlf(m, d_text, d_off, S, n_bytes);
-    if (rc) return rc;
-    text = m->text2.as<uint8_t>();
-    off = m->off2.as<uint64_t>();
-  }
-  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len);
+  rc = encode_enqueue(m, d_text, d_off, S, n_bytes, flags, d_ids, ids_cap, d_id_off, d_status, d_proc_len);
   if (rc) return rc;
-  // id offsets = exclusive scan of token counts (S+1 entries; ntok[S] was zeroed)
-  size_t tmp = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, m->ntok.as<unsigned long long>(),
-                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
-  CU(m->cubtmp.reserve(tmp));
-  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, m->ntok.as<unsigned long long>(),
-                                   reinterpret_cast<unsigned long long*>(d_id_off), (int)(S + 1), st));
-  m->stats.launches += 2;
-  rc = run_emit(m, text, n_bytes, d_ids, ids_cap, nullptr);
-  if (rc) return rc;
-  if (d_status) {  // (a kernel, not a D2D memcpy: keep the compute stream off the copy engines)
-    copy_u32<<<nblk(S, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(m->status.p),
-                                           reinterpret_cast<uint32_t*>(d_status), S);
-    m->stats.launches += 1;
-  }
-  unsigned long long tot = 0;
+  uint64_t tot = 0;
   int64_t bad = -1;
-  rc = first_bad(m, (uint32_t)S, &bad, d_id_off + S, &tot);  // waits for the whole chunk
+  rc = encode_finish(m, &tot, &bad);
   if (rc) return rc;
-  CU(cudaEventRecord(m->ev[7], st));
-  CU(cudaStreamSynchronize(st));
-  finish_stats(m, 1);
   if (total_ids) *total_ids = tot;
   if (first_bad_out) *first_bad_out = bad;
   if (tot > ids_cap) return fail(TGX_ERR_CAPACITY, "ids capacity too small: need " + std::to_string(tot));
@@ -1130,7 +1187,6 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
   // rebased offsets travel through pinned staging (one slice per chunk, alive until the end)
   if (m->h_off_cap < S + K + 1) {
     if (m->h_off) cudaFreeHost(m->h_off);
-    if (m->h_out) cudaFreeHost(m->h_out);
     m->h_off = nullptr;
     m->h_off_cap = 0;
     CU(cudaHostAlloc(reinterpret_cast<void**>(&m->h_off), (S + K + 1) * 8, cudaHostAllocDefault));
@@ -1154,7 +1210,7 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
     const uint64_t s0 = cut[k], s1 = cut[k + 1], b0 = off[s0], nb = off[s1] - b0;
     uint64_t* ho = m->h_off + s0 + k;
     for (uint64_t i = 0; i <= s1 - s0; i++) ho[i] = off[s0 + i] - b0;
-    cudaStream_t st = K > 1 ? m->stream_h2d : m->stream;
+    cudaStream_t st = K > 1 ? m->stream_h2d : m->w().stream;
     if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 0], st);
     if (nb) CU(cudaMemcpyAsync(d_text[b]->p, text + b0, nb, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_off[b]->p, ho, (s1 - s0 + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1172,9 +1228,34 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
   if (trace) {
     tev.resize(1 + 6 * K);
     for (auto& e : tev) cudaEventCreate(&e);
-    cudaEventRecord(tev[0], m->stream);
+    cudaEventRecord(tev[0], m->w().stream);
   }
+  // Pipeline over chunks k = 0..K-1 with two buffer sets and two workspaces (set / workspace k & 1):
+  //   H2D(k+1) on the copy-in stream, kernels(k+1) QUEUED on the other workspace before the host waits for
+  //   chunk k, D2H(k) on the copy-out stream.  Queuing the next chunk early lets its kernels take over the SMs
+  //   that chunk k's forward kernel frees while its last long samples finish on a few SMs.
+  const bool overlap = K > 1 && m->overlap_chunks;
+  auto enqueue = [&](uint64_t k) -> int {
+    const int b = (int)(k & 1);
+    const uint64_t s0 = cut[k], s1 = cut[k + 1], Sk = s1 - s0, nb = off[s1] - off[s0];
+    m->wi = overlap ? b : 0;
+    if (K > 1) {
+      CU(cudaStreamWaitEvent(m->w().stream, m->ev_h2d[b], 0));
+      if (k >= 2) CU(cudaStreamWaitEvent(m->w().stream, m->ev_d2h[b], 0));  // the set's previous results left the device
+    }
+    int32_t* dst = d_sc[b]->as<int32_t>();
+    uint64_t* dpl = reinterpret_cast<uint64_t*>(d_sc[b]->as<unsigned char>() + ((Sk * 4 + 15) & ~15ull));
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 2], m->w().stream);
+    if (Sk == 0) return TGX_OK;
+    int r = encode_enqueue(m, d_text[b]->as<uint8_t>(), d_off[b]->as<uint64_t>(), Sk, nb, flags,
+                           d_ids[b]->as<uint32_t>(), nb + 4, d_idoff[b]->as<uint64_t>(), dst, dpl);
+    if (r) return r;
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 3], m->w().stream);
+    return TGX_OK;
+  };
   rc = h2d(0);
+  if (rc) return rc;
+  rc = enqueue(0);
   if (rc) return rc;
   uint64_t base = 0;  // ids emitted by earlier chunks
   std::vector<uint64_t> bases(K, 0);
@@ -1184,51 +1265,55 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
   int final_rc = TGX_OK;
   for (uint64_t k = 0; k < K; k++) {
     const int b = (int)(k & 1);
-    const uint64_t s0 = cut[k], s1 = cut[k + 1], Sk = s1 - s0, nb = off[s1] - off[s0];
-    const double t_i0 = now_ms();
+    const uint64_t s0 = cut[k], s1 = cut[k + 1], Sk = s1 - s0;
     if (k + 1 < K) {
       rc = h2d(k + 1);
       if (rc) return rc;
-    }
-    if (trace) fprintf(stderr, "[tgx] chunk %llu: iteration starts at %.2f ms, next H2D enqueued by %.2f ms\n",
-                       (unsigned long long)k, t_i0 - t_begin, now_ms() - t_begin);
-    if (K > 1) {
-      CU(cudaStreamWaitEvent(m->stream, m->ev_h2d[b], 0));
-      if (k >= 2) CU(cudaStreamWaitEvent(m->stream, m->ev_d2h[b], 0));  // the set's previous results left the device
+      if (overlap) {
+        rc = enqueue(k + 1);
+        if (rc) return rc;
+      }
     }
     int32_t* dst = d_sc[b]->as<int32_t>();
     uint64_t* dpl = reinterpret_cast<uint64_t*>(d_sc[b]->as<unsigned char>() + ((Sk * 4 + 15) & ~15ull));
     uint64_t tot = 0;
     int64_t bad = -1;
-    const double t_c0 = now_ms();
-    if (trace) cudaEventRecord(tev[1 + 6 * k + 2], m->stream);
-    rc = tgx_encode_batch_dev(m, d_text[b]->as<uint8_t>(), d_off[b]->as<uint64_t>(), Sk, nb, flags,
-                              d_ids[b]->as<uint32_t>(), nb + 4, d_idoff[b]->as<uint64_t>(), dst, dpl, &tot, &bad);
-    if (rc != TGX_OK && rc != TGX_ERR_NO_PATH) return rc;
+    m->wi = overlap ? b : 0;
+    if (Sk) {
+      rc = encode_finish(m, &tot, &bad);
+      if (rc) return rc;
+    }
     if (trace)
-      fprintf(stderr, "[tgx] chunk %llu/%llu: %llu bytes, enqueue at %.2f ms, kernels done at %.2f ms (device %.2f ms)\n",
-              (unsigned long long)k, (unsigned long long)K, (unsigned long long)nb, t_c0 - t_begin, now_ms() - t_begin,
-              m->stats.total_ms);
-    if (rc == TGX_ERR_NO_PATH && bad_all < 0) {
+      fprintf(stderr, "[tgx] chunk %llu/%llu: kernels done at %.2f ms (device %.2f ms)\n", (unsigned long long)k,
+              (unsigned long long)K, now_ms() - t_begin, m->last_stats.total_ms);
+    if (tot > off[s1] - off[s0] + 4) return fail(TGX_ERR_CUDA, "internal: more ids than bytes");
+    if (bad >= 0 && bad_all < 0) {
       bad_all = (int64_t)s0 + bad;
       keep_err = "no path for sample " + std::to_string(bad_all);
-      final_rc = rc;
+      final_rc = TGX_ERR_NO_PATH;
     }
-    if (trace) cudaEventRecord(tev[1 + 6 * k + 3], m->stream);
-    cudaStream_t st = K > 1 ? m->stream_d2h : m->stream;  // tgx_encode_batch_dev returned synchronised
-    if (trace) cudaEventRecord(tev[1 + 6 * k + 4], st);
-    CU(cudaMemcpyAsync(st_idoff + s0 + k, d_idoff[b]->p, (Sk + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (status && Sk) CU(cudaMemcpyAsync(st_status + s0, dst, Sk * 4, cudaMemcpyDeviceToHost, st));
-    if (proc_len && Sk) CU(cudaMemcpyAsync(st_plen + s0, dpl, Sk * 8, cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = K > 1 ? m->stream_d2h : m->w().stream;  // the chunk's kernels have finished
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 4], st);
+    if (Sk) {
+      CU(cudaMemcpyAsync(st_idoff + s0 + k, d_idoff[b]->p, (Sk + 1) * 8, cudaMemcpyDeviceToHost, st));
+      if (status) CU(cudaMemcpyAsync(st_status + s0, dst, Sk * 4, cudaMemcpyDeviceToHost, st));
+      if (proc_len) CU(cudaMemcpyAsync(st_plen + s0, dpl, Sk * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+      st_idoff[s0 + k] = 0;
+    }
     if (base + tot > ids_cap) overflow = true;
     if (!overflow && tot) CU(cudaMemcpyAsync(ids + base, d_ids[b]->p, tot * 4, cudaMemcpyDeviceToHost, st));
     if (K > 1) CU(cudaEventRecord(m->ev_d2h[b], st));
-    if (trace) cudaEventRecord(tev[1 + 6 * k + 5], st);
-    if (trace) fprintf(stderr, "[tgx] chunk %llu: D2H enqueued by %.2f ms\n", (unsigned long long)k, now_ms() - t_begin);
+    if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 5], st);
     bases[k] = base;
     base += tot;
+    if (!overlap && k + 1 < K) {
+      rc = enqueue(k + 1);
+      if (rc) return rc;
+    }
   }
-  CU(cudaStreamSynchronize(K > 1 ? m->stream_d2h : m->stream));
+  CU(cudaStreamSynchronize(K > 1 ? m->stream_d2h : m->w().stream));
+  m->wi = 0;
   if (trace) {
     fprintf(stderr, "[tgx] all copies done at %.2f ms\n", now_ms() - t_begin);
     cudaDeviceSynchronize();
@@ -1263,18 +1348,18 @@ int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_
   if (rc) return rc;
   if (!d_off || !d_freq) return fail(TGX_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  m->stats = Stats();
-  cudaStream_t st = m->stream;
+  m->w().stats = Stats();
+  cudaStream_t st = m->w().stream;
   if (first_bad_out) *first_bad_out = -1;
   if (S == 0) return TGX_OK;
-  CU(cudaEventRecord(m->ev[6], st));
+  CU(cudaEventRecord(m->w().ev[6], st));
   const uint8_t* text = d_text;
   const uint64_t* off = d_off;
   if (flags & TGX_FLAG_CRLF) {
     rc = run_crlf(m, d_text, d_off, S, n_bytes);
     if (rc) return rc;
-    text = m->text2.as<uint8_t>();
-    off = m->off2.as<uint64_t>();
+    text = m->w().text2.as<uint8_t>();
+    off = m->w().off2.as<uint64_t>();
   }
   rc = run_viterbi(m, text, off, S, n_bytes, nullptr);
   if (rc) return rc;
@@ -1283,13 +1368,13 @@ int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_
   int64_t bad = -1;
   rc = first_bad(m, (uint32_t)S, &bad);
   if (rc) return rc;
-  CU(cudaEventRecord(m->ev[7], st));
+  CU(cudaEventRecord(m->w().ev[7], st));
   CU(cudaStreamSynchronize(st));
   finish_stats(m, 1);
   if (first_bad_out) *first_bad_out = bad;
   if (bad >= 0) {
     uint32_t l = 0;
-    CU(cudaMemcpy(&l, m->ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&l, m->w().ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
     if (bad_len) *bad_len = l;
     return fail(TGX_ERR_NO_PATH, "no path to position " + std::to_string(l) + "/" + std::to_string(l));
   }
@@ -1306,9 +1391,9 @@ int tgx_token_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off
   CU(m->text.reserve(N + 16));
   CU(m->off.reserve((S + 1) * 8));
   CU(m->freq.reserve(m->V * 8 + 8));
-  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
-  CU(dev_fill(m->freq.p, 0, m->V * 8 + 8, m->stream));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->w().stream));
+  CU(dev_fill(m->freq.p, 0, m->V * 8 + 8, m->w().stream));
   rc = tgx_token_frequencies_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, m->freq.as<uint64_t>(),
                                  first_bad_out, bad_len);
   if (rc) return rc;
@@ -1325,55 +1410,55 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   if (!d_off || !d_expected || snippet_len == 0) return fail(TGX_ERR_INVALID, "bad argument");
   if (snippet_len >= (1ull << 31)) return fail(TGX_ERR_INVALID, "snippet_len must be < 2^31");
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  m->stats = Stats();
-  cudaStream_t st = m->stream;
-  CU(cudaEventRecord(m->ev[6], st));
+  m->w().stats = Stats();
+  cudaStream_t st = m->w().stream;
+  CU(cudaEventRecord(m->w().ev[6], st));
   if (bad_sample) *bad_sample = -1;
   if (bad_z) *bad_z = 0.0;
   // 1. snippet table
-  CU(m->ntok.reserve((S + 2) * 16));
-  unsigned long long* cnt = m->ntok.as<unsigned long long>();
+  CU(m->w().ntok.reserve((S + 2) * 16));
+  unsigned long long* cnt = m->w().ntok.as<unsigned long long>();
   unsigned long long* first_unit = cnt + S + 1;
   CU(dev_fill(cnt, 0, (S + 1) * 8, st));
   if (S) {
     snippet_counts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, cnt);
-    m->stats.launches += 1;
+    m->w().stats.launches += 1;
   }
   size_t tmp = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, first_unit, (int)(S + 1), st));
-  CU(m->cubtmp.reserve(tmp));
-  CU(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp, cnt, first_unit, (int)(S + 1), st));
-  m->stats.launches += 2;
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceScan::ExclusiveSum(m->w().cubtmp.p, tmp, cnt, first_unit, (int)(S + 1), st));
+  m->w().stats.launches += 2;
   unsigned long long U64 = 0;
   CU(cudaMemcpyAsync(&U64, first_unit + S, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (U64 >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many snippets in one call (< 2^32)");
   uint32_t U = (uint32_t)U64;
   if (U == 0) {
-    CU(cudaEventRecord(m->ev[7], st));
+    CU(cudaEventRecord(m->w().ev[7], st));
     CU(cudaStreamSynchronize(st));
     return TGX_OK;
   }
-  CU(m->ustart.reserve((size_t)U * 8 + 8));
-  CU(m->ulen.reserve((size_t)U * 4 + 4));
-  CU(m->vals_in.reserve((size_t)U * 4 + 4));
-  CU(m->status.reserve((size_t)U * 4 + 4));
+  CU(m->w().ustart.reserve((size_t)U * 8 + 8));
+  CU(m->w().ulen.reserve((size_t)U * 4 + 4));
+  CU(m->w().vals_in.reserve((size_t)U * 4 + 4));
+  CU(m->w().status.reserve((size_t)U * 4 + 4));
   CU(m->idoff.reserve((size_t)U * 4 + 4));  // unit -> sample
   CU(m->A.reserve((n_bytes + U + 2) * 8));
-  CU(m->small.reserve(64));
-  units_from_snippets<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, first_unit, m->ustart.as<uint64_t>(),
-                                                   m->ulen.as<uint32_t>(), m->vals_in.as<uint32_t>(),
+  CU(m->w().small.reserve(64));
+  units_from_snippets<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, first_unit, m->w().ustart.as<uint64_t>(),
+                                                   m->w().ulen.as<uint32_t>(), m->w().vals_in.as<uint32_t>(),
                                                    m->idoff.as<uint32_t>());
-  m->stats.launches += 1;
+  m->w().stats.launches += 1;
   rc = sort_units(m, U);
   if (rc) return rc;
-  CU(dev_fill(m->status.p, 0, (size_t)U * 4 + 4, st));
+  CU(dev_fill(m->w().status.p, 0, (size_t)U * 4 + 4, st));
 
   FbParams p;
   p.u.text = d_text;
-  p.u.unit_start = m->ustart.as<uint64_t>();
-  p.u.unit_len = m->ulen.as<uint32_t>();
-  p.u.order = m->vals_out.as<uint32_t>();
+  p.u.unit_start = m->w().ustart.as<uint64_t>();
+  p.u.unit_len = m->w().ulen.as<uint32_t>();
+  p.u.order = m->w().vals_out.as<uint32_t>();
   p.u.first = 0;
   p.u.count = U;
   p.u.counts = nullptr;
@@ -1383,7 +1468,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.u.rows = std::max<uint32_t>(1, m->da.max_token_len);
   p.u.W = p.u.rows + 1;
   p.A = m->A.as<double>();
-  p.status = m->status.as<int32_t>();
+  p.status = m->w().status.as<int32_t>();
   p.expected = d_expected;
   p.hot_k = (uint32_t)std::min<uint64_t>(m->V, 4096);
   p.hot_r = 64;
@@ -1395,10 +1480,10 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   // stream; the many short ones run lane-per-snippet beside them.
   uint32_t n_long = 0;
   if (m->g_estep != 32) {
-    uint32_t* counts = m->small.as<uint32_t>();
+    uint32_t* counts = m->w().small.as<uint32_t>();
     uint32_t thr = (uint32_t)std::min<int64_t>(m->estep_long_threshold, 0x7FFFFFFF);
-    split_sorted<<<1, 32, 0, st>>>(m->keys_out.as<uint32_t>(), U, thr, thr, counts);
-    m->stats.launches += 1;
+    split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr, counts);
+    m->w().stats.launches += 1;
     uint32_t h[2];
     CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1411,32 +1496,32 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   pl.u.count = n_long;
   ps.u.first = n_long;
   ps.u.count = U - n_long;
-  CU(cudaEventRecord(m->ev[0], st));
+  CU(cudaEventRecord(m->w().ev[0], st));
   CU(launch_fb_g(m, 32, pl, false, m->stream2));
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
-  CU(cudaEventRecord(m->ev[1], st));
-  CU(cudaEventRecord(m->ev[2], st));
+  CU(cudaEventRecord(m->w().ev[1], st));
+  CU(cudaEventRecord(m->w().ev[2], st));
   CU(launch_fb_g(m, 32, pl, true, m->stream2));
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
-  CU(cudaEventRecord(m->ev[3], st));
+  CU(cudaEventRecord(m->w().ev[3], st));
   CU(cudaEventRecord(m->ev_join, m->stream2));
   CU(cudaStreamWaitEvent(st, m->ev_join, 0));
   if (p.hot_k) {
     fold_hot_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot, p.hot_k, p.hot_r, d_expected);
-    m->stats.launches += 1;
+    m->w().stats.launches += 1;
   }
   int64_t bad = -1;
   rc = first_bad(m, U, &bad);
   if (rc) return rc;
-  CU(cudaEventRecord(m->ev[7], st));
+  CU(cudaEventRecord(m->w().ev[7], st));
   CU(cudaStreamSynchronize(st));
   finish_stats(m, 2);
   if (bad >= 0) {
     uint32_t smp = 0, l = 0;
     uint64_t us = 0;
     CU(cudaMemcpy(&smp, m->idoff.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&l, m->ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&us, m->ustart.as<uint64_t>() + bad, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&l, m->w().ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&us, m->w().ustart.as<uint64_t>() + bad, 8, cudaMemcpyDeviceToHost));
     double z = 0;
     CU(cudaMemcpy(&z, m->A.as<double>() + us + bad + l, 8, cudaMemcpyDeviceToHost));
     if (bad_sample) *bad_sample = smp;
@@ -1458,9 +1543,9 @@ int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, 
   CU(m->text.reserve(N + 16));
   CU(m->off.reserve((S + 1) * 8));
   CU(m->expected.reserve(m->V * 8 + 8));
-  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->stream));
-  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->stream));
-  CU(dev_fill(m->expected.p, 0, m->V * 8 + 8, m->stream));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->w().stream));
+  CU(dev_fill(m->expected.p, 0, m->V * 8 + 8, m->w().stream));
   rc = tgx_expected_counts_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, snippet_len,
                                m->expected.as<double>(), bad_sample, bad_z);
   if (rc) return rc;
