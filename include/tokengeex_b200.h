@@ -124,6 +124,19 @@ int tgx_token_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_
                               uint64_t n_bytes, uint32_t flags, uint64_t* d_freq, int64_t* first_bad,
                               uint64_t* bad_len);
 
+/* Pair-frequency pass of ModelVocabularyMerger::merge (src/merge.rs:36-84): encode every
+ * sample (dropout 0.0) and count the adjacent token-id pairs inside each sample.  pairs[i] = (first id << 32) |
+ * second id and counts[i], for i < *n_pairs, ordered by count descending (`pairs.sort_unstable_by(|a, b|
+ * b.1.cmp(&a.1))`, :83; equal counts — undefined order in the reference — by (first, second) ascending).
+ * TGX_ERR_CAPACITY when there are more than cap distinct pairs (*n_pairs = needed); TGX_ERR_NO_PATH as for encode
+ * (the reference unwraps the error, :59).  One call handles fewer than 2^31 tokens. */
+int tgx_pair_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                         uint64_t* pairs, uint64_t* counts, uint64_t cap, uint64_t* n_pairs, int64_t* first_bad,
+                         uint64_t* bad_len);
+int tgx_pair_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t n_bytes,
+                             uint32_t flags, uint64_t* d_pairs, uint64_t* d_counts, uint64_t cap, uint64_t* n_pairs,
+                             int64_t* first_bad, uint64_t* bad_len);
+
 /* ---- host half of the EM pruning loop (no device work; see tokengeex_b200/csrc/prune_host.cpp) ----
  * ModelVocabularyPruner::run_m_step (src/prune.rs:124-170, digamma :322-335).  kept[i] = 1 iff
  * token i survives (expected[i] >= 0.5 || keep[i]); new_scores[i] = digamma(max(expected[i],

@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         L.orc_log_sum_exp.argtypes = [C.c_double, C.c_double, C.c_int]
         L.orc_run_m_step.restype = C.c_void_p
         L.orc_run_m_step.argtypes = [C.c_void_p, f64p, C.POINTER(C.c_int)]
+        L.orc_pair_frequencies.restype = C.c_int64
+        L.orc_pair_frequencies.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_int, u64p, u64p, C.c_uint64, u64p]
         L.orc_token_frequencies.restype = C.c_int
         L.orc_token_frequencies.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_int, u64p, u64p]
         L.orc_token_alternatives.restype = C.c_uint64
@@ -239,6 +241,21 @@ class OracleModel:
         if rc:
             raise NoPath(int(err[0]), int(err[1]))
         return fr
+
+    def pair_frequencies(self, blob: np.ndarray, off: np.ndarray, threads: int = 1):
+        """Pair-frequency pass of `tokengeex merge` (src/merge.rs:36-84): (pairs u32[n, 2], counts u64[n]),
+        frequency-descending, ties by (first, second) ascending."""
+        L = lib()
+        cap = max(int(off[-1]), 1)
+        pairs = np.zeros(cap, np.uint64)
+        counts = np.zeros(cap, np.uint64)
+        err = np.zeros(2, np.uint64)
+        n = L.orc_pair_frequencies(self._h, _p(blob, u8p), _p(off, u64p), len(off) - 1, threads, _p(pairs, u64p),
+                                   _p(counts, u64p), cap, _p(err, u64p))
+        if n < 0:
+            raise NoPath(int(err[0]), int(err[1]))
+        p = pairs[:n]
+        return np.stack([(p >> np.uint64(32)).astype(np.uint32), (p & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1), counts[:n].copy()
 
     def token_alternatives(self):
         L = lib()

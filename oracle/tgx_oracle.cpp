@@ -37,6 +37,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace orc {
@@ -724,6 +725,45 @@ static int token_frequencies(const Model& m, const uint8_t* blob, const uint64_t
   return err.load();
 }
 
+// ----------------------------------------------------------------------------
+// src/merge.rs:36-84  pair-frequency pass of ModelVocabularyMerger::merge:
+// encode every sample (dropout 0.0) and count adjacent id pairs within the sample
+// (chunk-local FnvHashMaps merged under a lock), then `pairs.sort_unstable_by(|a, b|
+// b.1.cmp(&a.1))`.  sort_unstable leaves the order of equal frequencies undefined;
+// here ties are ordered by (first id, second id) ascending.
+// ----------------------------------------------------------------------------
+static int pair_frequencies(const Model& m, const uint8_t* blob, const uint64_t* off, size_t S, int threads,
+                            std::vector<std::pair<uint64_t, uint64_t>>& out, uint64_t* err_pos, uint64_t* err_len) {
+  size_t chunk = par_chunk_size(S, (size_t)std::max(1, threads), 4);  // :41
+  std::unordered_map<uint64_t, uint64_t> all;
+  std::atomic<int> err{0};
+  std::mutex mu;
+  parallel_chunks(S, chunk, threads, [&](size_t, size_t lo, size_t hi, int) {
+    std::unordered_map<uint64_t, uint64_t> local;  // :56
+    std::vector<uint32_t> ids;
+    uint64_t rng = 0;
+    for (size_t s = lo; s < hi; s++) {
+      uint64_t ep = 0, el = 0;
+      int rc = encode(m, blob + off[s], off[s + 1] - off[s], 0.0, ids, &ep, &el, &rng);  // :59 (.unwrap())
+      if (rc) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!err.load()) { err.store(1); *err_pos = ep; *err_len = el; }
+        return;
+      }
+      for (size_t i = 1; i < ids.size(); i++)  // :61-64
+        local[((uint64_t)ids[i - 1] << 32) | ids[i]] += 1;
+    }
+    std::lock_guard<std::mutex> g(mu);  // :69-74
+    for (auto& kv : local) all[kv.first] += kv.second;
+  });
+  out.assign(all.begin(), all.end());
+  std::sort(out.begin(), out.end(), [](const std::pair<uint64_t, uint64_t>& a, const std::pair<uint64_t, uint64_t>& b) {
+    if (a.second != b.second) return a.second > b.second;  // :83
+    return a.first < b.first;
+  });
+  return err.load();
+}
+
 static int prune_vocab(const Model& m, const uint8_t* blob, const uint64_t* off, size_t S,
                        int threads, size_t target_vocab_size, double shrink_factor,
                        std::vector<ScoredToken>& pruned_vocab, PruneAudit* audit) {
@@ -961,6 +1001,19 @@ int orc_token_frequencies(orc_model* h, const uint8_t* blob, const uint64_t* off
   int rc = token_frequencies(*h->m, blob, off, S, threads, f, &err[0], &err[1]);
   if (!rc) std::memcpy(freq, f.data(), f.size() * 8);
   return rc;
+}
+
+// pairs[i] = (first id << 32) | second id, counts[i]; frequency-descending.  Returns the number of distinct
+// pairs (writes at most cap of them), or -1 on NoPath (err = pos, len).
+int64_t orc_pair_frequencies(orc_model* h, const uint8_t* blob, const uint64_t* off, uint64_t S, int threads,
+                             uint64_t* pairs, uint64_t* counts, uint64_t cap, uint64_t* err) {
+  std::vector<std::pair<uint64_t, uint64_t>> v;
+  if (pair_frequencies(*h->m, blob, off, S, threads, v, &err[0], &err[1])) return -1;
+  for (size_t i = 0; i < v.size() && i < cap; i++) {
+    pairs[i] = v[i].first;
+    counts[i] = v[i].second;
+  }
+  return (int64_t)v.size();
 }
 
 // always_keep[V] and alternatives (CSR: alt_off[V+1], alt_ids[cap]) of prune_vocab.

@@ -285,3 +285,29 @@ def test_full_prune_loop_runs_q20_q22():
     assert m2.V <= 30 or m2.V < 120
     assert iters[-1] == m2.V
     assert all(a >= b for a, b in zip(iters, iters[1:]))
+
+
+def test_pair_frequencies_brute_force():
+    """src/merge.rs:53-84: adjacent id pairs inside each sample, counted over a batch, frequency-descending."""
+    import collections
+    import random
+
+    from tests.util import rand_samples, rand_vocab
+    rng = random.Random(9)
+    for it in range(10):
+        toks, scores = rand_vocab(rng, alphabet=b"abc", n_tok=rng.randrange(4, 40), max_len=5)
+        om = O.OracleModel(toks, scores)
+        samples = rand_samples(rng, b"abc", 60, 0, 80)
+        want = collections.Counter()
+        for s in samples:
+            ids = om.encode(s)
+            for i in range(1, len(ids)):
+                want[(ids[i - 1], ids[i])] += 1
+        blob = np.frombuffer(b"".join(samples) or b"\0", np.uint8).copy()
+        off = np.zeros(len(samples) + 1, np.uint64)
+        off[1:] = np.cumsum([len(s) for s in samples])
+        ab, cnt = om.pair_frequencies(blob, off, threads=3)
+        got = {(int(a), int(b)): int(c) for (a, b), c in zip(ab.tolist(), cnt.tolist())}
+        assert got == dict(want)
+        order = sorted(want.items(), key=lambda kv: (-kv[1], kv[0]))
+        assert [list(k) for k, _ in order] == ab.tolist()

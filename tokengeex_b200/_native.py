@@ -52,6 +52,10 @@ SYMBOLS = [
     ("tgx_token_frequencies", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u64p, i64p, u64p]),
     ("tgx_token_frequencies_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                             C.c_void_p, i64p, u64p]),
+    ("tgx_pair_frequencies", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u64p, u64p, C.c_uint64, u64p, i64p,
+                                       u64p]),
+    ("tgx_pair_frequencies_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                           C.c_void_p, C.c_void_p, C.c_uint64, u64p, i64p, u64p]),
     ("tgx_m_step", C.c_int, [f64p, u8p, C.c_uint64, u8p, f64p, u64p]),
     ("tgx_prune_select", C.c_int, [u8p, u64p, f64p, u8p, C.c_uint64, u64p, C.c_uint64, C.c_uint64, C.c_double,
                                    C.c_int, u32p, u64p, f64p]),
@@ -212,6 +216,29 @@ class Model:
                                          _p(fr, u64p), C.byref(bad), C.byref(blen))
         _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
         return fr[:self.V], rc, int(bad.value), int(blen.value)
+
+    def pair_frequencies(self, blob: np.ndarray, off: np.ndarray, crlf: bool = False, cap: int = 0):
+        """Pair-frequency pass of `tokengeex merge` (/root/reference/src/merge.rs:36-84)
+        → (pairs u32[n, 2], counts u64[n], rc, first_bad, bad_len); count-descending, ties by ids ascending."""
+        S = len(off) - 1
+        cap = int(cap) or max(1, min(int(off[-1]), 1 << 22))
+        while True:
+            pairs = np.zeros(cap, np.uint64)
+            counts = np.zeros(cap, np.uint64)
+            n = C.c_uint64(0)
+            bad = C.c_int64(-1)
+            blen = C.c_uint64(0)
+            rc = lib().tgx_pair_frequencies(self._h, _p(blob, u8p), _p(off, u64p), S, TGX_FLAG_CRLF if crlf else 0,
+                                            _p(pairs, u64p), _p(counts, u64p), cap, C.byref(n), C.byref(bad),
+                                            C.byref(blen))
+            if rc == TGX_ERR_CAPACITY and int(n.value) > cap:
+                cap = int(n.value)
+                continue
+            _check(rc, (TGX_OK, TGX_ERR_NO_PATH))
+            k = int(n.value)
+            p = pairs[:k]
+            ab = np.stack([(p >> np.uint64(32)).astype(np.uint32), (p & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1)
+            return ab, counts[:k].copy(), rc, int(bad.value), int(blen.value)
 
     # ---- device-pointer API (torch tensors' data_ptr()) ---------------------------------
     def encode_batch_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, crlf: bool, d_ids: int, ids_cap: int,

@@ -404,6 +404,36 @@ __global__ void add_u64(unsigned long long* __restrict__ dst, const unsigned lon
   if (i < n) dst[i] += src[i];
 }
 
+// pair-frequency pass (src/merge.rs:61-64): key[t] = ids[t-1] * V + ids[t]; the first token of every sample gets
+// the sentinel V * V (sorted behind every real pair) by pair_keys_mark_starts, which runs afterwards.
+__global__ void pair_keys(const uint32_t* __restrict__ ids, unsigned long long T, unsigned long long V,
+                          unsigned long long* __restrict__ keys) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  keys[t] = t ? (unsigned long long)ids[t - 1] * V + ids[t] : V * V;
+}
+__global__ void pair_keys_mark_starts(const uint64_t* __restrict__ id_off, uint64_t S, unsigned long long V,
+                                      unsigned long long* __restrict__ keys) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  if (id_off[s] < id_off[s + 1]) keys[id_off[s]] = V * V;
+}
+// n_pairs = runs that are not the sentinel run (the sentinel, if present, is the last run of the sorted keys)
+__global__ void pair_count_runs(const unsigned long long* __restrict__ uniq, const unsigned long long* __restrict__ num_runs,
+                                unsigned long long V, unsigned long long* __restrict__ n_pairs) {
+  if (threadIdx.x || blockIdx.x) return;
+  unsigned long long n = *num_runs;
+  if (n && uniq[n - 1] == V * V) n--;
+  *n_pairs = n;
+}
+__global__ void pair_unpack(const unsigned long long* __restrict__ packed, unsigned long long n, unsigned long long V,
+                            unsigned long long* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = packed[i];
+  out[i] = ((k / V) << 32) | (k % V);
+}
+
 }  // namespace tgxk
 
 // =========================================================================================
@@ -1398,6 +1428,107 @@ int tgx_token_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off
                                  first_bad_out, bad_len);
   if (rc) return rc;
   CU(cudaMemcpy(freq, m->freq.p, m->V * 8, cudaMemcpyDeviceToHost));
+  return TGX_OK;
+}
+
+// ---------------------------------------------------------------------------- pair-frequency pass (merge)
+int tgx_pair_frequencies_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t n_bytes,
+                             uint32_t flags, uint64_t* d_pairs, uint64_t* d_counts, uint64_t cap, uint64_t* n_pairs,
+                             int64_t* first_bad_out, uint64_t* bad_len) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!d_off || !n_pairs || (cap && (!d_pairs || !d_counts))) return fail(TGX_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  *n_pairs = 0;
+  if (first_bad_out) *first_bad_out = -1;
+  if (S == 0 || n_bytes == 0) return TGX_OK;
+  if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
+  // 1. encode into the model's own id buffers
+  CU(m->ids.reserve((n_bytes + 4) * 4));
+  CU(m->idoff.reserve((S + 1) * 8));
+  rc = encode_enqueue(m, d_text, d_off, S, n_bytes, flags, m->ids.as<uint32_t>(), n_bytes + 4, m->idoff.as<uint64_t>(),
+                      nullptr, nullptr);
+  if (rc) return rc;
+  uint64_t T = 0;
+  int64_t bad = -1;
+  rc = encode_finish(m, &T, &bad);
+  if (rc) return rc;
+  if (bad >= 0) {  // the reference unwraps the encode error (src/merge.rs:59)
+    uint32_t l = 0;
+    CU(cudaMemcpy(&l, m->w().ulen.as<uint32_t>() + bad, 4, cudaMemcpyDeviceToHost));
+    if (first_bad_out) *first_bad_out = bad;
+    if (bad_len) *bad_len = l;
+    return fail(TGX_ERR_NO_PATH, "no path to position " + std::to_string(l) + "/" + std::to_string(l));
+  }
+  if (T < 2) return TGX_OK;
+  if (T >= (1ull << 31)) return fail(TGX_ERR_INVALID, "too many tokens in one call (< 2^31); split the batch");
+  // 2. keys -> sort -> run lengths -> sort by count (stable: ties stay key-ascending)
+  cudaStream_t st = m->w().stream;
+  const unsigned long long V = std::max<uint64_t>(m->V, 1);
+  int key_bits = 1;
+  while (key_bits < 64 && (V * V) >> key_bits) key_bits++;
+  DevBuf& kb = m->w().bp;      // scratch, free again after the encode: keys | sorted keys
+  DevBuf& ub = m->w().mark;    //                                      unique | counts | counts sorted | unique sorted
+  DevBuf& nb = m->w().small;
+  CU(kb.reserve(T * 16 + 64));
+  CU(ub.reserve(T * 32 + 64));
+  unsigned long long* keys = kb.as<unsigned long long>();
+  unsigned long long* keys_sorted = keys + T;
+  unsigned long long* uniq = ub.as<unsigned long long>();
+  unsigned long long* cnt = uniq + T;
+  unsigned long long* cnt_sorted = cnt + T;
+  unsigned long long* uniq_sorted = cnt_sorted + T;
+  unsigned long long* d_runs = nb.as<unsigned long long>() + 6;
+  unsigned long long* d_np = nb.as<unsigned long long>() + 7;
+  pair_keys<<<nblk(T, 256), 256, 0, st>>>(m->ids.as<uint32_t>(), T, V, keys);
+  pair_keys_mark_starts<<<nblk(S, 256), 256, 0, st>>>(m->idoff.as<uint64_t>(), S, V, keys);
+  size_t tmp = 0;
+  CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, keys_sorted, (int)T, 0, key_bits, st));
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceRadixSort::SortKeys(m->w().cubtmp.p, tmp, keys, keys_sorted, (int)T, 0, key_bits, st));
+  CU(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, keys_sorted, uniq, cnt, d_runs, (int)T, st));
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceRunLengthEncode::Encode(m->w().cubtmp.p, tmp, keys_sorted, uniq, cnt, d_runs, (int)T, st));
+  pair_count_runs<<<1, 32, 0, st>>>(uniq, d_runs, V, d_np);
+  unsigned long long np = 0;
+  rc = read_words(m, d_np, nullptr, &np, nullptr);
+  if (rc) return rc;
+  *n_pairs = np;
+  if (np == 0) return TGX_OK;
+  if (np > cap) return fail(TGX_ERR_CAPACITY, "pair capacity too small: need " + std::to_string(np));
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, cnt, cnt_sorted, uniq, uniq_sorted, (int)np, 0, 64, st));
+  CU(m->w().cubtmp.reserve(tmp));
+  CU(cub::DeviceRadixSort::SortPairsDescending(m->w().cubtmp.p, tmp, cnt, cnt_sorted, uniq, uniq_sorted, (int)np, 0, 64, st));
+  pair_unpack<<<nblk(np, 256), 256, 0, st>>>(uniq_sorted, np, V, reinterpret_cast<unsigned long long*>(d_pairs));
+  copy_u32<<<nblk(np * 2, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(cnt_sorted),
+                                              reinterpret_cast<uint32_t*>(d_counts), np * 2);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  return TGX_OK;
+}
+
+int tgx_pair_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off, uint64_t S, uint32_t flags,
+                         uint64_t* pairs, uint64_t* counts, uint64_t cap, uint64_t* n_pairs, int64_t* first_bad_out,
+                         uint64_t* bad_len) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!off || !n_pairs || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  const uint64_t N = off[S];
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  CU(m->text.reserve(N + 16));
+  CU(m->off.reserve((S + 1) * 8));
+  CU(m->freq.reserve(cap * 16 + 16));
+  CU(cudaMemcpyAsync(m->text.p, text, N, cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaMemcpyAsync(m->off.p, off, (S + 1) * 8, cudaMemcpyHostToDevice, m->w().stream));
+  uint64_t* d_pairs = m->freq.as<uint64_t>();
+  uint64_t* d_counts = d_pairs + cap;
+  rc = tgx_pair_frequencies_dev(m, m->text.as<uint8_t>(), m->off.as<uint64_t>(), S, N, flags, d_pairs, d_counts, cap, n_pairs,
+                                first_bad_out, bad_len);
+  if (rc) return rc;
+  if (*n_pairs) {
+    CU(cudaMemcpy(pairs, d_pairs, *n_pairs * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(counts, d_counts, *n_pairs * 8, cudaMemcpyDeviceToHost));
+  }
   return TGX_OK;
 }
 
