@@ -314,6 +314,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION/INFO prints to stdout, which has to carry exactly one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("TGX_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
