@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--what", default="encode,estep")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--single", type=int, default=0, help="encode only the N longest samples")
+    ap.add_argument("--estep-cfgs", default="", help="comma list of G:threshold pairs for the E-step")
     ap.add_argument("--algos", default="", help="comma list of forward algos to time (default all)")
     args = ap.parse_args()
     import torch
@@ -64,8 +65,10 @@ def main():
             rc, bad, bl = m.token_frequencies_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, False, d_fr.data_ptr())
             print(f"freq: {m.stat(4):.2f} ms  {NB / m.stat(4) / 1e6:.2f} GB/s sum={int(d_fr.sum())}", flush=True)
     if "estep" in what:
-        for g, thr in [(1, 1 << 30), (2, 1 << 30), (4, 1 << 30), (8, 1 << 30), (16, 1 << 30), (32, 1 << 30), (1, 4096),
-                       (2, 8192), (4, 16384), (8, 32768)]:
+        cfgs = [(4, 16384), (4, 32768), (4, 65536), (8, 32768), (8, 65536), (2, 16384), (2, 32768), (4, 8192)]
+        if args.single == 0 and args.estep_cfgs:
+            cfgs = [tuple(int(x) for x in c.split(":")) for c in args.estep_cfgs.split(",")]
+        for g, thr in cfgs:
             m.set_option(2, g)
             m.set_option(5, thr)
             for _ in range(args.reps):
