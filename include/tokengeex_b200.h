@@ -169,7 +169,7 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  * algorithm when max_token_len <= 16 (0 = pair-CTA kernel, the default; 1 = lane-group kernels; 2 = thread-per-sample
  * lane kernel; 3 = hybrid of 0 and 2),
  * 4 = producer warps per consumer warp of the pair kernel (2 or 4), 5 = E-step byte threshold from
- * which a snippet gets a full warp, 6 = consumer/producer groups per CTA of the pair kernel (0 = as
+ * which a snippet gets a full warp (0 = automatic, from the batch size), 6 = consumer/producer groups per CTA of the pair kernel (0 = as
  * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch, 8 = byte threshold from which a sample
  * goes to the pair body of the hybrid kernel, 9 = warps per CTA of the lane kernel (1..16), 10 = CTAs of the hybrid
  * kernel that start on the long samples, 11 = chunked host entry point queues the next chunk's kernels before the

@@ -108,7 +108,11 @@ struct tgx_model {
   int g_short = 8;
   int64_t long_threshold = 512;  // samples at least this long: full warp (lane-group forward kernels, backtrack)
   int g_estep = 4;
-  int64_t estep_long_threshold = 16384;  // snippets at least this long get a full warp (G = 32) on a second stream
+  // Snippets at least this long get a full warp (G = 32) on a second stream.  0 = automatic: a G-lane group runs a
+  // position in ~8 us, so the longest snippet handed to the lane groups should not outlast the batch itself
+  // (~3 GB/s): threshold = max(8192, n_bytes / 18000) — beyond 1.5 GB no snippet (<= 81920 B) takes the warp path
+  // (tools/probe.py --what estep at 0.2, 0.6, 2 and 4 GB: best thresholds 16 K, 32 K, >= 64 K, none)
+  int64_t estep_long_threshold = 0;
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
   // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
@@ -1022,7 +1026,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 0: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per sample must be 1,2,4,8,16,32"); m->g_short = (int)value; break;
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
-    case 5: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->estep_long_threshold = value; break;
+    case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
@@ -1612,7 +1616,9 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   uint32_t n_long = 0;
   if (m->g_estep != 32) {
     uint32_t* counts = m->w().small.as<uint32_t>();
-    uint32_t thr = (uint32_t)std::min<int64_t>(m->estep_long_threshold, 0x7FFFFFFF);
+    int64_t thr64 = m->estep_long_threshold;
+    if (thr64 <= 0) thr64 = std::max<int64_t>(8192, (int64_t)(n_bytes / 18000));
+    uint32_t thr = (uint32_t)std::min<int64_t>(thr64, 0x7FFFFFFF);
     split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr, counts);
     m->w().stats.launches += 1;
     uint32_t h[2];
