@@ -312,6 +312,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the native arm)")
     torch.cuda.set_device(local)
+    numa_node = None
+    if world > 1 and not os.environ.get("TGX_NO_NUMA_BIND"):
+        from tokengeex_b200.dist import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)  # host buffers next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG=VERSION/INFO prints to stdout, which has to carry exactly one JSON line
@@ -457,7 +461,8 @@ def main():
                 "config": {"workload": wname, "vocab": len(toks), "max_token_len": MAX_TOKEN_LEN,
                            "processor": "crlf", "bytes_per_gpu": NB, "samples_per_gpu": S,
                            "l2": "inputs (1 GB/GPU) larger than L2; no flush needed",
-                           "trie_slots": int(info.trie_slots), "parallelism": f"sample-sharded x{world}, no collective"},
+                           "trie_slots": int(info.trie_slots), "parallelism": f"sample-sharded x{world}, no collective",
+                           "host_numa_node_rank0": numa_node, "host_threads_rank0": synth.n_threads()},
                 "gpu_launches": launches * args.steps,
                 "clocks": clk,
                 "e2e": e2e,

@@ -354,3 +354,24 @@ def test_expected_counts_synth_vs_oracle(N):
         assert np.all(ex[~nz] == 0)
         lens = np.array([len(t) for t in toks], dtype=np.float64)
         assert abs(float((ex * lens).sum()) - int(off[-1])) < 1e-9 * int(off[-1])
+
+
+def test_very_long_samples(N):
+    """Samples far beyond the 64-position rounds, the 1024-position backtrack chunks and the 81920-byte snippet
+    length of the E-step (src/prune.rs:75,83): one of 400 KB, one of exactly 2 * 81920 bytes, one of 81920 + 1."""
+    rng = random.Random(2024)
+    toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=150, max_len=10)
+    gm, om = both(N, toks, scores)
+    samples = [bytes(rng.choice(b"abcd") for _ in range(n)) for n in (400_000, 2 * 81920, 81921, 7, 0, 81920)]
+    for algo in (0, 1):
+        gm.set_option(3, algo)
+        check_against_oracle(N, gm, om, samples, algo)
+    gm.set_option(3, 0)
+    blob, off = N.pack(samples)
+    ex, rc, bad, badz = gm.expected_counts(blob, off)
+    want = om.run_e_step(blob, off, threads=8)[0]
+    nz = want > 0
+    assert rc == 0 and float(np.max(np.abs(ex[nz] - want[nz]) / want[nz])) < REL_TOL
+    assert np.all(ex[~nz] == 0)
+    fr = gm.token_frequencies(blob, off)[0]
+    assert np.array_equal(fr, om.token_frequencies(blob, off, threads=8))

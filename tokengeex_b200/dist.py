@@ -73,3 +73,32 @@ class Collective:
 
     def __call__(self, v: np.ndarray) -> np.ndarray:
         return self.allreduce(v)
+
+
+def bind_to_gpu_numa_node(device: int) -> Optional[int]:
+    """Pin the calling process (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs off, so
+    that pinned host buffers are allocated next to the GPU's PCIe root (first touch) and the H2D / D2H copies of
+    several ranks do not cross the socket interconnect.  Returns the node, or None when it cannot be determined
+    (single-node machine, sysfs not available): then nothing is changed."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bus = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{getattr(p, 'pci_device_id', 0):02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
