@@ -173,7 +173,9 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch, 8 = byte threshold from which a sample
  * goes to the pair body of the hybrid kernel, 9 = warps per CTA of the lane kernel (1..16), 10 = CTAs of the hybrid
  * kernel that start on the long samples, 11 = chunked host entry point queues the next chunk's kernels before the
- * current chunk has finished (0 = off, the default). */
+ * current chunk has finished (0 = off, the default), 13 = leading trie levels the pair kernel may stage in shared
+ * memory (0..2), 14 = shape of the pair kernel (0 = by batch size, 1 = 5 groups / lowest latency per sample, 2 = 6
+ * groups / highest throughput). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

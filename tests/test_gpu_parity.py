@@ -90,9 +90,9 @@ def test_random_small_vs_oracle(N, g, thr):
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
 
 
-@pytest.mark.parametrize("producers", [2, 4])
-def test_random_small_vs_oracle_cta(N, producers):
-    """CTA-cooperative producer/consumer kernel (the default path)."""
+@pytest.mark.parametrize("producers,shape", [(2, 1), (4, 1), (2, 2), (4, 2)])
+def test_random_small_vs_oracle_cta(N, producers, shape):
+    """CTA-cooperative producer/consumer kernel (the default path), both shapes (option 14: 5 / 6 groups per CTA)."""
     rng = random.Random(300 + producers)
     for it in range(25):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 12),
@@ -100,6 +100,7 @@ def test_random_small_vs_oracle_cta(N, producers):
         gm, om = both(N, toks, scores)
         gm.set_option(3, 0)  # pair-CTA kernel
         gm.set_option(4, producers)
+        gm.set_option(14, shape)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 400)
         got, status, plen, rc, bad = gpu_encode(N, gm, samples)
         for i, s in enumerate(samples):
@@ -110,8 +111,8 @@ def test_random_small_vs_oracle_cta(N, producers):
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
 
 
-@pytest.mark.parametrize("producers", [2, 4])
-def test_pair_kernel_full_window(N, producers):
+@pytest.mark.parametrize("producers,shape,hot", [(2, 1, 2), (4, 1, 2), (4, 2, 1), (2, 2, 0), (4, 1, 0)])
+def test_pair_kernel_full_window(N, producers, shape, hot):
     """Tokens of every length 1..16 (length 16 re-uses the dp cell that is being finalised), samples that span many
     32-position tiles and rounds, sample switches inside a CTA, unreachable stretches, exact ties."""
     rng = random.Random(900 + producers)
@@ -124,6 +125,8 @@ def test_pair_kernel_full_window(N, producers):
         gm, om = both(N, toks, scores)
         gm.set_option(3, 0)  # pair-CTA kernel
         gm.set_option(4, producers)
+        gm.set_option(14, shape)
+        gm.set_option(13, hot)  # trie levels staged in shared memory
         samples = rand_samples(rng, alphabet, rng.randrange(3, 40), 0, 5000)
         samples += [alphabet[:1] * rng.randrange(1, 700), alphabet[1:2] * 333, alphabet[:2] * 517, b""]
         got, status, plen, rc, bad = gpu_encode(N, gm, samples)

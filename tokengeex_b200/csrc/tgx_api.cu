@@ -132,6 +132,9 @@ struct tgx_model {
   // chunk's persistent forward CTAs take every SM the moment the current forward kernel drains, and the current
   // chunk's backtrack / emit kernels then wait for registers until those CTAs exit.
   int overlap_chunks = 0;
+  int hot_levels = 2;  // leading trie levels the pair kernel may stage in shared memory (0..2)
+  int pair_shape = 0;  // 0 = by batch size, 1 = latency shape (5 groups), 2 = throughput shape (6 groups)
+  uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
   DevBuf text, off, idoff, A, expected, freq, ids, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
 };
@@ -471,45 +474,51 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
   return cudaGetLastError();
 }
 
-template <int R, int HOT>
+template <int R, int HOT, int MAXT>
 cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   constexpr int WG = 2 * R + 1;
   const size_t budget = (size_t)m->smem_optin;
   uint32_t groups = (uint32_t)std::min<size_t>({(budget - (size_t)p.hot_slots * 16) / pair_group_bytes(R),
-                                                (size_t)((R == 1 ? 960 : 800) / (32 * WG)), (size_t)15});
+                                                (size_t)(MAXT / (32 * WG)), (size_t)15});
   if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
   groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
   p.groups = groups;
   const size_t smem = pair_smem_bytes(R, groups, p.hot_slots);
-  cudaError_t e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // whatever the tables leave of the 256 KB L1/shared array caches trie slots beyond the staged prefix
-  e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1));
   if (e != cudaSuccess) return e;
   const uint32_t grid =
       (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
   e = dev_fill(p.counter, 0, 4, m->w().stream);
   if (e != cudaSuccess) return e;
-  viterbi_pair_kernel<R, HOT><<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
+  viterbi_pair_kernel<R, HOT, MAXT><<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
   m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
+// Two shapes (measured on B200, tools/probe.py, 1 GB / the 16 longest samples alone):
+//   latency   5 groups, two trie levels in shared memory, 72 registers: 35.8 ms / 13.5 ms
+//   throughput  6 groups (R = 2) with one staged level, 64 registers:    33.5 ms / 16.0 ms
+// A batch is bound by its longest sample unless it is large, so the throughput shape is used from
+// `wide_bytes` input bytes on (the chunks of the host entry point stay below it).
 template <int R>
-cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p) {
-  // stage as many leading trie levels in shared memory as fit a quarter of it
+cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p, uint64_t n_bytes) {
   const size_t cap = (size_t)m->smem_optin / 4;
-  if ((size_t)m->da.hot[2] * 16 <= cap) {
+  const bool wide = m->pair_shape == 2 || (m->pair_shape == 0 && n_bytes >= m->wide_bytes);
+  const int levels = std::min(m->hot_levels, wide ? 1 : 2);
+  if (levels >= 2 && (size_t)m->da.hot[2] * 16 <= cap) {
     p.hot_slots = m->da.hot[2];
-    return launch_viterbi_pair<R, 2>(m, p);
+    return wide ? launch_viterbi_pair<R, 2, 960>(m, p) : launch_viterbi_pair<R, 2, 800>(m, p);
   }
-  if ((size_t)m->da.hot[1] * 16 <= cap) {
+  if (levels >= 1 && (size_t)m->da.hot[1] * 16 <= cap) {
     p.hot_slots = m->da.hot[1];
-    return launch_viterbi_pair<R, 1>(m, p);
+    return wide ? launch_viterbi_pair<R, 1, 960>(m, p) : launch_viterbi_pair<R, 1, 800>(m, p);
   }
   p.hot_slots = 0;
-  return launch_viterbi_pair<R, 0>(m, p);
+  return wide ? launch_viterbi_pair<R, 0, 960>(m, p) : launch_viterbi_pair<R, 0, 800>(m, p);
 }
 
 constexpr int LANE_KW = 3, LANE_KC = 2;
@@ -762,9 +771,9 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.dbg = getenv("TGX_DBG") ? (uint32_t)atoi(getenv("TGX_DBG")) : 0u;
     if (!p.u.count) {
     } else if (m->producers >= 4) {
-      CU(launch_viterbi_pair_r<2>(m, p));
+      CU(launch_viterbi_pair_r<2>(m, p, N));
     } else {
-      CU(launch_viterbi_pair_r<1>(m, p));
+      CU(launch_viterbi_pair_r<1>(m, p, N));
     }
   } else {
     ViterbiParams p;
@@ -1031,6 +1040,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
     case 11: m->overlap_chunks = value ? 1 : 0; break;
+    case 14: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "pair shape must be 0..2"); m->pair_shape = (int)value; break;
+    case 13: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "hot levels must be 0..2"); m->hot_levels = (int)value; break;
     case 10: if (value < 0 || value > 1024) return fail(TGX_ERR_INVALID, "pair CTAs must be 0..1024"); m->pair_ctas = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;

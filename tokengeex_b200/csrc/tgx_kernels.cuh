@@ -472,8 +472,10 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
   }
 }
 
-template <int R, int HOT>
-__global__ void __launch_bounds__(R == 1 ? 960 : 800, 1) viterbi_pair_kernel(PairParams p) {
+// MAXT = threads the kernel is compiled for: 800 (5 groups of 5 warps, 72 registers, no spills: the lowest latency per
+// chain) or 960 (6 groups when R = 2, 10 when R = 1; 64 registers).
+template <int R, int HOT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   pair_body<R, HOT>(p, smem);
 }

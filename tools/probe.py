@@ -42,7 +42,7 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        cfgs = [(0, {6: 0}), (0, {6: 4}), (0, {6: 3}), (0, {6: 2}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
+        cfgs = [(0, {14: 0}), (0, {14: 1}), (0, {14: 2}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
                 (3, {9: 12, 8: 32768, 10: 48}), (3, {9: 8, 8: 24576, 10: 64})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
