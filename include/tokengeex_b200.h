@@ -163,6 +163,12 @@ int tgx_host_free(void* p);
  * host entry point these describe the LAST chunk.) */
 double tgx_model_last_stat(const tgx_model* m, int what);
 
+/* Developer counters of forward algorithm 4 (only collected when the environment variable TGX_SEG_DBG is set):
+ * out8[0] = segments, [1] = hard because longer than the solver's limit, [2] = hard because of a tie or near tie,
+ * [3] = hard because the segment end is unreachable, [4] = bytes in hard segments, [5] = exact segment solves,
+ * [6] = 16-start tiles walked by them, [7] = chain steps of 256 bytes. */
+int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
+
 /* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units of the lane-group
  * kernels (1,2,4,8,16,32), 1 = byte threshold from which a unit gets a full warp (lane-group forward
  * kernels; warp-cooperative backtrack), 2 = lanes per snippet in the E-step, 3 = Viterbi forward

@@ -152,7 +152,66 @@ def check_against_oracle(N, gm, om, samples, ctx=None):
     assert bad == first_bad and (rc == 0) == (first_bad < 0), (ctx, rc, bad, first_bad)
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+@pytest.mark.parametrize("hot", [0, 1, 2])
+def test_segment_kernels_random_vs_oracle(N, hot):
+    """Forward algo 4 (segment-parallel exact Viterbi, tgx_seg_kernels.cuh): random vocabularies incl. incomplete ones
+    (NoPath, unreachable stretches), integer scores (exact ties: every tied segment goes through the exact chain),
+    tokens of every length up to 16, samples crossing many 512-boundary tiles, empty samples."""
+    rng = random.Random(1700 + hot)
+    for it in range(30):
+        alphabet = [b"ab", b"abcd", b"abc"][it % 3]
+        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(4, 300), max_len=rng.randrange(1, 17),
+                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 4)
+        gm.set_option(15, hot)
+        samples = rand_samples(rng, alphabet, rng.randrange(1, 200), 0, 700) + rand_samples(rng, alphabet, 4, 1000, 9000)
+        samples += [alphabet[:1] * k for k in (1, 15, 16, 17, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
+        rng.shuffle(samples)
+        check_against_oracle(N, gm, om, samples, it)
+
+
+def test_segment_kernels_long_segments(N):
+    """Vocabularies whose tokens overlap everywhere (no cuts for thousands of bytes): every segment is longer than
+    SG_MAXSEG, so P2 solves whole samples exactly, tile after tile of 16 starts, through its 64-slot dp ring."""
+    rng = random.Random(1801)
+    for it in range(6):
+        toks = [b"a", b"b"] + [bytes(rng.choice(b"ab") for _ in range(rng.randrange(2, 17))) for _ in range(600)]
+        toks = sorted(set(toks))
+        scores = [-(rng.random() * 6 + 0.5) if it % 2 else -float(rng.randrange(2, 6)) for _ in toks]
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 4)
+        samples = rand_samples(rng, b"ab", 30, 0, 3000) + [b"ab" * 4000, b"a" * 70000, b"aab" * 1000]
+        check_against_oracle(N, gm, om, samples, it)
+
+
+def test_segment_kernels_synth_corpus(N):
+    """Bench-like corpus and vocabulary: ids, offsets and processed lengths bit-exact with and without crlf, device
+    entry point and chunked host entry point; the frequency pass through the same kernels."""
+    blob, off, toks, sc, kp = synth_setup(1, 11, 6_000_000, 32768, 16)
+    gm, om = both(N, toks, sc)
+    gm.set_option(3, 4)
+    for crlf in (True, False):
+        wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=crlf, threads=8)
+        for chunk in (1 << 30, 700_000):
+            gm.set_option(7, chunk)
+            ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=crlf)
+            assert rc == 0 and wbad == 0
+            assert np.array_equal(id_off, wid_off) and np.array_equal(ids, wids) and np.array_equal(plen, wplen)
+    fr, rc, bad, blen = gm.token_frequencies(blob, off)
+    want = om.token_frequencies(blob, off, threads=8)
+    assert rc == 0 and np.array_equal(fr, want)
+    # the pair kernel and the segment kernels agree on a second corpus kind (code + Chinese)
+    blob, off, toks, sc, kp = synth_setup(2, 12, 3_000_000, 20000, 16)
+    gm = N.Model(toks, sc, device=0)
+    gm.set_option(3, 0)
+    a = gm.encode_batch(blob, off, crlf=True)
+    gm.set_option(3, 4)
+    b = gm.encode_batch(blob, off, crlf=True)
+    assert a[4] == 0 and b[4] == 0 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
 def test_long_tokens(N, algo):
     """max_token_len > 16 cannot use the 16-cell windows of the pair / lane kernels: whatever forward algorithm is
     selected, the lane-group kernels take over."""

@@ -62,6 +62,7 @@ SYMBOLS = [
     ("tgx_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("tgx_host_free", C.c_int, [C.c_void_p]),
     ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
+    ("tgx_model_debug_counters", C.c_int, [C.c_void_p, u64p]),
     ("tgx_model_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     ("tgx_model_rebuild", C.c_int, [C.c_void_p, u8p, u64p, f64p, C.c_uint64]),
 ]
@@ -159,6 +160,11 @@ class Model:
 
     def stat(self, what: int) -> float:
         return float(lib().tgx_model_last_stat(self._h, what))
+
+    def debug_counters(self) -> np.ndarray:
+        out = np.zeros(8, np.uint64)
+        _check(lib().tgx_model_debug_counters(self._h, out.ctypes.data_as(u64p)))
+        return out
 
     def common_prefix_search(self, text: bytes):
         n = len(text)

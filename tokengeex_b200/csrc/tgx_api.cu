@@ -21,6 +21,7 @@
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
 #include "tgx_lane_kernel.cuh"
+#include "tgx_seg_kernels.cuh"
 #include "trie_build.h"
 
 namespace {
@@ -80,7 +81,8 @@ struct Workspace {
   cudaEvent_t ev[8] = {};
   Stats stats;
   DevBuf text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt, ntok, status,
-      small;
+      small, ids_at;
+  bool have_ids_at = false;  // the last run_viterbi was forward algo 4: run_emit takes the ids from ids_at
 };
 
 struct tgx_model {
@@ -89,6 +91,10 @@ struct tgx_model {
   int device = -1;
   uint4* d_trie = nullptr;
   size_t trie_cap = 0;  // slots allocated at d_trie
+  // forward algo 4 (tgx_seg_kernels.cuh): token hash, scores by id, max |score|; hash.mask == 0 = not available
+  tgx::TokenHash hash;
+  DevBuf d_hash, d_scores;
+  double wmax = 0;
   Workspace ws[2];
   int wi = 0;  // workspace the next launches go to
   Workspace& w() { return ws[wi]; }
@@ -133,6 +139,8 @@ struct tgx_model {
   // chunk's backtrack / emit kernels then wait for registers until those CTAs exit.
   int overlap_chunks = 0;
   int hot_levels = 2;  // leading trie levels the pair kernel may stage in shared memory (0..2)
+  int emit_hash = 1;   // emit: token ids through the token hash (1 probe per token) instead of re-walking the trie
+  int seg_hot = 1;     // trie levels the segment kernel (algo 4) stages in shared memory
   int pair_shape = 0;  // 0 = by batch size, 1 = latency shape (5 groups), 2 = throughput shape (6 groups)
   uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
@@ -640,6 +648,30 @@ int check_model(tgx_model* m) {
   return TGX_OK;
 }
 
+// Token hash + score table of forward algo 4 (max_token_len <= 16 only); a vocabulary it cannot serve simply leaves
+// hash.mask == 0 and run_viterbi uses the pair kernel.
+int upload_seg_tables(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                      uint64_t V, uint32_t max_token_len) {
+  m->hash.mask = 0;
+  m->hash.slots.clear();
+  m->wmax = 0;
+  if (m->device < 0 || V == 0 || max_token_len == 0 || max_token_len > 16) return TGX_OK;
+  for (uint64_t i = 0; i < V; i++) {
+    const double a = std::fabs(scores[i]);
+    if (!(a <= 1e300)) return TGX_OK;  // NaN / inf scores: not for the margin argument
+    m->wmax = std::max(m->wmax, a);
+  }
+  tgx::TokenHash h;
+  if (!tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty()) return TGX_OK;
+  CU(m->d_hash.reserve(h.slots.size() * sizeof(tgx::Slot)));
+  CU(m->d_scores.reserve(V * 8));
+  CU(cudaMemcpyAsync(m->d_hash.p, h.slots.data(), h.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaMemcpyAsync(m->d_scores.p, scores, V * 8, cudaMemcpyHostToDevice, m->w().stream));
+  CU(cudaStreamSynchronize(m->w().stream));
+  m->hash = std::move(h);
+  return TGX_OK;
+}
+
 // crlf on device: (d_text,d_off) -> (m->w().text2, m->w().off2).  N = total bytes.
 int run_crlf(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N) {
   cudaStream_t st = m->w().stream;
@@ -692,6 +724,100 @@ int sort_units(tgx_model* m, uint32_t U) {
   return TGX_OK;
 }
 
+template <int HOT>
+cudaError_t launch_seg_solve(tgx_model* m, SegParams p) {
+  const size_t smem = seg_smem_bytes(p.hot_slots);
+  cudaError_t e = cudaFuncSetAttribute(seg_solve_kernel<HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int per_sm = (2 * (smem + 1024) <= (size_t)228 * 1024) ? 2 : 1;
+  e = cudaFuncSetAttribute(seg_solve_kernel<HOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)std::min<size_t>(100, per_sm * (smem + 1024) * 100 / (228 * 1024) + 1));
+  if (e != cudaSuccess) return e;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)m->num_sms * per_sm);
+  seg_solve_kernel<HOT><<<grid, SG_THREADS, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
+  return cudaGetLastError();
+}
+
+// Forward algo 4: segment-parallel exact Viterbi (tgx_seg_kernels.cuh).  Same outputs as the pair kernel + backtrack
+// (mark, ntok, status), plus ids_at for run_emit.  The caller has sorted the units and zeroed mark / ntok / status.
+int run_viterbi_seg(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
+                    const UnitParams& u) {
+  cudaStream_t st = m->w().stream;
+  const uint64_t n_em_tiles = (N + EM_TILE - 1) / EM_TILE;
+  const uint64_t words = N / 32 + 4;
+  CU(m->w().bitmap.reserve(words * 4));
+  CU(m->w().ids_at.reserve((n_em_tiles * EM_TILE + 64) * 4));
+  CU(dev_fill(m->w().bitmap.p, 0, words * 4, st));
+  unsigned long long* dbg = nullptr;
+  if (getenv("TGX_SEG_DBG")) {  // developer counters, printed by tools/probe.py through tgx_model_debug_counters
+    CU(m->w().small.reserve(256));
+    dbg = m->w().small.as<unsigned long long>() + 16;
+    CU(dev_fill(dbg, 0, 64, st));
+  }
+  if (S > 1) {
+    crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->w().bitmap.as<uint32_t>());
+    m->w().stats.launches += 1;
+  }
+  CU(cudaEventRecord(m->w().ev[0], st));
+  if (N) {
+    SegParams p;
+    p.text = d_text;
+    p.N = N;
+    p.bitmap = m->w().bitmap.as<uint32_t>();
+    p.bitmap_words = words;
+    p.trie = m->d_trie;
+    p.root_base = m->da.root_base;
+    p.max_len = std::min<uint32_t>(16, m->da.max_token_len);
+    p.hash = m->d_hash.as<uint4>();
+    p.hash_mask = m->hash.mask;
+    p.hash_seed = m->hash.seed;
+    p.sorted_len = m->w().keys_out.as<uint32_t>();
+    p.wmax = m->wmax;
+    p.mark = m->w().mark.as<uint8_t>();
+    p.ids_at = m->w().ids_at.as<uint32_t>();
+    p.n_tiles = (N + SG_TP - 1) / SG_TP;
+    p.dbg = dbg;
+    int levels = std::min(m->seg_hot, 2);
+    while (levels > 0 && seg_smem_bytes(m->da.hot[levels]) > (size_t)m->smem_optin) levels--;
+    p.hot_slots = levels ? m->da.hot[levels] : 0;
+    if (levels == 2) CU(launch_seg_solve<2>(m, p));
+    else if (levels == 1) CU(launch_seg_solve<1>(m, p));
+    else CU(launch_seg_solve<0>(m, p));
+  }
+  CU(cudaEventRecord(m->w().ev[1], st));
+  CU(cudaEventRecord(m->w().ev[2], st));
+  if (S) {
+    ChainParams c;
+    c.text = d_text;
+    c.unit_start = u.unit_start;
+    c.unit_len = u.unit_len;
+    c.order = u.order;
+    c.counts = u.counts;
+    c.trie = m->d_trie;
+    c.root_base = m->da.root_base;
+    c.max_len = std::min<uint32_t>(16, m->da.max_token_len);
+    c.mark = m->w().mark.as<uint8_t>();
+    c.ids_at = m->w().ids_at.as<uint32_t>();
+    c.scores = m->d_scores.as<double>();
+    c.V = (uint32_t)m->V;
+    c.n_tokens = m->w().ntok.as<unsigned long long>();
+    c.status = m->w().status.as<int32_t>();
+    c.counter = m->w().small.as<unsigned int>() + 8;
+    c.dbg = dbg;
+    CU(dev_fill(c.counter, 0, 4, st));
+    const size_t smem = CH_WARPS * CH_WARP_BYTES;
+    CU(cudaFuncSetAttribute(seg_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((S + CH_WARPS - 1) / CH_WARPS, (uint64_t)m->num_sms * 2);
+    seg_chain_kernel<<<grid, CH_WARPS * 32, smem, st>>>(c);
+    m->w().stats.launches += 1;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(m->w().ev[3], st));
+  m->w().have_ids_at = true;
+  return TGX_OK;
+}
+
 // Viterbi over all samples: forward dp (back lengths) + backtrack (token-end marks).  On return
 // m->w().mark holds the length of the token ending at every marked byte, m->w().ntok token counts,
 // m->w().status per-sample status.
@@ -708,7 +834,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   CU(m->w().mark.reserve(n_tiles * EM_TILE + 64));
   CU(m->w().ntok.reserve(((size_t)U + 1) * 8));
   CU(m->w().status.reserve((size_t)U * 4 + 4));
-  CU(m->w().small.reserve(64));
+  CU(m->w().small.reserve(256));
   units_from_samples<<<nblk(U, 256), 256, 0, st>>>(d_off, S, m->w().ustart.as<uint64_t>(), m->w().ulen.as<uint32_t>(),
                                                   m->w().vals_in.as<uint32_t>(), d_proc_len);
   m->w().stats.launches += 1;
@@ -737,6 +863,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.first = 0;
   u.count = U;  // upper bound for the grids
 
+  m->w().have_ids_at = false;
+  if (m->algo == 4 && u.rows <= 16 && m->hash.mask != 0) return run_viterbi_seg(m, d_text, d_off, S, N, u);
   CU(cudaEventRecord(m->w().ev[0], st));
   if (m->algo == 3 && u.rows <= 16) {
     HybridParams hp;
@@ -829,6 +957,7 @@ int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, u
     EmitParams e;
     e.mark = m->w().mark.as<uint4>();
     e.text = d_text;
+    e.text_bytes = N;
     e.n_tiles = n_tiles;
     e.tile_prefix = prefix;
     e.trie = m->d_trie;
@@ -837,6 +966,11 @@ int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, u
     e.cap = ids_cap;
     e.freq = d_freq;
     e.V = (uint32_t)m->V;
+    e.ids_at = m->w().have_ids_at ? m->w().ids_at.as<uint32_t>() : nullptr;
+    const bool use_hash = m->emit_hash && m->hash.mask != 0;
+    e.hash = use_hash ? m->d_hash.as<uint4>() : nullptr;
+    e.hash_mask = use_hash ? m->hash.mask : 0;
+    e.hash_seed = m->hash.seed;
     emit_kernel<<<grid, EM_BLOCK, d_freq ? EM_HOT * 4 : 0, st>>>(e);
     m->w().stats.launches += 4;
     CU(cudaGetLastError());
@@ -935,6 +1069,8 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     m->trie_cap = m->da.slots.size();
     CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->w().stream));
     CU(cudaStreamSynchronize(m->w().stream));
+    int rc = upload_seg_tables(m.get(), token_bytes, token_offsets, scores, vocab_size, m->da.max_token_len);
+    if (rc) return rc;
   }
   *out = m.release();
   return TGX_OK;
@@ -960,6 +1096,8 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
     }
     CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
     CU(cudaStreamSynchronize(m->w().stream));
+    int rc = upload_seg_tables(m, token_bytes, token_offsets, scores, vocab_size, da.max_token_len);
+    if (rc) return rc;
   }
   m->da = std::move(da);
   m->V = vocab_size;
@@ -976,7 +1114,7 @@ void tgx_model_destroy(tgx_model* m) {
     for (auto* b : bufs) b->release();
     for (auto& w : m->ws) {
       DevBuf* wb[] = {&w.text2, &w.off2, &w.bitmap, &w.blk, &w.ustart, &w.ulen, &w.keys_out, &w.vals_in, &w.vals_out,
-                      &w.cubtmp, &w.bp, &w.mark, &w.tilecnt, &w.ntok, &w.status, &w.small};
+                      &w.cubtmp, &w.bp, &w.mark, &w.tilecnt, &w.ntok, &w.status, &w.small, &w.ids_at};
       for (auto* b : wb) b->release();
       for (auto& e : w.ev)
         if (e) cudaEventDestroy(e);
@@ -986,6 +1124,8 @@ void tgx_model_destroy(tgx_model* m) {
       if (w.h_words) cudaFreeHost(w.h_words);
     }
     if (m->d_trie) cudaFree(m->d_trie);
+    m->d_hash.release();
+    m->d_scores.release();
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
     if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
@@ -1036,7 +1176,9 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
-    case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
+    case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
+    case 16: m->emit_hash = value ? 1 : 0; break;
+    case 15: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "segment kernel hot levels must be 0..2"); m->seg_hot = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
     case 11: m->overlap_chunks = value ? 1 : 0; break;
@@ -1063,6 +1205,15 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
     case 6: return m->last_stats.emit_ms;
   }
   return 0;
+}
+
+int tgx_model_debug_counters(tgx_model* m, uint64_t* out8) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!out8 || !m->w().small.p) return fail(TGX_ERR_INVALID, "no counters");
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out8, m->w().small.as<unsigned long long>() + 16, 64, cudaMemcpyDeviceToHost));
+  return TGX_OK;
 }
 
 int tgx_host_alloc(void** p, uint64_t bytes) {
@@ -1591,7 +1742,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   CU(m->w().status.reserve((size_t)U * 4 + 4));
   CU(m->idoff.reserve((size_t)U * 4 + 4));  // unit -> sample
   CU(m->A.reserve((n_bytes + U + 2) * 8));
-  CU(m->w().small.reserve(64));
+  CU(m->w().small.reserve(256));
   units_from_snippets<<<nblk(S, 256), 256, 0, st>>>(d_off, S, snippet_len, first_unit, m->w().ustart.as<uint64_t>(),
                                                    m->w().ulen.as<uint32_t>(), m->w().vals_in.as<uint32_t>(),
                                                    m->idoff.as<uint32_t>());

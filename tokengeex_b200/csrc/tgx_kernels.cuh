@@ -18,6 +18,7 @@
 
 #include "tgx_libm.h"
 #include "tgx_libm_tables.h"
+#include "trie_build.h"
 
 namespace tgxk {
 
@@ -712,6 +713,7 @@ __global__ void __launch_bounds__(EM_BLOCK) mark_count_kernel(const uint4* __res
 struct EmitParams {
   const uint4* mark;
   const uint8_t* text;
+  uint64_t text_bytes;  // readable bytes at text (rounded up to 16)
   uint64_t n_tiles;
   const unsigned long long* tile_prefix;  // exclusive scan of tile_cnt
   const uint4* trie;
@@ -720,18 +722,32 @@ struct EmitParams {
   unsigned long long cap;
   unsigned long long* freq;  // may be null
   uint32_t V;
+  const uint32_t* ids_at;    // forward algo 4: the id of the token ending at every marked byte (no re-walk)
+  // token hash (trie_build.h; built when max_token_len <= 16): ONE probe per token instead of one dependent trie
+  // probe per byte.  hash_mask == 0: not available, walk the trie.
+  const uint4* hash;
+  uint32_t hash_mask;
+  unsigned long long hash_seed;
 };
 
 __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
   __shared__ uint32_t ws[EM_BLOCK / 32];
   __shared__ uint32_t s_tok[EM_TILE];  // (len << 16) | offset of the token's last byte in the tile
+  __shared__ __align__(16) uint8_t s_text[EM_TILE + 16];  // bytes tile * EM_TILE - 16 .. (hash path)
   extern __shared__ uint32_t s_hot[];  // [EM_HOT] when freq
+  const bool staged = p.hash_mask && !p.ids_at && (reinterpret_cast<unsigned long long>(p.text) & 15ull) == 0;
   if (p.freq) {
     for (uint32_t i = threadIdx.x; i < EM_HOT; i += EM_BLOCK) s_hot[i] = 0;
     __syncthreads();
   }
   for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const uint4 v = p.mark[tile * EM_BLOCK + threadIdx.x];
+    if (staged) {  // (text is padded like mark: reading the whole last tile stays inside the allocation)
+      const uint4* t16 = reinterpret_cast<const uint4*>(p.text) + tile * EM_BLOCK;
+      reinterpret_cast<uint4*>(s_text)[threadIdx.x + 1] =
+          (tile * EM_TILE + 16ull * threadIdx.x < p.text_bytes) ? __ldg(t16 + threadIdx.x) : make_uint4(0, 0, 0, 0);
+      if (threadIdx.x == 0) reinterpret_cast<uint4*>(s_text)[0] = tile ? __ldg(t16 - 1) : make_uint4(0, 0, 0, 0);
+    }
     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
     uint32_t c = 0;
 #pragma unroll
@@ -752,14 +768,39 @@ __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
     for (uint32_t k = threadIdx.x; k < total; k += EM_BLOCK) {
       const uint32_t tk = s_tok[k];
       const uint32_t len = tk >> 16;
-      const uint8_t* q = tt + (tk & 0xFFFFu) + 1 - len;  // first byte of the token (may lie in an earlier tile)
-      uint32_t xb = p.root_base;
-      uint4 e = make_uint4(0, 0, 0, 0);
-      for (uint32_t d = 0; d < len; d++) {  // the token is in the vocabulary: no checks needed
-        e = __ldg(p.trie + (xb ^ (0x100u | __ldg(q + d))));
-        xb = e.x >> 9;
+      uint32_t id;
+      if (p.ids_at) {
+        id = __ldg(p.ids_at + tile * EM_TILE + (tk & 0xFFFFu));
+      } else if (p.hash_mask) {
+        unsigned long long lo = 0, hi = 0;
+        if (staged) {  // token bytes from the staged tile (16-byte halo in front: a token may start in the previous tile)
+          const uint8_t* q = s_text + 16 + (tk & 0xFFFFu) + 1 - len;
+          for (uint32_t d = 0; d < len && d < 8; d++) lo |= (unsigned long long)q[d] << (8 * d);
+          for (uint32_t d = 8; d < len; d++) hi |= (unsigned long long)q[d] << (8 * (d - 8));
+        } else {
+          const uint8_t* q = tt + (tk & 0xFFFFu) + 1 - len;
+          for (uint32_t d = 0; d < len && d < 8; d++) lo |= (unsigned long long)__ldg(q + d) << (8 * d);
+          for (uint32_t d = 8; d < len; d++) hi |= (unsigned long long)__ldg(q + d) << (8 * (d - 8));
+        }
+        const unsigned long long key = tgx::token_key(lo, hi, len, p.hash_seed);
+        uint32_t s = tgx::token_key_slot(key, p.hash_mask);
+        id = NONE;
+        for (int it = 0; it < 256; it++) {
+          const uint4 e = __ldg(p.hash + s);
+          if ((((unsigned long long)e.y << 32) | e.x) == key) { id = e.z; break; }
+          if ((e.x | e.y) == 0) break;
+          s = (s + 1) & p.hash_mask;
+        }
+      } else {
+        const uint8_t* q = tt + (tk & 0xFFFFu) + 1 - len;  // first byte of the token (may lie in an earlier tile)
+        uint32_t xb = p.root_base;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        for (uint32_t d = 0; d < len; d++) {  // the token is in the vocabulary: no checks needed
+          e = __ldg(p.trie + (xb ^ (0x100u | __ldg(q + d))));
+          xb = e.x >> 9;
+        }
+        id = e.y & ID_MASK;
       }
-      const uint32_t id = e.y & ID_MASK;
       if (p.ids && base + k < p.cap) p.ids[base + k] = id;
       if (p.freq) {
         if (id < EM_HOT) atomicAdd(s_hot + id, 1u);

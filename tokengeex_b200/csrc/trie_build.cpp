@@ -200,4 +200,63 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   return "";
 }
 
+std::string build_token_hash(const uint8_t* bytes, const uint64_t* off, uint64_t V, TokenHash* out) {
+  out->slots.clear();
+  out->mask = 0;
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < V; i++) {
+    uint64_t len = off[i + 1] - off[i];
+    if (len >= 1 && len <= 16) n++;
+  }
+  uint64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  if (cap > (1ull << 30)) return "vocabulary too large for the token hash";
+  std::vector<std::pair<uint64_t, uint64_t>> lohi(V);
+  for (uint64_t i = 0; i < V; i++) {
+    uint64_t len = off[i + 1] - off[i], lo = 0, hi = 0;
+    if (len >= 1 && len <= 16) {
+      for (uint64_t k = 0; k < len; k++) {
+        uint64_t b = bytes[off[i] + k];
+        if (k < 8) lo |= b << (8 * k); else hi |= b << (8 * (k - 8));
+      }
+    }
+    lohi[i] = {lo, hi};
+  }
+  for (uint64_t attempt = 0; attempt < 64; attempt++) {
+    const uint64_t seed = 0x243F6A8885A308D3ull + attempt * 0x13198A2E03707344ull;
+    std::vector<Slot> slots(cap, Slot{0, 0, 0, 0});
+    const uint32_t mask = (uint32_t)(cap - 1);
+    // ids of a key -> the bytes that own it (to tell a duplicate token from a key collision)
+    bool collision = false;
+    for (uint64_t i = 0; i < V && !collision; i++) {
+      uint32_t len = (uint32_t)(off[i + 1] - off[i]);
+      if (len < 1 || len > 16) continue;
+      const uint64_t key = token_key(lohi[i].first, lohi[i].second, len, seed);
+      uint32_t s = token_key_slot(key, mask);
+      for (;;) {
+        Slot& e = slots[s];
+        const uint64_t k = ((uint64_t)e.y << 32) | e.x;
+        if (k == 0) {
+          e.x = (uint32_t)key; e.y = (uint32_t)(key >> 32); e.z = (uint32_t)i;
+          break;
+        }
+        if (k == key) {
+          const uint64_t j = e.z;  // same key: must be the same bytes (a duplicate token: last id wins)
+          if (off[j + 1] - off[j] == len && lohi[j] == lohi[i]) { e.z = (uint32_t)i; break; }
+          collision = true;
+          break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    if (!collision) {
+      out->slots.swap(slots);
+      out->mask = mask;
+      out->seed = seed;
+      return "";
+    }
+  }
+  return "token hash: could not find a collision-free seed";
+}
+
 }  // namespace tgx

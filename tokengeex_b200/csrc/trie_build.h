@@ -53,6 +53,36 @@ struct DoubleArray {
 std::string build_double_array(const uint8_t* token_bytes, const uint64_t* token_offsets,
                                const double* scores, uint64_t vocab_size, DoubleArray* out);
 
+// ---- token hash: bytes of a vocabulary token (1..16 bytes) -> id, ONE probe instead of one trie probe per byte.
+// Used by the emit kernel, which only ever looks up strings that ARE vocabulary tokens (the marked tokens of the
+// best path), so a 64-bit key stands for the bytes: the builder re-seeds until no two distinct tokens share a key.
+// Same duplicate rule as the trie: the LAST id of equal byte strings wins (src/trie.rs:19).
+#if defined(__CUDACC__)
+#define TGX_HD __host__ __device__
+#else
+#define TGX_HD
+#endif
+// lo = bytes 0..7, hi = bytes 8..15 (little endian, zero beyond len); never returns 0 (0 = empty slot)
+TGX_HD inline uint64_t token_key(uint64_t lo, uint64_t hi, uint32_t len, uint64_t seed) {
+  uint64_t h = (lo ^ seed) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 31;
+  h += (hi ^ (seed >> 7)) * 0xC2B2AE3D27D4EB4Full + (uint64_t)len * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h | 1ull;
+}
+TGX_HD inline uint32_t token_key_slot(uint64_t key, uint32_t mask) { return (uint32_t)(key >> 24) & mask; }
+
+struct TokenHash {
+  std::vector<Slot> slots;  // x,y = key (0 = empty), z = id; open addressing, linear probing
+  uint32_t mask = 0;        // slots.size() - 1 (power of two); 0 = not built
+  uint64_t seed = 0;
+};
+// Builds the table over every token of 1..16 bytes.  Returns "" on success.
+std::string build_token_hash(const uint8_t* token_bytes, const uint64_t* token_offsets, uint64_t vocab_size,
+                             TokenHash* out);
+
 // Host walk (used by Tokenizer::common_prefix_search, src/model.rs:132-138).
 template <class F>
 inline void da_common_prefix_search(const DoubleArray& da, const uint8_t* s, size_t n, F&& f) {
