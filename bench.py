@@ -255,7 +255,7 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     alg = NB + 8 * (S + 1) + 8 * len(vocab)
     out["roofline"] = {"bound": "hbm", "achieved": alg / (e_dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": alg / (e_dev_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
-                       "kernel": "fb_forward_kernel + fb_backward_kernel (whole E-step, device ms)"}
+                       "kernel": "fb_forward/backward_lane_kernel (snippets below the warp threshold) + fb_forward/backward_kernel<32> (whole E-step, device ms)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         threads = synth.n_threads()

@@ -173,7 +173,7 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * kernels (1,2,4,8,16,32), 1 = byte threshold from which a unit gets a full warp (lane-group forward
  * kernels; warp-cooperative backtrack), 2 = lanes per snippet in the E-step, 3 = Viterbi forward
  * algorithm when max_token_len <= 16 (0 = pair-CTA kernel, the default; 1 = lane-group kernels; 2 = thread-per-sample
- * lane kernel; 3 = hybrid of 0 and 2),
+ * lane kernel; 3 = hybrid of 0 and 2; 4 = segment-parallel exact Viterbi, tgx_seg_kernels.cuh),
  * 4 = producer warps per consumer warp of the pair kernel (2 or 4), 5 = E-step byte threshold from
  * which a snippet gets a full warp (0 = automatic, from the batch size), 6 = consumer/producer groups per CTA of the pair kernel (0 = as
  * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch, 8 = byte threshold from which a sample
@@ -181,7 +181,10 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * kernel that start on the long samples, 11 = chunked host entry point queues the next chunk's kernels before the
  * current chunk has finished (0 = off, the default), 13 = leading trie levels the pair kernel may stage in shared
  * memory (0..2), 14 = shape of the pair kernel (0 = by batch size, 1 = 5 groups / lowest latency per sample, 2 = 6
- * groups / highest throughput). */
+ * groups / highest throughput), 15 = trie levels the segment kernels stage in shared memory (0..2), 16 = emit looks
+ * token ids up in the token hash (1, the default when max_token_len <= 16) or re-walks the trie (0), 17 = E-step byte
+ * threshold below which a snippet runs on ONE lane (fb_*_lane_kernel; < 0 = automatic: everything below the full-warp
+ * threshold of key 5, the default; 0 = never, the lane-group kernels of key 2 take them). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

@@ -349,16 +349,27 @@ def test_token_frequencies_exact(N):
 
 
 # ----------------------------------------------------------------------------- E-step
+def estep_cfg(m, g):
+    """g = lanes per snippet of the lane-group kernels (lane-per-snippet kernels off); g = 0: every snippet below
+    the long threshold runs one lane each (fb_*_lane_kernel), the rest a warp each."""
+    if g == 0:
+        m.set_option(17, 1 << 30)
+        m.set_option(2, 4)
+    else:
+        m.set_option(17, 0)
+        m.set_option(2, g)
+
+
 LATTICE_VOCAB = [(b"<", -3.0), (b" value", -6.0), (b">", -3.0), (b"DC value", -8.0), (b"<DC", -4.0),
                  (b"<DC value>", -12.0)]
 
 
-@pytest.mark.parametrize("g", [1, 8, 32])
+@pytest.mark.parametrize("g", [0, 1, 8, 32])
 def test_reference_lattice_marginals(N, g):
     toks = [t for t, _ in LATTICE_VOCAB]
     sc = [s for _, s in LATTICE_VOCAB]
     m = N.Model(toks, sc)
-    m.set_option(2, g)
+    estep_cfg(m, g)
     blob, off = N.pack([b"<DC value>"])
     ex, rc, bad, badz = m.expected_counts(blob, off)
     want = {b"<DC value>": 0.665241, b">": 0.334759, b"<DC": 0.244728, b" value": 0.244728, b"<": 0.090031,
@@ -368,20 +379,20 @@ def test_reference_lattice_marginals(N, g):
         assert abs(e - want[t]) < 5e-7
     # Q7: positions nothing ends at keep log 1
     m = N.Model([b"ab", b"c", b"bc"], [-1.0, -2.0, -3.0])
-    m.set_option(2, g)
+    estep_cfg(m, g)
     blob, off = N.pack([b"abc"])
     ex, rc, bad, badz = m.expected_counts(blob, off)
     assert rc == 0 and np.allclose(ex, [0.5, 0.5, 0.5], rtol=1e-12)
 
 
-@pytest.mark.parametrize("g", [1, 4, 32])
+@pytest.mark.parametrize("g", [0, 1, 4, 32])
 def test_expected_counts_random_vs_oracle(N, g):
     rng = random.Random(200 + g)
     for it in range(20):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(5, 40), max_len=rng.randrange(1, 8),
                                   complete=True)
         gm, om = both(N, toks, scores)
-        gm.set_option(2, g)
+        estep_cfg(gm, g)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 60), 1, 300)
         blob, off = N.pack(samples)
         snip = rng.choice([7, 64, 81920])
@@ -404,10 +415,14 @@ def test_expected_counts_bad_z(N):
 def test_expected_counts_synth_vs_oracle(N):
     blob, off, toks, sc, kp = synth_setup(2, 13, 2_000_000, 30000, 16)
     gm, om = both(N, toks, sc)
-    for g in (1, 8):
-        gm.set_option(2, g)
+    want, wrc, wbad, _ = om.run_e_step(blob, off, threads=8, literal=False)
+    for g in (0, 1, 8, -1):
+        if g >= 0:
+            estep_cfg(gm, g)
+        else:  # the default split: lanes below 16 KB, lane groups above, warps for the longest
+            gm.set_option(17, 16384)
+            gm.set_option(2, 4)
         ex, rc, bad, badz = gm.expected_counts(blob, off)
-        want, wrc, wbad, _ = om.run_e_step(blob, off, threads=8, literal=False)
         assert rc == 0 and wrc == 0
         nz = want > 0
         rel = np.abs(ex[nz] - want[nz]) / want[nz]

@@ -101,6 +101,8 @@ struct tgx_model {
   const Workspace& w() const { return ws[wi]; }
   Stats last_stats;  // of the last finished call (tgx_model_last_stat)
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones (E-step)
+  cudaStream_t stream3 = nullptr;  // lane-per-snippet kernels (E-step)
+  cudaEvent_t ev_join3 = nullptr;
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
   uint64_t* h_off = nullptr;       // pinned staging for rebased chunk offsets
@@ -119,6 +121,12 @@ struct tgx_model {
   // (~3 GB/s): threshold = max(8192, n_bytes / 18000) — beyond 1.5 GB no snippet (<= 81920 B) takes the warp path
   // (tools/probe.py --what estep at 0.2, 0.6, 2 and 4 GB: best thresholds 16 K, 32 K, >= 64 K, none)
   int64_t estep_long_threshold = 0;
+  // Snippets shorter than this run one LANE each (fb_*_lane_kernel; max_token_len <= 16).  0 = off, < 0 = automatic:
+  // everything below the long threshold, and the automatic long threshold becomes 11000 + n_bytes / 73000 — measured on
+  // B200 (tools/probe.py --what estep): lanes fold 8 GB/s of short snippets against 2.9 GB/s for 4-lane groups, but
+  // run a position in ~11 us when the GPU is full, so the longest lane snippet must not outlast the warps' share
+  // (best thresholds: 24 K at 1 GB, 64 K at 4 GB).
+  int64_t estep_lane_threshold = -1;
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
   // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
@@ -1056,6 +1064,8 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
       for (auto& e : w.ev) CU(cudaEventCreate(&e));
     }
     CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->ev_join3, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
@@ -1127,6 +1137,8 @@ void tgx_model_destroy(tgx_model* m) {
     m->d_hash.release();
     m->d_scores.release();
     if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->stream3) cudaStreamDestroy(m->stream3);
+    if (m->ev_join3) cudaEventDestroy(m->ev_join3);
     if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
     if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
     for (int i = 0; i < 2; i++) {
@@ -1178,6 +1190,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
+    case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
     case 15: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "segment kernel hot levels must be 0..2"); m->seg_hot = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
@@ -1774,37 +1787,65 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.hot = m->hot.as<double>();
 
   // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second
-  // stream; the many short ones run lane-per-snippet beside them.
-  uint32_t n_long = 0;
-  if (m->g_estep != 32) {
+  // stream; the mid-sized ones run G lanes per snippet beside them, the short ones one lane each on a third.
+  uint32_t n_long = 0, n_lane = 0;
+  {
     uint32_t* counts = m->w().small.as<uint32_t>();
+    const bool lanes_ok = m->estep_lane_threshold != 0 && p.u.rows <= 16;
     int64_t thr64 = m->estep_long_threshold;
-    if (thr64 <= 0) thr64 = std::max<int64_t>(8192, (int64_t)(n_bytes / 18000));
+    if (thr64 <= 0)
+      thr64 = (lanes_ok && m->estep_lane_threshold < 0) ? std::max<int64_t>(8192, 11000 + (int64_t)(n_bytes / 73000))
+                                                         : std::max<int64_t>(8192, (int64_t)(n_bytes / 18000));
+    if (m->g_estep == 32 && !lanes_ok) thr64 = 0x7FFFFFFF;  // one kernel shape for everything
     uint32_t thr = (uint32_t)std::min<int64_t>(thr64, 0x7FFFFFFF);
-    split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr, counts);
+    uint32_t thr_lane = 0;
+    if (lanes_ok)
+      thr_lane = m->estep_lane_threshold < 0 ? thr : (uint32_t)std::min<int64_t>(m->estep_lane_threshold, (int64_t)thr);
+    split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr_lane, counts);
     m->w().stats.launches += 1;
-    uint32_t h[2];
-    CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
+    uint32_t h[3];
+    CU(cudaMemcpyAsync(h, counts, 12, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     n_long = h[0];
+    n_lane = lanes_ok ? U - h[2] : 0;  // h[2] = units of at least thr_lane bytes
   }
   CU(cudaEventRecord(m->ev_fork, st));
   CU(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+  CU(cudaStreamWaitEvent(m->stream3, m->ev_fork, 0));
   FbParams pl = p, ps = p;
   pl.u.first = 0;
   pl.u.count = n_long;
   ps.u.first = n_long;
-  ps.u.count = U - n_long;
-  CU(cudaEventRecord(m->w().ev[0], st));
+  ps.u.count = U - n_long - n_lane;
+  FbLaneParams pn;
+  pn.f = p;
+  pn.f.u.first = U - n_lane;
+  pn.f.u.count = n_lane;
+  pn.blob_end = d_text + n_bytes;
+  const uint32_t lane_blocks = nblk(n_lane, FL_WARPS * 32);
+  // forward / backward device times (tgx_model_last_stat 2, 3) are taken on the stream that carries most snippets
+  cudaStream_t st_ev = (n_lane > ps.u.count) ? m->stream3 : st;
+  CU(cudaEventRecord(m->w().ev[0], st_ev));
   CU(launch_fb_g(m, 32, pl, false, m->stream2));
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
-  CU(cudaEventRecord(m->w().ev[1], st));
-  CU(cudaEventRecord(m->w().ev[2], st));
+  if (n_lane) {
+    fb_forward_lane_kernel<<<lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pn);
+    m->w().stats.launches += 1;
+  }
+  CU(cudaEventRecord(m->w().ev[1], st_ev));
+  CU(cudaEventRecord(m->w().ev[2], st_ev));
   CU(launch_fb_g(m, 32, pl, true, m->stream2));
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
-  CU(cudaEventRecord(m->w().ev[3], st));
+  if (n_lane) {
+    fb_backward_lane_kernel<<<lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pn);
+    m->w().stats.launches += 1;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(m->w().ev[3], st_ev));
   CU(cudaEventRecord(m->ev_join, m->stream2));
   CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+  CU(cudaEventRecord(m->ev_join3, m->stream3));
+  CU(cudaStreamWaitEvent(st, m->ev_join3, 0));
   if (p.hot_k) {
     fold_hot_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot, p.hot_k, p.hot_r, d_expected);
     m->w().stats.launches += 1;

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--single", type=int, default=0, help="encode only the N longest samples")
     ap.add_argument("--estep-cfgs", default="", help="comma list of G:threshold pairs for the E-step")
+    ap.add_argument("--snippet", type=int, default=81920, help="E-step snippet length (throughput experiments)")
     ap.add_argument("--algos", default="", help="comma list of forward algos to time (default all)")
     args = ap.parse_args()
     import torch
@@ -71,13 +72,16 @@ def main():
         cfgs = [(4, 16384), (4, 32768), (4, 65536), (8, 32768), (8, 65536), (2, 16384), (2, 32768), (4, 8192)]
         if args.single == 0 and args.estep_cfgs:
             cfgs = [tuple(int(x) for x in c.split(":")) for c in args.estep_cfgs.split(",")]
-        for g, thr in cfgs:
+        for cfg in cfgs:
+            g, thr = cfg[0], cfg[1]
+            lane = cfg[2] if len(cfg) > 2 else 0
             m.set_option(2, g)
             m.set_option(5, thr)
+            m.set_option(17, lane)
             for _ in range(args.reps):
                 d_ex.zero_()
-                rc, bad, bz = m.expected_counts_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, d_ex.data_ptr())
-            print(f"estep G={g} thr={thr}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
+                rc, bad, bz = m.expected_counts_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, d_ex.data_ptr(), args.snippet)
+            print(f"estep G={g} thr={thr} lane={lane}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
                   f"{NB / m.stat(4) / 1e6:.3f} GB/s sum={float(d_ex.sum()):.3f}", flush=True)
 
 
