@@ -64,10 +64,12 @@ def main():
                       m.debug_counters().tolist(), flush=True)
         m.set_option(3, 0)
     if "freq" in what:
+      for eh in (0, 1):
+        m.set_option(16, eh)
         for _ in range(args.reps):
             d_fr.zero_()
             rc, bad, bl = m.token_frequencies_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, False, d_fr.data_ptr())
-            print(f"freq: {m.stat(4):.2f} ms  {NB / m.stat(4) / 1e6:.2f} GB/s sum={int(d_fr.sum())}", flush=True)
+            print(f"freq emit_hash={eh}: {m.stat(4):.2f} ms fwd {m.stat(1):.2f} back {m.stat(5):.2f} emit {m.stat(6):.2f}  {NB / m.stat(4) / 1e6:.2f} GB/s sum={int(d_fr.sum())}", flush=True)
     if "estep" in what:
         cfgs = [(4, 16384), (4, 32768), (4, 65536), (8, 32768), (8, 65536), (2, 16384), (2, 32768), (4, 8192)]
         if args.single == 0 and args.estep_cfgs:
