@@ -184,7 +184,10 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * groups / highest throughput), 15 = trie levels the segment kernels stage in shared memory (0..2), 16 = emit looks
  * token ids up in the token hash (1, the default when max_token_len <= 16) or re-walks the trie (0), 17 = E-step byte
  * threshold below which a snippet runs on ONE lane (fb_*_lane_kernel; < 0 = automatic: everything below the full-warp
- * threshold of key 5, the default; 0 = never, the lane-group kernels of key 2 take them). */
+ * threshold of key 5, the default; 0 = never, the lane-group kernels of key 2 take them), 18 = resident blocks per
+ * SM of the lane E-step kernels (0 = as many as fit), 19 = E-step in split form (1, the default: beta chains stored
+ * and run beside the alpha chains, counts by a third kernel; needs 8 more bytes of device memory per input byte and
+ * falls back to 0 = fused backward + counts without them). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

@@ -352,9 +352,10 @@ def test_token_frequencies_exact(N):
 def estep_cfg(m, g):
     """g = lanes per snippet of the lane-group kernels (lane-per-snippet kernels off); g = 0: every snippet below
     the long threshold runs one lane each (fb_*_lane_kernel), the rest a warp each."""
-    if g == 0:
+    if g in (0, -3):  # -3: fused backward + counts (no beta array); 0: split form, the default
         m.set_option(17, 1 << 30)
         m.set_option(2, 4)
+        m.set_option(19, 1 if g == 0 else 0)
     else:
         m.set_option(17, 0)
         m.set_option(2, g)
@@ -364,7 +365,7 @@ LATTICE_VOCAB = [(b"<", -3.0), (b" value", -6.0), (b">", -3.0), (b"DC value", -8
                  (b"<DC value>", -12.0)]
 
 
-@pytest.mark.parametrize("g", [0, 1, 8, 32])
+@pytest.mark.parametrize("g", [0, -3, 1, 8, 32])
 def test_reference_lattice_marginals(N, g):
     toks = [t for t, _ in LATTICE_VOCAB]
     sc = [s for _, s in LATTICE_VOCAB]
@@ -385,9 +386,9 @@ def test_reference_lattice_marginals(N, g):
     assert rc == 0 and np.allclose(ex, [0.5, 0.5, 0.5], rtol=1e-12)
 
 
-@pytest.mark.parametrize("g", [0, 1, 4, 32])
+@pytest.mark.parametrize("g", [0, -3, 1, 4, 32])
 def test_expected_counts_random_vs_oracle(N, g):
-    rng = random.Random(200 + g)
+    rng = random.Random(200 + abs(g))
     for it in range(20):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(5, 40), max_len=rng.randrange(1, 8),
                                   complete=True)
@@ -416,8 +417,8 @@ def test_expected_counts_synth_vs_oracle(N):
     blob, off, toks, sc, kp = synth_setup(2, 13, 2_000_000, 30000, 16)
     gm, om = both(N, toks, sc)
     want, wrc, wbad, _ = om.run_e_step(blob, off, threads=8, literal=False)
-    for g in (0, 1, 8, -1):
-        if g >= 0:
+    for g in (0, -3, 1, 8, -1):
+        if g != -1:
             estep_cfg(gm, g)
         else:  # the default split: lanes below 16 KB, lane groups above, warps for the longest
             gm.set_option(17, 16384)

@@ -101,8 +101,8 @@ struct tgx_model {
   const Workspace& w() const { return ws[wi]; }
   Stats last_stats;  // of the last finished call (tgx_model_last_stat)
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones (E-step)
-  cudaStream_t stream3 = nullptr;  // lane-per-snippet kernels (E-step)
-  cudaEvent_t ev_join3 = nullptr;
+  cudaStream_t stream3 = nullptr, stream4 = nullptr;  // lane-per-snippet kernels (E-step): forward / backward
+  cudaEvent_t ev_join3 = nullptr, ev_join4 = nullptr;
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
   uint64_t* h_off = nullptr;       // pinned staging for rebased chunk offsets
@@ -122,11 +122,15 @@ struct tgx_model {
   // (tools/probe.py --what estep at 0.2, 0.6, 2 and 4 GB: best thresholds 16 K, 32 K, >= 64 K, none)
   int64_t estep_long_threshold = 0;
   // Snippets shorter than this run one LANE each (fb_*_lane_kernel; max_token_len <= 16).  0 = off, < 0 = automatic:
-  // everything below the long threshold, and the automatic long threshold becomes 11000 + n_bytes / 73000 — measured on
-  // B200 (tools/probe.py --what estep): lanes fold 8 GB/s of short snippets against 2.9 GB/s for 4-lane groups, but
-  // run a position in ~11 us when the GPU is full, so the longest lane snippet must not outlast the warps' share
-  // (best thresholds: 24 K at 1 GB, 64 K at 4 GB).
+  // everything below the long threshold, and the automatic long threshold becomes 16000 + n_bytes / 30000 — measured on
+  // B200 (tools/probe.py --what estep): lanes fold 8 GB/s of short snippets against 2.9 GB/s for 4-lane groups, but a
+  // chain advances one position per ~4.3 us (forward) on a lane and per ~1.3 us on a warp, so the longest lane snippet
+  // must not outlast the rest (best thresholds in split form: 24-32 K at 0.5 GB, 32-48 K at 1 GB, none — every snippet on a lane — at 4 GB).
   int64_t estep_lane_threshold = -1;
+  // Lane kernels in split form: the backward chain only stores beta and runs beside the forward chain, a third
+  // kernel adds the expected counts (needs 8 more bytes per input byte; falls back to the fused form without them).
+  int estep_split = 1;
+  int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
   // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
@@ -152,6 +156,7 @@ struct tgx_model {
   int pair_shape = 0;  // 0 = by batch size, 1 = latency shape (5 groups), 2 = throughput shape (6 groups)
   uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
+  DevBuf Bbeta;
   DevBuf text, off, idoff, A, expected, freq, ids, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
 };
 
@@ -1065,7 +1070,9 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     }
     CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream4, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&m->ev_join3, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&m->ev_join4, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
@@ -1119,6 +1126,7 @@ void tgx_model_destroy(tgx_model* m) {
   if (m->device >= 0) {
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
+    m->Bbeta.release();
     DevBuf* bufs[] = {&m->text, &m->off, &m->idoff, &m->A, &m->expected, &m->freq, &m->ids, &m->scount, &m->hot,
                       &m->text_b, &m->off_b, &m->ids_b, &m->idoff_b, &m->scount_b};
     for (auto* b : bufs) b->release();
@@ -1138,7 +1146,9 @@ void tgx_model_destroy(tgx_model* m) {
     m->d_scores.release();
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream3) cudaStreamDestroy(m->stream3);
+    if (m->stream4) cudaStreamDestroy(m->stream4);
     if (m->ev_join3) cudaEventDestroy(m->ev_join3);
+    if (m->ev_join4) cudaEventDestroy(m->ev_join4);
     if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
     if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
     for (int i = 0; i < 2; i++) {
@@ -1191,6 +1201,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
+    case 19: m->estep_split = value ? 1 : 0; break;
+    case 18: if (value < 0 || value > 16) return fail(TGX_ERR_INVALID, "blocks per SM must be 0..16"); m->lane_blocks_per_sm = (int)value; break;
     case 15: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "segment kernel hot levels must be 0..2"); m->seg_hot = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
     case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
@@ -1794,7 +1806,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
     const bool lanes_ok = m->estep_lane_threshold != 0 && p.u.rows <= 16;
     int64_t thr64 = m->estep_long_threshold;
     if (thr64 <= 0)
-      thr64 = (lanes_ok && m->estep_lane_threshold < 0) ? std::max<int64_t>(8192, 11000 + (int64_t)(n_bytes / 73000))
+      thr64 = (lanes_ok && m->estep_lane_threshold < 0) ? std::max<int64_t>(8192, 16000 + (int64_t)(n_bytes / 30000))
                                                          : std::max<int64_t>(8192, (int64_t)(n_bytes / 18000));
     if (m->g_estep == 32 && !lanes_ok) thr64 = 0x7FFFFFFF;  // one kernel shape for everything
     uint32_t thr = (uint32_t)std::min<int64_t>(thr64, 0x7FFFFFFF);
@@ -1822,22 +1834,65 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   pn.f.u.first = U - n_lane;
   pn.f.u.count = n_lane;
   pn.blob_end = d_text + n_bytes;
+  pn.B = nullptr;
+  bool split = m->estep_split && (n_lane || n_long) && p.u.rows <= 16;
+  if (split) {  // beta array: only if the device has room for it
+    const size_t need = ((size_t)n_bytes + U + 2) * 8;
+    size_t fr = 0, tot = 0;
+    if (need > m->Bbeta.cap && (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < need + need / 8 + ((size_t)2 << 30))) split = false;
+    if (split && m->Bbeta.reserve(need) != cudaSuccess) {
+      (void)cudaGetLastError();
+      split = false;
+    }
+    pn.B = m->Bbeta.as<double>();
+  }
   const uint32_t lane_blocks = nblk(n_lane, FL_WARPS * 32);
+  // fewer resident warps = a larger share of the issue slots for each chain (the kernels are issue-bound)
+  size_t lane_pad = 0;
+  if (m->lane_blocks_per_sm > 0) {
+    const size_t per_block = (size_t)228 * 1024 / m->lane_blocks_per_sm;
+    lane_pad = per_block > 22 * 1024 ? std::min<size_t>(per_block - 22 * 1024, (size_t)m->smem_optin - 21 * 1024) : 0;
+    CU(cudaFuncSetAttribute(fb_forward_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
+    CU(cudaFuncSetAttribute(fb_backward_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
+    CU(cudaFuncSetAttribute(fb_split_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
+  }
   // forward / backward device times (tgx_model_last_stat 2, 3) are taken on the stream that carries most snippets
   cudaStream_t st_ev = (n_lane > ps.u.count) ? m->stream3 : st;
   CU(cudaEventRecord(m->w().ev[0], st_ev));
   CU(launch_fb_g(m, 32, pl, false, m->stream2));
+  if (split && pl.u.count) {  // the beta chains of the longest snippets run beside their forward chains
+    CU(cudaStreamWaitEvent(m->stream4, m->ev_fork, 0));
+    const size_t smem = warp_smem_bytes(pl.u.rows, pl.u.W, 32) * WPB;
+    CU(cudaFuncSetAttribute(fb_backward_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fb_backward_kernel<32, true><<<nblk(pl.u.count, WPB), WPB * 32, smem, m->stream4>>>(pl, pn.B);
+    m->w().stats.launches += 1;
+    CU(cudaEventRecord(m->ev_join4, m->stream4));
+  }
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
-  if (n_lane) {
-    fb_forward_lane_kernel<<<lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pn);
+  if (n_lane && split) {
+    fb_split_lane_kernel<<<2 * lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
+    m->w().stats.launches += 1;
+  } else if (n_lane) {
+    fb_forward_lane_kernel<<<lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
   CU(cudaEventRecord(m->w().ev[1], st_ev));
   CU(cudaEventRecord(m->w().ev[2], st_ev));
-  CU(launch_fb_g(m, 32, pl, true, m->stream2));
+  if (split && pl.u.count) {
+    CU(cudaStreamWaitEvent(m->stream2, m->ev_join4, 0));
+    FbLaneParams pc = pn;
+    pc.f.u = pl.u;
+    fb_contrib_kernel<<<nblk(pl.u.count, FC_WARPS), FC_WARPS * 32, 0, m->stream2>>>(pc);
+    m->w().stats.launches += 1;
+  } else {
+    CU(launch_fb_g(m, 32, pl, true, m->stream2));
+  }
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
-  if (n_lane) {
-    fb_backward_lane_kernel<<<lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pn);
+  if (n_lane && split) {  // alpha and beta are both there: the counts
+    fb_contrib_kernel<<<nblk(n_lane, FC_WARPS), FC_WARPS * 32, 0, m->stream3>>>(pn);
+    m->w().stats.launches += 1;
+  } else if (n_lane) {
+    fb_backward_lane_kernel<<<lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
   CU(cudaGetLastError());

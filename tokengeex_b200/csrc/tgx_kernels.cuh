@@ -946,8 +946,9 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
 //     length, of log_sum_exp(., score + B[p+len]) (src/lattice.rs:275-287); contribution
 //     exp(A[p] + score + B[p+len] - z) added to expected[id] (:295-309).
 // -----------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
+// STORE_B: only the beta chain, written to Bout (layout of A); the counts are added by fb_contrib_kernel.
+template <int G, bool STORE_B = false>
+__global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, double* Bout = nullptr) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = 32 / G;
   const UnitParams& u = p.u;
@@ -965,12 +966,14 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
   unit_range(u.counts, u.part, ufirst, ucount);
   bool has = gidx < ucount;
   const uint32_t unit = has ? u.order[ufirst + gidx] : 0;
-  if (has && p.status[unit] != 0) has = false;  // bad z: the reference panics; nothing is added
+  if (!STORE_B && has && p.status[unit] != 0) has = false;  // bad z: the reference panics; nothing is added
   const uint32_t n = has ? u.unit_len[unit] : 0;
   const uint64_t start = has ? u.unit_start[unit] : 0;
   const uint8_t* text = u.text + start;
   const double* A = p.A + start + unit;
-  const double z = has ? A[n] : 0.0;
+  double* Bo = Bout + start + unit;
+  const double z = (has && !STORE_B) ? A[n] : 0.0;
+  if (STORE_B && has && lig == 0) Bo[n] = 0.0;
 
   uint32_t nmax = n;
 #pragma unroll
@@ -984,7 +987,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
   for (uint32_t tile = tiles; tile-- > 0;) {
     const uint32_t p0 = tile * G;
     s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
-    const double a_mine = (has && p0 + lig < n) ? A[p0 + lig] : 0.0;
+    const double a_mine = (!STORE_B && has && p0 + lig < n) ? A[p0 + lig] : 0.0;
     __syncwarp();
     uint32_t sl = (p0 + G - 1) % W;  // slot of the tile's last position
 #pragma unroll 1
@@ -1001,7 +1004,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
         const double y = __dadd_rn(sc, wB[ts]);  // nodes[rid].score + beta[rid]
         b = (k == 0) ? y : log_sum_exp(b, y, lt);
       }
-      for (uint32_t k = lig; k < c; k += G) {
+      for (uint32_t k = lig; !STORE_B && k < c; k += G) {
         const double sc = s.mscore[k * ROW_STRIDE + src];
         const uint32_t mp = s.mpack[k * ROW_STRIDE + src];
         uint32_t ts = sl + (mp >> 24);
@@ -1013,7 +1016,10 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p) {
         atomicAdd(dst, tgx_exp(total, lt));
       }
       __syncwarp();
-      if (pp < n && lig == 0) wB[sl] = b;
+      if (pp < n && lig == 0) {
+        wB[sl] = b;
+        if (STORE_B) Bo[pp] = b;
+      }
       __syncwarp();
       sl = sl == 0 ? W - 1 : sl - 1;
     }
@@ -1036,6 +1042,7 @@ constexpr int FL_WARPS = 4;
 struct FbLaneParams {
   FbParams f;
   const uint8_t* blob_end;
+  double* B;  // [N + U] backward log-probabilities (split form only)
 };
 
 __device__ __forceinline__ unsigned long long fl_word(const uint8_t* a, const uint8_t* blob_end) {
@@ -1050,16 +1057,13 @@ __device__ __forceinline__ uint32_t fl_byte(unsigned long long lo, unsigned long
   return (uint32_t)((d < 8 ? lo : hi) >> (8 * (d & 7u))) & 0xFFu;
 }
 
-__global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLaneParams q) {
-  __shared__ double s_acc[FL_WARPS][16 * 32];
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
+__device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
+                                                     const LibmTabs& lt) {
   const FbParams& p = q.f;
   const UnitParams& u = p.u;
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = s_acc[warp] + lane;  // slot s at acc[s * 32]
-  const uint64_t gidx = (uint64_t)blockIdx.x * (FL_WARPS * 32) + threadIdx.x;
+  double* acc = s_win + warp * (16 * 32) + lane;  // slot s at acc[s * 32]
+  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
   const bool has = gidx < u.count;
   const uint32_t unit = has ? u.order[u.first + gidx] : 0;
   const uint32_t n = has ? u.unit_len[unit] : 0;
@@ -1138,26 +1142,29 @@ __global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLanePa
   }
 }
 
-__global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneParams q) {
-  __shared__ double s_b[FL_WARPS][16 * 32];
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
+// STORE_B: only the beta chain, written to q.B (same layout as A) — it needs neither A nor z, so it runs BESIDE the
+// forward kernel and fb_contrib_kernel adds the expected counts afterwards; the longest snippet then costs
+// max(forward, backward) instead of their sum.  !STORE_B: the fused form (after the forward kernel).
+template <bool STORE_B>
+__device__ __forceinline__ void fb_backward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
+                                                      const LibmTabs& lt) {
   const FbParams& p = q.f;
   const UnitParams& u = p.u;
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* wB = s_b[warp] + lane;
-  const uint64_t gidx = (uint64_t)blockIdx.x * (FL_WARPS * 32) + threadIdx.x;
+  double* wB = s_win + warp * (16 * 32) + lane;
+  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
   const bool has = gidx < u.count;
   const uint32_t unit = has ? u.order[u.first + gidx] : 0;
   const uint32_t n = has ? u.unit_len[unit] : 0;
   // bad z: the reference panics; nothing is added
-  bool active = has && n != 0 && p.status[unit] == 0;
+  bool active = has && n != 0 && (STORE_B || p.status[unit] == 0);
   const uint64_t start = has ? u.unit_start[unit] : 0;
   const double* A = p.A + start + unit;
-  const double z = active ? A[n] : 0.0;
-  double* hot = p.hot + (size_t)(blockIdx.x % p.hot_r) * p.hot_k;
+  double* Bout = q.B + start + unit;
+  const double z = (active && !STORE_B) ? A[n] : 0.0;
+  double* hot = p.hot + (size_t)(bid % p.hot_r) * p.hot_k;
   wB[(n & 15u) * 32] = 0.0;  // beta at the end of the sentence (EOS)
+  if (STORE_B && has) Bout[n] = 0.0;
   uint32_t pos = active ? n - 1 : 0;
   const uint8_t* tp = u.text + start + pos;
   const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<unsigned long long>(tp) & ~7ull);
@@ -1170,7 +1177,7 @@ __global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneP
   }
   unsigned long long lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
   unsigned long long hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
-  double a = active ? A[pos] : 0.0, a_next = (active && pos) ? A[pos - 1] : 0.0;
+  double a = (active && !STORE_B) ? A[pos] : 0.0, a_next = (active && !STORE_B && pos) ? A[pos - 1] : 0.0;
   double b = 0.0;  // stays 0.0 when nothing begins at pos (Q7)
   bool first = true;
   uint32_t d = 0, limit = 1, xb = u.root_base;
@@ -1207,25 +1214,101 @@ __global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneP
         const double y = __dadd_rn(sc, bt);  // nodes[rid].score + beta[rid]
         b = first ? y : log_sum_exp(b, y, lt);
         first = false;
-        // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
-        const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), bt), -z);
-        atomicAdd(id < p.hot_k ? hot + id : p.expected + id, tgx_exp(total, lt));
+        if (!STORE_B) {
+          // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
+          const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), bt), -z);
+          atomicAdd(id < p.hot_k ? hot + id : p.expected + id, tgx_exp(total, lt));
+        }
       }
       d = nd;
       xb = nxb;
       if (!cont) {
         wB[(pos & 15u) * 32] = b;
+        if (STORE_B) Bout[pos] = b;
         if (pos == 0) {
           active = false;
         } else {
           pos--;
-          a = a_next;
-          a_next = pos ? A[pos - 1] : 0.0;
+          if (!STORE_B) {
+            a = a_next;
+            a_next = pos ? A[pos - 1] : 0.0;
+          }
           b = 0.0;
           first = true;
           limit = min(16u, n - pos);
         }
       }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  fb_forward_lane_body(q, blockIdx.x, s_win, lt);
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  fb_backward_lane_body<false>(q, blockIdx.x, s_win, lt);
+}
+
+// Split form: even blocks run the forward chains of 128 snippets, odd blocks the beta chains of the same snippets,
+// so the block scheduler starts the longest snippets of BOTH directions first (two kernels on two streams do not
+// interleave: the second kernel's blocks wait for the first kernel's to be dispatched).
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_split_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  if (blockIdx.x & 1u) fb_backward_lane_body<true>(q, blockIdx.x >> 1, s_win, lt);
+  else fb_forward_lane_body(q, blockIdx.x >> 1, s_win, lt);
+}
+
+// Expected counts from stored alpha and beta (split form): one warp per snippet, a lane per start position.
+// exp(alpha[pos] + score + beta[pos + len] - z) per matched token, in the reference's operation order
+// (src/lattice.rs:295-309), so every contribution equals the fused kernels' bit for bit.
+constexpr int FC_WARPS = 8;
+
+__global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams q) {
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const FbParams& p = q.f;
+  const UnitParams& u = p.u;
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t widx = (uint64_t)blockIdx.x * FC_WARPS + warp;
+  if (widx >= u.count) return;
+  const uint32_t unit = u.order[u.first + widx];
+  if (p.status[unit] != 0) return;  // bad z: the reference panics; nothing is added
+  const uint32_t n = u.unit_len[unit];
+  const uint64_t start = u.unit_start[unit];
+  const double* A = p.A + start + unit;
+  const double* B = q.B + start + unit;
+  const uint8_t* text = u.text + start;
+  const double z = A[n];
+  double* hot = p.hot + (size_t)(blockIdx.x % p.hot_r) * p.hot_k;
+  for (uint32_t pos = lane; pos < n; pos += 32) {
+    const double a = A[pos];
+    const uint32_t limit = min(16u, n - pos);
+    uint32_t xb = u.root_base;
+    for (uint32_t d = 0; d < limit; d++) {
+      const uint32_t cw = 0x100u | __ldg(text + pos + d);
+      const uint4 e = __ldg(u.trie + (xb ^ cw));
+      if ((e.x ^ cw) & 0x1FFu) break;
+      if (e.y & F_TERM) {
+        const double sc = __hiloint2double((int)e.w, (int)e.z);
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), B[pos + d + 1]), -z);
+        const uint32_t id = e.y & ID_MASK;
+        atomicAdd(id < p.hot_k ? hot + id : p.expected + id, tgx_exp(total, lt));
+      }
+      if (!(e.y & F_HASCH)) break;
+      xb = e.x >> 9;
     }
   }
 }
