@@ -152,6 +152,14 @@ int tgx_prune_select(const uint8_t* token_bytes, const uint64_t* token_offsets, 
                      uint64_t target_vocab_size, double shrink_factor, int threads, uint32_t* out_ids,
                      uint64_t* out_n, double* audit);
 
+/* tgx_prune_select over the trie the model already holds: (token_bytes, token_offsets, scores) must be the vocabulary
+ * of the last tgx_model_create / tgx_model_rebuild of `m` (checked by size only).  Saves the second trie build per
+ * EM iteration (src/prune.rs:53 rebuilds the model right before prune_vocab walks it). */
+int tgx_model_prune_select(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                           const uint8_t* keep, uint64_t vocab_size, const uint64_t* freq, uint64_t n_samples,
+                           uint64_t target_vocab_size, double shrink_factor, int threads, uint32_t* out_ids,
+                           uint64_t* out_n, double* audit);
+
 /* Pinned host memory for callers that want asynchronous H2D/D2H (cudaHostAlloc). */
 int tgx_host_alloc(void** p, uint64_t bytes);
 int tgx_host_free(void* p);

@@ -41,6 +41,10 @@ def test_prune_select_matches_oracle():
             continue  # non-normal loss: the reference panics; covered below
         wt, ws, wk = want.export()
         ids, audit = N.prune_select(toks, scores, keep, fr, len(samples), target, shrink, threads=3)
+        # the same through a (host-only) model's own trie: tgx_model_prune_select
+        ids_m, audit_m = N.Model(toks, scores, device=None).prune_select(toks, scores, keep, fr, len(samples), target,
+                                                                        shrink, threads=2)
+        assert np.array_equal(ids, ids_m) and np.array_equal(audit, audit_m)
         assert [toks[i] for i in ids] == wt
         assert np.array_equal(np.asarray(scores)[ids], ws)
         assert np.array_equal(audit[:7], waudit[:7])

@@ -59,6 +59,8 @@ SYMBOLS = [
     ("tgx_m_step", C.c_int, [f64p, u8p, C.c_uint64, u8p, f64p, u64p]),
     ("tgx_prune_select", C.c_int, [u8p, u64p, f64p, u8p, C.c_uint64, u64p, C.c_uint64, C.c_uint64, C.c_double,
                                    C.c_int, u32p, u64p, f64p]),
+    ("tgx_model_prune_select", C.c_int, [C.c_void_p, u8p, u64p, f64p, u8p, C.c_uint64, u64p, C.c_uint64, C.c_uint64,
+                                         C.c_double, C.c_int, u32p, u64p, f64p]),
     ("tgx_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("tgx_host_free", C.c_int, [C.c_void_p]),
     ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
@@ -137,6 +139,24 @@ class Model:
             sc = np.zeros(1, np.float64)
         _check(lib().tgx_model_rebuild(self._h, _p(blob, u8p), _p(off, u64p), _p(sc, f64p), len(tokens)))
         self.V = len(tokens)
+
+    def prune_select(self, tokens: Sequence[bytes], scores, keep, freq, n_samples: int, target: int, shrink: float,
+                     threads: int = 0):
+        """prune_select() over the trie this model already holds (tokens / scores = the model's vocabulary)."""
+        V = len(tokens)
+        blob, off = pack(tokens)
+        sc = np.ascontiguousarray(scores, np.float64)
+        kp = np.ascontiguousarray(keep, np.uint8)
+        fr = np.ascontiguousarray(freq, np.uint64)
+        out = np.zeros(max(V, 1), np.uint32)
+        n = C.c_uint64(0)
+        audit = np.zeros(8, np.float64)
+        if threads <= 0:
+            threads = max(1, len(os.sched_getaffinity(0)))
+        _check(lib().tgx_model_prune_select(self._h, _p(blob, u8p), _p(off, u64p), _p(sc, f64p), _p(kp, u8p), V,
+                                            _p(fr, u64p), n_samples, target, shrink, threads, _p(out, u32p),
+                                            C.byref(n), _p(audit, f64p)))
+        return out[:int(n.value)].copy(), audit
 
     def close(self):
         if getattr(self, "_h", None):

@@ -234,6 +234,19 @@ int tgx_prune_select(const uint8_t* token_bytes, const uint64_t* token_offsets, 
   tgx::DoubleArray da;
   std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, V, &da);
   if (!err.empty()) return TGX_ERR_UNSUPPORTED;
+  return tgx::prune_select_with(da, token_bytes, token_offsets, scores, keep, V, freq, n_samples, target_vocab_size,
+                                shrink_factor, threads, out_ids, out_n, audit);
+}
+
+}  // extern "C"
+
+// prune_vocab over a double-array that already holds this vocabulary (tgx_model_prune_select: the model's own trie,
+// so the EM loop does not build it a second time per iteration).
+int tgx::prune_select_with(const tgx::DoubleArray& da, const uint8_t* token_bytes, const uint64_t* token_offsets,
+                           const double* scores, const uint8_t* keep, uint64_t V, const uint64_t* freq,
+                           uint64_t n_samples, uint64_t target_vocab_size, double shrink_factor, int threads,
+                           uint32_t* out_ids, uint64_t* out_n, double* audit) {
+  if (!token_offsets || !scores || !freq || !out_ids || !out_n) return TGX_ERR_INVALID;
 
   size_t pruned_size = (size_t)((double)V * shrink_factor);         // :174  (truncation)
   pruned_size = std::max<size_t>(pruned_size, target_vocab_size);   // :175
@@ -333,5 +346,3 @@ int tgx_prune_select(const uint8_t* token_bytes, const uint64_t* token_offsets, 
   }
   return TGX_OK;
 }
-
-}  // extern "C"

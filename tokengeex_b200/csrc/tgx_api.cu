@@ -1232,6 +1232,19 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
   return 0;
 }
 
+int tgx_model_prune_select(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+                           const uint8_t* keep, uint64_t vocab_size, const uint64_t* freq, uint64_t n_samples,
+                           uint64_t target_vocab_size, double shrink_factor, int threads, uint32_t* out_ids,
+                           uint64_t* out_n, double* audit) {
+  if (!m) return fail(TGX_ERR_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  if (vocab_size != m->V) return fail(TGX_ERR_INVALID, "vocabulary is not the one the model was built from");
+  int rc = tgx::prune_select_with(m->da, token_bytes, token_offsets, scores, keep, vocab_size, freq, n_samples,
+                                  target_vocab_size, shrink_factor, threads, out_ids, out_n, audit);
+  if (rc) return fail(rc, "prune_vocab failed (loss is not normal, or bad argument)");
+  return TGX_OK;
+}
+
 int tgx_model_debug_counters(tgx_model* m, uint64_t* out8) {
   int rc = check_model(m);
   if (rc) return rc;

@@ -5,6 +5,9 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace tgx {
 namespace {
@@ -18,38 +21,27 @@ struct Node {
   uint8_t label = 0;
 };
 
-// Doubly linked list of free slots, kept in increasing order.
-struct FreeList {
-  std::vector<uint32_t> prev, next;  // valid for free slots; index n_slots is the sentinel
-  std::vector<uint8_t> used;
-  std::vector<uint8_t> base_used;
-  uint32_t head = 0;  // first free slot or END
-  static constexpr uint32_t END = 0xFFFFFFFFu;
-  uint32_t tail = END;
-
-  uint32_t size() const { return (uint32_t)used.size(); }
-
-  void add_block() {
-    uint32_t lo = size();
-    used.resize(lo + 256, 0);
-    base_used.resize(lo + 256, 0);
-    prev.resize(lo + 256);
-    next.resize(lo + 256);
-    for (uint32_t s = lo; s < lo + 256; s++) {
-      prev[s] = (s == lo) ? tail : s - 1;
-      next[s] = (s == lo + 255) ? END : s + 1;
-    }
-    if (tail != END) next[tail] = lo; else head = lo;
-    tail = lo + 255;
-  }
-
-  void take(uint32_t s) {
-    uint32_t p = prev[s], n = next[s];
-    if (p != END) next[p] = n; else head = n;
-    if (n != END) prev[n] = p; else tail = p;
-    used[s] = 1;
-  }
+// Free slots and unused base values of one 256-entry block, as bitmaps (bit set = free / unused).
+struct Block {
+  uint64_t free_slots[4];
+  uint64_t free_bases[4];
 };
+
+// out bit f = in bit (f ^ L): the XOR with a constant permutes the 256 positions — whole words by L's two high
+// bits, and inside a word by one butterfly stage per set low bit.
+inline void xor_permute(const uint64_t (&in)[4], uint32_t L, uint64_t (&out)[4]) {
+  static const uint64_t M[6] = {0x5555555555555555ull, 0x3333333333333333ull, 0x0F0F0F0F0F0F0F0Full,
+                                0x00FF00FF00FF00FFull, 0x0000FFFF0000FFFFull, 0x00000000FFFFFFFFull};
+  for (int w = 0; w < 4; w++) {
+    uint64_t x = in[w ^ (L >> 6)];
+    for (int j = 0; j < 6; j++)
+      if ((L >> j) & 1u) {
+        const int sft = 1 << j;
+        x = ((x & M[j]) << sft) | ((x >> sft) & M[j]);
+      }
+    out[w] = x;
+  }
+}
 
 }  // namespace
 
@@ -64,19 +56,43 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     max_len = std::max<uint32_t>(max_len, (uint32_t)l);
   }
 
+  auto T0 = std::chrono::steady_clock::now();
+  const bool timing = getenv("TGX_BUILD_TIMING") != nullptr;  // developer aid: phase times on stderr
+  auto lap = [&](const char* w) {
+    if (!timing) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "  build_double_array %s %.1f ms\n", w, std::chrono::duration<double, std::milli>(t - T0).count());
+    T0 = t;
+  };
   // 1. sort token indices by bytes (ties: id ascending, so the last duplicate is seen last)
-  std::vector<uint32_t> order;
-  order.reserve(V);
-  for (uint64_t i = 0; i < V; i++)
-    if (off[i + 1] > off[i]) order.push_back((uint32_t)i);  // the empty token never matches
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+  //    (the first 8 bytes, big endian, decide most comparisons without touching the blob)
+  struct Key {
+    uint64_t k;
+    uint32_t id;
+  };
+  std::vector<Key> keyed;
+  keyed.reserve(V);
+  for (uint64_t i = 0; i < V; i++) {
+    const uint64_t l = off[i + 1] - off[i];
+    if (!l) continue;  // the empty token never matches
+    uint64_t k = 0;
+    for (uint64_t d = 0; d < 8; d++) k = (k << 8) | (d < l ? bytes[off[i] + d] : 0u);
+    keyed.push_back(Key{k, (uint32_t)i});
+  }
+  std::sort(keyed.begin(), keyed.end(), [&](const Key& x, const Key& y) {
+    if (x.k != y.k) return x.k < y.k;
+    const uint32_t a = x.id, b = y.id;
     size_t la = off[a + 1] - off[a], lb = off[b + 1] - off[b];
     int c = std::memcmp(bytes + off[a], bytes + off[b], std::min(la, lb));
     if (c) return c < 0;
     if (la != lb) return la < lb;
     return a < b;
   });
+  std::vector<uint32_t> order;
+  order.reserve(keyed.size());
+  for (const Key& x : keyed) order.push_back(x.id);
 
+  lap("sort");
   // 2. pointer trie by sorted insertion (a matching child is always the last child)
   std::vector<Node> nodes(1);
   nodes.reserve(V * 4 + 16);
@@ -102,6 +118,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     nodes[cur].term_id = std::max(nodes[cur].term_id, (int32_t)id);  // last id wins
   }
 
+  lap("trie");
   // 3. BFS order: shallow nodes get the lowest slots (the part staged in shared memory)
   std::vector<uint32_t> bfs;
   bfs.reserve(nodes.size());
@@ -113,67 +130,80 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
       bfs.push_back(c);
     }
 
-  // 4. slot allocation
-  FreeList fl;
-  fl.add_block();
-  fl.take(0);  // root
+  lap("bfs");
+  // 4. slot allocation.  A node needs a base b that no other node uses (trie_build.h) with every child slot
+  //    b ^ label free; both stay inside b's 256-entry block.  Per block the admissible bases are one bitmap
+  //    expression: unused_bases & AND_i permute(free_slots, label_i), so a block is tested in O(k) word operations
+  //    (a walk over the free-slot list spent 85 % of its tries on bases that were taken: 150 ms for 230k nodes).
+  std::vector<Block> blocks;
+  auto add_block = [&]() {
+    Block nb;
+    for (int w = 0; w < 4; w++) nb.free_slots[w] = nb.free_bases[w] = ~0ull;
+    blocks.push_back(nb);
+  };
+  add_block();
+  blocks[0].free_slots[0] &= ~1ull;  // slot 0 = root
   nodes[0].slot = 0;
   std::vector<uint32_t> base_of(nodes.size(), 0);
   uint8_t labels[256];
-  uint32_t hint[3] = {0, 0, 0};
+  uint32_t first_open = 0;  // blocks below it have (next to) no free slot left
   for (uint32_t nidx : bfs) {
     uint32_t k = 0;
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) labels[k++] = nodes[c].label;
     if (!k) continue;
-    uint32_t base = FreeList::END;
-    // Candidates: free slots f taken as the home of the first label.  Narrow nodes first
-    // try the global head of the free list (they fill the holes wide nodes left behind);
-    // then every node scans the recent blocks only, so the search stays short.
-    auto scan = [&](uint32_t f, uint32_t max_tries) {
-      uint32_t tries = 0;
-      for (; f != FreeList::END && tries < max_tries; f = fl.next[f], tries++) {
-        uint32_t b = f ^ labels[0];
-        if (fl.base_used[b]) continue;
-        bool ok = true;
-        for (uint32_t i = 1; i < k; i++)
-          if (fl.used[b ^ labels[i]]) { ok = false; break; }
-        if (ok) return b;
+    auto try_block = [&](uint32_t bi) -> uint32_t {  // an admissible base inside block bi, or END
+      const Block& B = blocks[bi];
+      uint64_t cand[4] = {B.free_bases[0], B.free_bases[1], B.free_bases[2], B.free_bases[3]};
+      for (uint32_t i = 0; i < k; i++) {
+        uint64_t pm[4];
+        xor_permute(B.free_slots, labels[i], pm);
+        uint64_t any = 0;
+        for (int w = 0; w < 4; w++) any |= (cand[w] &= pm[w]);
+        if (!any) return 0xFFFFFFFFu;
       }
-      return FreeList::END;
+      for (int w = 0; w < 4; w++)
+        if (cand[w]) return (bi << 8) | (uint32_t)(w * 64 + __builtin_ctzll(cand[w]));
+      return 0xFFFFFFFFu;
     };
-    if (k <= 2) base = scan(fl.head, 64);
-    if (base == FreeList::END) {
-      int cls = k >= 64 ? 0 : k >= 8 ? 1 : 2;
-      static const uint32_t BACK[3] = {2, 16, 64};
-      uint32_t nblocks = fl.size() >> 8;
-      uint32_t start = nblocks > BACK[cls] ? (nblocks - BACK[cls]) << 8 : 0;
-      uint32_t& h = hint[cls];
-      if (h < start) h = start;
-      while (h < fl.size() && fl.used[h]) h++;  // used slots never become free: monotone
-      if (h < fl.size()) base = scan(h, 2048);
-    }
-    if (base == FreeList::END) {
+    auto nfree = [&](uint32_t bi) {
+      const Block& B = blocks[bi];
+      return __builtin_popcountll(B.free_slots[0]) + __builtin_popcountll(B.free_slots[1]) +
+             __builtin_popcountll(B.free_slots[2]) + __builtin_popcountll(B.free_slots[3]);
+    };
+    while (first_open < blocks.size() && nfree(first_open) < 4) first_open++;  // (gives up on <= 3 slots of 256)
+    uint32_t base = 0xFFFFFFFFu;
+    const uint32_t nb = (uint32_t)blocks.size();
+    // Narrow nodes fill the holes wide nodes left behind: they look at the lowest open blocks first; every node
+    // then looks at the most recent blocks only, so the search stays short.
+    const uint32_t back = k >= 64 ? 1 : k >= 8 ? 2 : 4;
+    const uint32_t recent = nb > back ? nb - back : 0;
+    if (k <= 2)
+      for (uint32_t bi = first_open; bi < std::min(nb, first_open + 2) && base == 0xFFFFFFFFu; bi++) base = try_block(bi);
+    for (uint32_t bi = std::max(recent, first_open); bi < nb && base == 0xFFFFFFFFu; bi++) base = try_block(bi);
+    if (base == 0xFFFFFFFFu) {
       // open a fresh block: any base inside it works (all slots free, no base used)
-      uint32_t lo = fl.size();
-      if (lo + 256 > MAX_SLOTS) return "trie too large (slot index must fit 23 bits)";
-      fl.add_block();
-      base = lo;
+      if ((blocks.size() + 1) * 256 > MAX_SLOTS) return "trie too large (slot index must fit 23 bits)";
+      base = (uint32_t)blocks.size() << 8;
+      add_block();
     }
-    fl.base_used[base] = 1;
+    Block& B = blocks[base >> 8];
+    B.free_bases[(base & 255u) >> 6] &= ~(1ull << (base & 63u));
     base_of[nidx] = base;
     if (depth[nidx] < 2) {  // every probe out of this node stays inside base's 256-slot block
       uint32_t end = (base | 255u) + 1u;
       for (int d = depth[nidx] + 1; d <= 2; d++) out->hot[d] = std::max(out->hot[d], end);
     }
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) {
-      uint32_t s = base ^ nodes[c].label;
-      fl.take(s);
-      nodes[c].slot = s;
+      const uint32_t sl = base ^ nodes[c].label;
+      B.free_slots[(sl & 255u) >> 6] &= ~(1ull << (sl & 63u));
+      nodes[c].slot = sl;
     }
   }
+  const uint32_t n_slots = (uint32_t)blocks.size() * 256u;
 
+  lap("alloc");
   // 5. emit slots
-  out->slots.assign(fl.size(), Slot{0, 0, 0, 0});
+  out->slots.assign(n_slots, Slot{0, 0, 0, 0});
   for (size_t i = 0; i < nodes.size(); i++) {
     const Node& nd = nodes[i];
     Slot s{0, 0, 0, 0};
@@ -192,11 +222,12 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     s.y |= flags;
     out->slots[nd.slot] = s;
   }
+  lap("emit");
   out->root_base = base_of[0] ^ 0x100u;
   out->max_token_len = max_len;
   out->n_nodes = (uint32_t)nodes.size();
   out->n_terminals = n_term;
-  for (int d = 1; d <= 2; d++) out->hot[d] = std::min<uint32_t>(std::max(out->hot[d], 256u), (uint32_t)fl.size());
+  for (int d = 1; d <= 2; d++) out->hot[d] = std::min<uint32_t>(std::max(out->hot[d], 256u), n_slots);
   return "";
 }
 

@@ -83,6 +83,13 @@ struct TokenHash {
 std::string build_token_hash(const uint8_t* token_bytes, const uint64_t* token_offsets, uint64_t vocab_size,
                              TokenHash* out);
 
+// prune_vocab (src/prune.rs:173-319) minus its frequency pass, over a double-array that already holds the vocabulary
+// (prune_host.cpp; see tgx_prune_select in include/tokengeex_b200.h for the arguments).
+int prune_select_with(const DoubleArray& da, const uint8_t* token_bytes, const uint64_t* token_offsets,
+                      const double* scores, const uint8_t* keep, uint64_t V, const uint64_t* freq, uint64_t n_samples,
+                      uint64_t target_vocab_size, double shrink_factor, int threads, uint32_t* out_ids, uint64_t* out_n,
+                      double* audit);
+
 // Host walk (used by Tokenizer::common_prefix_search, src/model.rs:132-138).
 template <class F>
 inline void da_common_prefix_search(const DoubleArray& da, const uint8_t* s, size_t n, F&& f) {

@@ -136,8 +136,9 @@ class ModelVocabularyPruner:
         report.freq_s.append(time.perf_counter() - t)
         t = time.perf_counter()
         n_samples = self.n_samples_global if self.n_samples_global is not None else len(off) - 1
-        ids, audit = N.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
-                                    self.shrink_factor)
+        # the model was rebuilt from `vocab` just before (src/prune.rs:48): its trie serves the n-best alternatives
+        ids, audit = model.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
+                                        self.shrink_factor)
         report.select_s.append(time.perf_counter() - t)
         report.audits.append(audit)
         return Vocab([vocab.tokens[i] for i in ids], vocab.scores[ids].copy(), vocab.keep[ids].copy())
