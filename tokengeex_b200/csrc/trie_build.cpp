@@ -136,13 +136,16 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   //    expression: unused_bases & AND_i permute(free_slots, label_i), so a block is tested in O(k) word operations
   //    (a walk over the free-slot list spent 85 % of its tries on bases that were taken: 150 ms for 230k nodes).
   std::vector<Block> blocks;
+  std::vector<uint32_t> n_free;  // free slots per block
   auto add_block = [&]() {
     Block nb;
     for (int w = 0; w < 4; w++) nb.free_slots[w] = nb.free_bases[w] = ~0ull;
     blocks.push_back(nb);
+    n_free.push_back(256);
   };
   add_block();
   blocks[0].free_slots[0] &= ~1ull;  // slot 0 = root
+  n_free[0]--;
   nodes[0].slot = 0;
   std::vector<uint32_t> base_of(nodes.size(), 0);
   uint8_t labels[256];
@@ -152,6 +155,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) labels[k++] = nodes[c].label;
     if (!k) continue;
     auto try_block = [&](uint32_t bi) -> uint32_t {  // an admissible base inside block bi, or END
+      if (n_free[bi] < k) return 0xFFFFFFFFu;
       const Block& B = blocks[bi];
       uint64_t cand[4] = {B.free_bases[0], B.free_bases[1], B.free_bases[2], B.free_bases[3]};
       for (uint32_t i = 0; i < k; i++) {
@@ -165,12 +169,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
         if (cand[w]) return (bi << 8) | (uint32_t)(w * 64 + __builtin_ctzll(cand[w]));
       return 0xFFFFFFFFu;
     };
-    auto nfree = [&](uint32_t bi) {
-      const Block& B = blocks[bi];
-      return __builtin_popcountll(B.free_slots[0]) + __builtin_popcountll(B.free_slots[1]) +
-             __builtin_popcountll(B.free_slots[2]) + __builtin_popcountll(B.free_slots[3]);
-    };
-    while (first_open < blocks.size() && nfree(first_open) < 4) first_open++;  // (gives up on <= 3 slots of 256)
+    while (first_open < blocks.size() && n_free[first_open] < 4) first_open++;  // (gives up on <= 3 slots of 256)
     uint32_t base = 0xFFFFFFFFu;
     const uint32_t nb = (uint32_t)blocks.size();
     // Narrow nodes fill the holes wide nodes left behind: they look at the lowest open blocks first; every node
@@ -196,6 +195,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) {
       const uint32_t sl = base ^ nodes[c].label;
       B.free_slots[(sl & 255u) >> 6] &= ~(1ull << (sl & 63u));
+      n_free[base >> 8]--;
       nodes[c].slot = sl;
     }
   }
