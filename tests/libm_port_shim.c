@@ -17,14 +17,15 @@ static void init(void) {
 }
 double shim_exp(double x) { init(); return tgx_exp_impl(x, H_exp, TGX_EXP_TAB); }
 double shim_log(double x) { init(); return tgx_log_impl(x, H_log, T_log); }
+double shim_softplus(double x) { init(); return tgx_softplus_impl(x, H_exp, TGX_EXP_TAB, H_log, T_log); }
 
 /* returns the number of arguments where the port differs from libm (bitwise; NaNs compare equal) */
 uint64_t shim_compare(const double* xs, uint64_t n, int which, double* first_bad) {
   init();
   uint64_t bad = 0;
   for (uint64_t i = 0; i < n; i++) {
-    double a = which ? shim_log(xs[i]) : shim_exp(xs[i]);
-    double b = which ? log(xs[i]) : exp(xs[i]);
+    double a = which == 2 ? shim_softplus(xs[i]) : which ? shim_log(xs[i]) : shim_exp(xs[i]);
+    double b = which == 2 ? log(exp(xs[i]) + 1.0) : which ? log(xs[i]) : exp(xs[i]);
     uint64_t ua, ub;
     memcpy(&ua, &a, 8);
     memcpy(&ub, &b, 8);

@@ -70,3 +70,21 @@ def test_log_matches_libm_bitwise(shim):
         n, bad = compare(shim, xs, 1)
         assert n == 0, (n, bad)
     assert np.isnan(shim.shim_log(-1.0)) and np.isnan(shim.shim_log(float("nan")))
+
+
+def test_softplus_matches_libm_bitwise(shim):
+    """log(exp(d) + 1.0), the inner term of log_sum_exp (src/lattice.rs:321-333), as one specialised function."""
+    rng = np.random.default_rng(3)
+    sets = [
+        -rng.random(3_000_000) * 50.0,                # the domain log_sum_exp produces
+        -rng.random(500_000) * 3.0,                   # both sides of the near-1 window of log (d ~ -2.74)
+        -np.exp(rng.uniform(-45, 4.2, 500_000)),      # tiny |d| up to ~-66: the |d| < 2^-54 select, the fallback beyond -60
+        np.array([0.0, -0.0, -2.0 ** -54, -2.0 ** -55, -1e-300, -36.7, -36.8, -37.5, -50.0, -60.0, -60.000001, -700.0,
+                  -2.7436, -2.7437, 1.0, 5.0, -np.inf]),
+    ]
+    for xs in sets:
+        n, bad = compare(shim, xs, 2)
+        assert n == 0, (n, bad)
+    shim.shim_softplus.restype = C.c_double
+    shim.shim_softplus.argtypes = [C.c_double]
+    assert np.isnan(shim.shim_softplus(float("nan")))

@@ -855,7 +855,9 @@ __device__ __forceinline__ double log_sum_exp(double x, double y, const LibmTabs
   double vmin, vmax;
   if (x > y) { vmin = y; vmax = x; } else { vmin = x; vmax = y; }
   if (vmax > __dadd_rn(vmin, 50.0)) return vmax;
-  return __dadd_rn(vmax, tgx_log(__dadd_rn(tgx_exp(__dadd_rn(vmin, -vmax), t), 1.0), t));
+  // ln(exp(vmin - vmax) + 1.0): exp and log fused over the only domain this call produces (tgx_libm.h)
+  return __dadd_rn(vmax, tgx_softplus_impl(__dadd_rn(vmin, -vmax), reinterpret_cast<const double*>(c_exp_hdr), t.et,
+                                           reinterpret_cast<const double*>(c_log_hdr), t.lt));
 }
 
 // -----------------------------------------------------------------------------------------

@@ -159,3 +159,85 @@ TGX_HD double tgx_log_impl(double x, const double* H, const double* T) {
   const double y = TGX_FMA(r3, p, lo);
   return TGX_ADD(y, hi);
 }
+
+// log(exp(x) + 1.0) for the x = vmin - vmax of log_sum_exp (src/lattice.rs:321-333): the composition of the two
+// functions above restricted to -60 <= x <= 0, where exp has no over/underflow class and its result + 1.0 lies in
+// [1, 2], so the class tests of both collapse to one select (|x| < 2^-54) and one branch (the near-1 window of log).
+// Same operations in the same order on that domain => the same bits; anything else (NaN included) takes the general
+// functions.  He/Te, Hl/Tl as above.
+TGX_HD double tgx_softplus_impl(double x, const double* He, const uint64_t* Te, const double* Hl, const double* Tl) {
+  if (!(x >= -60.0 && x <= 0.0)) return tgx_log_impl(TGX_ADD(tgx_exp_impl(x, He, Te), 1.0), Hl, Tl);
+  // ---- exp(x), main path
+  double kd = TGX_FMA(x, He[0], He[1]);
+  const uint64_t ki = TGX_AS_U64(kd);
+  kd = TGX_ADD(kd, -He[1]);
+  double r = TGX_FMA(kd, He[2], x);
+  r = TGX_FMA(kd, He[3], r);
+  const uint32_t idx = 2u * (uint32_t)(ki & 127u);
+  const uint64_t top = ki << 45;
+  const double tail = TGX_AS_F64(Te[idx]);
+  const uint64_t sbits = Te[idx + 1] + top;
+  const double p23 = TGX_FMA(r, He[5], He[4]);
+  const double t3 = TGX_ADD(r, tail);
+  const double r2 = TGX_MUL(r, r);
+  const double p45 = TGX_FMA(r, He[7], He[6]);
+  const double t = TGX_FMA(p23, r2, t3);
+  const double r4 = TGX_MUL(r2, r2);
+  const double tmp = TGX_FMA(r4, p45, t);
+  const double scale = TGX_AS_F64(sbits);
+  const uint32_t abstop = (uint32_t)(TGX_AS_U64(x) >> 52) & 0x7ffu;
+  const double e = (abstop < 0x3c9u) ? TGX_ADD(x, 1.0) : TGX_FMA(scale, tmp, scale);  // |x| < 2^-54: 1 + x
+  // ---- log(s), s = e + 1.0 in [1, 2]
+  const double s = TGX_ADD(e, 1.0);
+  const uint64_t ix = TGX_AS_U64(s);
+  const double* A = Hl + 2;
+  const double* B = Hl + 7;
+  if (ix - 0x3fee000000000000ull <= 0x308ffffffffffull) {  // s < 1 + 0x1.09p-4
+    const double q0 = TGX_ADD(s, -1.0);
+    double q1 = TGX_FMA(q0, B[2], B[1]);
+    double q4 = TGX_FMA(q0, B[5], B[4]);
+    const double q02 = TGX_MUL(q0, q0);
+    double q7 = TGX_FMA(q0, B[8], B[7]);
+    q1 = TGX_FMA(q02, B[3], q1);
+    q4 = TGX_FMA(q02, B[6], q4);
+    const double q03 = TGX_MUL(q0, q02);
+    q7 = TGX_FMA(q02, B[9], q7);
+    q7 = TGX_FMA(q03, B[10], q7);
+    q4 = TGX_FMA(q7, q03, q4);
+    const double q = TGX_FMA(q4, q03, q1);
+    const double c27 = 134217728.0;  // 0x1p27
+    const double w = TGX_FMA(q0, c27, q0);
+    const double rhi = TGX_FMA(-c27, q0, w);
+    const double rhi2 = TGX_MUL(rhi, rhi);
+    const double rlo = TGX_ADD(q0, -rhi);
+    const double hi = TGX_FMA(rhi2, B[0], q0);
+    const double rmhi = TGX_ADD(q0, -hi);
+    const double rprhi = TGX_ADD(q0, rhi);
+    double lo = TGX_FMA(rhi2, B[0], rmhi);
+    const double b0rlo = TGX_MUL(B[0], rlo);
+    lo = TGX_FMA(b0rlo, rprhi, lo);
+    const double y = TGX_FMA(q, q03, lo);
+    return (ix == 0x3ff0000000000000ull) ? 0.0 : TGX_ADD(hi, y);
+  }
+  const uint64_t tm = ix - 0x3fe6000000000000ull;
+  const uint32_t i = (uint32_t)(tm >> 45) & 127u;
+  const int32_t k = (int32_t)((int64_t)tm >> 52);  // 0, or 1 for s == 2
+  const uint64_t iz = ix - (tm & 0xfff0000000000000ull);
+  const double invc = Tl[2 * i], logc = Tl[2 * i + 1];
+  const double z = TGX_AS_F64(iz);
+  const double kf = (double)k;
+  const double w = TGX_FMA(kf, Hl[0], logc);
+  const double rr = TGX_FMA(z, invc, -1.0);
+  const double p12 = TGX_FMA(rr, A[2], A[1]);
+  const double hi = TGX_ADD(rr, w);
+  const double rr2 = TGX_MUL(rr, rr);
+  double lo = TGX_ADD(w, -hi);
+  lo = TGX_ADD(lo, rr);
+  lo = TGX_FMA(kf, Hl[1], lo);
+  const double rr3 = TGX_MUL(rr, rr2);
+  const double p34 = TGX_FMA(rr, A[4], A[3]);
+  lo = TGX_FMA(rr2, A[0], lo);
+  const double pp = TGX_FMA(p34, rr2, p12);
+  const double y = TGX_FMA(rr3, pp, lo);
+  return TGX_ADD(y, hi);
+}
