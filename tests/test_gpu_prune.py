@@ -65,3 +65,30 @@ def test_model_rebuild_in_place():
         assert float(np.max(np.abs(ex[nz] - want[nz]) / want[nz])) < 1e-9
         fr = gm.token_frequencies(blob, off)[0]
         assert np.array_equal(fr, om.token_frequencies(blob, off, threads=4))
+
+
+def test_prune_command_line(tmp_path):
+    """`python -m tokengeex_b200.cli prune` end to end: tokenizer JSON in, NUL-separated corpus with a proportion, EM
+    pruning on the GPU, tokenizer JSON out — the same vocabulary the pruner gives on the same samples."""
+    from tokengeex_b200 import _native as N, cli
+    from tokengeex_b200.prune import ModelVocabularyPruner, Vocab
+    from tokengeex_b200.tokenizer import Tokenizer, _Processor
+    blob, off, toks, sc, kp = synth_setup(1, 23, 600_000, 1500, 16)
+    samples = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
+    corpus = tmp_path / "train.bin"
+    corpus.write_bytes(b"\x00".join(samples))
+    tok_in, tok_out = str(tmp_path / "in.json"), str(tmp_path / "out.json")
+    Tokenizer(toks, sc, kp, [_Processor("crlf")], ["<|eos|>"]).save(tok_in)
+    rc = cli.main(["prune", "-i", tok_in, "-o", tok_out, "-v", "1000", "--train", f"code:{corpus}:0.5",
+                   "--em-subiters", "1"])
+    assert rc == 0
+    out = Tokenizer.from_file(tok_out)
+    assert out.special_tokens() == ["<|eos|>"] and out.base_vocab_size() <= 1200
+    # the same run through the library
+    (src,) = cli.load_sources([f"code:{corpus}:0.5"], [_Processor("crlf")])
+    b2, o2 = N.pack(src.processed_samples)
+    t_in = Tokenizer.from_file(tok_in)
+    vocab, _ = ModelVocabularyPruner(1000, 0.8, 1, 0.0).prune(Vocab(list(t_in._tokens), t_in._scores.copy(),
+                                                                    t_in._keep.copy()), b2, o2)
+    assert set(out._tokens) == set(vocab.tokens)
+    assert out.encode("def f(x):\r\n    return x<|eos|>", 0.0)[-1] == out.base_vocab_size()
