@@ -137,8 +137,12 @@ class ModelVocabularyPruner:
         t = time.perf_counter()
         n_samples = self.n_samples_global if self.n_samples_global is not None else len(off) - 1
         # the model was rebuilt from `vocab` just before (src/prune.rs:48): its trie serves the n-best alternatives
+        # (every rank of a box runs this replica of the host step: share the cores instead of oversubscribing them)
+        import os
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        threads = max(2, len(os.sched_getaffinity(0)) // local_world)
         ids, audit = model.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
-                                        self.shrink_factor)
+                                        self.shrink_factor, threads=threads)
         report.select_s.append(time.perf_counter() - t)
         report.audits.append(audit)
         return Vocab([vocab.tokens[i] for i in ids], vocab.scores[ids].copy(), vocab.keep[ids].copy())
