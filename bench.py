@@ -231,6 +231,10 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
 
     model, t_build0 = timed(lambda: N.Model(vocab.tokens, vocab.scores, device=local))
     pr.run_e_step(model, blob, off, d)  # warm-up: workspaces are allocated on the first call
+    # same for the frequency pass (back lengths, marks: ~8 GB of cudaMalloc the EM loop pays once, not per iteration)
+    d_wfr = torch.zeros(max(model.V, 1), dtype=torch.int64, device=dev)
+    model.token_frequencies_dev(d["text"].data_ptr(), d["off"].data_ptr(), d["S"], d["N"], False, d_wfr.data_ptr())
+    del d_wfr
     expected, t_e = timed(lambda: pr.run_e_step(model, blob, off, d))
     e_dev_ms, fwd_ms, bwd_ms = model.stat(4), model.stat(2), model.stat(3)
     new_vocab, t_m = timed(lambda: pr.run_m_step(vocab, expected))

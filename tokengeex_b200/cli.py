@@ -27,8 +27,6 @@ import sys
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
-import numpy as np
-
 log = logging.getLogger("tokengeex_b200.cli")
 
 

@@ -101,7 +101,8 @@ struct tgx_model {
   const Workspace& w() const { return ws[wi]; }
   Stats last_stats;  // of the last finished call (tgx_model_last_stat)
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones (E-step)
-  cudaStream_t stream3 = nullptr, stream4 = nullptr;  // lane-per-snippet kernels (E-step): forward / backward
+  cudaStream_t stream3 = nullptr;  // lane-per-snippet kernels (E-step)
+  cudaStream_t stream4 = nullptr;  // beta chains of the warp-per-snippet kernels in split form
   cudaEvent_t ev_join3 = nullptr, ev_join4 = nullptr;
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
