@@ -733,7 +733,7 @@ struct EmitParams {
 __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
   __shared__ uint32_t ws[EM_BLOCK / 32];
   __shared__ uint32_t s_tok[EM_TILE];  // (len << 16) | offset of the token's last byte in the tile
-  __shared__ __align__(16) uint8_t s_text[EM_TILE + 16];  // bytes tile * EM_TILE - 16 .. (hash path)
+  __shared__ __align__(16) uint8_t s_text[EM_TILE + 48];  // bytes tile * EM_TILE - 16 .. (hash path; +32: word reads past the tile)
   extern __shared__ uint32_t s_hot[];  // [EM_HOT] when freq
   const bool staged = p.hash_mask && !p.ids_at && (reinterpret_cast<unsigned long long>(p.text) & 15ull) == 0;
   if (p.freq) {
@@ -774,9 +774,19 @@ __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
       } else if (p.hash_mask) {
         unsigned long long lo = 0, hi = 0;
         if (staged) {  // token bytes from the staged tile (16-byte halo in front: a token may start in the previous tile)
-          const uint8_t* q = s_text + 16 + (tk & 0xFFFFu) + 1 - len;
-          for (uint32_t d = 0; d < len && d < 8; d++) lo |= (unsigned long long)q[d] << (8 * d);
-          for (uint32_t d = 8; d < len; d++) hi |= (unsigned long long)q[d] << (8 * (d - 8));
+          // 16 bytes from the token's first byte: five aligned words + funnel shifts, then cut to `len`
+          const uint32_t o = 16u + (tk & 0xFFFFu) + 1u - len;
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(s_text) + (o >> 2);
+          const uint32_t sh = 8u * (o & 3u);
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+          lo = (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+          hi = (unsigned long long)__funnelshift_r(w2, w3, sh) | ((unsigned long long)__funnelshift_r(w3, w4, sh) << 32);
+          if (len < 8) {
+            lo &= (1ull << (8 * len)) - 1ull;
+            hi = 0;
+          } else if (len < 16) {
+            hi &= (1ull << (8 * (len - 8))) - 1ull;
+          }
         } else {
           const uint8_t* q = tt + (tk & 0xFFFFu) + 1 - len;
           for (uint32_t d = 0; d < len && d < 8; d++) lo |= (unsigned long long)__ldg(q + d) << (8 * d);
