@@ -195,7 +195,8 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * threshold of key 5, the default; 0 = never, the lane-group kernels of key 2 take them), 18 = resident blocks per
  * SM of the lane E-step kernels (0 = as many as fit), 19 = E-step in split form (1, the default: beta chains stored
  * and run beside the alpha chains, counts by a third kernel; needs 8 more bytes of device memory per input byte and
- * falls back to 0 = fused backward + counts without them). */
+ * falls back to 0 = fused backward + counts without them), 20 / 21 = E-step: replicas of the count vector (default
+ * 256) for the hottest ids (default: ids below 4096), so that their atomics do not queue on one L2 address. */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 #ifdef __cplusplus

@@ -131,6 +131,7 @@ struct tgx_model {
   // Lane kernels in split form: the backward chain only stores beta and runs beside the forward chain, a third
   // kernel adds the expected counts (needs 8 more bytes per input byte; falls back to the fused form without them).
   int estep_split = 1;
+  int hot_k = 4096, hot_r = 256;  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids
   int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
@@ -1203,6 +1204,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
     case 19: m->estep_split = value ? 1 : 0; break;
+    case 20: if (value < 1 || value > 4096) return fail(TGX_ERR_INVALID, "replicas must be 1..4096"); m->hot_r = (int)value; break;
+    case 21: if (value < 0 || value > (1 << 20)) return fail(TGX_ERR_INVALID, "hot ids must be 0..2^20"); m->hot_k = (int)value; break;
     case 18: if (value < 0 || value > 16) return fail(TGX_ERR_INVALID, "blocks per SM must be 0..16"); m->lane_blocks_per_sm = (int)value; break;
     case 15: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "segment kernel hot levels must be 0..2"); m->seg_hot = (int)value; break;
     case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
@@ -1806,8 +1809,8 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.A = m->A.as<double>();
   p.status = m->w().status.as<int32_t>();
   p.expected = d_expected;
-  p.hot_k = (uint32_t)std::min<uint64_t>(m->V, 4096);
-  p.hot_r = 64;
+  p.hot_k = (uint32_t)std::min<uint64_t>(m->V, (uint64_t)m->hot_k);
+  p.hot_r = (uint32_t)m->hot_r;
   CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8));
   CU(dev_fill(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8, st));
   p.hot = m->hot.as<double>();

@@ -79,13 +79,15 @@ def main():
             lane = cfg[2] if len(cfg) > 2 else 0
             m.set_option(18, cfg[3] if len(cfg) > 3 else 0)
             m.set_option(19, cfg[4] if len(cfg) > 4 else 1)
+            m.set_option(20, cfg[5] if len(cfg) > 5 else 64)
+            m.set_option(21, cfg[6] if len(cfg) > 6 else 4096)
             m.set_option(2, g)
             m.set_option(5, thr)
             m.set_option(17, lane)
             for _ in range(args.reps):
                 d_ex.zero_()
                 rc, bad, bz = m.expected_counts_dev(d_text.data_ptr(), d_off.data_ptr(), S, NB, d_ex.data_ptr(), args.snippet)
-            print(f"estep G={g} thr={thr} lane={lane} blocks/SM={cfg[3] if len(cfg) > 3 else 0} split={cfg[4] if len(cfg) > 4 else 1}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
+            print(f"estep G={g} thr={thr} lane={lane} blocks/SM={cfg[3] if len(cfg) > 3 else 0} split={cfg[4] if len(cfg) > 4 else 1} hot={cfg[5:] if len(cfg) > 5 else ''}: total {m.stat(4):.2f} ms fwd {m.stat(2):.2f} bwd {m.stat(3):.2f}  "
                   f"{NB / m.stat(4) / 1e6:.3f} GB/s sum={float(d_ex.sum()):.3f}", flush=True)
 
 
