@@ -406,6 +406,22 @@ def test_expected_counts_random_vs_oracle(N, g):
         assert abs(tot - int(off[-1])) < 1e-9 * int(off[-1])  # invariant (i)
 
 
+def test_expected_counts_long_tokens(N):
+    """max_token_len > 16: the lane-per-snippet and split-form kernels do not apply (16-slot windows); the lane-group
+    kernels take every snippet, whatever the options say."""
+    rng = random.Random(4242)
+    toks = [bytes([c]) for c in b"ab"] + [b"ab" * 10, b"a" * 17, b"b" * 32, b"ba" * 7, b"abb"]
+    scores = [-3.0, -3.5, -9.0, -8.0, -20.0, -5.0, -4.0]
+    gm, om = both(N, toks, scores)
+    samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 1, 300)
+    blob, off = N.pack(samples)
+    want = om.run_e_step(blob, off, threads=1, literal=True)[0]
+    for g in (0, -3, 4, 32):
+        estep_cfg(gm, g)
+        ex, rc, bad, badz = gm.expected_counts(blob, off)
+        assert rc == 0 and np.allclose(ex, want, rtol=ORDER_TOL, atol=0), (g, np.max(np.abs(ex - want)))
+
+
 def test_expected_counts_bad_z(N):
     m = N.Model([b"a"], [-1.0])
     blob, off = N.pack([b"aa", b"ab", b"a"])
