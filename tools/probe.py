@@ -43,7 +43,7 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        cfgs = [(4, {15: 1}), (4, {15: 2}), (4, {15: 0}), (0, {14: 0, 16: 0}), (0, {14: 0, 16: 1}), (0, {14: 1}), (0, {14: 2}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
+        cfgs = [(4, {15: 1}), (4, {15: 2}), (4, {15: 0}), (0, {14: 0, 16: 0}), (0, {14: 0, 16: 1}), (0, {14: 2, 6: 5, 13: 1}), (0, {14: 2, 6: 5, 13: 0}), (0, {14: 2, 6: 6, 13: 0}), (0, {14: 2, 6: 4, 13: 1}), (0, {14: 2, 6: 0, 13: 2}), (0, {14: 1}), (0, {14: 2}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
                 (3, {9: 12, 8: 32768, 10: 48}), (3, {9: 8, 8: 24576, 10: 64})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
