@@ -199,6 +199,21 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * 256) for the hottest ids (default: ids below 4096), so that their atomics do not queue on one L2 address. */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
+/* The `dropout` argument of Model::encode (src/model.rs:59,100) for the encode entry points
+ * (tgx_encode_batch{,_dev}); the frequency passes always encode with dropout 0.0, as the reference
+ * does (src/prune.rs:218, src/merge.rs:58).  dropout must be in [0, 1); 0.0 (the default, and every
+ * benchmark configuration) switches it off.  dropout >= 1.0 is not a draw at all — every multi-byte
+ * token is skipped (src/model.rs:218-236) — and is served by a model created from the single-byte
+ * tokens (see tokengeex_b200/tokenizer.py).
+ * The reference draws rand::random::<f64>() from an unseeded thread_rng for every multi-byte candidate
+ * of a reachable position, so only the distribution of its output is defined.  Here the draw of
+ * candidate (sample index within the call, start byte within the processed sample, token length) is a
+ * pure function of `seed` (two rounds of the splitmix64 finaliser, 53-bit uniform in [0, 1); the
+ * candidate is kept iff dropout < u): independent uniform draws like the reference's, but
+ * reproducible, independent of chunking and sharding, and restated in oracle/ for bit-exact tests.
+ * With dropout > 0 the forward pass runs on the lane-group kernel (viterbi_kernel<G, true>). */
+int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,9 @@ def lib() -> C.CDLL:
         L.orc_model_export.argtypes = [C.c_void_p, u8p, u64p, f64p, u8p]
         L.orc_encode.restype = C.c_int64
         L.orc_encode.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, u32p, C.c_uint64, u64p]
+        L.orc_encode_keyed.restype = C.c_int64
+        L.orc_encode_keyed.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, u32p,
+                                       C.c_uint64, u64p]
         L.orc_crlf.restype = C.c_uint64
         L.orc_crlf.argtypes = [u8p, C.c_uint64, u8p]
         L.orc_encode_batch.restype = C.c_uint64
@@ -170,6 +173,21 @@ class OracleModel:
         out = np.zeros(max(n, 1), np.uint32)
         err = np.zeros(2, np.uint64)
         k = L.orc_encode(self._h, _p(a, u8p), n, dropout, _p(out, u32p), out.size, _p(err, u64p))
+        if k == -1:
+            raise NoPath(int(err[0]), int(err[1]))
+        assert k >= 0
+        return out[:k].tolist()
+
+    def encode_keyed(self, text: bytes, dropout: float, seed: int, sample: int) -> List[int]:
+        """Model::encode with the product's keyed dropout draw (tgx_model_set_dropout): `sample` is the index of
+        `text` in the call, positions are bytes of the processed text."""
+        L = lib()
+        a = _bytes_arr(text)
+        n = len(text)
+        out = np.zeros(max(n, 1), np.uint32)
+        err = np.zeros(2, np.uint64)
+        k = L.orc_encode_keyed(self._h, _p(a, u8p), n, dropout, seed & 0xFFFFFFFFFFFFFFFF, sample, _p(out, u32p),
+                               out.size, _p(err, u64p))
         if k == -1:
             raise NoPath(int(err[0]), int(err[1]))
         assert k >= 0

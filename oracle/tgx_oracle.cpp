@@ -180,6 +180,23 @@ static inline double next_f64(uint64_t& s) {
   return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// Keyed draw for dropout parity tests: the product's documented stand-in for rand::random::<f64>()
+// (include/tokengeex_b200.h, tgx_model_set_dropout) restated — a pure function of (seed, sample index,
+// start position, token length): two rounds of the splitmix64 finaliser, 53-bit uniform in [0,1).
+static inline uint64_t drop_mix(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+struct KeyedDraw {
+  uint64_t unit_key;
+  KeyedDraw(uint64_t seed, uint64_t sample) : unit_key(drop_mix(seed + 0x9E3779B97F4A7C15ULL * (sample + 1))) {}
+  double operator()(uint64_t pos, uint32_t len) const {
+    uint64_t z = drop_mix(unit_key + 0x9E3779B97F4A7C15ULL * ((pos << 8) | len));
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
 // ----------------------------------------------------------------------------
 // src/model.rs:59-129  Model::encode  (Viterbi, "SentencePiece DP")
 // Returns 0 on success; 1 = Error::NoPath(pos,len) (src/lib.rs:243-245).
@@ -193,7 +210,7 @@ struct DpNode {  // src/model.rs:63-68  struct Node { id, score, start: Option<u
 
 static int encode(const Model& m, const uint8_t* input, size_t n, double dropout,
                   std::vector<uint32_t>& ids, uint64_t* err_pos, uint64_t* err_len,
-                  uint64_t* rng) {
+                  uint64_t* rng, const KeyedDraw* keyed = nullptr) {
   ids.clear();
   std::vector<DpNode> dp(n + 1, DpNode{0, 0.0, 0, false});  // :72-79
   dp[0].has_start = true;                                   // :81  dp[0].start = Some(0)
@@ -208,7 +225,7 @@ static int encode(const Model& m, const uint8_t* input, size_t n, double dropout
       // :100  (dropout <= 0.0 || len <= 1 || dropout < rand::random::<f64>())
       //       && (node.start.is_none() || score > node.score)
       bool keep = dropout <= 0.0 || len <= 1;
-      if (!keep) keep = dropout < next_f64(*rng);
+      if (!keep) keep = dropout < (keyed ? (*keyed)(pos, len32) : next_f64(*rng));
       if (keep && (!node.has_start || score > node.score)) {
         dp[pos + len] = DpNode{id, score, pos, true};          // :103-107
       }
@@ -891,6 +908,19 @@ int64_t orc_encode(orc_model* h, const uint8_t* text, uint64_t n, double dropout
   std::vector<uint32_t> ids;
   uint64_t ep = 0, el = 0;
   int rc = encode(*h->m, text, n, dropout, ids, &ep, &el, &h->m->rng_state);
+  if (rc) { err[0] = ep; err[1] = el; return -1; }
+  if (ids.size() > cap) return -2;
+  std::memcpy(out, ids.data(), ids.size() * 4);
+  return (int64_t)ids.size();
+}
+
+// Model::encode with the keyed dropout draw of tgx_model_set_dropout (sample = index of this text in the call).
+int64_t orc_encode_keyed(orc_model* h, const uint8_t* text, uint64_t n, double dropout, uint64_t seed,
+                         uint64_t sample, uint32_t* out, uint64_t cap, uint64_t* err) {
+  std::vector<uint32_t> ids;
+  uint64_t ep = 0, el = 0;
+  KeyedDraw kd(seed, sample);
+  int rc = encode(*h->m, text, n, dropout, ids, &ep, &el, &h->m->rng_state, &kd);
   if (rc) { err[0] = ep; err[1] = el; return -1; }
   if (ids.size() > cap) return -2;
   std::memcpy(out, ids.data(), ids.size() * 4);

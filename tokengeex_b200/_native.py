@@ -67,6 +67,7 @@ SYMBOLS = [
     ("tgx_model_debug_counters", C.c_int, [C.c_void_p, u64p]),
     ("tgx_model_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     ("tgx_model_rebuild", C.c_int, [C.c_void_p, u8p, u64p, f64p, C.c_uint64]),
+    ("tgx_model_set_dropout", C.c_int, [C.c_void_p, C.c_double, C.c_uint64]),
 ]
 
 _lib = None
@@ -177,6 +178,10 @@ class Model:
 
     def set_option(self, key: int, value: int):
         _check(lib().tgx_model_set_option(self._h, key, value))
+
+    def set_dropout(self, dropout: float, seed: int = 0):
+        """Model::encode's dropout argument for the following encode calls (include/tokengeex_b200.h)."""
+        _check(lib().tgx_model_set_dropout(self._h, float(dropout), int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def stat(self, what: int) -> float:
         return float(lib().tgx_model_last_stat(self._h, what))

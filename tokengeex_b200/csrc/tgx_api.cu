@@ -156,6 +156,11 @@ struct tgx_model {
   int emit_hash = 1;   // emit: token ids through the token hash (1 probe per token) instead of re-walking the trie
   int seg_hot = 1;     // trie levels the segment kernel (algo 4) stages in shared memory
   int pair_shape = 0;  // 0 = by batch size, 1 = latency shape (5 groups), 2 = throughput shape (6 groups)
+  // tgx_model_set_dropout: Model::encode's dropout argument for the encode entry points (src/model.rs:59,100).
+  // 0.0 = off (every BASELINE configuration); in (0, 1) the keyed draw of tgx_kernels.cuh::drop_draw.
+  double dropout = 0.0;
+  uint64_t drop_seed = 0;
+  uint64_t drop_unit_base = 0;  // first sample of the chunk being queued (chunked host entry point)
   uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
   DevBuf Bbeta;
@@ -484,15 +489,15 @@ cudaError_t dev_fill(void* p, int byte, size_t n, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int G>
+template <int G, bool DROP = false>
 cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
   if (!p.u.count) return cudaSuccess;
   size_t smem = warp_smem_bytes(p.u.rows, p.u.W, G) * WPB;
-  cudaError_t e = cudaFuncSetAttribute(viterbi_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(viterbi_kernel<G, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   uint32_t per_block = WPB * (32 / G);
   uint32_t blocks = (p.u.count + per_block - 1) / per_block;
-  viterbi_kernel<G><<<blocks, WPB * 32, smem, m->w().stream>>>(p);
+  viterbi_kernel<G, DROP><<<blocks, WPB * 32, smem, m->w().stream>>>(p);
   m->w().stats.launches += 1;
   return cudaGetLastError();
 }
@@ -610,6 +615,7 @@ cudaError_t launch_viterbi_hybrid(tgx_model* m, const HybridParams& p) {
 }
 
 cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
+  if (p.dropout > 0.0) return G >= 32 ? launch_viterbi<32, true>(m, p) : launch_viterbi<8, true>(m, p);
   switch (G) {
     case 1: return launch_viterbi<1>(m, p);
     case 2: return launch_viterbi<2>(m, p);
@@ -837,7 +843,7 @@ int run_viterbi_seg(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, 
 // m->w().mark holds the length of the token ending at every marked byte, m->w().ntok token counts,
 // m->w().status per-sample status.
 int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
-                uint64_t* d_proc_len) {
+                uint64_t* d_proc_len, bool with_dropout = false) {
   cudaStream_t st = m->w().stream;
   if (S >= (1ull << 32)) return fail(TGX_ERR_INVALID, "too many samples in one call (< 2^32)");
   uint32_t U = (uint32_t)S;
@@ -879,9 +885,12 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.count = U;  // upper bound for the grids
 
   m->w().have_ids_at = false;
-  if (m->algo == 4 && u.rows <= 16 && m->hash.mask != 0) return run_viterbi_seg(m, d_text, d_off, S, N, u);
+  // dropout in (0, 1): always the lane-group kernels (the only forward kernel that takes the draw)
+  const double dropout = with_dropout ? m->dropout : 0.0;  // the frequency passes encode with dropout 0.0
+  const int algo = dropout > 0.0 ? 1 : m->algo;
+  if (algo == 4 && u.rows <= 16 && m->hash.mask != 0) return run_viterbi_seg(m, d_text, d_off, S, N, u);
   CU(cudaEventRecord(m->w().ev[0], st));
-  if (m->algo == 3 && u.rows <= 16) {
+  if (algo == 3 && u.rows <= 16) {
     HybridParams hp;
     hp.pair.u = u;
     hp.pair.u.part = 3;
@@ -896,7 +905,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     hp.lane.counter = m->w().small.as<unsigned int>() + 9;
     hp.pair_ctas = hp.lane_warps = 0;
     CU(launch_viterbi_hybrid(m, hp));
-  } else if (m->algo == 2 && u.rows <= 16) {
+  } else if (algo == 2 && u.rows <= 16) {
     LaneParams p;
     p.u = u;
     p.u.part = 0;
@@ -904,7 +913,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.bp = m->w().bp.as<uint8_t>();
     p.counter = m->w().small.as<unsigned int>() + 9;
     CU(launch_viterbi_lane<16>(m, p));
-  } else if (m->algo == 0 && u.rows <= 16) {
+  } else if (algo == 0 && u.rows <= 16) {
     PairParams p;
     p.u = u;
     p.u.part = 0;
@@ -922,6 +931,9 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     ViterbiParams p;
     p.u = u;
     p.bp = m->w().bp.as<uint8_t>();
+    p.dropout = dropout;
+    p.drop_seed = m->drop_seed;
+    p.unit_base = m->drop_unit_base;
     p.u.part = 1;
     CU(launch_viterbi_g(m, 32, p));
     p.u.part = 2;
@@ -1222,6 +1234,16 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
   return TGX_OK;
 }
 
+int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed) {
+  if (!m) return fail(TGX_ERR_INVALID, "null model");
+  if (!(dropout >= 0.0) || dropout >= 1.0)
+    return fail(TGX_ERR_INVALID, "dropout must be in [0, 1): dropout >= 1 is a bytes-only vocabulary, not a draw");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  m->dropout = dropout;
+  m->drop_seed = seed;
+  return TGX_OK;
+}
+
 double tgx_model_last_stat(const tgx_model* m, int what) {
   if (!m) return 0;
   switch (what) {
@@ -1296,7 +1318,7 @@ namespace {
 // Queues every kernel of one encode batch on the current workspace; nothing here waits for the device.
 int encode_enqueue(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t n_bytes,
                    uint32_t flags, uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_id_off, int32_t* d_status,
-                   uint64_t* d_proc_len) {
+                   uint64_t* d_proc_len, bool with_dropout = false) {
   m->w().stats = Stats();
   cudaStream_t st = m->w().stream;
   CU(cudaEventRecord(m->w().ev[6], st));
@@ -1309,7 +1331,7 @@ int encode_enqueue(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, u
     text = m->w().text2.as<uint8_t>();
     off = m->w().off2.as<uint64_t>();
   }
-  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len);
+  rc = run_viterbi(m, text, off, S, n_bytes, d_proc_len, with_dropout);
   if (rc) return rc;
   // id offsets = exclusive scan of token counts (S+1 entries; ntok[S] was zeroed)
   size_t tmp = 0;
@@ -1368,7 +1390,8 @@ int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     CU(cudaStreamSynchronize(m->w().stream));
     return TGX_OK;
   }
-  rc = encode_enqueue(m, d_text, d_off, S, n_bytes, flags, d_ids, ids_cap, d_id_off, d_status, d_proc_len);
+  m->drop_unit_base = 0;
+  rc = encode_enqueue(m, d_text, d_off, S, n_bytes, flags, d_ids, ids_cap, d_id_off, d_status, d_proc_len, true);
   if (rc) return rc;
   uint64_t tot = 0;
   int64_t bad = -1;
@@ -1485,8 +1508,9 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
     uint64_t* dpl = reinterpret_cast<uint64_t*>(d_sc[b]->as<unsigned char>() + ((Sk * 4 + 15) & ~15ull));
     if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 2], m->w().stream);
     if (Sk == 0) return TGX_OK;
+    m->drop_unit_base = cut[k];  // the draw is keyed by the sample's index in the whole call, not in its chunk
     int r = encode_enqueue(m, d_text[b]->as<uint8_t>(), d_off[b]->as<uint64_t>(), Sk, nb, flags,
-                           d_ids[b]->as<uint32_t>(), nb + 4, d_idoff[b]->as<uint64_t>(), dst, dpl);
+                           d_ids[b]->as<uint32_t>(), nb + 4, d_idoff[b]->as<uint64_t>(), dst, dpl, true);
     if (r) return r;
     if (!tev.empty()) cudaEventRecord(tev[1 + 6 * k + 3], m->w().stream);
     return TGX_OK;

@@ -50,7 +50,28 @@ struct UnitParams {
 struct ViterbiParams {
   UnitParams u;
   uint8_t* bp;  // [N] byte length of the best last token per end position (0 = unreachable)
+  // dropout in (0, 1) (viterbi_kernel<G, true> only): see drop_draw
+  double dropout;
+  unsigned long long drop_seed, unit_base;  // unit_base = index of this launch's unit 0 within the caller's batch
 };
+
+// dropout (src/model.rs:100): the reference draws rand::random::<f64>() — an unseeded thread_rng — once per
+// multi-byte candidate of a reachable position, so only the DISTRIBUTION of its output is defined.  Here the draw
+// of candidate (sample, start position, length) is a pure function of a caller-provided seed (two rounds of the
+// splitmix64 finaliser), which gives independent uniform draws with the same keep rule (`dropout < u`), is
+// reproducible, and is restated in the oracle (orc_encode_keyed) for bit-exact parity tests.
+__host__ __device__ __forceinline__ unsigned long long drop_mix(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ unsigned long long drop_unit_key(unsigned long long seed, unsigned long long sample) {
+  return drop_mix(seed + 0x9E3779B97F4A7C15ULL * (sample + 1));
+}
+__host__ __device__ __forceinline__ double drop_draw(unsigned long long unit_key, unsigned long long pos, uint32_t len) {
+  const unsigned long long z = drop_mix(unit_key + 0x9E3779B97F4A7C15ULL * ((pos << 8) | len));
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);  // uniform in [0, 1), 53 bits
+}
 
 struct FbParams {
   UnitParams u;
@@ -105,8 +126,10 @@ __device__ inline WarpSmem carve(unsigned char* base, uint32_t rows, uint32_t W,
 
 // Phase A: common_prefix_search from `pos` (src/trie.rs:51-63 restated on the double-array):
 // one 16-byte load per byte walked; stops at the first missing edge.
+template <bool DROP = false>
 __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint8_t* text, uint32_t pos,
-                                                 uint32_t n, const WarpSmem& s, int lane) {
+                                                 uint32_t n, const WarpSmem& s, int lane, double dropout = 0.0,
+                                                 unsigned long long unit_key = 0) {
   uint32_t cnt = 0;
   if (pos < n) {
     uint32_t xb = u.root_base;
@@ -117,7 +140,9 @@ __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint
       uint4 e = __ldg(u.trie + (xb ^ cw));
       if ((e.x ^ cw) & 0x1FFu) break;
       d++;
-      if (e.y & F_TERM) {
+      // (the draw of a dropped candidate does not depend on the position being reachable, so it can be taken here:
+      //  an unreachable start never relaxes anything either way, src/model.rs:85-87)
+      if ((e.y & F_TERM) && (!DROP || d <= 1 || dropout < drop_draw(unit_key, pos, d))) {
         s.mscore[cnt * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
         s.mpack[cnt * ROW_STRIDE + lane] = (d << 24) | (e.y & ID_MASK);
         cnt++;
@@ -135,7 +160,7 @@ __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint
 //      src/model.rs:83-110.  Output: bp[start + e - 1] = byte length of the best last token
 //      ending at position e (0 = position unreachable).
 // -----------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool DROP = false>
 __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = 32 / G;
@@ -155,6 +180,7 @@ __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
   const uint32_t n = has ? u.unit_len[unit] : 0;
   const uint64_t start = has ? u.unit_start[unit] : 0;
   const uint8_t* text = u.text + start;
+  const unsigned long long unit_key = DROP ? drop_unit_key(p.drop_seed, p.unit_base + unit) : 0ull;
 
   for (uint32_t i = lig; i < W; i += G) wbp[i] = NONE;
   uint32_t nmax = n;
@@ -168,7 +194,7 @@ __global__ void __launch_bounds__(WPB * 32) viterbi_kernel(ViterbiParams p) {
   for (uint32_t tile = 0; tile < tiles; tile++) {
     const uint32_t p0 = tile * G;
     // ---- phase A
-    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    s.mcnt[lane] = walk_matches<DROP>(u, text, p0 + lig, n, s, lane, p.dropout, unit_key);
     __syncwarp();
     // ---- phase B
     uint32_t my_bp = NONE;  // back-pointer of end position p0 + lig

@@ -12,6 +12,8 @@ from __future__ import annotations
 import base64
 import json
 import os
+import secrets
+import threading
 import unicodedata
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -137,6 +139,10 @@ class Tokenizer:
         self._device = device if device is not None else int(os.environ.get("TGX_DEVICE", "0"))
         self._model: Optional[N.Model] = None          # device model, created on first encode
         self._model_bytes_only: Optional[N.Model] = None  # dropout >= 1.0: multi-byte tokens never match
+        # 0 < dropout < 1: None = a fresh 64-bit seed per call (the reference's unseeded behaviour); an int makes the
+        # calls reproducible (draw keyed by seed, piece index within the call, start byte, token length)
+        self.dropout_seed: Optional[int] = None
+        self._dropout_lock = threading.Lock()  # set_dropout .. encode .. reset must not interleave between threads
         self._host_model: Optional[N.Model] = None
 
     # ---- construction / serialisation (src/tokenizer.rs:261-297, 349-435; src/lib.rs:109-204) --------
@@ -318,10 +324,15 @@ class Tokenizer:
                     toks = [t if len(t) <= 1 else b"" for t in self._tokens]
                     self._model_bytes_only = N.Model(toks, self._scores, device=self._device)
                 return self._model_bytes_only
+            if dropout != dropout:
+                raise TokenGeeXError("dropout is NaN")
+            # 0 < dropout < 1: the reference draws from an unseeded thread_rng (src/model.rs:100), so each call
+            # takes a fresh seed unless `dropout_seed` is set; the draw itself is keyed (tgx_model_set_dropout)
+            if self._model is None:
+                self._model = N.Model(self._tokens, self._scores, device=self._device)
+            return self._model
         except N.TgxError as e:
             raise TokenGeeXError(e.msg)
-        raise TokenGeeXError("dropout in (0, 1) is not supported by the B200 path: the reference draws from an "
-                             "unseeded thread_rng, so only dropout == 0.0 (and the degenerate >= 1.0) is defined")
 
     def common_prefix_search(self, text: str) -> Iterable[int]:
         return self._host().common_prefix_search(text.encode("utf-8"))[0]
@@ -341,8 +352,18 @@ class Tokenizer:
             return []
         model = self._dev(dropout)
         blob, off = N.pack(pieces)
+        drawn = 0.0 < dropout < 1.0
         try:
-            ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
+            if drawn:
+                seed = self.dropout_seed
+                with self._dropout_lock:
+                    model.set_dropout(dropout, secrets.randbits(64) if seed is None else seed)
+                    try:
+                        ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
+                    finally:
+                        model.set_dropout(0.0, 0)
+            else:
+                ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
         except N.TgxError as e:
             raise TokenGeeXError(e.msg)
         if rc == N.TGX_ERR_NO_PATH:
