@@ -196,12 +196,14 @@ int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
  * SM of the lane E-step kernels (0 = as many as fit), 19 = E-step in split form (1, the default: beta chains stored
  * and run beside the alpha chains, counts by a third kernel; needs 8 more bytes of device memory per input byte and
  * falls back to 0 = fused backward + counts without them), 20 / 21 = E-step: replicas of the count vector (default
- * 256) for the hottest ids (default: ids below 4096), so that their atomics do not queue on one L2 address. */
+ * 256) for the hottest ids (default: ids below 4096), so that their atomics do not queue on one L2 address,
+ * 22 = byte offset of the E-step's text in the whole corpus (keyed dropout draw, see tgx_model_set_dropout). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 /* The `dropout` argument of Model::encode (src/model.rs:59,100) for the encode entry points
- * (tgx_encode_batch{,_dev}); the frequency passes always encode with dropout 0.0, as the reference
- * does (src/prune.rs:218, src/merge.rs:58).  dropout must be in [0, 1); 0.0 (the default, and every
+ * (tgx_encode_batch{,_dev}) and of Model::populate_nodes (src/model.rs:34-55, called by run_e_step with the
+ * pruner's dropout, src/prune.rs:87) for tgx_expected_counts{,_dev}; the frequency passes always encode with
+ * dropout 0.0, as the reference does (src/prune.rs:218, src/merge.rs:58).  dropout must be in [0, 1); 0.0 (the default, and every
  * benchmark configuration) switches it off.  dropout >= 1.0 is not a draw at all — every multi-byte
  * token is skipped (src/model.rs:218-236) — and is served by a model created from the single-byte
  * tokens (see tokengeex_b200/tokenizer.py).
@@ -211,7 +213,11 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value);
  * pure function of `seed` (two rounds of the splitmix64 finaliser, 53-bit uniform in [0, 1); the
  * candidate is kept iff dropout < u): independent uniform draws like the reference's, but
  * reproducible, independent of chunking and sharding, and restated in oracle/ for bit-exact tests.
- * With dropout > 0 the forward pass runs on the lane-group kernel (viterbi_kernel<G, true>). */
+ * In the E-step the candidate is (byte offset of its first byte in the call's text + option 22, token length):
+ * option 22 of tgx_model_set_option = offset of the call's text in the whole corpus when it is one shard of it, so
+ * that the lattices do not depend on the sharding; use a new seed for every E-step.
+ * With dropout > 0 the forward pass runs on the lane-group kernel (viterbi_kernel<G, true>) and the E-step on the
+ * lane-group kernels in fused form (fb_{forward,backward}_kernel<G, .., true>). */
 int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed);
 
 #ifdef __cplusplus

@@ -67,6 +67,9 @@ def lib() -> C.CDLL:
         L.orc_run_e_step.restype = C.c_int
         L.orc_run_e_step.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_int, C.c_int,
                                      C.c_uint64, f64p, i64p, f64p]
+        L.orc_run_e_step_dropout.restype = C.c_int
+        L.orc_run_e_step_dropout.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_int, C.c_uint64, C.c_double,
+                                             C.c_int, C.c_uint64, C.c_uint64, f64p, i64p, f64p]
         L.orc_digamma.restype = C.c_double
         L.orc_digamma.argtypes = [C.c_double]
         L.orc_log_sum_exp.restype = C.c_double
@@ -238,6 +241,19 @@ class OracleModel:
         badz = C.c_double(0.0)
         rc = L.orc_run_e_step(self._h, _p(blob, u8p), _p(off, u64p), len(off) - 1, threads, int(literal),
                               max_sample_length, _p(ex, f64p), C.byref(bad), C.byref(badz))
+        return ex, rc, int(bad.value), float(badz.value)
+
+    def run_e_step_dropout(self, blob: np.ndarray, off: np.ndarray, dropout: float, seed: int, keyed: bool = True,
+                           byte_base: int = 0, threads: int = 1, max_sample_length: int = 81920):
+        """run_e_step with populate_nodes(.., dropout): keyed = the product's draw (tgx_model_set_dropout), else a
+        sequential seeded generator in the reference's loop order."""
+        L = lib()
+        ex = np.zeros(self.V, np.float64)
+        bad = C.c_int64(-1)
+        badz = C.c_double(0.0)
+        rc = L.orc_run_e_step_dropout(self._h, _p(blob, u8p), _p(off, u64p), len(off) - 1, threads,
+                                      max_sample_length, dropout, int(keyed), seed & 0xFFFFFFFFFFFFFFFF, byte_base,
+                                      _p(ex, f64p), C.byref(bad), C.byref(badz))
         return ex, rc, int(bad.value), float(badz.value)
 
     def run_m_step(self, expected: np.ndarray) -> "OracleModel":

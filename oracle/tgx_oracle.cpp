@@ -343,11 +343,16 @@ struct Lattice {
 
 // src/model.rs:34-55  Model::populate_nodes (dropout restated with the same
 // caveat as encode; every position is walked, reachable or not).
-static void populate_nodes(const Model& m, Lattice& lat, double dropout, uint64_t* rng) {
+// `keyed`: the product's keyed draw (tgx_model_set_dropout) instead of the sequential one; position = pos_base + pos.
+// The reference drops when `rand < dropout`; the keyed rule is the encode rule, keep iff `dropout < u` (the two
+// differ only on the null event u == dropout).
+static void populate_nodes(const Model& m, Lattice& lat, double dropout, uint64_t* rng,
+                           const KeyedDraw* keyed = nullptr, uint64_t pos_base = 0) {
   for (size_t pos = 0; pos < lat.len; pos++) {
     common_prefix_search(m.trie, lat.sentence + pos, lat.len - pos, [&](uint32_t id, uint32_t len) {
       double score = m.vocab[id].score;
-      if (len > 1 && dropout > 0.0 && next_f64(*rng) < dropout) return;  // :48-50
+      if (len > 1 && dropout > 0.0 &&
+          (keyed ? !(dropout < (*keyed)(pos_base + pos, len)) : next_f64(*rng) < dropout)) return;  // :48-50
       lat.insert(pos, id, len, score);                                  // :52
     });
   }
@@ -597,7 +602,8 @@ static void parallel_chunks(size_t n_items, size_t chunk, int threads, F&& f) {
 // ----------------------------------------------------------------------------
 static int run_e_step(const Model& m, const uint8_t* blob, const uint64_t* off, size_t S,
                       int threads, int literal, size_t max_sample_length, double* expected_out,
-                      int64_t* bad_sample, double* bad_z) {
+                      int64_t* bad_sample, double* bad_z, double dropout = 0.0, const KeyedDraw* keyed = nullptr,
+                      uint64_t byte_base = 0) {
   size_t V = m.vocab_size();
   size_t chunk = par_chunk_size(S, (size_t)std::max(1, threads), 8);  // :66
   size_t n_chunks = S ? (S + chunk - 1) / chunk : 0;
@@ -618,9 +624,9 @@ static int run_e_step(const Model& m, const uint8_t* blob, const uint64_t* off, 
       for (size_t o = 0; o < n; o += max_sample_length) {  // :83 sample.as_bytes().chunks(MAX)
         size_t sn = std::min(max_sample_length, n - o);
         double z;
-        if (literal) {
+        if (literal || dropout > 0.0) {
           lat.from(p + o, sn);
-          populate_nodes(m, lat, 0.0, &rng);
+          populate_nodes(m, lat, dropout, &rng, keyed, byte_base + off[s] + o);  // :87
           z = populate_marginal(lat, ef.data());
         } else {
           z = marginal_per_position(m, p + o, sn, ef.data(), A, B, seen);
@@ -1011,6 +1017,17 @@ int orc_run_e_step(orc_model* h, const uint8_t* blob, const uint64_t* off, uint6
                    double* bad_z) {
   return run_e_step(*h->m, blob, off, S, threads, literal, max_sample_length, expected, bad_sample,
                     bad_z);
+}
+
+// run_e_step with populate_nodes(.., dropout) (src/prune.rs:87).  keyed != 0: the product's keyed draw (key = seed,
+// position = byte_base + byte offset in `blob`); keyed == 0: a sequential splitmix64 per rayon chunk, i.e. the
+// reference's loop with a seeded generator.
+int orc_run_e_step_dropout(orc_model* h, const uint8_t* blob, const uint64_t* off, uint64_t S, int threads,
+                           uint64_t max_sample_length, double dropout, int keyed, uint64_t seed, uint64_t byte_base,
+                           double* expected, int64_t* bad_sample, double* bad_z) {
+  KeyedDraw kd(seed, ~0ull);
+  return run_e_step(*h->m, blob, off, S, threads, 1, max_sample_length, expected, bad_sample, bad_z, dropout,
+                    keyed ? &kd : nullptr, byte_base);
 }
 
 double orc_digamma(double x) { return digamma(x); }

@@ -46,6 +46,7 @@ def test_load_sources_rejects_invalid_utf8(tmp_path):
         cli.load_sources([f"bad:{path}"])
 
 
-def test_prune_cmd_refuses_dropout(tmp_path):
-    with pytest.raises(ValueError, match="dropout"):
-        cli.prune_cmd("in.json", "out.json", 10, ["a:b"], dropout=0.01)
+def test_prune_cmd_refuses_dropout_outside_unit_interval(tmp_path):
+    for bad in (-0.01, 1.0, float("nan")):
+        with pytest.raises(ValueError, match="dropout"):
+            cli.prune_cmd("in.json", "out.json", 10, ["a:b"], dropout=bad)

@@ -165,3 +165,85 @@ def test_tokenizer_dropout_through_the_python_surface():
     runs = {tuple(t.encode(texts[0] * 4, 0.5)) for _ in range(4)}  # unseeded like the reference: calls differ
     assert len(runs) > 1
     assert t.encode(texts[0], 0.0) == plain[0]
+
+
+# ----------------------------------------------------------------------------- E-step: populate_nodes(.., dropout)
+def test_estep_keyed_dropout_oracle_properties():
+    """src/prune.rs:87 + src/model.rs:48-50 with the keyed draw: still a distribution over segmentations (property
+    (i): sum of expected * len = bytes), fewer multi-byte counts than without dropout, same multi-byte mass as the
+    sequential-draw restatement of the reference loop, reproducible, and keyed by seed and byte base."""
+    toks, scores, samples = _vocab_text(seed=17)
+    om = O.OracleModel(toks, scores)
+    from tokengeex_b200 import _native as N
+    blob, off = N.pack(samples)
+    lens = np.array([len(t) for t in toks], np.float64)
+    nbytes = float(off[-1])
+    plain = om.run_e_step(blob, off, literal=True)[0]
+    multi = lambda ex: float((ex * lens)[lens > 1].sum())
+    for p in (0.1, 0.5):
+        keyed, rc, bad, _ = om.run_e_step_dropout(blob, off, p, seed=4, keyed=True)
+        seq = om.run_e_step_dropout(blob, off, p, seed=4, keyed=False)[0]
+        assert rc == 0 and bad == -1
+        assert abs(float((keyed * lens).sum()) - nbytes) < 1e-9 * nbytes
+        assert multi(keyed) < multi(plain)
+        assert abs(multi(keyed) - multi(seq)) / multi(seq) < 0.03, (p, multi(keyed), multi(seq))
+        assert np.array_equal(keyed, om.run_e_step_dropout(blob, off, p, seed=4, keyed=True, threads=4)[0]) or \
+            np.allclose(keyed, om.run_e_step_dropout(blob, off, p, seed=4, keyed=True, threads=4)[0], rtol=1e-12)
+        assert not np.allclose(keyed, om.run_e_step_dropout(blob, off, p, seed=5)[0], rtol=1e-6)
+        assert not np.allclose(keyed, om.run_e_step_dropout(blob, off, p, seed=4, byte_base=1000)[0], rtol=1e-6)
+    # sharding: two halves with their byte bases = the whole
+    S = len(off) - 1
+    h = S // 2
+    a = om.run_e_step_dropout(blob[:int(off[h])], off[:h + 1], 0.3, seed=9)[0]
+    b = om.run_e_step_dropout(blob[int(off[h]):], (off[h:] - off[h]).astype(np.uint64), 0.3, seed=9,
+                              byte_base=int(off[h]))[0]
+    np.testing.assert_allclose(a + b, om.run_e_step_dropout(blob, off, 0.3, seed=9)[0], rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("g", [4, 32])
+def test_gpu_estep_dropout_vs_keyed_oracle(N, g):
+    rng = random.Random(40 + g)
+    for it in range(5):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(8, 60), max_len=rng.randrange(2, 9),
+                                  complete=(it != 3))
+        gm, om = N.Model(toks, scores, device=0), O.OracleModel(toks, scores)
+        gm.set_option(2, g)
+        samples = rand_samples(rng, b"abcd", 60, 1, 200) + rand_samples(rng, b"abcd", 3, 700, 2500)
+        blob, off = N.pack(samples)
+        for p, seed, base, snip in ((0.3, 11, 0, 81920), (0.7, 2 ** 62 + 5, 123456, 300)):
+            gm.set_option(22, base)
+            gm.set_dropout(p, seed)
+            ex, rc, bad, badz = gm.expected_counts(blob, off, snippet_len=snip)
+            want, wrc, wbad, _ = om.run_e_step_dropout(blob, off, p, seed, keyed=True, byte_base=base,
+                                                       max_sample_length=snip)
+            assert (rc != 0) == (wrc != 0)
+            if wrc == 0:
+                np.testing.assert_allclose(ex, want, rtol=1e-9, atol=1e-300)
+        gm.set_dropout(0.0, 0)
+        ex, rc, *_ = gm.expected_counts(blob, off)
+        if rc == 0:
+            np.testing.assert_allclose(ex, om.run_e_step(blob, off)[0], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_gpu_estep_dropout_synth_and_pruner(N):
+    blob, off, toks, sc, kp = synth_setup(2, 13, 2_000_000, 30000, 16)
+    gm, om = N.Model(toks, sc, device=0), O.OracleModel(toks, sc)
+    gm.set_dropout(0.01, 77)  # the reference CLI's default dropout (src/cli.rs:687)
+    ex, rc, bad, badz = gm.expected_counts(blob, off)
+    gm.set_dropout(0.0, 0)
+    want, wrc, *_ = om.run_e_step_dropout(blob, off, 0.01, 77, keyed=True, threads=8)
+    assert rc == 0 and wrc == 0
+    np.testing.assert_allclose(ex, want, rtol=1e-9, atol=1e-300)
+    lens = np.array([len(t) for t in toks], np.float64)
+    assert abs(float((ex * lens).sum()) - float(off[-1])) < 1e-9 * float(off[-1])
+    # the EM loop with dropout: reproducible with a seed (up to the atomics' last-bit jitter in the counts)
+    from tokengeex_b200.prune import ModelVocabularyPruner, Vocab
+    sizes = []
+    for rep in range(2):
+        pruner = ModelVocabularyPruner(12000, shrink_factor=0.8, em_subiters=1, dropout=0.05, dropout_seed=5)
+        v, report = pruner.prune(Vocab(list(toks), np.array(sc, np.float64), np.array(kp, np.uint8)), blob, off)
+        sizes.append(len(v))
+        assert len(v) <= 12000 and pruner._e_steps == len(report.e_step_s) >= 1
+    assert abs(sizes[0] - sizes[1]) <= 3

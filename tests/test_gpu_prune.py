@@ -80,7 +80,7 @@ def test_prune_command_line(tmp_path):
     tok_in, tok_out = str(tmp_path / "in.json"), str(tmp_path / "out.json")
     Tokenizer(toks, sc, kp, [_Processor("crlf")], ["<|eos|>"]).save(tok_in)
     rc = cli.main(["prune", "-i", tok_in, "-o", tok_out, "-v", "1000", "--train", f"code:{corpus}:0.5",
-                   "--em-subiters", "1"])
+                   "--em-subiters", "1", "--dropout", "0.0"])
     assert rc == 0
     out = Tokenizer.from_file(tok_out)
     assert out.special_tokens() == ["<|eos|>"] and out.base_vocab_size() <= 1200
@@ -91,4 +91,11 @@ def test_prune_command_line(tmp_path):
     vocab, _ = ModelVocabularyPruner(1000, 0.8, 1, 0.0).prune(Vocab(list(t_in._tokens), t_in._scores.copy(),
                                                                     t_in._keep.copy()), b2, o2)
     assert set(out._tokens) == set(vocab.tokens)
+    # the reference's default --dropout 0.01 (src/cli.rs:687): a keyed draw here, reproducible with --dropout-seed
+    tok_d = str(tmp_path / "out_d.json")
+    assert cli.main(["prune", "-i", tok_in, "-o", tok_d, "-v", "1000", "--train", f"code:{corpus}:0.5",
+                     "--dropout-seed", "3"]) == 0
+    out_d = Tokenizer.from_file(tok_d)
+    assert out_d.base_vocab_size() <= 1200
+    assert len(set(out_d._tokens) & set(vocab.tokens)) > 0.8 * len(vocab.tokens)
     assert out.encode("def f(x):\r\n    return x<|eos|>", 0.0)[-1] == out.base_vocab_size()

@@ -13,8 +13,11 @@ the tokenizer's processors are applied and samples that became empty are dropped
 samples with an unseeded RNG (:370-379), which only changes the order of f64 additions in the E-step; here the
 order is the file order unless --shuffle-seed is given.
 
---dropout must be 0.0: the reference's dropout draws from an unseeded thread RNG (src/model.rs:48,100) and cannot
-be reproduced; its default of 0.01 is therefore NOT the default here.  Under torchrun (WORLD_SIZE > 1) every rank
+--dropout defaults to 0.01 like the reference (src/cli.rs:687): every multi-byte match of the E-step lattice is dropped
+with that probability (src/model.rs:48-50).  The reference draws from an unseeded thread RNG; here the draw is keyed
+(seed, byte offset in the corpus, token length: include/tokengeex_b200.h, tgx_model_set_dropout), fresh per run unless
+--dropout-seed is given, and independent of the number of GPUs.  --dropout 0.0 (the benchmark configurations) runs
+the faster default E-step kernels.  Under torchrun (WORLD_SIZE > 1) every rank
 loads the same sources, keeps a byte-balanced shard of the samples and all-reduces the count vectors (dist.py).
 """
 from __future__ import annotations
@@ -86,15 +89,15 @@ def load_sources(sources: Sequence[str], processors=(), mode: str = "train") -> 
 
 def prune_cmd(input: str, output: str, vocab_size: int, train: Sequence[str], dropout: float = 0.0,
               shrink_factor: float = 0.8, em_subiters: int = 1, device: Optional[int] = None,
-              shuffle_seed: Optional[int] = None):
+              shuffle_seed: Optional[int] = None, dropout_seed: Optional[int] = None):
     """src/cli.rs:455-494.  Returns the PruneReport of the run."""
     from . import _native as N
     from . import dist
     from .prune import ModelVocabularyPruner, Vocab
     from .tokenizer import Tokenizer
 
-    if dropout != 0.0:
-        raise ValueError("tokengeex_b200 prunes with --dropout 0.0 only (the reference's dropout is an unseeded RNG)")
+    if not (0.0 <= dropout < 1.0):
+        raise ValueError("--dropout must be in [0, 1)")
     log.info("Pruning vocabulary input=%r output=%r vocab_size=%d dropout=%s shrink_factor=%s em_subiters=%d", input,
              output, vocab_size, dropout, shrink_factor, em_subiters)
     tok = Tokenizer.from_file(input)
@@ -110,6 +113,7 @@ def prune_cmd(input: str, output: str, vocab_size: int, train: Sequence[str], dr
     allreduce = None
     n_global = len(samples)
     blob, off = N.pack(samples)
+    byte_base = 0
     if world > 1:
         import torch
         import torch.distributed as td
@@ -118,10 +122,15 @@ def prune_cmd(input: str, output: str, vocab_size: int, train: Sequence[str], dr
             if backend == "nccl":
                 torch.cuda.set_device(device)
             td.init_process_group(backend)
+        byte_base = int(off[dist.shard_ranges(off, world)[rank][0]])
         blob, off, _ = dist.take_shard(blob, off, rank, world)  # byte-balanced contiguous sample range
+        if dropout > 0.0 and dropout_seed is None:  # one seed for the job: rank 0's
+            box = [random.SystemRandom().getrandbits(63)]
+            td.broadcast_object_list(box, src=0)
+            dropout_seed = box[0]
         allreduce = dist.Collective(device=f"cuda:{device}" if td.get_backend() == "nccl" else None)
     pruner = ModelVocabularyPruner(vocab_size, shrink_factor, em_subiters, dropout, device=device, allreduce=allreduce,
-                                   n_samples_global=n_global)
+                                   n_samples_global=n_global, dropout_seed=dropout_seed, byte_base=byte_base)
     vocab, report = pruner.prune(Vocab(list(tok._tokens), tok._scores.copy(), tok._keep.copy()), blob, off)
     log.info("Pruned vocabulary from=%d to=%d mem=%.2fMB", initial, len(vocab), sum(len(t) for t in vocab.tokens) / 1e6)
     if rank == 0:
@@ -138,7 +147,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     pr.add_argument("-o", "--output", required=True, help="output tokenizer JSON")
     pr.add_argument("-v", "--vocab-size", type=int, required=True)
     pr.add_argument("--train", action="append", default=[], metavar="NAME:PATH[:PROPORTION]")
-    pr.add_argument("--dropout", type=float, default=0.0, help="must be 0.0 (reference default: 0.01, unseeded)")
+    pr.add_argument("--dropout", type=float, default=0.01, help="E-step dropout in [0, 1) (src/cli.rs:687)")
+    pr.add_argument("--dropout-seed", type=int, default=None, help="seed of the keyed dropout draw (default: fresh)")
     pr.add_argument("--shrink-factor", type=float, default=0.8)
     pr.add_argument("--em-subiters", type=int, default=1)
     pr.add_argument("--device", type=int, default=None)
@@ -148,7 +158,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     if not args.train:
         ap.error("at least one --train source is required")
     prune_cmd(args.input, args.output, args.vocab_size, args.train, args.dropout, args.shrink_factor, args.em_subiters,
-              args.device, args.shuffle_seed)
+              args.device, args.shuffle_seed, args.dropout_seed)
     return 0
 
 

@@ -161,6 +161,7 @@ struct tgx_model {
   double dropout = 0.0;
   uint64_t drop_seed = 0;
   uint64_t drop_unit_base = 0;  // first sample of the chunk being queued (chunked host entry point)
+  uint64_t drop_byte_base = 0;  // E-step: offset of this call's text in the whole (sharded) corpus, option 22
   uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
   DevBuf Bbeta;
@@ -626,7 +627,7 @@ cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
   }
 }
 
-template <int G>
+template <int G, bool DROP = false>
 cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward, cudaStream_t st) {
   if (!p.u.count) return cudaSuccess;
   size_t smem = warp_smem_bytes(p.u.rows, p.u.W, G) * WPB;
@@ -634,19 +635,20 @@ cudaError_t launch_fb(tgx_model* m, FbParams p, bool backward, cudaStream_t st) 
   uint32_t per_block = WPB * (32 / G);
   uint32_t blocks = (p.u.count + per_block - 1) / per_block;
   if (!backward) {
-    e = cudaFuncSetAttribute(fb_forward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(fb_forward_kernel<G, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fb_forward_kernel<G><<<blocks, WPB * 32, smem, st>>>(p);
+    fb_forward_kernel<G, DROP><<<blocks, WPB * 32, smem, st>>>(p);
   } else {
-    e = cudaFuncSetAttribute(fb_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(fb_backward_kernel<G, false, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fb_backward_kernel<G><<<blocks, WPB * 32, smem, st>>>(p);
+    fb_backward_kernel<G, false, DROP><<<blocks, WPB * 32, smem, st>>>(p);
   }
   m->w().stats.launches += 1;
   return cudaGetLastError();
 }
 
 cudaError_t launch_fb_g(tgx_model* m, int G, const FbParams& p, bool backward, cudaStream_t st) {
+  if (p.dropout > 0.0) return G >= 32 ? launch_fb<32, true>(m, p, backward, st) : launch_fb<4, true>(m, p, backward, st);
   switch (G) {
     case 1: return launch_fb<1>(m, p, backward, st);
     case 2: return launch_fb<2>(m, p, backward, st);
@@ -1228,6 +1230,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 10: if (value < 0 || value > 1024) return fail(TGX_ERR_INVALID, "pair CTAs must be 0..1024"); m->pair_ctas = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
+    case 22: if (value < 0) return fail(TGX_ERR_INVALID, "byte base must be >= 0"); m->drop_byte_base = (uint64_t)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -1833,6 +1836,9 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.A = m->A.as<double>();
   p.status = m->w().status.as<int32_t>();
   p.expected = d_expected;
+  p.dropout = m->dropout;
+  p.drop_key = drop_unit_key(m->drop_seed, ~0ull);  // (its own stream of draws, apart from the encode samples')
+  p.drop_base = m->drop_byte_base;
   p.hot_k = (uint32_t)std::min<uint64_t>(m->V, (uint64_t)m->hot_k);
   p.hot_r = (uint32_t)m->hot_r;
   CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8));
@@ -1844,7 +1850,8 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   uint32_t n_long = 0, n_lane = 0;
   {
     uint32_t* counts = m->w().small.as<uint32_t>();
-    const bool lanes_ok = m->estep_lane_threshold != 0 && p.u.rows <= 16;
+    // dropout > 0: the lane-group kernels in fused form (the only E-step kernels that take the draw)
+    const bool lanes_ok = m->estep_lane_threshold != 0 && p.u.rows <= 16 && !(p.dropout > 0.0);
     int64_t thr64 = m->estep_long_threshold;
     if (thr64 <= 0)
       thr64 = (lanes_ok && m->estep_lane_threshold < 0) ? std::max<int64_t>(8192, 16000 + (int64_t)(n_bytes / 30000))
@@ -1876,7 +1883,7 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   pn.f.u.count = n_lane;
   pn.blob_end = d_text + n_bytes;
   pn.B = nullptr;
-  bool split = m->estep_split && (n_lane || n_long) && p.u.rows <= 16;
+  bool split = m->estep_split && (n_lane || n_long) && p.u.rows <= 16 && !(p.dropout > 0.0);
   if (split) {  // beta array: only if the device has room for it
     const size_t need = ((size_t)n_bytes + U + 2) * 8;
     size_t fr = 0, tot = 0;

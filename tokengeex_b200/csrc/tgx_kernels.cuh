@@ -83,6 +83,11 @@ struct FbParams {
   // (picked per block) that fold_hot_kernel sums into expected[] afterwards.
   double* hot;        // [hot_r][hot_k]
   uint32_t hot_k, hot_r;
+  // populate_nodes' dropout (src/model.rs:48-50; fb_*_kernel<G, .., true> only): the draw of the multi-byte match
+  // (start byte, length) is keyed by the byte's offset in the call's text (+ drop_base, the shard's offset in a
+  // sharded corpus), so the forward and the backward kernel — which both re-derive the matches — see one lattice.
+  double dropout;
+  unsigned long long drop_key, drop_base;
 };
 
 __device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uint32_t& first, uint32_t& count) {
@@ -129,7 +134,7 @@ __device__ inline WarpSmem carve(unsigned char* base, uint32_t rows, uint32_t W,
 template <bool DROP = false>
 __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint8_t* text, uint32_t pos,
                                                  uint32_t n, const WarpSmem& s, int lane, double dropout = 0.0,
-                                                 unsigned long long unit_key = 0) {
+                                                 unsigned long long unit_key = 0, unsigned long long pos_base = 0) {
   uint32_t cnt = 0;
   if (pos < n) {
     uint32_t xb = u.root_base;
@@ -142,7 +147,7 @@ __device__ __forceinline__ uint32_t walk_matches(const UnitParams& u, const uint
       d++;
       // (the draw of a dropped candidate does not depend on the position being reachable, so it can be taken here:
       //  an unreachable start never relaxes anything either way, src/model.rs:85-87)
-      if ((e.y & F_TERM) && (!DROP || d <= 1 || dropout < drop_draw(unit_key, pos, d))) {
+      if ((e.y & F_TERM) && (!DROP || d <= 1 || dropout < drop_draw(unit_key, pos_base + pos, d))) {
         s.mscore[cnt * ROW_STRIDE + lane] = __hiloint2double((int)e.w, (int)e.z);
         s.mpack[cnt * ROW_STRIDE + lane] = (d << 24) | (e.y & ID_MASK);
         cnt++;
@@ -901,7 +906,7 @@ __device__ __forceinline__ double log_sum_exp(double x, double y, const LibmTabs
 //     log_sum_exp(., score + A[start]); first term assigns; nothing ends at e -> 0.0.
 //     Lattice::populate_marginal alpha loop, src/lattice.rs:259-272 (per-position form).
 // -----------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool DROP = false>
 __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = 32 / G;
@@ -936,7 +941,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
   uint32_t slot0 = 0;
   for (uint32_t tile = 0; tile < tiles; tile++) {
     const uint32_t p0 = tile * G;
-    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    s.mcnt[lane] = walk_matches<DROP>(u, text, p0 + lig, n, s, lane, p.dropout, p.drop_key, p.drop_base + start);
     __syncwarp();
     double my_a = 0.0;
     uint32_t sl = slot0;
@@ -985,7 +990,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_forward_kernel(FbParams p) {
 //     exp(A[p] + score + B[p+len] - z) added to expected[id] (:295-309).
 // -----------------------------------------------------------------------------------------
 // STORE_B: only the beta chain, written to Bout (layout of A); the counts are added by fb_contrib_kernel.
-template <int G, bool STORE_B = false>
+template <int G, bool STORE_B = false, bool DROP = false>
 __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, double* Bout = nullptr) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = 32 / G;
@@ -1024,7 +1029,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, doubl
   const uint32_t tiles = (nmax + G - 1) / G;
   for (uint32_t tile = tiles; tile-- > 0;) {
     const uint32_t p0 = tile * G;
-    s.mcnt[lane] = walk_matches(u, text, p0 + lig, n, s, lane);
+    s.mcnt[lane] = walk_matches<DROP>(u, text, p0 + lig, n, s, lane, p.dropout, p.drop_key, p.drop_base + start);
     const double a_mine = (!STORE_B && has && p0 + lig < n) ? A[p0 + lig] : 0.0;
     __syncwarp();
     uint32_t sl = (p0 + G - 1) % W;  // slot of the tile's last position

@@ -55,15 +55,23 @@ class PruneReport:
 class ModelVocabularyPruner:
     """new(vocab_size, shrink_factor, em_subiters, dropout) — src/prune.rs:13-21.
 
-    dropout must be 0.0: the GPU path is specified for the deterministic setting
-    (the reference's dropout uses an unseeded thread_rng and cannot be reproduced).
+    dropout is the E-step's `populate_nodes(.., self.dropout)` (src/prune.rs:87): 0.0 = the default kernels (every
+    BASELINE configuration); in (0, 1) every multi-byte match is dropped with that probability by a keyed draw
+    (tgx_model_set_dropout: key = seed of this E-step, byte offset in the whole corpus, token length — so the result
+    does not depend on how the corpus is sharded), on the lane-group E-step kernels.  The reference's draw is an
+    unseeded thread_rng: `dropout_seed=None` takes a fresh seed per prune(), an int makes the run reproducible.
+    The frequency pass encodes with dropout 0.0 like the reference (src/prune.rs:218).
     """
 
     def __init__(self, vocab_size: int, shrink_factor: float = 0.8, em_subiters: int = 1, dropout: float = 0.0,
                  device: int = 0, allreduce: Optional[Callable[[np.ndarray], np.ndarray]] = None,
-                 n_samples_global: Optional[int] = None):
-        if dropout != 0.0:
-            raise ValueError("tokengeex_b200 prunes with dropout == 0.0 only")
+                 n_samples_global: Optional[int] = None, dropout_seed: Optional[int] = None, byte_base: int = 0):
+        if not (0.0 <= dropout < 1.0):
+            raise ValueError("dropout must be in [0, 1)")
+        self.dropout = float(dropout)
+        self.dropout_seed = dropout_seed
+        self.byte_base = int(byte_base)  # offset of this rank's shard in the whole corpus (keyed dropout draw)
+        self._e_steps = 0
         self.vocab_size = vocab_size
         self.shrink_factor = shrink_factor
         self.em_subiters = em_subiters
@@ -96,6 +104,20 @@ class ModelVocabularyPruner:
 
     # -- steps --------------------------------------------------------------------------------
     def run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray, dev=None) -> np.ndarray:
+        if self.dropout > 0.0:  # a new set of draws for every E-step, like the reference's running generator
+            if self.dropout_seed is None:
+                import secrets
+                self.dropout_seed = secrets.randbits(63)
+            model.set_option(22, self.byte_base)
+            model.set_dropout(self.dropout, self.dropout_seed + self._e_steps)
+            self._e_steps += 1
+            try:
+                return self._run_e_step(model, blob, off, dev)
+            finally:
+                model.set_dropout(0.0, 0)
+        return self._run_e_step(model, blob, off, dev)
+
+    def _run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray, dev=None) -> np.ndarray:
         if dev is not None:
             torch = dev["torch"]
             d_ex = torch.zeros(max(model.V, 1), dtype=torch.float64, device=dev["dev"])
