@@ -237,6 +237,13 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     del d_wfr
     expected, t_e = timed(lambda: pr.run_e_step(model, blob, off, d))
     e_dev_ms, fwd_ms, bwd_ms = model.stat(4), model.stat(2), model.stat(3)
+    # property (i) at the full size: every byte of the corpus is covered by exactly one token on
+    # every path of its snippet, so sum over ids of expected[id] * len(id) == corpus bytes (all ranks, after the
+    # all-reduce) — checked on the counts of the timed E-step itself
+    tok_len = np.array([len(t) for t in vocab.tokens], np.float64)
+    total_bytes = coll.sum_int(NB) if coll is not None else NB
+    covered = float(np.dot(np.asarray(expected, np.float64), tok_len))
+    cover_err = abs(covered - total_bytes) / total_bytes
     new_vocab, t_m = timed(lambda: pr.run_m_step(vocab, expected))
 
     def rebuild():  # *model = Model::from(vocab): new trie, same handle and workspaces
@@ -253,6 +260,7 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
            "prune_select_s": t_sel, "vocab_after_m_step": len(new_vocab), "vocab_after_prune": len(pruned),
            "e_step_device_ms": e_dev_ms, "fb_forward_ms": fwd_ms, "fb_backward_ms": bwd_ms,
            "e_step_input_MBps": args.prune_bytes / t_e / 1e6,
+           "property_sum_expected_len_eq_bytes_rel_err": cover_err, "property_holds_1e-9": bool(cover_err < 1e-9),
            "bytes_per_gpu": NB, "samples_per_gpu": S,
            "roofline": None, "cpu_baseline": None}
     peak, peak_src = measured_peak()

@@ -216,6 +216,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value);
  * In the E-step the candidate is (byte offset of its first byte in the call's text + option 22, token length):
  * option 22 of tgx_model_set_option = offset of the call's text in the whole corpus when it is one shard of it, so
  * that the lattices do not depend on the sharding; use a new seed for every E-step.
+ * The setting belongs to the model handle and applies to the calls that follow it: threads that encode through one
+ * handle with different dropout values serialise set + call themselves (tokengeex_b200/tokenizer.py holds a lock).
  * With dropout > 0 the forward pass runs on the lane-group kernel (viterbi_kernel<G, true>) and the E-step on the
  * lane-group kernels in fused form (fb_{forward,backward}_kernel<G, .., true>). */
 int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed);
