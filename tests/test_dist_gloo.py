@@ -49,7 +49,13 @@ def _worker(rank, world, port, q):
         fr = coll(om.token_frequencies(sub, soff, threads=1))
         n_samples = coll.sum_int(len(soff) - 1)
         kept, ns = N.m_step(ex, keep)
-        q.put((rank, ex, fr, n_samples, kept, ns))
+        # E-step dropout (src/prune.rs:87): one seed for the job (rank 0's, as cli.prune_cmd shares it) and the keyed
+        # draw's byte base = the shard's offset in the corpus, so the sharded sum is the unsharded lattice's
+        box = [1234567 + 1000 * rank]
+        dist.broadcast_object_list(box, src=0)
+        base = int(off[shard_ranges(off, world)[rank][0]])
+        exd = coll(om.run_e_step_dropout(sub, soff, 0.2, box[0], keyed=True, byte_base=base)[0])
+        q.put((rank, ex, fr, n_samples, kept, ns, exd))
     finally:
         dist.destroy_process_group()
 
@@ -83,7 +89,10 @@ def test_two_ranks_allreduce_counts():
     om = O.OracleModel(toks, scores, keep)
     want_ex, _, _, _ = om.run_e_step(blob, off, threads=1)
     want_fr = om.token_frequencies(blob, off, threads=1)
-    for rank, ex, fr, n_samples, kept, ns in res:
+    want_exd = om.run_e_step_dropout(blob, off, 0.2, 1234567, keyed=True)[0]
+    assert not np.allclose(want_exd, want_ex, rtol=1e-6)
+    for rank, ex, fr, n_samples, kept, ns, exd in res:
+        assert np.allclose(exd, want_exd, rtol=1e-12, atol=0)
         assert np.allclose(ex, want_ex, rtol=1e-12, atol=0)
         assert np.array_equal(fr, want_fr) and n_samples == len(samples)
     # identical inputs on every rank -> identical host steps ("replicas only")
