@@ -218,7 +218,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value);
  * that the lattices do not depend on the sharding; use a new seed for every E-step.
  * The setting belongs to the model handle and applies to the calls that follow it: threads that encode through one
  * handle with different dropout values serialise set + call themselves (tokengeex_b200/tokenizer.py holds a lock).
- * With dropout > 0 the forward pass runs on the lane-group kernel (viterbi_kernel<G, true>) and the E-step on the
+ * With dropout > 0 the forward pass runs on the pair kernel with the draw in its producers
+ * (viterbi_pair_kernel<2, HOT, 800, true>; lane-group viterbi_kernel<G, true> for tokens > 16 bytes) and the E-step on the
  * lane-group kernels in fused form (fb_{forward,backward}_kernel<G, .., true>). */
 int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed);
 

@@ -77,12 +77,14 @@ def N():
 
 
 @pytest.mark.gpu
-def test_gpu_dropout_small_random_vs_keyed_oracle(N):
-    rng = random.Random(21)
+@pytest.mark.parametrize("algo", [0, 1])  # pair kernel with the draw in its producers / lane-group kernels
+def test_gpu_dropout_small_random_vs_keyed_oracle(N, algo):
+    rng = random.Random(21 + algo)
     for it in range(12):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(6, 50), max_len=rng.randrange(2, 9),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = N.Model(toks, scores, device=0), O.OracleModel(toks, scores)
+        gm.set_option(3, algo)
         samples = rand_samples(rng, b"abcd", 70, 0, 90) + rand_samples(rng, b"abcd", 4, 600, 3000) + [b""]
         blob, off = N.pack(samples)
         for p, seed in ((0.3, it), (0.85, 2 ** 63 + it)):
@@ -116,11 +118,13 @@ def test_gpu_dropout_synth_corpus_chunked_with_crlf(N):
     p, seed = 0.2, 0xC0FFEE
     want = [om.encode_keyed(O.crlf(blob[int(off[i]):int(off[i + 1])].tobytes()), p, seed, i) for i in range(S)]
     gm.set_dropout(p, seed)
-    for chunk in (1 << 30, 100_000, 4096):
+    for algo, chunk in ((0, 1 << 30), (0, 100_000), (1, 100_000), (0, 4096), (1, 1 << 30)):
+        gm.set_option(3, algo)
         gm.set_option(7, chunk)
         ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
         assert rc == 0 and not status.any()
-        assert split_ids(ids, id_off) == want, chunk
+        assert split_ids(ids, id_off) == want, (algo, chunk)
+    gm.set_option(3, 0)
     lens = np.array([len(t) for t in toks])
     assert int(lens[ids].sum()) == int(plen.sum())  # still a segmentation of every processed sample
     # more tokens than without dropout, and the frequency pass keeps encoding with dropout 0.0 (src/prune.rs:218)

@@ -287,6 +287,9 @@ struct PairParams {
   uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
   uint32_t groups;     // consumer/producer groups per CTA
   uint32_t dbg;        // developer timing experiments (tools/probe.py): 1 = skip walks, 2 = skip the dp
+  // dropout in (0, 1) (viterbi_pair_kernel<.., true> only): see drop_draw
+  double dropout;
+  unsigned long long drop_seed, unit_base;
 };
 
 // shared memory of one CTA: [hot trie prefix][per group: tables 2 x 2 x R tiles | 4 x 2 PairInfo]
@@ -328,10 +331,11 @@ __device__ __forceinline__ unsigned long long window_bytes(const unsigned long l
 // Phase A for one start position: TrieIterator::next (src/trie.rs:51-63) unrolled over the 16
 // possible depths.  The walk may run past the end of the sample (into the next sample's bytes):
 // such a token lands on a dp cell beyond position n, which is never read.
-template <int HOT>
+template <int HOT, bool DROP = false>
 __device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, const uint4* __restrict__ hot,
                                              uint32_t root, const unsigned long long (&w)[3], uint32_t sh, bool active,
-                                             double* row, int lane) {
+                                             double* row, int lane, double dropout = 0.0,
+                                             unsigned long long unit_key = 0, uint32_t pos = 0) {
   const double ninf = __longlong_as_double(0xFFF0000000000000ll);
 #pragma unroll
   for (int c = 0; c < 16; c++) row[c] = ninf;
@@ -351,7 +355,9 @@ __device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, con
       // depth < HOT lands in the staged prefix, hit or miss; see trie_build.h)
       const uint4 e = (d < HOT) ? hot[xb ^ cw] : __ldg(trie + (xb ^ cw));
       if ((e.x ^ cw) & 0x1FFu) return;
-      if (e.y & F_TERM)  // target cell (start + len) % 16 = (lane + d + 1) % 16
+      // target cell (start + len) % 16 = (lane + d + 1) % 16; a dropped multi-byte candidate (src/model.rs:100) is
+      // simply never parked
+      if ((e.y & F_TERM) && (!DROP || d == 0 || dropout < drop_draw(unit_key, pos, (uint32_t)d + 1u)))
         *reinterpret_cast<double*>(rb + ((l18 + 8u * d) & 120u)) = __hiloint2double((int)e.w, (int)e.z);
       if (!(e.y & F_HASCH)) return;
       xb = e.x >> 9;
@@ -392,7 +398,7 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
 
 // Body shared by viterbi_pair_kernel and the hybrid kernel; called by every thread of the CTA
 // (warps beyond p.groups * WG only help staging the hot trie prefix).
-template <int R, int HOT>
+template <int R, int HOT, bool DROP = false>
 __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem) {
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
@@ -493,7 +499,8 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
         } else {
           pf_unit = -1;
         }
-        pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane);
+        pair_produce<HOT, DROP>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane, p.dropout,
+                                DROP ? drop_unit_key(p.drop_seed, p.unit_base + (uint32_t)pi.unit) : 0ull, pos);
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie
@@ -506,10 +513,10 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
 
 // MAXT = threads the kernel is compiled for: 800 (5 groups of 5 warps, 72 registers, no spills: the lowest latency per
 // chain) or 960 (6 groups when R = 2, 10 when R = 1; 64 registers).
-template <int R, int HOT, int MAXT>
+template <int R, int HOT, int MAXT, bool DROP = false>
 __global__ void __launch_bounds__(MAXT, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  pair_body<R, HOT>(p, smem);
+  pair_body<R, HOT, DROP>(p, smem);
 }
 
 // -----------------------------------------------------------------------------------------
