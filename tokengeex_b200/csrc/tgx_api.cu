@@ -504,7 +504,11 @@ cudaError_t launch_viterbi(tgx_model* m, ViterbiParams p) {
 }
 
 template <int R, int HOT, int MAXT, bool DROP = false>
-cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
+cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p, DropInfo di = DropInfo()) {
+  auto kernel = [] {
+    if constexpr (DROP) return viterbi_pair_drop_kernel<R, HOT, MAXT>;
+    else return viterbi_pair_kernel<R, HOT, MAXT>;
+  }();
   constexpr int WG = 2 * R + 1;
   const size_t budget = (size_t)m->smem_optin;
   uint32_t groups = (uint32_t)std::min<size_t>({(budget - (size_t)p.hot_slots * 16) / pair_group_bytes(R),
@@ -513,17 +517,18 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
   groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
   p.groups = groups;
   const size_t smem = pair_smem_bytes(R, groups, p.hot_slots);
-  cudaError_t e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT, MAXT, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // whatever the tables leave of the 256 KB L1/shared array caches trie slots beyond the staged prefix
-  e = cudaFuncSetAttribute(viterbi_pair_kernel<R, HOT, MAXT, DROP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1));
   if (e != cudaSuccess) return e;
   const uint32_t grid =
       (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
   e = dev_fill(p.counter, 0, 4, m->w().stream);
   if (e != cudaSuccess) return e;
-  viterbi_pair_kernel<R, HOT, MAXT, DROP><<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
+  if constexpr (DROP) kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p, di);
+  else kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
   m->w().stats.launches += 1;
   return cudaGetLastError();
 }
@@ -534,15 +539,15 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p) {
 // A batch is bound by its longest sample unless it is large, so the throughput shape is used from
 // `wide_bytes` input bytes on (the chunks of the host entry point stay below it).
 template <int R>
-cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p, uint64_t n_bytes) {
+cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p, uint64_t n_bytes, DropInfo di = DropInfo()) {
   const size_t cap = (size_t)m->smem_optin / 4;
-  if (p.dropout > 0.0) {  // one shape with the keyed draw in the producers: 5 groups, 72 registers
+  if (di.dropout > 0.0) {  // one shape with the keyed draw in the producers: 5 groups, 72 registers
     if ((size_t)m->da.hot[1] * 16 <= cap) {
       p.hot_slots = m->da.hot[1];
-      return launch_viterbi_pair<2, 1, 800, true>(m, p);
+      return launch_viterbi_pair<2, 1, 800, true>(m, p, di);
     }
     p.hot_slots = 0;
-    return launch_viterbi_pair<2, 0, 800, true>(m, p);
+    return launch_viterbi_pair<2, 0, 800, true>(m, p, di);
   }
   const bool wide = m->pair_shape == 2 || (m->pair_shape == 0 && n_bytes >= m->wide_bytes);
   const int levels = std::min(m->hot_levels, wide ? 1 : 2);
@@ -930,12 +935,13 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.bp = m->w().bp.as<uint8_t>();
     p.counter = m->w().small.as<unsigned int>() + 8;
     p.dbg = getenv("TGX_DBG") ? (uint32_t)atoi(getenv("TGX_DBG")) : 0u;
-    p.dropout = dropout;
-    p.drop_seed = m->drop_seed;
-    p.unit_base = m->drop_unit_base;
+    DropInfo di;
+    di.dropout = dropout;
+    di.seed = m->drop_seed;
+    di.unit_base = m->drop_unit_base;
     if (!p.u.count) {
     } else if (m->producers >= 4 || dropout > 0.0) {
-      CU(launch_viterbi_pair_r<2>(m, p, N));
+      CU(launch_viterbi_pair_r<2>(m, p, N, di));
     } else {
       CU(launch_viterbi_pair_r<1>(m, p, N));
     }

@@ -287,9 +287,12 @@ struct PairParams {
   uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
   uint32_t groups;     // consumer/producer groups per CTA
   uint32_t dbg;        // developer timing experiments (tools/probe.py): 1 = skip walks, 2 = skip the dp
-  // dropout in (0, 1) (viterbi_pair_kernel<.., true> only): see drop_draw
+};
+// dropout in (0, 1): a second kernel parameter of viterbi_pair_drop_kernel only (see drop_draw) — the default
+// kernel's parameter block and code stay exactly what they were (its 64-register shape is sensitive to both)
+struct DropInfo {
   double dropout;
-  unsigned long long drop_seed, unit_base;
+  unsigned long long seed, unit_base;
 };
 
 // shared memory of one CTA: [hot trie prefix][per group: tables 2 x 2 x R tiles | 4 x 2 PairInfo]
@@ -399,7 +402,7 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
 // Body shared by viterbi_pair_kernel and the hybrid kernel; called by every thread of the CTA
 // (warps beyond p.groups * WG only help staging the hot trie prefix).
 template <int R, int HOT, bool DROP = false>
-__device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem) {
+__device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem, const DropInfo* di = nullptr) {
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -499,8 +502,11 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
         } else {
           pf_unit = -1;
         }
-        pair_produce<HOT, DROP>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane, p.dropout,
-                                DROP ? drop_unit_key(p.drop_seed, p.unit_base + (uint32_t)pi.unit) : 0ull, pos);
+        if constexpr (DROP)
+          pair_produce<HOT, true>(u.trie, hot, u.root_base, w3, sh, pos < pi.n, row, lane, di->dropout,
+                                  drop_unit_key(di->seed, di->unit_base + (uint32_t)pi.unit), pos);
+        else
+          pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane);
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie
@@ -513,10 +519,17 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
 
 // MAXT = threads the kernel is compiled for: 800 (5 groups of 5 warps, 72 registers, no spills: the lowest latency per
 // chain) or 960 (6 groups when R = 2, 10 when R = 1; 64 registers).
-template <int R, int HOT, int MAXT, bool DROP = false>
+template <int R, int HOT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  pair_body<R, HOT, DROP>(p, smem);
+  pair_body<R, HOT>(p, smem);
+}
+
+// The same kernel with the keyed dropout draw in its producers (src/model.rs:100).
+template <int R, int HOT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) viterbi_pair_drop_kernel(PairParams p, DropInfo di) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pair_body<R, HOT, true>(p, smem, &di);
 }
 
 // -----------------------------------------------------------------------------------------
