@@ -317,15 +317,13 @@ class Tokenizer:
                 if self._model is None:
                     self._model = N.Model(self._tokens, self._scores, device=self._device)
                 return self._model
-            if dropout >= 1.0:
+            if dropout >= 1.0 or dropout != dropout:  # (NaN: `dropout < rand` is false for every draw, like >= 1.0)
                 # every token longer than one byte is skipped (src/model.rs:100 with rand() in [0,1)):
                 # same ids, but the multi-byte entries can never match
                 if self._model_bytes_only is None:
                     toks = [t if len(t) <= 1 else b"" for t in self._tokens]
                     self._model_bytes_only = N.Model(toks, self._scores, device=self._device)
                 return self._model_bytes_only
-            if dropout != dropout:
-                raise TokenGeeXError("dropout is NaN")
             # 0 < dropout < 1: the reference draws from an unseeded thread_rng (src/model.rs:100), so each call
             # takes a fresh seed unless `dropout_seed` is set; the draw itself is keyed (tgx_model_set_dropout)
             if self._model is None:
