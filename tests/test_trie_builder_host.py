@@ -1,0 +1,48 @@
+"""Rows a1/a2 on the host: the product's double-array trie (csrc/trie_build.cpp, the structure every kernel walks)
+against the oracle's restatement of the reference's pointer trie (src/trie.rs), through
+tgx_model_common_prefix_search — no device needed.  Random vocabularies with duplicates (last id wins, Q1), empty
+tokens (never yielded), all 256 byte values, tokens up to the 64-byte limit; and the builder's density."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tokengeex_b200 import _native as N
+
+
+def _rand_vocab(rng, alphabet, n_tok, max_len, dup_frac=0.1):
+    toks = [bytes(rng.choice(alphabet) for _ in range(rng.randrange(0 if rng.random() < 0.02 else 1, max_len + 1)))
+            for _ in range(n_tok)]
+    for _ in range(int(n_tok * dup_frac)):
+        toks.append(rng.choice(toks))  # duplicates: the later id must win
+    rng.shuffle(toks)
+    return toks, [-(rng.random() * 8 + 0.1) for _ in toks]
+
+
+@pytest.mark.parametrize("alphabet,n_tok,max_len", [(b"ab", 40, 6), (b"abcdefgh", 400, 8), (bytes(range(256)), 3000, 5),
+                                                    (b"xyz", 300, 64), (bytes(range(200, 256)), 500, 16)])
+def test_double_array_matches_pointer_trie(alphabet, n_tok, max_len):
+    rng = random.Random(n_tok * 131 + max_len)
+    toks, scores = _rand_vocab(rng, alphabet, n_tok, max_len)
+    hm, om = N.Model(toks, scores, device=None), O.OracleModel(toks, scores)
+    info = hm.info()
+    assert info.max_token_len == max(map(len, toks))
+    queries = [rng.choice(toks) + bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 8))) for _ in range(600)]
+    queries += [bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 70))) for _ in range(600)] + [b""]
+    for q in queries:
+        assert hm.common_prefix_search(q) == om.common_prefix_search(q), q
+
+
+def test_double_array_is_dense_and_byte_complete():
+    rng = random.Random(9)
+    toks = [bytes([b]) for b in range(255)]  # generate's byte tokens (0xFF absent, Q19)
+    toks += list({bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz_ (){};=\n") for _ in range(rng.randrange(2, 17)))
+                  for _ in range(20000)})
+    hm = N.Model(toks, [-1.0 - (i % 97) * 0.01 for i in range(len(toks))], device=None)
+    info = hm.info()
+    n_nodes = len({t[:k] for t in toks for k in range(1, len(t) + 1)}) + 1
+    assert n_nodes <= info.trie_slots <= 1.25 * n_nodes + 512  # the bitmap allocator packs the slots
+    ids, lens = hm.common_prefix_search(bytes([0xFF]))
+    assert ids == [] and lens == []
+    assert hm.common_prefix_search(b"\x00")[0] == [0]
