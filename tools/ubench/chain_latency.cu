@@ -23,6 +23,10 @@
 #include <vector>
 #include <cuda_runtime.h>
 
+// B and C: steps unrolled per loop trip.  Without it (first measurement, profiles/r01_ubench_chain_latency.txt) the
+// score loads of a step cannot move above the back-edge and their shared-memory latency sits on the chain; the
+// product's consumer prefetches its scores two steps ahead inside a 32-step unrolled tile for the same reason.
+constexpr int UNROLL = 8;
 constexpr int TAB = 1024;  // positions in the (repeating) score table
 constexpr int ROW = 17;    // doubles per start position: column = target cell (start + len) % 16, padded
 
@@ -75,6 +79,7 @@ __global__ void __launch_bounds__(32) chain_b(const double* __restrict__ g_tab, 
 #pragma unroll
   for (int d = 0; d < Q; d++) { pq[d] = ninf(); pqp[d] = 0; }
   const long long t0 = clock64();
+#pragma unroll UNROLL
   for (int j = 0; j < n; j++) {
     const double* row = tab + (j & (TAB - 1)) * ROW;
     if (threadIdx.x == 0) { out_best[j] = bj; out_start[j] = bjp; }
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(32) chain_c(const double* __restrict__ g_tab, 
 #pragma unroll
   for (int d = 0; d < Q; d++) { pq[d] = ninf(); pqp[d] = 0; }
   const long long t0 = clock64();
+#pragma unroll UNROLL
   for (int j = 0; j < n; j++) {
     const double* row = tab + (j & (TAB - 1)) * ROW;
     const double* rowp = tab + ((j - 1) & (TAB - 1)) * ROW;
