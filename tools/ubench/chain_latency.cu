@@ -15,6 +15,9 @@
 //      r01_ubench_chain_latency.txt) because a warp issues in order: its shuffle -> relax -> shuffle sequence inside one
 //      iteration stalls the next iteration's chain instructions behind it.
 //
+//   D  C with both hand-overs through shared memory and __syncwarp() (see chain_d; written after the SASS of C
+//      showed ptxas sinking each shuffle to its consumer).  Not measured yet.
+//
 // All variants write the final score and the start of the best last token per position; the host compares them.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o chain_latency chain_latency.cu
 #include <cstdio>
@@ -196,6 +199,88 @@ __global__ void __launch_bounds__(32) chain_c(const double* __restrict__ g_tab, 
   if (threadIdx.x == 0) cycles[0] = clock64() - t0;
 }
 
+// ---------------------------------------------------------------------------------------------------------- D
+// C with shared memory instead of shuffles for both hand-overs (dp[j] -> owners, partial -> chain): a store is
+// fire-and-forget, the loads are issued at the top of an iteration and consumed late in it, and the __syncwarp()s
+// pin the order that ptxas otherwise undoes by sinking a shuffle to its consumer.
+template <int K>
+__global__ void __launch_bounds__(32) chain_d(const double* __restrict__ g_tab, int n, double* out_best, int* out_start,
+                                              long long* cycles) {
+  static_assert(K >= 4, "the partial needs one iteration in flight");
+  extern __shared__ double tab[];
+  __shared__ double sm_b[2][4];      // [half][j & 3]: dp[j] for the owners
+  __shared__ double sm_cell[2][16];  // [half][owner]: the owners' cells after each relax
+  __shared__ int sm_cps[2][16];
+  for (int i = threadIdx.x; i < TAB * ROW; i += 32) tab[i] = g_tab[i];
+  const int g = threadIdx.x & 15, h = threadIdx.x >> 4;
+  if (g < 4) sm_b[h][g] = ninf();
+  sm_cell[h][g] = ninf();
+  sm_cps[h][g] = 0;
+  __syncwarp();
+  double cell = ninf();
+  int cps = 0;
+  double bj = 0.0;
+  int bjp = 0;
+  double acc[K + 1];
+  int accp[K + 1];
+  constexpr int Q = K - 3;
+  double pq[Q];
+  int pqp[Q];
+#pragma unroll
+  for (int d = 0; d <= K; d++) { acc[d] = ninf(); accp[d] = 0; }
+#pragma unroll
+  for (int d = 0; d < Q; d++) { pq[d] = ninf(); pqp[d] = 0; }
+  const long long t0 = clock64();
+#pragma unroll UNROLL
+  for (int j = 0; j < n; j++) {
+    const double* row = tab + (j & (TAB - 1)) * ROW;
+    const double* rowp = tab + ((j - 1) & (TAB - 1)) * ROW;
+    if (threadIdx.x == 0) { out_best[j] = bj; out_start[j] = bjp; }
+    // (1) loads of this iteration: partial of target j + K - 1 (complete since the previous iteration), dp[j - 1]
+    const double pvn = sm_cell[h][(j + K - 1) & 15];
+    const int ppn = sm_cps[h][(j + K - 1) & 15];
+    const double bq = sm_b[h][(j - 1) & 3];
+    // (3) dp[j] for the owners' next iteration
+    if (g == 0) sm_b[h][j & 3] = bj;
+    __syncwarp();
+    // (2) the chain
+    double c[K + 1];
+#pragma unroll
+    for (int d = 1; d <= K; d++) c[d] = __dadd_rn(bj, row[(j + d) & 15]);
+    double nb = acc[1];
+    int nbp = accp[1];
+    TEMAX(nb, nbp, c[1], j);
+    // (4) owners: start j - 1
+    {
+      const int s = j - 1;
+      const int len = ((g - s) & 15) == 0 ? 16 : ((g - s) & 15);
+      const double cand = __dadd_rn(bq, rowp[g]);
+      if (j >= 1 && (len == 16 || (len > K && cand > cell))) { cell = cand; cps = s; }
+      sm_cell[h][g] = cell;
+      sm_cps[h][g] = cps;
+    }
+    // (5) chain, off the critical path
+    double x = pq[0];
+    int xp = pqp[0];
+    TEMAX(x, xp, acc[2], accp[2]);
+    TEMAX(x, xp, c[2], j);
+    acc[1] = x; accp[1] = xp;
+#pragma unroll
+    for (int d = 3; d <= K; d++) {
+      double y = acc[d];
+      int yp = accp[d];
+      if (d == K) { y = c[K]; yp = j; } else TEMAX(y, yp, c[d], j);
+      acc[d - 1] = y; accp[d - 1] = yp;
+    }
+#pragma unroll
+    for (int d = 0; d + 1 < Q; d++) { pq[d] = pq[d + 1]; pqp[d] = pqp[d + 1]; }
+    pq[Q - 1] = pvn; pqp[Q - 1] = ppn;
+    bj = nb; bjp = nbp;
+    __syncwarp();
+  }
+  if (threadIdx.x == 0) cycles[0] = clock64() - t0;
+}
+
 // ---------------------------------------------------------------------------------------------------------- host
 static void reference(const std::vector<double>& tab, int n, std::vector<double>& best, std::vector<int>& start) {
   const double NINF = -1.0 / 0.0;
@@ -237,10 +322,11 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(chain_b<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(chain_c<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(chain_c<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(chain_d<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   std::vector<double> want(n), got(n);
   std::vector<int> wants(n), gots(n);
   reference(tab, n, want, wants);
-  for (int v = 0; v < 6; v++) {
+  for (int v = 0; v < 7; v++) {
     long long cyc = 0;
     for (int rep = 0; rep < 2; rep++) {
       cudaMemset(d_best, 0, (size_t)n * 8);
@@ -250,6 +336,7 @@ int main(int argc, char** argv) {
       if (v == 3) chain_b<4><<<1, 32, smem>>>(d_tab, n, d_best, d_start, d_cyc);
       if (v == 4) chain_c<4><<<1, 32, smem>>>(d_tab, n, d_best, d_start, d_cyc);
       if (v == 5) chain_c<5><<<1, 32, smem>>>(d_tab, n, d_best, d_start, d_cyc);
+      if (v == 6) chain_d<4><<<1, 32, smem>>>(d_tab, n, d_best, d_start, d_cyc);
       if (cudaDeviceSynchronize() != cudaSuccess) { printf("variant %d: %s\n", v, cudaGetErrorString(cudaGetLastError())); return 1; }
       cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
     }
@@ -259,7 +346,7 @@ int main(int argc, char** argv) {
     for (int j = 0; j < n; j++)
       if (memcmp(&got[j], &want[j], 8) != 0 || (want[j] != -1.0 / 0.0 && j > 0 && gots[j] != wants[j])) { if (first < 0) first = j; bad++; }
     printf("%s: %.1f cycles per position (%d positions), %lld mismatches vs the host chain (first at %lld)\n",
-           v == 0 ? "A shuffle on the chain (today)" : v == 1 ? "B K=2" : v == 2 ? "B K=3" : v == 3 ? "B K=4" : v == 4 ? "C K=4 (pipelined)" : "C K=5 (pipelined)", (double)cyc / n, n, bad,
+           v == 0 ? "A shuffle on the chain (today)" : v == 1 ? "B K=2" : v == 2 ? "B K=3" : v == 3 ? "B K=4" : v == 4 ? "C K=4 (pipelined)" : v == 5 ? "C K=5 (pipelined)" : "D K=4 (pipelined, hand-overs through shared memory)", (double)cyc / n, n, bad,
            first);
   }
   return 0;
