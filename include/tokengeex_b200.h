@@ -167,37 +167,32 @@ int tgx_host_free(void* p);
 /* Counters of the last compute call on this model (for bench.py): number of kernels
  * launched and device milliseconds of the dominant kernel(s), measured with CUDA events
  * on the model's stream.  what: 0 = kernels launched, 1 = Viterbi forward ms, 2 = fb-forward ms,
- * 3 = fb-backward ms, 4 = whole call device ms, 5 = backtrack ms, 6 = emit ms.  (For the chunked
+ * 3 = fb-backward ms, 4 = whole call device ms, 5 = backtrack ms, 6 = emit ms, 7 = match_kernel ms (forward algo 0;
+ * then 1 = viterbi_rows_kernel alone).  (For the chunked
  * host entry point these describe the LAST chunk.) */
 double tgx_model_last_stat(const tgx_model* m, int what);
 
-/* Developer counters of forward algorithm 4 (only collected when the environment variable TGX_SEG_DBG is set):
- * out8[0] = segments, [1] = hard because longer than the solver's limit, [2] = hard because of a tie or near tie,
- * [3] = hard because the segment end is unreachable, [4] = bytes in hard segments, [5] = exact segment solves,
- * [6] = 16-start tiles walked by them, [7] = chain steps of 256 bytes. */
-int tgx_model_debug_counters(tgx_model* m, uint64_t* out8);
-
-/* Tuning knobs (bench / tests): key 0 = lanes per sample for "short" units of the lane-group
- * kernels (1,2,4,8,16,32), 1 = byte threshold from which a unit gets a full warp (lane-group forward
- * kernels; warp-cooperative backtrack), 2 = lanes per snippet in the E-step, 3 = Viterbi forward
- * algorithm when max_token_len <= 16 (0 = pair-CTA kernel, the default; 1 = lane-group kernels; 2 = thread-per-sample
- * lane kernel; 3 = hybrid of 0 and 2; 4 = segment-parallel exact Viterbi, tgx_seg_kernels.cuh),
- * 4 = producer warps per consumer warp of the pair kernel (2 or 4), 5 = E-step byte threshold from
- * which a snippet gets a full warp (0 = automatic, from the batch size), 6 = consumer/producer groups per CTA of the pair kernel (0 = as
- * many as fit), 7 = bytes per chunk of the pipelined host entry point tgx_encode_batch, 8 = byte threshold from which a sample
- * goes to the pair body of the hybrid kernel, 9 = warps per CTA of the lane kernel (1..16), 10 = CTAs of the hybrid
- * kernel that start on the long samples, 11 = chunked host entry point queues the next chunk's kernels before the
- * current chunk has finished (0 = off, the default), 13 = leading trie levels the pair kernel may stage in shared
- * memory (0..2), 14 = shape of the pair kernel (0 = by batch size, 1 = 5 groups / lowest latency per sample, 2 = 6
- * groups / highest throughput), 15 = trie levels the segment kernels stage in shared memory (0..2), 16 = emit looks
- * token ids up in the token hash (1, the default when max_token_len <= 16) or re-walks the trie (0), 17 = E-step byte
- * threshold below which a snippet runs on ONE lane (fb_*_lane_kernel; < 0 = automatic: everything below the full-warp
- * threshold of key 5, the default; 0 = never, the lane-group kernels of key 2 take them), 18 = resident blocks per
- * SM of the lane E-step kernels (0 = as many as fit), 19 = E-step in split form (1, the default: beta chains stored
- * and run beside the alpha chains, counts by a third kernel; needs 8 more bytes of device memory per input byte and
- * falls back to 0 = fused backward + counts without them), 20 / 21 = E-step: replicas of the count vector (default
- * 256) for the hottest ids (default: ids below 4096), so that their atomics do not queue on one L2 address,
- * 22 = byte offset of the E-step's text in the whole corpus (keyed dropout draw, see tgx_model_set_dropout). */
+/* Options.  Two of them are for callers:
+ *    7 = bytes per chunk of the pipelined host entry point tgx_encode_batch (default ~352 MiB);
+ *   22 = byte offset of the E-step's text in the whole corpus when the call handles one shard of it (keyed dropout
+ *        draw, see tgx_model_set_dropout).
+ * The rest select between tested kernel variants and their launch shapes (bench / tests / tools/probe.py; not a stable
+ * interface — defaults are what the measurements in profiles/ picked):
+ *    3 = Viterbi forward pass when max_token_len <= 16: 0 = match stream + row consumer (tgx_match_kernels.cuh, the
+ *        default), 1 = lane-group kernels (always used for longer tokens), 2 = pair-CTA kernel;
+ *   23 / 24 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory;
+ *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;
+ *    0 / 1 = lane-group kernels: lanes per short sample (1,2,4,8,16,32), byte threshold from which a sample gets a
+ *        full warp (also: warp-cooperative backtrack);
+ *    4 / 6 / 13 / 14 = pair-CTA kernel: producer warps per consumer (2, 4), groups per CTA (0 = as many as fit), trie
+ *        levels staged in shared memory (0..2), shape (0 = by batch size, 1 = 5 groups, 2 = 6 groups);
+ *   11 = chunked host entry point queues the next chunk's kernels before the current chunk has finished (default 0);
+ *   16 = emit looks token ids up in the token hash (1, default when max_token_len <= 16) or re-walks the trie (0);
+ *    2 / 5 / 17 / 18 / 19 / 20 / 21 = E-step: lanes per snippet of the lane-group kernels; byte threshold from which a
+ *        snippet gets a full warp (0 = automatic); byte threshold below which a snippet runs on ONE lane (< 0 =
+ *        automatic, 0 = never); resident blocks per SM of the lane kernels; split form (beta chains stored and run
+ *        beside the alpha chains, default 1); replicas (default 256) of the count vector for the hottest ids (default:
+ *        ids below 4096). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 /* The `dropout` argument of Model::encode (src/model.rs:59,100) for the encode entry points

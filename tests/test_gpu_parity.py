@@ -98,7 +98,7 @@ def test_random_small_vs_oracle_cta(N, producers, shape):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 12),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 0)  # pair-CTA kernel
+        gm.set_option(3, 2)  # pair-CTA kernel
         gm.set_option(4, producers)
         gm.set_option(14, shape)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 400)
@@ -123,7 +123,7 @@ def test_pair_kernel_full_window(N, producers, shape, hot):
         toks = list(toks) + [alphabet[:1] * 16, alphabet[1:2] * 16, (alphabet[:2] * 8)]
         scores = list(scores) + [-2.5, -30.0, -4.0]
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 0)  # pair-CTA kernel
+        gm.set_option(3, 2)  # pair-CTA kernel
         gm.set_option(4, producers)
         gm.set_option(14, shape)
         gm.set_option(13, hot)  # trie levels staged in shared memory
@@ -152,45 +152,53 @@ def check_against_oracle(N, gm, om, samples, ctx=None):
     assert bad == first_bad and (rc == 0) == (first_bad < 0), (ctx, rc, bad, first_bad)
 
 
-@pytest.mark.parametrize("hot", [0, 1, 2])
-def test_segment_kernels_random_vs_oracle(N, hot):
-    """Forward algo 4 (segment-parallel exact Viterbi, tgx_seg_kernels.cuh): random vocabularies incl. incomplete ones
-    (NoPath, unreachable stretches), integer scores (exact ties: every tied segment goes through the exact chain),
-    tokens of every length up to 16, samples crossing many 512-boundary tiles, empty samples."""
-    rng = random.Random(1700 + hot)
+@pytest.mark.parametrize("stage,hot,warps,threads", [(0, 0, 1, 32), (4096, 256, 4, 256), (160 << 10, 96 << 10, 16, 1024),
+                                                     (1 << 30, 1 << 30, 32, 512)])
+def test_match_rows_random_vs_oracle(N, stage, hot, warps, threads):
+    """The default forward pass (match_kernel + viterbi_rows_kernel, tgx_match_kernels.cuh) alone, for every staging
+    split of the trie / the row table between shared memory and L2: random vocabularies incl. incomplete ones (NoPath,
+    positions where no token starts, unreachable stretches), integer scores (exact ties), tokens of every length up to
+    16, samples crossing many 32-position tiles, empty samples, more samples than half-warps (work fetch)."""
+    rng = random.Random(1700 + warps)
     for it in range(30):
         alphabet = [b"ab", b"abcd", b"abc"][it % 3]
         toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(4, 300), max_len=rng.randrange(1, 17),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 4)
-        gm.set_option(15, hot)
+        gm.set_option(3, 0)
+        gm.set_option(23, threads)
+        gm.set_option(24, stage)
+        gm.set_option(25, warps)
+        gm.set_option(26, hot)
         samples = rand_samples(rng, alphabet, rng.randrange(1, 200), 0, 700) + rand_samples(rng, alphabet, 4, 1000, 9000)
-        samples += [alphabet[:1] * k for k in (1, 15, 16, 17, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
+        samples += [alphabet[:1] * k for k in (1, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
         rng.shuffle(samples)
         check_against_oracle(N, gm, om, samples, it)
 
 
-def test_segment_kernels_long_segments(N):
-    """Vocabularies whose tokens overlap everywhere (no cuts for thousands of bytes): every segment is longer than
-    SG_MAXSEG, so P2 solves whole samples exactly, tile after tile of 16 starts, through its 64-slot dp ring."""
+def test_match_rows_full_window(N):
+    """Tokens of every length 1..16 (length 16 lands on the cell that was just recycled), vocabularies whose tokens
+    overlap everywhere, long samples, rows deeper than the staged prefix."""
     rng = random.Random(1801)
-    for it in range(6):
+    for it in range(8):
         toks = [b"a", b"b"] + [bytes(rng.choice(b"ab") for _ in range(rng.randrange(2, 17))) for _ in range(600)]
-        toks = sorted(set(toks))
+        toks = sorted(set(toks)) + [b"a" * 16, b"b" * 16, b"ab" * 8]
         scores = [-(rng.random() * 6 + 0.5) if it % 2 else -float(rng.randrange(2, 6)) for _ in toks]
         gm, om = both(N, toks, scores)
-        gm.set_option(3, 4)
-        samples = rand_samples(rng, b"ab", 30, 0, 3000) + [b"ab" * 4000, b"a" * 70000, b"aab" * 1000]
+        gm.set_option(3, 0)
+        gm.set_option(26, [0, 512, 4096, 1 << 20][it % 4])
+        samples = rand_samples(rng, b"ab", 30, 0, 3000) + [b"ab" * 4000, b"a" * 70000, b"aab" * 1000, b"b" * 333]
+        samples += [b"a" * k for k in range(1, 20)]
         check_against_oracle(N, gm, om, samples, it)
 
 
-def test_segment_kernels_synth_corpus(N):
+def test_match_rows_synth_corpus(N):
     """Bench-like corpus and vocabulary: ids, offsets and processed lengths bit-exact with and without crlf, device
-    entry point and chunked host entry point; the frequency pass through the same kernels."""
+    entry point and chunked host entry point; the frequency pass through the same kernels; the three forward passes
+    agree on a second corpus kind (code + Chinese)."""
     blob, off, toks, sc, kp = synth_setup(1, 11, 6_000_000, 32768, 16)
     gm, om = both(N, toks, sc)
-    gm.set_option(3, 4)
+    gm.set_option(3, 0)
     for crlf in (True, False):
         wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=crlf, threads=8)
         for chunk in (1 << 30, 700_000):
@@ -201,17 +209,17 @@ def test_segment_kernels_synth_corpus(N):
     fr, rc, bad, blen = gm.token_frequencies(blob, off)
     want = om.token_frequencies(blob, off, threads=8)
     assert rc == 0 and np.array_equal(fr, want)
-    # the pair kernel and the segment kernels agree on a second corpus kind (code + Chinese)
     blob, off, toks, sc, kp = synth_setup(2, 12, 3_000_000, 20000, 16)
     gm = N.Model(toks, sc, device=0)
-    gm.set_option(3, 0)
-    a = gm.encode_batch(blob, off, crlf=True)
-    gm.set_option(3, 4)
-    b = gm.encode_batch(blob, off, crlf=True)
-    assert a[4] == 0 and b[4] == 0 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    res = []
+    for algo in (0, 1, 2):
+        gm.set_option(3, algo)
+        res.append(gm.encode_batch(blob, off, crlf=True))
+    for r in res[1:]:
+        assert r[4] == 0 and np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1])
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_long_tokens(N, algo):
     """max_token_len > 16 cannot use the 16-cell windows of the pair / lane kernels: whatever forward algorithm is
     selected, the lane-group kernels take over."""
@@ -224,56 +232,6 @@ def test_long_tokens(N, algo):
         gm.set_option(3, algo)
         samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 0, 300)
         check_against_oracle(N, gm, om, samples)
-
-
-@pytest.mark.parametrize("warps", [1, 4, 12])
-def test_lane_kernel_random_vs_oracle(N, warps):
-    """Thread-per-sample lane kernel alone (algo 2): random vocabularies incl. incomplete ones (NoPath, positions
-    without any match), exact ties, every sample alignment, more samples than lanes (work fetch)."""
-    rng = random.Random(500 + warps)
-    for it in range(20):
-        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 17),
-                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
-        gm, om = both(N, toks, scores)
-        gm.set_option(3, 2)
-        gm.set_option(9, warps)
-        samples = rand_samples(rng, b"abcd", rng.randrange(1, 300), 0, 400)
-        check_against_oracle(N, gm, om, samples, it)
-
-
-def test_lane_kernel_full_window(N):
-    """Tokens of every length 1..16 (length 16 lands on the cell that was just recycled), long samples (many packed
-    8-byte back-length stores, head/tail byte stores at every alignment), unreachable stretches."""
-    rng = random.Random(901)
-    for it in range(10):
-        alphabet = b"ab" if it % 2 == 0 else b"abc"
-        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(30, 400), max_len=16,
-                                  complete=(it % 3 != 0), int_scores=(it % 2 == 1))
-        toks = list(toks) + [alphabet[:1] * 16, alphabet[1:2] * 16, (alphabet[:2] * 8)]
-        scores = list(scores) + [-2.5, -30.0, -4.0]
-        gm, om = both(N, toks, scores)
-        gm.set_option(3, 2)
-        samples = rand_samples(rng, alphabet, rng.randrange(3, 40), 0, 5000)
-        samples += [alphabet[:1] * k for k in range(1, 20)] + [alphabet[1:2] * 333, alphabet[:2] * 517, b""]
-        check_against_oracle(N, gm, om, samples, it)
-
-
-@pytest.mark.parametrize("thr,pair_ctas", [(1, 148), (200, 64), (200, 1), (1 << 30, 64), (300, 0)])
-def test_hybrid_kernel_vs_oracle(N, thr, pair_ctas):
-    """Hybrid forward kernel (algo 3): the first pair_ctas CTAs run the pair-CTA body over the samples of at least `thr`
-    bytes and then join the lane body; every split of the samples between the two bodies gives the same ids."""
-    rng = random.Random(1300 + pair_ctas)
-    for it in range(8):
-        alphabet = b"ab" if it % 2 == 0 else b"abcd"
-        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(20, 300), max_len=rng.randrange(2, 17),
-                                  complete=(it % 3 != 0), int_scores=(it % 2 == 1))
-        gm, om = both(N, toks, scores)
-        gm.set_option(3, 3)
-        gm.set_option(8, thr)
-        gm.set_option(10, pair_ctas)
-        samples = rand_samples(rng, alphabet, rng.randrange(3, 400), 0, 600) + rand_samples(rng, alphabet, 5, 1000, 9000)
-        rng.shuffle(samples)
-        check_against_oracle(N, gm, om, samples, it)
 
 
 def test_chunked_host_entry_point(N):
@@ -316,7 +274,7 @@ def test_synth_corpus_bit_exact_with_crlf(N):
     blob, off, toks, sc, kp = synth_setup(1, 11, 6_000_000, 32768, 16)
     gm, om = both(N, toks, sc)
     wids, wid_off, wstatus, wplen, wbad = om.encode_batch(blob, off, crlf=True, threads=8)
-    for algo, g, thr in [(0, 8, 32768), (1, 8, 32768), (1, 4, 4096), (1, 1, 2048)]:
+    for algo, g, thr in [(0, 8, 32768), (2, 8, 32768), (1, 8, 32768), (1, 4, 4096), (1, 1, 2048)]:
         gm.set_option(3, algo)
         gm.set_option(0, g)
         gm.set_option(1, thr)
@@ -457,7 +415,7 @@ def test_very_long_samples(N):
     toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=150, max_len=10)
     gm, om = both(N, toks, scores)
     samples = [bytes(rng.choice(b"abcd") for _ in range(n)) for n in (400_000, 2 * 81920, 81921, 7, 0, 81920)]
-    for algo in (0, 1):
+    for algo in (0, 1, 2):
         gm.set_option(3, algo)
         check_against_oracle(N, gm, om, samples, algo)
     gm.set_option(3, 0)

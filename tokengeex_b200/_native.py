@@ -8,6 +8,7 @@ fails with TGX_ERR_NO_DEVICE when no CUDA device is present.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 from typing import Optional, Sequence, Tuple
 
@@ -64,7 +65,6 @@ SYMBOLS = [
     ("tgx_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("tgx_host_free", C.c_int, [C.c_void_p]),
     ("tgx_model_last_stat", C.c_double, [C.c_void_p, C.c_int]),
-    ("tgx_model_debug_counters", C.c_int, [C.c_void_p, u64p]),
     ("tgx_model_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     ("tgx_model_rebuild", C.c_int, [C.c_void_p, u8p, u64p, f64p, C.c_uint64]),
     ("tgx_model_set_dropout", C.c_int, [C.c_void_p, C.c_double, C.c_uint64]),
@@ -186,11 +186,6 @@ class Model:
     def stat(self, what: int) -> float:
         return float(lib().tgx_model_last_stat(self._h, what))
 
-    def debug_counters(self) -> np.ndarray:
-        out = np.zeros(8, np.uint64)
-        _check(lib().tgx_model_debug_counters(self._h, out.ctypes.data_as(u64p)))
-        return out
-
     def common_prefix_search(self, text: bytes):
         n = len(text)
         a = np.frombuffer(text, np.uint8) if n else np.zeros(1, np.uint8)
@@ -301,28 +296,20 @@ class Model:
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:
-    """uint8 numpy array over cudaHostAlloc'd memory (freed when the array is collected)."""
+    """uint8 numpy array over cudaHostAlloc'd memory.  The allocation lives as long as the ctypes buffer every view of
+    the array keeps alive through `.base`, and is released (tgx_host_free) when that buffer is collected."""
     p = C.c_void_p()
     _check(lib().tgx_host_alloc(C.byref(p), nbytes))
     buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=np.uint8)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib().tgx_host_free(self.ptr)
-            except Exception:
-                pass
-
-    arr = arr[:nbytes]
-    _OWNERS[arr.ctypes.data] = _Owner(p)
-    return arr
+    weakref.finalize(buf, _free_pinned, p.value)
+    return np.frombuffer(buf, dtype=np.uint8)[:nbytes]
 
 
-_OWNERS = {}
+def _free_pinned(addr: int) -> None:
+    try:
+        lib().tgx_host_free(C.c_void_p(addr))
+    except Exception:
+        pass
 
 
 # ---- host half of the EM pruning loop (tokengeex_b200/csrc/prune_host.cpp) -------------------------

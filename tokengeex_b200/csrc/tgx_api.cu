@@ -20,8 +20,7 @@
 
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
-#include "tgx_lane_kernel.cuh"
-#include "tgx_seg_kernels.cuh"
+#include "tgx_match_kernels.cuh"
 #include "trie_build.h"
 
 namespace {
@@ -62,7 +61,7 @@ struct DevBuf {
 };
 
 struct Stats {
-  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0;
+  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0, match_ms = 0;
 };
 
 }  // namespace
@@ -78,11 +77,10 @@ struct Workspace {
   cudaStream_t stream_ctl = nullptr;
   cudaEvent_t ev_ctl = nullptr;
   unsigned long long* h_words = nullptr;  // pinned, 8 words
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
   Stats stats;
   DevBuf text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt, ntok, status,
-      small, ids_at;
-  bool have_ids_at = false;  // the last run_viterbi was forward algo 4: run_emit takes the ids from ids_at
+      small, rec;
 };
 
 struct tgx_model {
@@ -91,10 +89,13 @@ struct tgx_model {
   int device = -1;
   uint4* d_trie = nullptr;
   size_t trie_cap = 0;  // slots allocated at d_trie
-  // forward algo 4 (tgx_seg_kernels.cuh): token hash, scores by id, max |score|; hash.mask == 0 = not available
+  // emit: token hash (bytes -> id, one probe per token); hash.mask == 0 = not available
   tgx::TokenHash hash;
-  DevBuf d_hash, d_scores;
-  double wmax = 0;
+  DevBuf d_hash;
+  // match tables (trie_build.h: slots8 / rows / row_ids; max_token_len <= 16 only): have_rows == false = not available
+  DevBuf d_trie8, d_rows, d_rowids;
+  bool have_rows = false;
+  uint32_t rows16 = 0;  // 16-byte units in the row table
   Workspace ws[2];
   int wi = 0;  // workspace the next launches go to
   Workspace& w() { return ws[wi]; }
@@ -134,15 +135,13 @@ struct tgx_model {
   int hot_k = 4096, hot_r = 256;  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids
   int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
-  // 0 = pair-CTA kernel (default), 1 = lane-group kernels, 2 = thread-per-sample lane kernel, 3 = hybrid (first
-  // pair_ctas CTAs run the pair body over the samples of at least lane_threshold bytes, then join the lane body).
-  // Measured on B200 (profiles/r01_probe_lane_kernel.txt): a lane advances one position per ~6800 cycles however
-  // many warps share the SM, so 2 and 3 lose to 0 on every corpus with samples beyond a few KB; they stay as
-  // tested alternatives.
+  // 0 = match stream + row consumer (tgx_match_kernels.cuh; the default), 1 = lane-group kernels, 2 = pair-CTA kernel
+  // (the default of the first round; still what encodes with dropout in (0, 1)).
   int algo = 0;
-  int64_t lane_threshold = 24576;
-  int lane_warps = 12;  // warps per CTA of the lane kernel
-  int pair_ctas = 64;   // CTAs that start on the long samples in the hybrid kernel
+  int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
+  int64_t match_stage_bytes = 160 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
+  int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
+  int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
   int num_sms = 148;
   int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
@@ -154,7 +153,6 @@ struct tgx_model {
   int overlap_chunks = 0;
   int hot_levels = 2;  // leading trie levels the pair kernel may stage in shared memory (0..2)
   int emit_hash = 1;   // emit: token ids through the token hash (1 probe per token) instead of re-walking the trie
-  int seg_hot = 1;     // trie levels the segment kernel (algo 4) stages in shared memory
   int pair_shape = 0;  // 0 = by batch size, 1 = latency shape (5 groups), 2 = throughput shape (6 groups)
   // tgx_model_set_dropout: Model::encode's dropout argument for the encode entry points (src/model.rs:59,100).
   // 0.0 = off (every BASELINE configuration); in (0, 1) the keyed draw of tgx_kernels.cuh::drop_draw.
@@ -392,7 +390,7 @@ __global__ void units_from_snippets(const uint64_t* __restrict__ off, uint64_t S
 }
 
 // counts[0] = #units with len >= long_threshold, counts[1] = #units with len >= 1,
-// counts[2] = #units with len >= lane_threshold
+// counts[2] = #units with len >= lane_threshold (E-step: snippets below it run one lane each)
 __global__ void split_sorted(const uint32_t* __restrict__ sorted_len, uint32_t U, uint32_t long_threshold,
                              uint32_t lane_threshold, uint32_t* __restrict__ counts) {
   if (threadIdx.x || blockIdx.x) return;
@@ -563,71 +561,6 @@ cudaError_t launch_viterbi_pair_r(tgx_model* m, PairParams p, uint64_t n_bytes, 
   return wide ? launch_viterbi_pair<R, 0, 960>(m, p) : launch_viterbi_pair<R, 0, 800>(m, p);
 }
 
-constexpr int LANE_KW = 3, LANE_KC = 2;
-
-// hot trie prefix for the lane / hybrid kernels: as many leading levels as fit `cap` bytes
-uint32_t pick_hot(const tgx_model* m, size_t cap, int* levels) {
-  for (int l = 2; l >= 1; l--)
-    if ((size_t)m->da.hot[l] * 16 <= cap) {
-      if (levels) *levels = l;
-      return m->da.hot[l];
-    }
-  if (levels) *levels = 0;
-  return 0;
-}
-
-template <int CELLS>
-cudaError_t launch_viterbi_lane(tgx_model* m, LaneParams p) {
-  if (!p.u.count) return cudaSuccess;
-  p.hot_slots = pick_hot(m, (size_t)m->smem_optin / 4, nullptr);
-  const size_t per_warp = lane_warp_bytes<CELLS>();
-  uint32_t warps = (uint32_t)std::min<size_t>((size_t)m->lane_warps, ((size_t)m->smem_optin - (size_t)p.hot_slots * 16) / per_warp);
-  warps = std::max<uint32_t>(1, std::min<uint32_t>(warps, (p.u.count + 31) / 32));
-  const size_t smem = (size_t)p.hot_slots * 16 + warps * per_warp;
-  cudaError_t e = cudaFuncSetAttribute(viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 32 * warps - 1) / (32 * warps), (uint64_t)m->num_sms);
-  e = dev_fill(p.counter, 0, 4, m->w().stream);
-  if (e != cudaSuccess) return e;
-  viterbi_lane_kernel<CELLS, LANE_KW, LANE_KC><<<grid, warps * 32, smem, m->w().stream>>>(p);
-  m->w().stats.launches += 1;
-  return cudaGetLastError();
-}
-
-template <int HOT>
-cudaError_t launch_viterbi_hybrid_h(tgx_model* m, HybridParams p, uint32_t hot_slots) {
-  constexpr int R = 2, WG = 2 * R + 1;
-  p.pair.hot_slots = p.lane.hot_slots = hot_slots;
-  const size_t budget = (size_t)m->smem_optin - (size_t)hot_slots * 16;
-  uint32_t groups = (uint32_t)std::min<size_t>({budget / pair_group_bytes(R), (size_t)(800 / (32 * WG)), (size_t)15});
-  if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
-  p.pair.groups = std::max<uint32_t>(1, groups);
-  p.lane_warps = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)m->lane_warps, budget / lane_warp_bytes<16>()));
-  const size_t smem = (size_t)hot_slots * 16 + std::max<size_t>(p.pair.groups * pair_group_bytes(R), p.lane_warps * lane_warp_bytes<16>());
-  const uint32_t threads = std::max<uint32_t>(p.pair.groups * WG * 32, p.lane_warps * 32);
-  cudaError_t e = cudaFuncSetAttribute(viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)p.lane.u.count + 31) / 32, (uint64_t)m->num_sms);
-  p.pair_ctas = std::min<uint32_t>((uint32_t)m->pair_ctas, grid);
-  if (p.pair_ctas == 0) p.lane.u.part = 0;  // nobody runs the pair body: the lanes take every sample
-  e = dev_fill(p.pair.counter, 0, 8, m->w().stream);  // both counters
-  if (e != cudaSuccess) return e;
-  viterbi_hybrid_kernel<R, HOT, LANE_KW, LANE_KC><<<grid, threads, smem, m->w().stream>>>(p);
-  m->w().stats.launches += 1;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_viterbi_hybrid(tgx_model* m, const HybridParams& p) {
-  if (!p.lane.u.count) return cudaSuccess;
-  int levels = 0;
-  const uint32_t hot_slots = pick_hot(m, (size_t)m->smem_optin / 4, &levels);
-  if (levels == 2) return launch_viterbi_hybrid_h<2>(m, p, hot_slots);
-  if (levels == 1) return launch_viterbi_hybrid_h<1>(m, p, hot_slots);
-  return launch_viterbi_hybrid_h<0>(m, p, 0);
-}
-
 cudaError_t launch_viterbi_g(tgx_model* m, int G, const ViterbiParams& p) {
   if (p.dropout > 0.0) return G >= 32 ? launch_viterbi<32, true>(m, p) : launch_viterbi<8, true>(m, p);
   switch (G) {
@@ -684,27 +617,38 @@ int check_model(tgx_model* m) {
   return TGX_OK;
 }
 
-// Token hash + score table of forward algo 4 (max_token_len <= 16 only); a vocabulary it cannot serve simply leaves
-// hash.mask == 0 and run_viterbi uses the pair kernel.
-int upload_seg_tables(tgx_model* m, const uint8_t* token_bytes, const uint64_t* token_offsets, const double* scores,
+// Token hash of the emit kernel and the match tables of the default forward pass (max_token_len <= 16 only); a
+// vocabulary they cannot serve simply leaves hash.mask == 0 / have_rows == false and the older kernels take over.
+// On failure nothing the model already holds has been touched.
+int upload_aux_tables(tgx_model* m, const tgx::DoubleArray& da, const uint8_t* token_bytes, const uint64_t* token_offsets,
                       uint64_t V, uint32_t max_token_len) {
+  if (m->device < 0) return TGX_OK;
+  cudaStream_t st = m->w().stream;
+  tgx::TokenHash h;
+  const bool hash_ok = V != 0 && max_token_len >= 1 && max_token_len <= 16 &&
+                       tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty();
+  const bool rows_ok = !da.slots8.empty();
+  if (hash_ok) CU(m->d_hash.reserve(h.slots.size() * sizeof(tgx::Slot)));
+  if (rows_ok) {
+    CU(m->d_trie8.reserve(da.slots8.size() * 8));
+    CU(m->d_rows.reserve(da.rows.size() * 8 + 256));
+    CU(m->d_rowids.reserve(da.row_ids.size() * 4 + 256));
+  }
   m->hash.mask = 0;
   m->hash.slots.clear();
-  m->wmax = 0;
-  if (m->device < 0 || V == 0 || max_token_len == 0 || max_token_len > 16) return TGX_OK;
-  for (uint64_t i = 0; i < V; i++) {
-    const double a = std::fabs(scores[i]);
-    if (!(a <= 1e300)) return TGX_OK;  // NaN / inf scores: not for the margin argument
-    m->wmax = std::max(m->wmax, a);
+  m->have_rows = false;
+  if (hash_ok) CU(cudaMemcpyAsync(m->d_hash.p, h.slots.data(), h.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, st));
+  if (rows_ok) {
+    CU(cudaMemcpyAsync(m->d_trie8.p, da.slots8.data(), da.slots8.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->d_rows.p, da.rows.data(), da.rows.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->d_rowids.p, da.row_ids.data(), da.row_ids.size() * 4, cudaMemcpyHostToDevice, st));
   }
-  tgx::TokenHash h;
-  if (!tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty()) return TGX_OK;
-  CU(m->d_hash.reserve(h.slots.size() * sizeof(tgx::Slot)));
-  CU(m->d_scores.reserve(V * 8));
-  CU(cudaMemcpyAsync(m->d_hash.p, h.slots.data(), h.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
-  CU(cudaMemcpyAsync(m->d_scores.p, scores, V * 8, cudaMemcpyHostToDevice, m->w().stream));
-  CU(cudaStreamSynchronize(m->w().stream));
-  m->hash = std::move(h);
+  CU(cudaStreamSynchronize(st));
+  if (hash_ok) m->hash = std::move(h);
+  if (rows_ok) {
+    m->have_rows = true;
+    m->rows16 = (uint32_t)(da.rows.size() / 2);
+  }
   return TGX_OK;
 }
 
@@ -760,100 +704,6 @@ int sort_units(tgx_model* m, uint32_t U) {
   return TGX_OK;
 }
 
-template <int HOT>
-cudaError_t launch_seg_solve(tgx_model* m, SegParams p) {
-  const size_t smem = seg_smem_bytes(p.hot_slots);
-  cudaError_t e = cudaFuncSetAttribute(seg_solve_kernel<HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int per_sm = (2 * (smem + 1024) <= (size_t)228 * 1024) ? 2 : 1;
-  e = cudaFuncSetAttribute(seg_solve_kernel<HOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (int)std::min<size_t>(100, per_sm * (smem + 1024) * 100 / (228 * 1024) + 1));
-  if (e != cudaSuccess) return e;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)m->num_sms * per_sm);
-  seg_solve_kernel<HOT><<<grid, SG_THREADS, smem, m->w().stream>>>(p);
-  m->w().stats.launches += 1;
-  return cudaGetLastError();
-}
-
-// Forward algo 4: segment-parallel exact Viterbi (tgx_seg_kernels.cuh).  Same outputs as the pair kernel + backtrack
-// (mark, ntok, status), plus ids_at for run_emit.  The caller has sorted the units and zeroed mark / ntok / status.
-int run_viterbi_seg(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t N,
-                    const UnitParams& u) {
-  cudaStream_t st = m->w().stream;
-  const uint64_t n_em_tiles = (N + EM_TILE - 1) / EM_TILE;
-  const uint64_t words = N / 32 + 4;
-  CU(m->w().bitmap.reserve(words * 4));
-  CU(m->w().ids_at.reserve((n_em_tiles * EM_TILE + 64) * 4));
-  CU(dev_fill(m->w().bitmap.p, 0, words * 4, st));
-  unsigned long long* dbg = nullptr;
-  if (getenv("TGX_SEG_DBG")) {  // developer counters, printed by tools/probe.py through tgx_model_debug_counters
-    CU(m->w().small.reserve(256));
-    dbg = m->w().small.as<unsigned long long>() + 16;
-    CU(dev_fill(dbg, 0, 64, st));
-  }
-  if (S > 1) {
-    crlf_mark_starts<<<nblk(S, 256), 256, 0, st>>>(d_off, S, m->w().bitmap.as<uint32_t>());
-    m->w().stats.launches += 1;
-  }
-  CU(cudaEventRecord(m->w().ev[0], st));
-  if (N) {
-    SegParams p;
-    p.text = d_text;
-    p.N = N;
-    p.bitmap = m->w().bitmap.as<uint32_t>();
-    p.bitmap_words = words;
-    p.trie = m->d_trie;
-    p.root_base = m->da.root_base;
-    p.max_len = std::min<uint32_t>(16, m->da.max_token_len);
-    p.hash = m->d_hash.as<uint4>();
-    p.hash_mask = m->hash.mask;
-    p.hash_seed = m->hash.seed;
-    p.sorted_len = m->w().keys_out.as<uint32_t>();
-    p.wmax = m->wmax;
-    p.mark = m->w().mark.as<uint8_t>();
-    p.ids_at = m->w().ids_at.as<uint32_t>();
-    p.n_tiles = (N + SG_TP - 1) / SG_TP;
-    p.dbg = dbg;
-    int levels = std::min(m->seg_hot, 2);
-    while (levels > 0 && seg_smem_bytes(m->da.hot[levels]) > (size_t)m->smem_optin) levels--;
-    p.hot_slots = levels ? m->da.hot[levels] : 0;
-    if (levels == 2) CU(launch_seg_solve<2>(m, p));
-    else if (levels == 1) CU(launch_seg_solve<1>(m, p));
-    else CU(launch_seg_solve<0>(m, p));
-  }
-  CU(cudaEventRecord(m->w().ev[1], st));
-  CU(cudaEventRecord(m->w().ev[2], st));
-  if (S) {
-    ChainParams c;
-    c.text = d_text;
-    c.unit_start = u.unit_start;
-    c.unit_len = u.unit_len;
-    c.order = u.order;
-    c.counts = u.counts;
-    c.trie = m->d_trie;
-    c.root_base = m->da.root_base;
-    c.max_len = std::min<uint32_t>(16, m->da.max_token_len);
-    c.mark = m->w().mark.as<uint8_t>();
-    c.ids_at = m->w().ids_at.as<uint32_t>();
-    c.scores = m->d_scores.as<double>();
-    c.V = (uint32_t)m->V;
-    c.n_tokens = m->w().ntok.as<unsigned long long>();
-    c.status = m->w().status.as<int32_t>();
-    c.counter = m->w().small.as<unsigned int>() + 8;
-    c.dbg = dbg;
-    CU(dev_fill(c.counter, 0, 4, st));
-    const size_t smem = CH_WARPS * CH_WARP_BYTES;
-    CU(cudaFuncSetAttribute(seg_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((S + CH_WARPS - 1) / CH_WARPS, (uint64_t)m->num_sms * 2);
-    seg_chain_kernel<<<grid, CH_WARPS * 32, smem, st>>>(c);
-    m->w().stats.launches += 1;
-    CU(cudaGetLastError());
-  }
-  CU(cudaEventRecord(m->w().ev[3], st));
-  m->w().have_ids_at = true;
-  return TGX_OK;
-}
-
 // Viterbi over all samples: forward dp (back lengths) + backtrack (token-end marks).  On return
 // m->w().mark holds the length of the token ending at every marked byte, m->w().ntok token counts,
 // m->w().status per-sample status.
@@ -878,8 +728,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   if (rc) return rc;
   uint32_t* counts = m->w().small.as<uint32_t>();
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
-  split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr,
-                                 (uint32_t)std::min<int64_t>(m->lane_threshold, 0x7FFFFFFF), counts);
+  split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr, counts);
   m->w().stats.launches += 1;
   CU(dev_fill(m->w().ntok.p, 0, ((size_t)U + 1) * 8, st));
   CU(dev_fill(m->w().status.p, 0, (size_t)U * 4 + 4, st));
@@ -899,42 +748,59 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.first = 0;
   u.count = U;  // upper bound for the grids
 
-  m->w().have_ids_at = false;
   const double dropout = with_dropout ? m->dropout : 0.0;  // the frequency passes encode with dropout 0.0
-  const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 0) : m->algo;  // with the draw: pair or lane-group kernels
-  if (algo == 4 && u.rows <= 16 && m->hash.mask != 0) return run_viterbi_seg(m, d_text, d_off, S, N, u);
+  // with the draw: pair-CTA or lane-group kernels
+  const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : (m->algo == 0 && !m->have_rows ? 2 : m->algo);
+  CU(cudaEventRecord(m->w().ev[8], st));
+  if (algo == 0 && u.rows <= 16 && N) {
+    CU(m->w().rec.reserve((N + 64) * 4));
+    MatchParams mp;
+    mp.text = d_text;
+    mp.blob_end = d_text + N;
+    mp.N = N;
+    mp.trie8 = m->d_trie8.as<uint2>();
+    mp.root_base = m->da.root_base;
+    mp.rec = m->w().rec.as<uint32_t>();
+    const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
+    mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
+    const size_t smem = (size_t)mp.staged * 8;
+    CU(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t threads = (uint32_t)m->match_threads;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)m->num_sms);
+    match_kernel<<<grid, threads, smem, st>>>(mp);
+    m->w().stats.launches += 1;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(m->w().ev[9], st));
   CU(cudaEventRecord(m->w().ev[0], st));
-  if (algo == 3 && u.rows <= 16) {
-    HybridParams hp;
-    hp.pair.u = u;
-    hp.pair.u.part = 3;
-    hp.pair.blob_end = d_text + N;
-    hp.pair.bp = m->w().bp.as<uint8_t>();
-    hp.pair.counter = m->w().small.as<unsigned int>() + 8;
-    hp.pair.dbg = 0;
-    hp.lane.u = u;
-    hp.lane.u.part = 4;
-    hp.lane.blob_end = d_text + N;
-    hp.lane.bp = m->w().bp.as<uint8_t>();
-    hp.lane.counter = m->w().small.as<unsigned int>() + 9;
-    hp.pair_ctas = hp.lane_warps = 0;
-    CU(launch_viterbi_hybrid(m, hp));
+  if (algo == 0 && u.rows <= 16) {
+    if (N && U) {
+      RowsParams rp;
+      rp.u = u;
+      rp.u.part = 0;
+      rp.rec = m->w().rec.as<uint32_t>();
+      rp.rows = m->d_rows.as<double>();
+      const size_t budget = (size_t)std::min<int64_t>(m->rows_hot_bytes, (int64_t)m->smem_optin - 1024);
+      rp.hot16 = (uint32_t)std::min<size_t>(m->rows16, budget / 16);
+      rp.bp = m->w().bp.as<uint8_t>();
+      rp.counter = m->w().small.as<unsigned int>() + 8;
+      const size_t smem = (size_t)rp.hot16 * 16;
+      CU(cudaFuncSetAttribute(viterbi_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(dev_fill(rp.counter, 0, 4, st));
+      const uint32_t warps = (uint32_t)std::max(1, std::min(16, m->rows_warps));
+      const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)U + 2 * warps - 1) / (2 * warps), (uint64_t)m->num_sms);
+      viterbi_rows_kernel<<<grid, warps * 32, smem, st>>>(rp);
+      m->w().stats.launches += 1;
+      CU(cudaGetLastError());
+    }
   } else if (algo == 2 && u.rows <= 16) {
-    LaneParams p;
-    p.u = u;
-    p.u.part = 0;
-    p.blob_end = d_text + N;
-    p.bp = m->w().bp.as<uint8_t>();
-    p.counter = m->w().small.as<unsigned int>() + 9;
-    CU(launch_viterbi_lane<16>(m, p));
-  } else if (algo == 0 && u.rows <= 16) {
     PairParams p;
     p.u = u;
     p.u.part = 0;
     p.blob_end = d_text + N;
     p.bp = m->w().bp.as<uint8_t>();
     p.counter = m->w().small.as<unsigned int>() + 8;
-    p.dbg = getenv("TGX_DBG") ? (uint32_t)atoi(getenv("TGX_DBG")) : 0u;
+    p.dbg = 0;
     DropInfo di;
     di.dropout = dropout;
     di.seed = m->drop_seed;
@@ -1011,7 +877,6 @@ int run_emit(tgx_model* m, const uint8_t* d_text, uint64_t N, uint32_t* d_ids, u
     e.cap = ids_cap;
     e.freq = d_freq;
     e.V = (uint32_t)m->V;
-    e.ids_at = m->w().have_ids_at ? m->w().ids_at.as<uint32_t>() : nullptr;
     const bool use_hash = m->emit_hash && m->hash.mask != 0;
     e.hash = use_hash ? m->d_hash.as<uint4>() : nullptr;
     e.hash_mask = use_hash ? m->hash.mask : 0;
@@ -1060,6 +925,7 @@ void finish_stats(tgx_model* m, int which) {
   if (which == 2 && cudaEventElapsedTime(&ms, m->w().ev[2], m->w().ev[3]) == cudaSuccess) m->w().stats.bwd_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[2], m->w().ev[3]) == cudaSuccess) m->w().stats.back_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[4], m->w().ev[5]) == cudaSuccess) m->w().stats.emit_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[8], m->w().ev[9]) == cudaSuccess) m->w().stats.match_ms = ms;
   if (cudaEventElapsedTime(&ms, m->w().ev[6], m->w().ev[7]) == cudaSuccess) m->w().stats.total_ms = ms;
   m->last_stats = m->w().stats;
 }
@@ -1118,7 +984,7 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     m->trie_cap = m->da.slots.size();
     CU(cudaMemcpyAsync(m->d_trie, m->da.slots.data(), bytes, cudaMemcpyHostToDevice, m->w().stream));
     CU(cudaStreamSynchronize(m->w().stream));
-    int rc = upload_seg_tables(m.get(), token_bytes, token_offsets, scores, vocab_size, m->da.max_token_len);
+    int rc = upload_aux_tables(m.get(), m->da, token_bytes, token_offsets, vocab_size, m->da.max_token_len);
     if (rc) return rc;
   }
   *out = m.release();
@@ -1145,7 +1011,7 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
     }
     CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
     CU(cudaStreamSynchronize(m->w().stream));
-    int rc = upload_seg_tables(m, token_bytes, token_offsets, scores, vocab_size, da.max_token_len);
+    int rc = upload_aux_tables(m, da, token_bytes, token_offsets, vocab_size, da.max_token_len);
     if (rc) return rc;
   }
   m->da = std::move(da);
@@ -1164,7 +1030,7 @@ void tgx_model_destroy(tgx_model* m) {
     for (auto* b : bufs) b->release();
     for (auto& w : m->ws) {
       DevBuf* wb[] = {&w.text2, &w.off2, &w.bitmap, &w.blk, &w.ustart, &w.ulen, &w.keys_out, &w.vals_in, &w.vals_out,
-                      &w.cubtmp, &w.bp, &w.mark, &w.tilecnt, &w.ntok, &w.status, &w.small, &w.ids_at};
+                      &w.cubtmp, &w.bp, &w.mark, &w.tilecnt, &w.ntok, &w.status, &w.small, &w.rec};
       for (auto* b : wb) b->release();
       for (auto& e : w.ev)
         if (e) cudaEventDestroy(e);
@@ -1175,7 +1041,9 @@ void tgx_model_destroy(tgx_model* m) {
     }
     if (m->d_trie) cudaFree(m->d_trie);
     m->d_hash.release();
-    m->d_scores.release();
+    m->d_trie8.release();
+    m->d_rows.release();
+    m->d_rowids.release();
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream3) cudaStreamDestroy(m->stream3);
     if (m->stream4) cudaStreamDestroy(m->stream4);
@@ -1230,23 +1098,23 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
-    case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
+    case 3: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "algo must be 0..2"); m->algo = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
     case 19: m->estep_split = value ? 1 : 0; break;
     case 20: if (value < 1 || value > 4096) return fail(TGX_ERR_INVALID, "replicas must be 1..4096"); m->hot_r = (int)value; break;
     case 21: if (value < 0 || value > (1 << 20)) return fail(TGX_ERR_INVALID, "hot ids must be 0..2^20"); m->hot_k = (int)value; break;
     case 18: if (value < 0 || value > 16) return fail(TGX_ERR_INVALID, "blocks per SM must be 0..16"); m->lane_blocks_per_sm = (int)value; break;
-    case 15: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "segment kernel hot levels must be 0..2"); m->seg_hot = (int)value; break;
-    case 8: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->lane_threshold = value; break;
-    case 9: if (value < 1 || value > tgxk::LN_MAX_WARPS) return fail(TGX_ERR_INVALID, "lane warps must be 1..16"); m->lane_warps = (int)value; break;
     case 11: m->overlap_chunks = value ? 1 : 0; break;
     case 14: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "pair shape must be 0..2"); m->pair_shape = (int)value; break;
     case 13: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "hot levels must be 0..2"); m->hot_levels = (int)value; break;
-    case 10: if (value < 0 || value > 1024) return fail(TGX_ERR_INVALID, "pair CTAs must be 0..1024"); m->pair_ctas = (int)value; break;
     case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
     case 22: if (value < 0) return fail(TGX_ERR_INVALID, "byte base must be >= 0"); m->drop_byte_base = (uint64_t)value; break;
+    case 23: if (value < 32 || value > 1024 || value % 32) return fail(TGX_ERR_INVALID, "match threads must be 32..1024, a multiple of 32"); m->match_threads = (int)value; break;
+    case 24: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->match_stage_bytes = value; break;
+    case 25: if (value < 1 || value > 32) return fail(TGX_ERR_INVALID, "warps must be 1..32"); m->rows_warps = (int)value; break;
+    case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -1273,6 +1141,7 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
     case 4: return m->last_stats.total_ms;
     case 5: return m->last_stats.back_ms;
     case 6: return m->last_stats.emit_ms;
+    case 7: return m->last_stats.match_ms;
   }
   return 0;
 }
@@ -1287,15 +1156,6 @@ int tgx_model_prune_select(tgx_model* m, const uint8_t* token_bytes, const uint6
   int rc = tgx::prune_select_with(m->da, token_bytes, token_offsets, scores, keep, vocab_size, freq, n_samples,
                                   target_vocab_size, shrink_factor, threads, out_ids, out_n, audit);
   if (rc) return fail(rc, "prune_vocab failed (loss is not normal, or bad argument)");
-  return TGX_OK;
-}
-
-int tgx_model_debug_counters(tgx_model* m, uint64_t* out8) {
-  int rc = check_model(m);
-  if (rc) return rc;
-  if (!out8 || !m->w().small.p) return fail(TGX_ERR_INVALID, "no counters");
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(out8, m->w().small.as<unsigned long long>() + 16, 64, cudaMemcpyDeviceToHost));
   return TGX_OK;
 }
 

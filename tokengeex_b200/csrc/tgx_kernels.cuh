@@ -95,8 +95,6 @@ __device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uin
   const uint32_t nl = counts[0], nn = counts[1];
   if (part == 1) { first = 0; count = nl; }
   else if (part == 2) { first = nl; count = nn - nl; }
-  else if (part == 3) { first = 0; count = counts[2]; }                    // at least lane_threshold bytes
-  else if (part == 4) { first = counts[2]; count = nn - counts[2]; }       // shorter than that
   else { first = 0; count = nn; }
 }
 
@@ -773,7 +771,6 @@ struct EmitParams {
   unsigned long long cap;
   unsigned long long* freq;  // may be null
   uint32_t V;
-  const uint32_t* ids_at;    // forward algo 4: the id of the token ending at every marked byte (no re-walk)
   // token hash (trie_build.h; built when max_token_len <= 16): ONE probe per token instead of one dependent trie
   // probe per byte.  hash_mask == 0: not available, walk the trie.
   const uint4* hash;
@@ -786,7 +783,7 @@ __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
   __shared__ uint32_t s_tok[EM_TILE];  // (len << 16) | offset of the token's last byte in the tile
   __shared__ __align__(16) uint8_t s_text[EM_TILE + 48];  // bytes tile * EM_TILE - 16 .. (hash path; +32: word reads past the tile)
   extern __shared__ uint32_t s_hot[];  // [EM_HOT] when freq
-  const bool staged = p.hash_mask && !p.ids_at && (reinterpret_cast<unsigned long long>(p.text) & 15ull) == 0;
+  const bool staged = p.hash_mask && (reinterpret_cast<unsigned long long>(p.text) & 15ull) == 0;
   if (p.freq) {
     for (uint32_t i = threadIdx.x; i < EM_HOT; i += EM_BLOCK) s_hot[i] = 0;
     __syncthreads();
@@ -820,9 +817,7 @@ __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
       const uint32_t tk = s_tok[k];
       const uint32_t len = tk >> 16;
       uint32_t id;
-      if (p.ids_at) {
-        id = __ldg(p.ids_at + tile * EM_TILE + (tk & 0xFFFFu));
-      } else if (p.hash_mask) {
+      if (p.hash_mask) {
         unsigned long long lo = 0, hi = 0;
         if (staged) {  // token bytes from the staged tile (16-byte halo in front: a token may start in the previous tile)
           // 16 bytes from the token's first byte: five aligned words + funnel shifts, then cut to `len`

@@ -1,0 +1,249 @@
+// Match stream + row consumer: the default Viterbi forward pass (max_token_len <= 16).
+//
+// Model::encode's inner loop (src/model.rs:83-110) interleaves two things: common_prefix_search from every
+// position (src/trie.rs:51-63) — independent of the dp, embarrassingly parallel — and the ordered relax chain.
+// Here they are two kernels coupled through a 4-byte record per position in HBM:
+//
+//   match_kernel        one thread per start position walks the 8-byte double-array (trie_build.h: slots8; the leading
+//                       slots staged in shared memory, the rest from L2), no barriers, no dp, and writes
+//                       rec[p] = (L - 1) << 28 | row offset   of the DEEPEST token that starts at p.
+//   viterbi_rows_kernel the relax chain.  The row of that token (trie_build.h: rows) lists, dense by length, the score of
+//                       every token on the trie path down to it, i.e. everything the reference's iterator yields at p;
+//                       a half-warp owns one sample, lane g the dp cell of the positions = g (mod 16), as in the
+//                       pair-CTA kernel — but the candidate scores come from ONE coalesced read of the row (hot rows
+//                       from shared memory, the rest from L1/L2) instead of a dense f64 table that producer warps park
+//                       in shared memory (136 B per buffered position: what capped that kernel at 10-12 chains per SM).
+//
+// The evaluation order is the reference's (ascending start, strict '>', f64 sums built left to right), so the back
+// lengths — the only output — are bit-identical to the pair kernel's.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tgx_kernels.cuh"
+
+namespace tgxk {
+
+constexpr uint32_t REC_NOMATCH = 15u << 28;  // row 0: 16 x -inf
+constexpr uint32_t REC_OFF = 0x0FFFFFFFu;
+
+// -----------------------------------------------------------------------------------------
+// K2a  match_kernel: TrieIterator::next (src/trie.rs:51-63) from every byte of the blob.
+// -----------------------------------------------------------------------------------------
+struct MatchParams {
+  const uint8_t* text;      // blob (after the processors)
+  const uint8_t* blob_end;  // text + N
+  unsigned long long N;
+  const uint2* trie8;       // tgx::DoubleArray::slots8
+  uint32_t root_base;
+  uint32_t staged;          // leading slots staged in shared memory
+  uint32_t* rec;            // [N]
+};
+
+// The walk may run past the end of a sample (into the next sample's bytes): such a match lands on a dp cell beyond
+// the sample, which the consumer never reads; the E-step consumers cut it at the snippet's end.
+__global__ void __launch_bounds__(1024, 1) match_kernel(MatchParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint2* s_trie = reinterpret_cast<uint2*>(smem);
+  for (uint32_t i = threadIdx.x; i < p.staged; i += blockDim.x) s_trie[i] = __ldg(p.trie8 + i);
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long pos = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long w[3] = {0, 0, 0};
+  uint32_t sh = 0;
+  if (pos < p.N) load_window(p.text + pos, p.blob_end, w, sh);
+  while (pos < p.N) {
+    const unsigned long long w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t s0 = sh;
+    const unsigned long long npos = pos + stride;
+    if (npos < p.N) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during this walk
+    const unsigned long long cur[3] = {w0, w1, w2};
+    uint32_t best = REC_NOMATCH;
+    uint32_t xb = p.root_base;
+    bool go = true;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const unsigned long long a = window_bytes(cur, s0, g);
+      const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (go) {
+          const int d = g * 8 + k;
+          const uint32_t cw = __byte_perm(k < 4 ? alo : ahi, 1u, 0x5540 + (k & 3));  // 0x100 | byte
+          const uint32_t t = xb ^ cw;
+          const uint2 e = (t < p.staged) ? s_trie[t] : __ldg(p.trie8 + t);
+          if ((e.x ^ cw) & 0x1FFu) {
+            go = false;
+          } else {
+            if (e.y & tgx::SLOT8_TERM) best = ((uint32_t)d << 28) | (e.y & tgx::SLOT8_OFF_MASK);
+            if (!(e.y & tgx::SLOT8_HASCH)) go = false;
+            xb = e.x >> 9;
+          }
+        }
+      }
+    }
+    p.rec[pos] = best;
+    pos = npos;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// K2b  viterbi_rows_kernel: the relax chain of Model::encode (src/model.rs:83-110) over the match stream.
+// -----------------------------------------------------------------------------------------
+struct RowsParams {
+  UnitParams u;         // unit_start / unit_len / order / counts+part (text and trie unused)
+  const uint32_t* rec;  // [N] match stream
+  const double* rows;   // row table
+  uint32_t hot16;       // leading 16-byte units of the row table staged in shared memory
+  uint8_t* bp;          // [N] back length per end position (0 = unreachable)
+  unsigned int* counter;
+};
+
+struct RowsUnit {
+  unsigned long long start;
+  uint32_t n, ntiles, tile;
+  int32_t unit;  // < 0: nothing to do
+};
+
+// rows[idx] from the staged prefix of the row table (shared memory) or from L1/L2: two predicated loads, no branch
+// (as C++ the select compiled to divergent branches in front of every step of the chain).
+__device__ __forceinline__ double ld_row(uint32_t idx, uint32_t hot_dbl, uint32_t s_base, const double* rows) {
+  double v;
+  asm("{\n\t"
+      ".reg .pred ph;\n\t"
+      ".reg .u32 sa;\n\t"
+      ".reg .u64 ga;\n\t"
+      "setp.lt.u32 ph, %1, %2;\n\t"
+      "mad.lo.u32 sa, %1, 8, %3;\n\t"
+      "mad.wide.u32 ga, %1, 8, %4;\n\t"
+      "@ph ld.shared.f64 %0, [sa];\n\t"
+      "@!ph ld.global.nc.f64 %0, [ga];\n\t"
+      "}"
+      : "=d"(v)
+      : "r"(idx), "r"(hot_dbl), "r"(s_base), "l"(rows));
+  return v;
+}
+
+// One 32-position tile of both halves of the warp.  r0 / r1: this lane's records of positions g and 16 + g of the
+// tile.  Lane g's candidate at step j is the token of length ((g - j - 1) & 15) + 1 starting at position j — the one
+// that lands on its cell (a length beyond the row's reads row 0: -inf); "unreached" is best == -inf exactly as in
+// pair_consume (tgx_kernels.cuh).
+__device__ __forceinline__ void rows_consume(const double* __restrict__ rows, uint32_t s_base,
+                                             uint32_t hot_dbl, uint32_t r0, uint32_t r1, int g, double& best,
+                                             uint32_t& ps, uint32_t& len0, uint32_t& len1) {
+  auto fetch = [&](int j) -> double {
+    const uint32_t rs = __shfl_sync(0xFFFFFFFFu, j < 16 ? r0 : r1, j & 15, 16);  // record of position j
+    const uint32_t li = (uint32_t)(g - j - 1) & 15u;                            // candidate length - 1
+    const uint32_t idx = (li <= (rs >> 28)) ? (rs & REC_OFF) * 2u + li : li;
+    return ld_row(idx, hot_dbl, s_base, rows);  // (element-wise: a row may straddle the staged prefix)
+  };
+  double sc[4];
+  sc[0] = fetch(0);
+  sc[1] = fetch(1);
+  sc[2] = fetch(2);
+  uint32_t sv_hi = 0, sv_ps = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    if (j + 3 < 32) sc[(j + 3) & 3] = fetch(j + 3);
+    const double bs = __shfl_sync(0xFFFFFFFFu, best, j & 15, 16);  // dp[pos].score, final
+    const bool own = g == (j & 15);
+    if (own) {  // this lane's cell is position j of the tile: keep its result, the cell moves on to j + 16
+      sv_hi = (uint32_t)__double2hiint(best);
+      sv_ps = ps;
+    }
+    const double cand = __dadd_rn(bs, sc[j & 3]);  // dp[pos].score + vocab[id].score  (src/model.rs:98)
+    if (cand > best || own) {                      // (:100-101); a fresh cell takes its first candidate
+      best = cand;
+      ps = j;
+    }
+    if ((j & 15) == 15) {
+      const uint32_t l = (sv_hi == 0xFFF00000u) ? 0u : (((uint32_t)(j - 15 + g) - sv_ps) & 31u);
+      if (j == 15) len0 = l; else len1 = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512, 1) viterbi_rows_kernel(RowsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.rows);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = threadIdx.x; i < p.hot16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 15;
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
+  uint32_t ufirst = u.first, ucount = u.count;
+  unit_range(u.counts, u.part, ufirst, ucount);
+
+  RowsUnit cur;
+  cur.unit = -1; cur.start = 0; cur.n = 0; cur.ntiles = 0; cur.tile = 0;
+  // the half's leader takes the next sample of the length-descending order (LPT); everybody gets a copy
+  // (called by all 32 lanes: the shuffle is a full-warp one)
+  auto fetch_unit = [&](bool need) {
+    uint32_t idx = 0;
+    if (need && g == 0) idx = atomicAdd(p.counter, 1u);
+    idx = __shfl_sync(0xFFFFFFFFu, idx, 0, 16);
+    if (!need) return;
+    if (idx < ucount) {
+      cur.unit = (int32_t)u.order[ufirst + idx];
+      cur.n = u.unit_len[cur.unit];
+      cur.start = u.unit_start[cur.unit];
+      cur.tile = 0;
+      cur.ntiles = cur.n / 32 + 1;  // positions 0..n
+    } else {
+      cur.unit = -1;
+    }
+  };
+  auto load_rec = [&](uint32_t tile, uint32_t& a, uint32_t& b) {
+    const uint32_t q0 = tile * 32 + g, q1 = q0 + 16;
+    a = (cur.unit >= 0 && q0 < cur.n) ? __ldg(p.rec + cur.start + q0) : REC_NOMATCH;
+    b = (cur.unit >= 0 && q1 < cur.n) ? __ldg(p.rec + cur.start + q1) : REC_NOMATCH;
+  };
+  auto pull_rows = [&](uint32_t a, uint32_t b) {  // cold rows of a tile that is about to be consumed: into L1
+    if ((a & REC_OFF) >= p.hot16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.rows + (size_t)(a & REC_OFF) * 2));
+    if ((b & REC_OFF) >= p.hot16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.rows + (size_t)(b & REC_OFF) * 2));
+  };
+  fetch_unit(true);
+  double best = ninf;
+  uint32_t ps = 0;
+  // records of the current tile, the next one (its cold rows are pulled into L1 while this tile is consumed) and the
+  // one after (in flight)
+  uint32_t r0, r1, n0, n1, m0 = REC_NOMATCH, m1 = REC_NOMATCH;
+  load_rec(0, r0, r1);
+  load_rec(1, n0, n1);
+  while (__any_sync(0xFFFFFFFFu, cur.unit >= 0)) {
+    const bool act = cur.unit >= 0;
+    if (act && cur.tile == 0) {  // dp[0] = { score 0.0, start Some(0) }  (src/model.rs:72-81); the rest unreached
+      best = (g == 0) ? 0.0 : ninf;
+      ps = 0;
+    }
+    const bool more = act && cur.tile + 1 < cur.ntiles;
+    if (more) {
+      load_rec(cur.tile + 2, m0, m1);
+      pull_rows(n0, n1);
+    }
+    uint32_t len0, len1;
+    rows_consume(p.rows, s_base, p.hot16 * 2u, r0, r1, g, best, ps, len0, len1);  // both halves always run it (full-warp shuffles)
+    if (act) {
+      const uint32_t e0 = cur.tile * 32 + g, e1 = e0 + 16;
+      if (e0 >= 1 && e0 <= cur.n) p.bp[cur.start + e0 - 1] = (uint8_t)len0;
+      if (e1 <= cur.n) p.bp[cur.start + e1 - 1] = (uint8_t)len1;
+    }
+    if (more) {
+      cur.tile++;
+      r0 = n0; r1 = n1;
+      n0 = m0; n1 = m1;
+    }
+    fetch_unit(act && !more);
+    if (!more) {
+      load_rec(0, r0, r1);
+      load_rec(1, n0, n1);
+    }
+  }
+}
+
+}  // namespace tgxk

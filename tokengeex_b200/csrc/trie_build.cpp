@@ -124,9 +124,11 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   bfs.reserve(nodes.size());
   bfs.push_back(0);
   std::vector<uint8_t> depth(nodes.size(), 0);
+  std::vector<uint32_t> parent(nodes.size(), 0);
   for (size_t i = 0; i < bfs.size(); i++)
     for (uint32_t c = nodes[bfs[i]].first_child; c; c = nodes[c].next_sibling) {
       depth[c] = (uint8_t)std::min<uint32_t>(depth[bfs[i]] + 1u, 255u);
+      parent[c] = bfs[i];
       bfs.push_back(c);
     }
 
@@ -223,6 +225,53 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     out->slots[nd.slot] = s;
   }
   lap("emit");
+  // 6. match tables (trie_build.h): one row per terminal node, hottest (highest score) first
+  out->slots8.clear();
+  out->rows.clear();
+  out->row_ids.clear();
+  if (max_len >= 1 && max_len <= 16) {
+    std::vector<uint32_t> terms;  // terminal nodes
+    terms.reserve(n_term);
+    for (uint32_t i = 1; i < nodes.size(); i++)
+      if (nodes[i].term_id >= 0) terms.push_back(i);
+    auto hotter = [&](uint32_t a, uint32_t b) {
+      const double sa = scores[nodes[a].term_id], sb = scores[nodes[b].term_id];
+      if (sa != sb) return sa > sb;
+      return nodes[a].term_id < nodes[b].term_id;
+    };
+    // (node order is byte order; score-sorted vocabularies are the common case, so sort by id first: then the
+    //  second, stable sort by score finds its input already ordered)
+    std::sort(terms.begin(), terms.end(), [&](uint32_t a, uint32_t b) { return nodes[a].term_id < nodes[b].term_id; });
+    if (!std::is_sorted(terms.begin(), terms.end(), hotter)) std::stable_sort(terms.begin(), terms.end(), hotter);
+    const double ninf = -INFINITY;
+    std::vector<uint32_t> row_of(nodes.size(), 0);
+    uint64_t units16 = 8;  // row 0: 16 x -inf
+    for (uint32_t nd : terms) {
+      row_of[nd] = (uint32_t)units16;
+      units16 += (depth[nd] + 1u) / 2u;
+    }
+    if (units16 > SLOT8_OFF_MASK) return "row table too large";
+    out->rows.assign(units16 * 2, ninf);
+    out->row_ids.assign(units16 * 2, 0xFFFFFFFFu);
+    for (uint32_t nd : terms) {
+      const size_t base = (size_t)row_of[nd] * 2;
+      for (uint32_t a = nd; a; a = parent[a])
+        if (nodes[a].term_id >= 0) {
+          out->rows[base + depth[a] - 1] = scores[nodes[a].term_id];
+          out->row_ids[base + depth[a] - 1] = (uint32_t)nodes[a].term_id;
+        }
+    }
+    out->slots8.assign(n_slots, 0);
+    for (size_t i = 0; i < nodes.size(); i++) {
+      const Node& nd = nodes[i];
+      const Slot& s = out->slots[nd.slot];
+      uint32_t y = 0;
+      if (nd.first_child) y |= SLOT8_HASCH;
+      if (nd.term_id >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
+      out->slots8[nd.slot] = (uint64_t)s.x | ((uint64_t)y << 32);
+    }
+  }
+  lap("rows");
   out->root_base = base_of[0] ^ 0x100u;
   out->max_token_len = max_len;
   out->n_nodes = (uint32_t)nodes.size();

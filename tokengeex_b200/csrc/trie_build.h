@@ -47,7 +47,21 @@ struct DoubleArray {
   // [0, hot[d]).  hot[1] covers the root's children, hot[2] also their children.  The kernels
   // stage that prefix in shared memory.
   uint32_t hot[3] = {0, 0, 0};
+
+  // ---- match tables (max_token_len <= 16 only; empty otherwise): what match_kernel / viterbi_rows_kernel read.
+  // slots8[t] = slots[t].x | y8 << 32 with y8 = TERM8 | HASCH8 | row offset: the 8-byte form of the same double-array
+  // (transition check + flags + the ROW of the token that ends at this node), half the footprint of `slots`.
+  // A row lists, dense by length, the score of every vocabulary token that is a prefix of the row's token
+  // (= everything common_prefix_search yields on the way down to it, src/trie.rs:51-63): rows[2 * off16 + l - 1] =
+  // score of the prefix of length l, or -inf when that prefix is not a token; padded with -inf to an even count
+  // (16-byte units).  row_ids has the same layout with the token ids (0xFFFFFFFF = no token).  Rows are laid out by
+  // descending score of their own token (frequent tokens first), so the first bytes of the table are the hot ones
+  // the kernels stage in shared memory.  Row 0 = 16 x -inf = "no token starts here".
+  std::vector<uint64_t> slots8;
+  std::vector<double> rows;
+  std::vector<uint32_t> row_ids;
 };
+constexpr uint32_t SLOT8_TERM = 1u << 31, SLOT8_HASCH = 1u << 30, SLOT8_OFF_MASK = 0x0FFFFFFFu;
 
 // Returns "" on success, else an error message.
 std::string build_double_array(const uint8_t* token_bytes, const uint64_t* token_offsets,

@@ -345,29 +345,31 @@ class Tokenizer:
             s = p.preprocess(s)
         return s.encode("utf-8"), gpu_crlf
 
-    def _encode_pieces(self, pieces: List[bytes], gpu_crlf: bool, dropout: float) -> List[np.ndarray]:
+    def _encode_pieces(self, pieces: List[bytes], gpu_crlf: bool, dropout: float) -> Tuple[np.ndarray, np.ndarray]:
+        """→ (ids u32[T], id_off u64[len(pieces) + 1])"""
         if not pieces:
-            return []
+            return np.zeros(0, np.uint32), np.zeros(1, np.uint64)
         model = self._dev(dropout)
         blob, off = N.pack(pieces)
         drawn = 0.0 < dropout < 1.0
         try:
-            if drawn:
-                seed = self.dropout_seed
-                with self._dropout_lock:
+            # The dropout setting is state of the native handle: EVERY encode through the handle takes the lock, so a
+            # deterministic call (dropout 0.0) can never run between another thread's set_dropout(p) and its reset.
+            with self._dropout_lock:
+                if drawn:
+                    seed = self.dropout_seed
                     model.set_dropout(dropout, secrets.randbits(64) if seed is None else seed)
-                    try:
-                        ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
-                    finally:
+                try:
+                    ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
+                finally:
+                    if drawn:
                         model.set_dropout(0.0, 0)
-            else:
-                ids, id_off, status, plen, rc, bad = model.encode_batch(blob, off, crlf=gpu_crlf)
         except N.TgxError as e:
             raise TokenGeeXError(e.msg)
         if rc == N.TGX_ERR_NO_PATH:
             n = int(plen[bad])
             raise TokenGeeXError(f"no path to position {n}/{n}")  # Display of Error::NoPath, src/lib.rs:243-245
-        return [ids[int(id_off[i]):int(id_off[i + 1])] for i in range(len(pieces))]
+        return ids, id_off
 
     def _encode_many(self, texts: Sequence[str], dropout: float, ordinary: bool) -> List[List[int]]:
         V = len(self._tokens)
@@ -386,16 +388,20 @@ class Tokenizer:
                     row.append(("p", len(pieces)))
                     pieces.append(raw)
             plan.append(row)
-        enc = self._encode_pieces(pieces, gpu_crlf, dropout)
+        ids, id_off = self._encode_pieces(pieces, gpu_crlf, dropout)
+        flat = ids.tolist()  # one conversion for the whole batch; the rows below are list slices
+        cut = id_off.tolist()
+        if len(pieces) == len(plan) and all(len(row) == 1 and row[0][0] == "p" for row in plan):
+            return [flat[cut[i]:cut[i + 1]] for i in range(len(plan))]  # no special token anywhere: the common batch
         out = []
         for row in plan:
-            ids: List[int] = []
+            r: List[int] = []
             for kind, v in row:
                 if kind == "s":
-                    ids.append(v)
+                    r.append(v)
                 else:
-                    ids.extend(enc[v].tolist())
-            out.append(ids)
+                    r.extend(flat[cut[v]:cut[v + 1]])
+            out.append(r)
         return out
 
     def encode(self, text: str, dropout: float) -> List[int]:

@@ -43,8 +43,9 @@ def main():
     print(f"V={len(toks)} S={S} N={NB} slots={m.info().trie_slots}", flush=True)
     what = args.what.split(",")
     if "encode" in what:
-        cfgs = [(4, {15: 1}), (4, {15: 2}), (4, {15: 0}), (0, {14: 0, 16: 0}), (0, {14: 0, 16: 1}), (0, {14: 2, 6: 5, 13: 1}), (0, {14: 2, 6: 5, 13: 0}), (0, {14: 2, 6: 6, 13: 0}), (0, {14: 2, 6: 4, 13: 1}), (0, {14: 2, 6: 0, 13: 2}), (0, {14: 1}), (0, {14: 2}), (2, {9: 8}), (2, {9: 12}), (2, {9: 16}), (3, {9: 12, 8: 24576, 10: 64}), (3, {9: 12, 8: 16384, 10: 74}),
-                (3, {9: 12, 8: 32768, 10: 48}), (3, {9: 8, 8: 24576, 10: 64})]
+        K = 1024
+        cfgs = [(2, {14: 0}), (0, {}), (0, {25: 8}), (0, {25: 12}), (0, {25: 16, 26: 160 * K}), (0, {26: 32 * K}),
+                (0, {26: 96 * K, 24: 64 * K}), (0, {24: 0})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
         for algo, opts in cfgs:
@@ -58,10 +59,7 @@ def main():
                 best = min(best, m.stat(4))
             chk = int(d_ids[:tot].to(torch.int64).sum()) if tot else 0
             print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  forward {m.stat(1):.2f} ms "
-                  f"backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot} idsum={chk} rc={rc}", flush=True)
-            if algo == 4 and os.environ.get("TGX_SEG_DBG"):
-                print("   seg counters [segments, hard_long, hard_tie, hard_unreach, hard_bytes, solves, solve_tiles, chain_steps]:",
-                      m.debug_counters().tolist(), flush=True)
+                  f"match {m.stat(7):.2f} ms backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot} idsum={chk} rc={rc}", flush=True)
         m.set_option(3, 0)
     if "freq" in what:
       for eh in (0, 1):
