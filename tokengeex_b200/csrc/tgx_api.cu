@@ -139,7 +139,8 @@ struct tgx_model {
   // (the default of the first round; still what encodes with dropout in (0, 1)).
   int algo = 0;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
-  int64_t match_stage_bytes = 160 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
+  int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
+  int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
@@ -764,10 +765,21 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
     mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
     const size_t smem = (size_t)mp.staged * 8;
-    CU(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t threads = (uint32_t)m->match_threads;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)m->num_sms);
-    match_kernel<<<grid, threads, smem, st>>>(mp);
+    auto launch = [&](auto kernel, int ilp) -> cudaError_t {
+      const uint32_t threads = (uint32_t)std::min(m->match_threads, mk_max_threads(ilp));
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      const uint64_t per_cta = (uint64_t)threads * ilp;
+      const uint32_t grid = (uint32_t)std::min<uint64_t>((N + per_cta - 1) / per_cta, (uint64_t)m->num_sms);
+      kernel<<<grid, threads, smem, st>>>(mp);
+      return cudaGetLastError();
+    };
+    switch (m->match_ilp) {
+      case 1: CU(launch(match_kernel<1>, 1)); break;
+      case 2: CU(launch(match_kernel<2>, 2)); break;
+      case 8: CU(launch(match_kernel<8>, 8)); break;
+      default: CU(launch(match_kernel<4>, 4)); break;
+    }
     m->w().stats.launches += 1;
     CU(cudaGetLastError());
   }
@@ -1115,6 +1127,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 24: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->match_stage_bytes = value; break;
     case 25: if (value < 1 || value > 32) return fail(TGX_ERR_INVALID, "warps must be 1..32"); m->rows_warps = (int)value; break;
     case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
+    case 27: if (value != 1 && value != 2 && value != 4 && value != 8) return fail(TGX_ERR_INVALID, "positions per thread must be 1, 2, 4 or 8"); m->match_ilp = (int)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -1156,6 +1169,32 @@ int tgx_model_prune_select(tgx_model* m, const uint8_t* token_bytes, const uint6
   int rc = tgx::prune_select_with(m->da, token_bytes, token_offsets, scores, keep, vocab_size, freq, n_samples,
                                   target_vocab_size, shrink_factor, threads, out_ids, out_n, audit);
   if (rc) return fail(rc, "prune_vocab failed (loss is not normal, or bad argument)");
+  return TGX_OK;
+}
+
+// Developer aid (tools/analyse_rows.py; not part of include/tokengeex_b200.h): host walk of the 8-byte trie from every
+// byte of `text`.  out[0] = probes, out[1] = probes of slots below `staged` (what match_kernel would serve from shared
+// memory), out[2] = positions, out[3] = matches.
+int tgx_debug_probe_stats(const tgx_model* m, const uint8_t* text, uint64_t n, uint32_t staged, uint64_t* out) {
+  if (!m || !text || !out || m->da.slots8.empty()) return fail(TGX_ERR_INVALID, "no match tables");
+  uint64_t probes = 0, low = 0, matches = 0;
+  for (uint64_t p = 0; p < n; p++) {
+    uint32_t xb = m->da.root_base;
+    for (uint64_t d = 0; d < 16 && p + d < n; d++) {
+      const uint32_t cw = 0x100u | text[p + d];
+      const uint32_t t = xb ^ cw;
+      probes++;
+      if (t < staged) low++;
+      if (t >= m->da.slots8.size()) break;
+      const uint64_t e = m->da.slots8[t];
+      const uint32_t ex = (uint32_t)e, ey = (uint32_t)(e >> 32);
+      if ((ex ^ cw) & 0x1FFu) break;
+      if (ey & tgx::SLOT8_TERM) matches++;
+      if (!(ey & tgx::SLOT8_HASCH)) break;
+      xb = ex >> 9;
+    }
+  }
+  out[0] = probes; out[1] = low; out[2] = n; out[3] = matches;
   return TGX_OK;
 }
 

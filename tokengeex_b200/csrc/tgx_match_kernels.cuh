@@ -40,49 +40,101 @@ struct MatchParams {
   uint32_t* rec;            // [N]
 };
 
-// The walk may run past the end of a sample (into the next sample's bytes): such a match lands on a dp cell beyond
+// A thread owns ILP consecutive start positions and walks them side by side, one trie level per step: ILP independent
+// probes in flight per thread.  Every probe is two predicated loads — shared memory for the staged prefix of the
+// array (the hottest nodes: trie_build.cpp lays the slots out by descending walk frequency, 87 % of the probes of the
+// bench corpus land in the first 64 KB), L1/L2 for the rest — and a finished walk keeps probing slot 0, so the step
+// has no branch.  The window slides one byte per level, so walk i always reads byte i of it (a rolled loop: the
+// 16-fold unrolled form spilled ~100 bytes per walk).
+// A walk may run past the end of a sample (into the next sample's bytes): such a match lands on a dp cell beyond
 // the sample, which the consumer never reads; the E-step consumers cut it at the snippet's end.
-__global__ void __launch_bounds__(1024, 1) match_kernel(MatchParams p) {
+__device__ __forceinline__ uint2 mk_probe(uint32_t t, uint32_t staged, uint32_t s_base, const uint2* trie8) {
+  uint2 e;
+  asm volatile("{\n\t"
+      ".reg .pred ps;\n\t"
+      ".reg .u32 sa;\n\t"
+      ".reg .u64 ga;\n\t"
+      "setp.lt.u32 ps, %2, %3;\n\t"
+      "mad.lo.u32 sa, %2, 8, %4;\n\t"
+      "mad.wide.u32 ga, %2, 8, %5;\n\t"
+      "@ps ld.shared.v2.u32 {%0, %1}, [sa];\n\t"
+      "@!ps ld.global.nc.v2.u32 {%0, %1}, [ga];\n\t"
+      "}"
+      : "=r"(e.x), "=r"(e.y)
+      : "r"(t), "r"(staged), "r"(s_base), "l"(trie8));
+  return e;
+}
+
+constexpr int mk_max_threads(int ilp) { return ilp <= 4 ? 1024 : 768; }  // registers: 64 / 85
+
+template <int ILP>
+__global__ void __launch_bounds__(mk_max_threads(ILP), 1) match_kernel(MatchParams p) {
+  static_assert(ILP == 1 || ILP == 2 || ILP == 4 || ILP == 8, "positions per thread");
   extern __shared__ __align__(16) unsigned char smem[];
-  uint2* s_trie = reinterpret_cast<uint2*>(smem);
-  for (uint32_t i = threadIdx.x; i < p.staged; i += blockDim.x) s_trie[i] = __ldg(p.trie8 + i);
+  {
+    uint2* s_trie = reinterpret_cast<uint2*>(smem);
+    for (uint32_t i = threadIdx.x; i < p.staged; i += blockDim.x) s_trie[i] = __ldg(p.trie8 + i);
+  }
   __syncthreads();
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  unsigned long long pos = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * ILP;
+  unsigned long long pos = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * ILP;
   unsigned long long w[3] = {0, 0, 0};
   uint32_t sh = 0;
   if (pos < p.N) load_window(p.text + pos, p.blob_end, w, sh);
   while (pos < p.N) {
-    const unsigned long long w0 = w[0], w1 = w[1], w2 = w[2];
-    const uint32_t s0 = sh;
+    // 24 bytes from `pos` on (the last sh of them read as zero: the walks need 16 + ILP - 1 <= 23)
+    const unsigned long long a0 = sh ? ((w[0] >> (8 * sh)) | (w[1] << (64 - 8 * sh))) : w[0];
+    const unsigned long long a1 = sh ? ((w[1] >> (8 * sh)) | (w[2] << (64 - 8 * sh))) : w[1];
+    const unsigned long long a2 = sh ? (w[2] >> (8 * sh)) : w[2];
     const unsigned long long npos = pos + stride;
-    if (npos < p.N) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during this walk
-    const unsigned long long cur[3] = {w0, w1, w2};
-    uint32_t best = REC_NOMATCH;
-    uint32_t xb = p.root_base;
-    bool go = true;
+    if (npos < p.N) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during these walks
+    uint32_t xb[ILP], best[ILP];
+    bool go[ILP];
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-      const unsigned long long a = window_bytes(cur, s0, g);
-      const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (go) {
-          const int d = g * 8 + k;
-          const uint32_t cw = __byte_perm(k < 4 ? alo : ahi, 1u, 0x5540 + (k & 3));  // 0x100 | byte
-          const uint32_t t = xb ^ cw;
-          const uint2 e = (t < p.staged) ? s_trie[t] : __ldg(p.trie8 + t);
-          if ((e.x ^ cw) & 0x1FFu) {
-            go = false;
-          } else {
-            if (e.y & tgx::SLOT8_TERM) best = ((uint32_t)d << 28) | (e.y & tgx::SLOT8_OFF_MASK);
-            if (!(e.y & tgx::SLOT8_HASCH)) go = false;
-            xb = e.x >> 9;
-          }
-        }
-      }
+    for (int i = 0; i < ILP; i++) {
+      xb[i] = p.root_base;
+      best[i] = REC_NOMATCH;
+      go[i] = true;
     }
-    p.rec[pos] = best;
+    uint32_t b0 = (uint32_t)a0, b1 = (uint32_t)(a0 >> 32), b2 = (uint32_t)a1, b3 = (uint32_t)(a1 >> 32),
+             b4 = (uint32_t)a2, b5 = (uint32_t)(a2 >> 32);
+#pragma unroll 1
+    for (uint32_t d = 0; d < 16u; d++) {
+      uint2 e[ILP];
+      uint32_t cw[ILP];
+#pragma unroll
+      for (int i = 0; i < ILP; i++) {
+        cw[i] = __byte_perm(i < 4 ? b0 : b1, 1u, 0x5540 + (i & 3));  // 0x100 | byte i
+        e[i] = mk_probe(go[i] ? (xb[i] ^ cw[i]) : 0u, p.staged, s_base, p.trie8);
+      }
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < ILP; i++) {
+        const bool hit = go[i] && ((e[i].x ^ cw[i]) & 0x1FFu) == 0u;
+        if (hit && (e[i].y & tgx::SLOT8_TERM)) best[i] = (d << 28) | (e[i].y & tgx::SLOT8_OFF_MASK);
+        go[i] = hit && (e[i].y & tgx::SLOT8_HASCH);
+        xb[i] = e[i].x >> 9;
+        any |= go[i];
+      }
+      if (!any) break;
+      b0 = __funnelshift_r(b0, b1, 8);
+      b1 = __funnelshift_r(b1, b2, 8);
+      b2 = __funnelshift_r(b2, b3, 8);
+      b3 = __funnelshift_r(b3, b4, 8);
+      b4 = __funnelshift_r(b4, b5, 8);
+      b5 >>= 8;
+    }
+    if (ILP == 4 && pos + 4 <= p.N && (reinterpret_cast<unsigned long long>(p.rec) & 15ull) == 0) {
+      *reinterpret_cast<uint4*>(p.rec + pos) = make_uint4(best[0], best[1 % ILP], best[2 % ILP], best[3 % ILP]);
+    } else if (ILP == 8 && pos + 8 <= p.N && (reinterpret_cast<unsigned long long>(p.rec) & 15ull) == 0) {
+      *reinterpret_cast<uint4*>(p.rec + pos) = make_uint4(best[0], best[1 % ILP], best[2 % ILP], best[3 % ILP]);
+      *reinterpret_cast<uint4*>(p.rec + pos + 4) = make_uint4(best[4 % ILP], best[5 % ILP], best[6 % ILP], best[7 % ILP]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < ILP; i++)
+        if (pos + i < p.N) p.rec[pos + i] = best[i];
+    }
     pos = npos;
   }
 }

@@ -152,7 +152,32 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   std::vector<uint32_t> base_of(nodes.size(), 0);
   uint8_t labels[256];
   uint32_t first_open = 0;  // blocks below it have (next to) no free slot left
-  for (uint32_t nidx : bfs) {
+  // Allocation order: the root and its children first (BFS, so that hot[1] / hot[2] below hold), then every deeper
+  // node by descending weight = sum of exp(score) over the tokens below it, i.e. roughly how often a walk reaches it:
+  // a parent's children land in the lowest block that has room when the parent is processed, so the nodes walks
+  // visit most sit at the front of the array — the part match_kernel stages in shared memory.
+  std::vector<uint32_t> alloc_order;
+  {
+    double smax = -INFINITY;
+    for (uint64_t i = 0; i < V; i++) smax = std::max(smax, scores[i]);
+    std::vector<float> weight(nodes.size(), 0.f);
+    for (size_t i = bfs.size(); i-- > 1;) {  // children before parents
+      const uint32_t nd = bfs[i];
+      if (nodes[nd].term_id >= 0) weight[nd] += (float)std::exp(scores[nodes[nd].term_id] - smax);
+      weight[parent[nd]] += weight[nd];
+    }
+    alloc_order.reserve(bfs.size());
+    size_t shallow = 0;
+    while (shallow < bfs.size() && depth[bfs[shallow]] < 2) alloc_order.push_back(bfs[shallow++]);
+    std::vector<uint32_t> deep;
+    deep.reserve(bfs.size() - shallow);
+    for (size_t i = shallow; i < bfs.size(); i++)
+      if (nodes[bfs[i]].first_child) deep.push_back(bfs[i]);
+    std::stable_sort(deep.begin(), deep.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+    alloc_order.insert(alloc_order.end(), deep.begin(), deep.end());
+  }
+  lap("order");
+  for (uint32_t nidx : alloc_order) {
     uint32_t k = 0;
     for (uint32_t c = nodes[nidx].first_child; c; c = nodes[c].next_sibling) labels[k++] = nodes[c].label;
     if (!k) continue;

@@ -44,8 +44,8 @@ def main():
     what = args.what.split(",")
     if "encode" in what:
         K = 1024
-        cfgs = [(2, {14: 0}), (0, {}), (0, {25: 8}), (0, {25: 12}), (0, {25: 16, 26: 160 * K}), (0, {26: 32 * K}),
-                (0, {26: 96 * K, 24: 64 * K}), (0, {24: 0})]
+        cfgs = [(2, {14: 0}), (0, {}), (0, {27: 1}), (0, {27: 2}), (0, {27: 8, 23: 768}), (0, {27: 8, 23: 512}), (0, {27: 4, 23: 1024, 24: 32 * K}),
+                (0, {24: 128 * K}), (0, {24: 0}), (0, {24: 64 * K, 23: 768}), (0, {23: 512})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
         for algo, opts in cfgs:
