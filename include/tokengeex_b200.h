@@ -15,6 +15,10 @@
  *  - token ids are uint32 (TokenID = u32, src/lib.rs:19); id == index in the vocab array.
  *  - `_dev` variants take DEVICE pointers (text 16-byte aligned) and leave results in
  *    device memory; the others take HOST pointers and perform the H2D / D2H copies.
+ *    Stream contract of the `_dev` variants: the library works on streams of its own.  Work queued on the legacy
+ *    default stream (where torch and plain CUDA runtime calls put it unless told otherwise) before the call is ordered
+ *    before the library's kernels; a caller that produces its buffers on another stream synchronises that stream
+ *    first.  Results are complete when the call returns.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *    TGX_ERR_NO_DEVICE.
  */
@@ -114,6 +118,19 @@ int tgx_expected_counts(tgx_model* m, const uint8_t* text, const uint64_t* off, 
 int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
                             uint64_t n_bytes, uint64_t snippet_len, double* d_expected, int64_t* bad_sample,
                             double* bad_z);
+
+/* The same E-step with the counts in exact integer form: limbs[5 * id + 0 .. 4] += (the four 32-bit words of the
+ * 128-bit fraction, low to high, and the integer part) of token id's count.  The kernels accumulate in 192-bit fixed
+ * point with integer atomics, so a count is the EXACT sum of its contributions (each truncated to 2^-128) —
+ * bit-identical from run to run, for every chunking of the corpus and, after an integer (int64 SUM) all-reduce of the
+ * limbs, for every number of GPUs — where the reference's f64 sum depends on rayon's completion order
+ * (src/prune.rs:104-112).  Counts below ~1e-29 are below the resolution (the M-step's only threshold is 0.5).
+ * tgx_counts_from_limbs_dev turns (summed) limbs into the f64 vector the M-step reads: expected[id] = value (overwritten).
+ * tgx_expected_counts{,_dev} are this followed by that conversion. */
+int tgx_expected_counts_fixed_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                                  uint64_t n_bytes, uint64_t snippet_len, int64_t* d_limbs, int64_t* bad_sample,
+                                  double* bad_z);
+int tgx_counts_from_limbs_dev(tgx_model* m, const int64_t* d_limbs, uint64_t vocab_size, double* d_expected);
 
 /* Frequency pass of prune_vocab (src/prune.rs:205-246): freq[id] += 1 over
  * Model::encode(sample, 0.0) of WHOLE samples.  freq[V] is overwritten (host variant) /

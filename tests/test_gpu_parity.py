@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.util import rand_samples, rand_vocab, split_ids, synth_setup
+from tests.util import counts_rel_err, rand_samples, rand_vocab, split_ids, synth_setup
 
 pytestmark = pytest.mark.gpu
 
@@ -358,8 +358,8 @@ def test_expected_counts_random_vs_oracle(N, g):
         ex, rc, bad, badz = gm.expected_counts(blob, off, snippet_len=snip)
         want, wrc, wbad, _ = om.run_e_step(blob, off, threads=1, literal=True, max_sample_length=snip)
         assert rc == 0 and wrc == 0
-        assert np.allclose(ex, want, rtol=REL_TOL, atol=0), np.max(np.abs(ex - want) / np.maximum(want, 1e-300))
-        assert np.allclose(ex, want, rtol=ORDER_TOL, atol=0), np.max(np.abs(ex - want) / np.maximum(want, 1e-300))
+        assert np.allclose(ex, want, rtol=REL_TOL, atol=1e-27), np.max(np.abs(ex - want) / np.maximum(want, 1e-300))
+        assert np.allclose(ex, want, rtol=ORDER_TOL, atol=1e-27), np.max(np.abs(ex - want) / np.maximum(want, 1e-300))
         tot = sum(e * len(t) for e, t in zip(ex, toks))
         assert abs(tot - int(off[-1])) < 1e-9 * int(off[-1])  # invariant (i)
 
@@ -377,7 +377,7 @@ def test_expected_counts_long_tokens(N):
     for g in (0, -3, 4, 32):
         estep_cfg(gm, g)
         ex, rc, bad, badz = gm.expected_counts(blob, off)
-        assert rc == 0 and np.allclose(ex, want, rtol=ORDER_TOL, atol=0), (g, np.max(np.abs(ex - want)))
+        assert rc == 0 and np.allclose(ex, want, rtol=ORDER_TOL, atol=1e-27), (g, np.max(np.abs(ex - want)))
 
 
 def test_expected_counts_bad_z(N):
@@ -399,11 +399,9 @@ def test_expected_counts_synth_vs_oracle(N):
             gm.set_option(2, 4)
         ex, rc, bad, badz = gm.expected_counts(blob, off)
         assert rc == 0 and wrc == 0
-        nz = want > 0
-        rel = np.abs(ex[nz] - want[nz]) / want[nz]
-        assert rel.max() < REL_TOL, rel.max()
-        assert rel.max() < ORDER_TOL, rel.max()
-        assert np.all(ex[~nz] == 0)
+        rel = counts_rel_err(ex, want)
+        assert rel < REL_TOL, rel
+        assert rel < ORDER_TOL, rel
         lens = np.array([len(t) for t in toks], dtype=np.float64)
         assert abs(float((ex * lens).sum()) - int(off[-1])) < 1e-9 * int(off[-1])
 
@@ -422,8 +420,6 @@ def test_very_long_samples(N):
     blob, off = N.pack(samples)
     ex, rc, bad, badz = gm.expected_counts(blob, off)
     want = om.run_e_step(blob, off, threads=8)[0]
-    nz = want > 0
-    assert rc == 0 and float(np.max(np.abs(ex[nz] - want[nz]) / want[nz])) < REL_TOL
-    assert np.all(ex[~nz] == 0)
+    assert rc == 0 and counts_rel_err(ex, want) < REL_TOL
     fr = gm.token_frequencies(blob, off)[0]
     assert np.array_equal(fr, om.token_frequencies(blob, off, threads=8))

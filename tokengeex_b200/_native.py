@@ -50,6 +50,9 @@ SYMBOLS = [
     ("tgx_expected_counts", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, f64p, i64p, f64p]),
     ("tgx_expected_counts_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                           C.c_void_p, i64p, f64p]),
+    ("tgx_expected_counts_fixed_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                C.c_void_p, i64p, f64p]),
+    ("tgx_counts_from_limbs_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("tgx_token_frequencies", C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u64p, i64p, u64p]),
     ("tgx_token_frequencies_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                             C.c_void_p, i64p, u64p]),
@@ -285,6 +288,19 @@ class Model:
                                            C.byref(bad), C.byref(badz))
         _check(rc, (TGX_OK, TGX_ERR_BAD_Z))
         return rc, int(bad.value), float(badz.value)
+
+    def expected_counts_fixed_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, d_limbs: int,
+                                  snippet_len: int = SNIPPET_LEN):
+        """E-step with exact integer counts: d_limbs int64[3 V] += limbs (see include/tokengeex_b200.h).  → (rc, bad_sample, bad_z)"""
+        bad = C.c_int64(-1)
+        badz = C.c_double(0.0)
+        rc = lib().tgx_expected_counts_fixed_dev(self._h, d_text, d_off, S, n_bytes, snippet_len, d_limbs, C.byref(bad),
+                                                 C.byref(badz))
+        _check(rc, (TGX_OK, TGX_ERR_BAD_Z))
+        return rc, int(bad.value), float(badz.value)
+
+    def counts_from_limbs_dev(self, d_limbs: int, V: int, d_expected: int):
+        _check(lib().tgx_counts_from_limbs_dev(self._h, d_limbs, V, d_expected))
 
     def token_frequencies_dev(self, d_text: int, d_off: int, S: int, n_bytes: int, crlf: bool, d_freq: int):
         bad = C.c_int64(-1)

@@ -352,6 +352,18 @@ void tgx_synth_corpus(int kind, uint64_t seed, const uint64_t* offsets, uint64_t
   });
 }
 
+// Samples [first, first + count) of the same corpus, written from blob[0] on (offsets = the offsets of the WHOLE
+// corpus): every rank of a sharded run generates exactly its own shard of ONE corpus.
+void tgx_synth_corpus_range(int kind, uint64_t seed, const uint64_t* offsets, uint64_t first, uint64_t count,
+                            uint8_t* blob, int threads) {
+  Lexicon lx(seed);
+  const uint64_t b0 = offsets[first];
+  parallel_for(count, threads, [&](size_t i) {
+    gen_sample(kind, seed, first + i, lx, blob + (offsets[first + i] - b0),
+               (size_t)(offsets[first + i + 1] - offsets[first + i]));
+  });
+}
+
 int tgx_synth_allow_exact(const uint8_t* s, uint64_t n) { return allow_exact(s, n) ? 1 : 0; }
 
 // VocabularyGenerator::feed + generate (/root/reference/src/generate.rs:54-243).

@@ -21,6 +21,7 @@
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
 #include "tgx_match_kernels.cuh"
+#include "tgx_fb_rows_kernels.cuh"
 #include "trie_build.h"
 
 namespace {
@@ -112,7 +113,7 @@ struct tgx_model {
   unsigned char* h_out = nullptr;  // pinned staging for the small per-sample outputs (id_off, status, proc_len)
   uint64_t h_out_cap = 0;
   uint64_t chunk_bytes = 352ull << 20;  // ~3 chunks per GB: below that the longest sample's dp chain dominates a chunk
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_caller = nullptr;
   std::recursive_mutex mu;
   // options
   int g_short = 8;
@@ -132,6 +133,7 @@ struct tgx_model {
   // Lane kernels in split form: the backward chain only stores beta and runs beside the forward chain, a third
   // kernel adds the expected counts (needs 8 more bytes per input byte; falls back to the fused form without them).
   int estep_split = 1;
+  int estep_rows = 1;  // E-step over the match stream (tgx_fb_rows_kernels.cuh) when the match tables exist
   int hot_k = 4096, hot_r = 256;  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids
   int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
@@ -141,6 +143,7 @@ struct tgx_model {
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
+  int rows_consumer = 1;          // 0 = pair-CTA consumer with ROWS producers, 1 = viterbi_rows_kernel
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
@@ -163,7 +166,7 @@ struct tgx_model {
   uint64_t drop_byte_base = 0;  // E-step: offset of this call's text in the whole (sharded) corpus, option 22
   uint64_t wide_bytes = 600ull << 20;
   // buffers of the host entry points (two sets for the chunk pipeline) and of the E-step / frequency pass
-  DevBuf Bbeta;
+  DevBuf Bbeta, accfix;
   DevBuf text, off, idoff, A, expected, freq, ids, scount, hot, text_b, off_b, ids_b, idoff_b, scount_b;
 };
 
@@ -532,6 +535,26 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p, DropInfo di = DropIn
   return cudaGetLastError();
 }
 
+// ROWS form: one producer warp per chain is plenty (a row copy, not a walk), so R = 1 and as many groups as fit.
+cudaError_t launch_viterbi_pair_rows(tgx_model* m, PairParams p) {
+  constexpr int R = 1, WG = 2 * R + 1, MAXT = 960;
+  auto kernel = viterbi_pair_rows_kernel<R, MAXT>;
+  uint32_t groups = (uint32_t)std::min<size_t>({(size_t)m->smem_optin / pair_group_bytes(R), (size_t)(MAXT / (32 * WG)), (size_t)15});
+  if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
+  groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
+  p.groups = groups;
+  const size_t smem = pair_smem_bytes(R, groups, 0);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint32_t grid =
+      (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
+  e = dev_fill(p.counter, 0, 4, m->w().stream);
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
+  m->w().stats.launches += 1;
+  return cudaGetLastError();
+}
+
 // Two shapes (measured on B200, tools/probe.py, 1 GB / the 16 longest samples alone):
 //   latency   5 groups, two trie levels in shared memory, 72 registers: 35.8 ms / 13.5 ms
 //   throughput  6 groups (R = 2) with one staged level, 64 registers:    33.5 ms / 16.0 ms
@@ -615,6 +638,16 @@ int check_model(tgx_model* m) {
     return fail(TGX_ERR_NO_DEVICE, "model was created host-only (device = -1); there is no CPU compute path");
   CU(cudaSetDevice(m->device));
   (void)cudaGetLastError();  // a stale non-sticky error of an earlier call must not fail this one
+  return TGX_OK;
+}
+
+// The `_dev` entry points take buffers the caller has (maybe) just produced on ITS stream, while the library works on
+// streams of its own.  Contract (include/tokengeex_b200.h): work queued on the legacy default stream — where torch and
+// plain CUDA runtime calls put it unless told otherwise — before the call is ordered before the library's kernels;
+// callers on other streams synchronise them first.  Results are complete when the call returns.
+int order_after_caller(tgx_model* m) {
+  CU(cudaEventRecord(m->ev_caller, cudaStreamLegacy));
+  CU(cudaStreamWaitEvent(m->w().stream, m->ev_caller, 0));
   return TGX_OK;
 }
 
@@ -705,6 +738,39 @@ int sort_units(tgx_model* m, uint32_t U) {
   return TGX_OK;
 }
 
+// match_kernel over the whole blob: m->w().rec[p] = record of start position p (tgx_match_kernels.cuh)
+int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
+  cudaStream_t st = m->w().stream;
+  CU(m->w().rec.reserve((N + 64) * 4));
+  MatchParams mp;
+  mp.text = d_text;
+  mp.blob_end = d_text + N;
+  mp.N = N;
+  mp.trie8 = m->d_trie8.as<uint2>();
+  mp.root_base = m->da.root_base;
+  mp.rec = m->w().rec.as<uint32_t>();
+  const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
+  mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
+  const size_t smem = (size_t)mp.staged * 8;
+  auto launch = [&](auto kernel, int ilp) -> cudaError_t {
+    const uint32_t threads = (uint32_t)std::min(m->match_threads, mk_max_threads(ilp));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t per_cta = (uint64_t)threads * ilp;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((N + per_cta - 1) / per_cta, (uint64_t)m->num_sms);
+    kernel<<<grid, threads, smem, st>>>(mp);
+    return cudaGetLastError();
+  };
+  switch (m->match_ilp) {
+    case 1: CU(launch(match_kernel<1>, 1)); break;
+    case 2: CU(launch(match_kernel<2>, 2)); break;
+    case 8: CU(launch(match_kernel<8>, 8)); break;
+    default: CU(launch(match_kernel<4>, 4)); break;
+  }
+  m->w().stats.launches += 1;
+  return TGX_OK;
+}
+
 // Viterbi over all samples: forward dp (back lengths) + backtrack (token-end marks).  On return
 // m->w().mark holds the length of the token ending at every marked byte, m->w().ntok token counts,
 // m->w().status per-sample status.
@@ -754,38 +820,26 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : (m->algo == 0 && !m->have_rows ? 2 : m->algo);
   CU(cudaEventRecord(m->w().ev[8], st));
   if (algo == 0 && u.rows <= 16 && N) {
-    CU(m->w().rec.reserve((N + 64) * 4));
-    MatchParams mp;
-    mp.text = d_text;
-    mp.blob_end = d_text + N;
-    mp.N = N;
-    mp.trie8 = m->d_trie8.as<uint2>();
-    mp.root_base = m->da.root_base;
-    mp.rec = m->w().rec.as<uint32_t>();
-    const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
-    mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
-    const size_t smem = (size_t)mp.staged * 8;
-    auto launch = [&](auto kernel, int ilp) -> cudaError_t {
-      const uint32_t threads = (uint32_t)std::min(m->match_threads, mk_max_threads(ilp));
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      const uint64_t per_cta = (uint64_t)threads * ilp;
-      const uint32_t grid = (uint32_t)std::min<uint64_t>((N + per_cta - 1) / per_cta, (uint64_t)m->num_sms);
-      kernel<<<grid, threads, smem, st>>>(mp);
-      return cudaGetLastError();
-    };
-    switch (m->match_ilp) {
-      case 1: CU(launch(match_kernel<1>, 1)); break;
-      case 2: CU(launch(match_kernel<2>, 2)); break;
-      case 8: CU(launch(match_kernel<8>, 8)); break;
-      default: CU(launch(match_kernel<4>, 4)); break;
-    }
-    m->w().stats.launches += 1;
-    CU(cudaGetLastError());
+    rc = run_match(m, d_text, N);
+    if (rc) return rc;
   }
   CU(cudaEventRecord(m->w().ev[9], st));
   CU(cudaEventRecord(m->w().ev[0], st));
-  if (algo == 0 && u.rows <= 16) {
+  if (algo == 0 && u.rows <= 16 && m->rows_consumer == 0) {
+    if (N && U) {  // the pair-CTA consumer over the match stream
+      PairParams p;
+      p.u = u;
+      p.u.part = 0;
+      p.blob_end = d_text + N;
+      p.bp = m->w().bp.as<uint8_t>();
+      p.counter = m->w().small.as<unsigned int>() + 8;
+      p.dbg = 0;
+      p.hot_slots = 0;
+      p.rec = m->w().rec.as<uint32_t>();
+      p.rows = m->d_rows.as<double>();
+      CU(launch_viterbi_pair_rows(m, p));
+    }
+  } else if (algo == 0 && u.rows <= 16) {
     if (N && U) {
       RowsParams rp;
       rp.u = u;
@@ -813,6 +867,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.bp = m->w().bp.as<uint8_t>();
     p.counter = m->w().small.as<unsigned int>() + 8;
     p.dbg = 0;
+    p.rec = nullptr;
+    p.rows = nullptr;
     DropInfo di;
     di.dropout = dropout;
     di.seed = m->drop_seed;
@@ -991,6 +1047,7 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     }
     CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&m->ev_caller, cudaEventDisableTiming));
     size_t bytes = m->da.slots.size() * sizeof(tgx::Slot);
     CU(cudaMalloc(&m->d_trie, bytes));
     m->trie_cap = m->da.slots.size();
@@ -1037,6 +1094,7 @@ void tgx_model_destroy(tgx_model* m) {
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     m->Bbeta.release();
+    m->accfix.release();
     DevBuf* bufs[] = {&m->text, &m->off, &m->idoff, &m->A, &m->expected, &m->freq, &m->ids, &m->scount, &m->hot,
                       &m->text_b, &m->off_b, &m->ids_b, &m->idoff_b, &m->scount_b};
     for (auto* b : bufs) b->release();
@@ -1071,6 +1129,7 @@ void tgx_model_destroy(tgx_model* m) {
     if (m->h_out) cudaFreeHost(m->h_out);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_caller) cudaEventDestroy(m->ev_caller);
     (void)cudaGetLastError();  // nothing above is allowed to leak an error into the next call
   }
   delete m;
@@ -1113,7 +1172,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 3: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "algo must be 0..2"); m->algo = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
-    case 19: m->estep_split = value ? 1 : 0; break;
+    case 19: m->estep_rows = m->estep_split = value ? 1 : 0; break;
     case 20: if (value < 1 || value > 4096) return fail(TGX_ERR_INVALID, "replicas must be 1..4096"); m->hot_r = (int)value; break;
     case 21: if (value < 0 || value > (1 << 20)) return fail(TGX_ERR_INVALID, "hot ids must be 0..2^20"); m->hot_k = (int)value; break;
     case 18: if (value < 0 || value > 16) return fail(TGX_ERR_INVALID, "blocks per SM must be 0..16"); m->lane_blocks_per_sm = (int)value; break;
@@ -1128,6 +1187,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 25: if (value < 1 || value > 32) return fail(TGX_ERR_INVALID, "warps must be 1..32"); m->rows_warps = (int)value; break;
     case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
     case 27: if (value != 1 && value != 2 && value != 4 && value != 8) return fail(TGX_ERR_INVALID, "positions per thread must be 1, 2, 4 or 8"); m->match_ilp = (int)value; break;
+    case 28: m->rows_consumer = value ? 1 : 0; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -1683,16 +1743,22 @@ int tgx_pair_frequencies(tgx_model* m, const uint8_t* text, const uint64_t* off,
 }
 
 // ---------------------------------------------------------------------------- E-step
-int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
-                            uint64_t n_bytes, uint64_t snippet_len, double* d_expected, int64_t* bad_sample,
-                            double* bad_z) {
+namespace {
+
+// The E-step over device-resident text.  Results: d_expected[V] += counts (f64) and / or d_limbs[3V] += counts as exact
+// integer limbs (tgx_expected_counts_fixed_dev); either may be null.
+int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S, uint64_t n_bytes,
+                         uint64_t snippet_len, double* d_expected, long long* d_limbs, int64_t* bad_sample,
+                         double* bad_z) {
   int rc = check_model(m);
   if (rc) return rc;
-  if (!d_off || !d_expected || snippet_len == 0) return fail(TGX_ERR_INVALID, "bad argument");
+  if (!d_off || (!d_expected && !d_limbs) || snippet_len == 0) return fail(TGX_ERR_INVALID, "bad argument");
   if (snippet_len >= (1ull << 31)) return fail(TGX_ERR_INVALID, "snippet_len must be < 2^31");
   std::lock_guard<std::recursive_mutex> g(m->mu);
   m->w().stats = Stats();
   cudaStream_t st = m->w().stream;
+  rc = order_after_caller(m);
+  if (rc) return rc;
   CU(cudaEventRecord(m->w().ev[6], st));
   if (bad_sample) *bad_sample = -1;
   if (bad_z) *bad_z = 0.0;
@@ -1750,23 +1816,46 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   p.u.W = p.u.rows + 1;
   p.A = m->A.as<double>();
   p.status = m->w().status.as<int32_t>();
-  p.expected = d_expected;
   p.dropout = m->dropout;
   p.drop_key = drop_unit_key(m->drop_seed, ~0ull);  // (its own stream of draws, apart from the encode samples')
   p.drop_base = m->drop_byte_base;
   p.hot_k = (uint32_t)std::min<uint64_t>(m->V, (uint64_t)m->hot_k);
   p.hot_r = (uint32_t)m->hot_r;
-  CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8));
-  CU(dev_fill(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8, st));
-  p.hot = m->hot.as<double>();
+  // fixed-point accumulators of this call (tgx_kernels.cuh: acc_add)
+  CU(m->accfix.reserve(m->V * 8 * ACC_LIMBS + 16));
+  CU(dev_fill(m->accfix.p, 0, m->V * 8 * ACC_LIMBS + 16, st));
+  CU(m->hot.reserve((size_t)p.hot_k * p.hot_r * 8 * ACC_LIMBS + 16));
+  CU(dev_fill(m->hot.p, 0, (size_t)p.hot_k * p.hot_r * 8 * ACC_LIMBS, st));
+  p.acc = m->accfix.as<unsigned long long>();
+  p.hot_acc = m->hot.as<unsigned long long>();
+  const bool drop = p.dropout > 0.0;
 
-  // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second
-  // stream; the mid-sized ones run G lanes per snippet beside them, the short ones one lane each on a third.
+  // The kernels over the match stream (one lane per snippet; counts from stored alpha / beta) need the match tables
+  // and 8 more bytes of device memory per input byte for beta; without them the lane-group kernels take every snippet.
+  bool rows_ok = m->estep_rows && m->have_rows && p.u.rows <= 16;
+  if (rows_ok) {
+    const size_t need = ((size_t)n_bytes + U + 2) * 8 + ((size_t)n_bytes + 64) * 4;
+    size_t fr = 0, tot = 0;
+    const size_t have = m->Bbeta.cap + m->w().rec.cap;
+    if (need > have && (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr + have < need + need / 8 + ((size_t)2 << 30))) rows_ok = false;
+    if (rows_ok && m->Bbeta.reserve(((size_t)n_bytes + U + 2) * 8) != cudaSuccess) {
+      (void)cudaGetLastError();
+      rows_ok = false;
+    }
+  }
+  CU(cudaEventRecord(m->w().ev[8], st));
+  if (rows_ok) {
+    rc = run_match(m, d_text, n_bytes);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(m->w().ev[9], st));
+
+  // Long snippets (latency-critical: one ordered chain each) get a whole warp on a second stream; the short ones run
+  // one lane each on a third; whatever is in between (only when option 17 sets a lane threshold) G lanes per snippet.
   uint32_t n_long = 0, n_lane = 0;
   {
     uint32_t* counts = m->w().small.as<uint32_t>();
-    // dropout > 0: the lane-group kernels in fused form (the only E-step kernels that take the draw)
-    const bool lanes_ok = m->estep_lane_threshold != 0 && p.u.rows <= 16 && !(p.dropout > 0.0);
+    const bool lanes_ok = rows_ok && m->estep_lane_threshold != 0;
     int64_t thr64 = m->estep_long_threshold;
     if (thr64 <= 0)
       thr64 = (lanes_ok && m->estep_lane_threshold < 0) ? std::max<int64_t>(8192, 16000 + (int64_t)(n_bytes / 30000))
@@ -1792,33 +1881,16 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   pl.u.count = n_long;
   ps.u.first = n_long;
   ps.u.count = U - n_long - n_lane;
-  FbLaneParams pn;
+  FbRowsParams pn;
   pn.f = p;
   pn.f.u.first = U - n_lane;
   pn.f.u.count = n_lane;
-  pn.blob_end = d_text + n_bytes;
-  pn.B = nullptr;
-  bool split = m->estep_split && (n_lane || n_long) && p.u.rows <= 16 && !(p.dropout > 0.0);
-  if (split) {  // beta array: only if the device has room for it
-    const size_t need = ((size_t)n_bytes + U + 2) * 8;
-    size_t fr = 0, tot = 0;
-    if (need > m->Bbeta.cap && (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < need + need / 8 + ((size_t)2 << 30))) split = false;
-    if (split && m->Bbeta.reserve(need) != cudaSuccess) {
-      (void)cudaGetLastError();
-      split = false;
-    }
-    pn.B = m->Bbeta.as<double>();
-  }
-  const uint32_t lane_blocks = nblk(n_lane, FL_WARPS * 32);
-  // fewer resident warps = a larger share of the issue slots for each chain (the kernels are issue-bound)
-  size_t lane_pad = 0;
-  if (m->lane_blocks_per_sm > 0) {
-    const size_t per_block = (size_t)228 * 1024 / m->lane_blocks_per_sm;
-    lane_pad = per_block > 22 * 1024 ? std::min<size_t>(per_block - 22 * 1024, (size_t)m->smem_optin - 21 * 1024) : 0;
-    CU(cudaFuncSetAttribute(fb_forward_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
-    CU(cudaFuncSetAttribute(fb_backward_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
-    CU(cudaFuncSetAttribute(fb_split_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_pad));
-  }
+  pn.rec = m->w().rec.as<uint32_t>();
+  pn.rows = m->d_rows.as<double>();
+  pn.row_ids = m->d_rowids.as<uint32_t>();
+  pn.B = m->Bbeta.as<double>();
+  const bool split = rows_ok;  // beta chains stored and run beside the alpha chains, counts by fbr_contrib_kernel
+  const uint32_t lane_blocks = nblk(n_lane, FR_WARPS * 32);
   // forward / backward device times (tgx_model_last_stat 2, 3) are taken on the stream that carries most snippets
   cudaStream_t st_ev = (n_lane > ps.u.count) ? m->stream3 : st;
   CU(cudaEventRecord(m->w().ev[0], st_ev));
@@ -1826,36 +1898,38 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   if (split && pl.u.count) {  // the beta chains of the longest snippets run beside their forward chains
     CU(cudaStreamWaitEvent(m->stream4, m->ev_fork, 0));
     const size_t smem = warp_smem_bytes(pl.u.rows, pl.u.W, 32) * WPB;
-    CU(cudaFuncSetAttribute(fb_backward_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fb_backward_kernel<32, true><<<nblk(pl.u.count, WPB), WPB * 32, smem, m->stream4>>>(pl, pn.B);
+    if (drop) {
+      CU(cudaFuncSetAttribute(fb_backward_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fb_backward_kernel<32, true, true><<<nblk(pl.u.count, WPB), WPB * 32, smem, m->stream4>>>(pl, pn.B);
+    } else {
+      CU(cudaFuncSetAttribute(fb_backward_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fb_backward_kernel<32, true><<<nblk(pl.u.count, WPB), WPB * 32, smem, m->stream4>>>(pl, pn.B);
+    }
     m->w().stats.launches += 1;
     CU(cudaEventRecord(m->ev_join4, m->stream4));
   }
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
-  if (n_lane && split) {
-    fb_split_lane_kernel<<<2 * lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
-    m->w().stats.launches += 1;
-  } else if (n_lane) {
-    fb_forward_lane_kernel<<<lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
+  if (n_lane) {
+    if (drop) fbr_split_kernel<true><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
+    else fbr_split_kernel<false><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
   CU(cudaEventRecord(m->w().ev[1], st_ev));
   CU(cudaEventRecord(m->w().ev[2], st_ev));
   if (split && pl.u.count) {
     CU(cudaStreamWaitEvent(m->stream2, m->ev_join4, 0));
-    FbLaneParams pc = pn;
+    FbRowsParams pc = pn;
     pc.f.u = pl.u;
-    fb_contrib_kernel<<<nblk(pl.u.count, FC_WARPS), FC_WARPS * 32, 0, m->stream2>>>(pc);
+    if (drop) fbr_contrib_kernel<true><<<nblk(pl.u.count, FRC_WARPS), FRC_WARPS * 32, 0, m->stream2>>>(pc);
+    else fbr_contrib_kernel<false><<<nblk(pl.u.count, FRC_WARPS), FRC_WARPS * 32, 0, m->stream2>>>(pc);
     m->w().stats.launches += 1;
   } else {
     CU(launch_fb_g(m, 32, pl, true, m->stream2));
   }
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
-  if (n_lane && split) {  // alpha and beta are both there: the counts
-    fb_contrib_kernel<<<nblk(n_lane, FC_WARPS), FC_WARPS * 32, 0, m->stream3>>>(pn);
-    m->w().stats.launches += 1;
-  } else if (n_lane) {
-    fb_backward_lane_kernel<<<lane_blocks, FL_WARPS * 32, lane_pad, m->stream3>>>(pn);
+  if (n_lane) {  // alpha and beta are both there: the counts
+    if (drop) fbr_contrib_kernel<true><<<nblk(n_lane, FRC_WARPS), FRC_WARPS * 32, 0, m->stream3>>>(pn);
+    else fbr_contrib_kernel<false><<<nblk(n_lane, FRC_WARPS), FRC_WARPS * 32, 0, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
   CU(cudaGetLastError());
@@ -1865,15 +1939,19 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
   CU(cudaEventRecord(m->ev_join3, m->stream3));
   CU(cudaStreamWaitEvent(st, m->ev_join3, 0));
   if (p.hot_k) {
-    fold_hot_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot, p.hot_k, p.hot_r, d_expected);
+    fold_hot_acc_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot_acc, p.hot_k, p.hot_r, p.acc);
     m->w().stats.launches += 1;
   }
+  export_acc_kernel<<<nblk(m->V, 256), 256, 0, st>>>(p.acc, (uint32_t)m->V, d_expected, d_limbs);
+  m->w().stats.launches += 1;
   int64_t bad = -1;
   rc = first_bad(m, U, &bad);
   if (rc) return rc;
   CU(cudaEventRecord(m->w().ev[7], st));
   CU(cudaStreamSynchronize(st));
   finish_stats(m, 2);
+  float mms = 0;
+  if (cudaEventElapsedTime(&mms, m->w().ev[8], m->w().ev[9]) == cudaSuccess) m->last_stats.match_ms = mms;
   if (bad >= 0) {
     uint32_t smp = 0, l = 0;
     uint64_t us = 0;
@@ -1888,6 +1966,38 @@ int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t*
     snprintf(buf, sizeof buf, "normalization constant is f64::NaN (z=%g, sample=%u)", z, smp);
     return fail(TGX_ERR_BAD_Z, buf);
   }
+  return TGX_OK;
+}
+
+}  // namespace
+
+int tgx_expected_counts_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                            uint64_t n_bytes, uint64_t snippet_len, double* d_expected, int64_t* bad_sample,
+                            double* bad_z) {
+  if (!d_expected) return fail(TGX_ERR_INVALID, "bad argument");
+  return expected_counts_impl(m, d_text, d_off, S, n_bytes, snippet_len, d_expected, nullptr, bad_sample, bad_z);
+}
+
+int tgx_expected_counts_fixed_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
+                                  uint64_t n_bytes, uint64_t snippet_len, int64_t* d_limbs, int64_t* bad_sample,
+                                  double* bad_z) {
+  if (!d_limbs) return fail(TGX_ERR_INVALID, "bad argument");
+  return expected_counts_impl(m, d_text, d_off, S, n_bytes, snippet_len, nullptr, reinterpret_cast<long long*>(d_limbs),
+                              bad_sample, bad_z);
+}
+
+int tgx_counts_from_limbs_dev(tgx_model* m, const int64_t* d_limbs, uint64_t vocab_size, double* d_expected) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!d_limbs || !d_expected || vocab_size >= (1ull << 32)) return fail(TGX_ERR_INVALID, "bad argument");
+  std::lock_guard<std::recursive_mutex> g(m->mu);
+  rc = order_after_caller(m);
+  if (rc) return rc;
+  if (vocab_size)
+    limbs_to_double_kernel<<<nblk(vocab_size, 256), 256, 0, m->w().stream>>>(reinterpret_cast<const long long*>(d_limbs),
+                                                                          (uint32_t)vocab_size, d_expected);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(m->w().stream));
   return TGX_OK;
 }
 

@@ -77,11 +77,15 @@ struct FbParams {
   UnitParams u;
   double* A;          // [N + U] forward log-probabilities: unit k owns A[start_k + k .. + n_k]
   int32_t* status;    // [U] 0 ok / 7 bad z
-  double* expected;   // [V]
+  // Expected counts are accumulated in 192-bit fixed point with integer atomics (acc_add below): acc[3 * id + 0 / 1]
+  // = fraction bits 65..128 / 1..64, acc[3 * id + 2] = integer part.  The sum of the contributions (each truncated to
+  // 2^-128) is exact, so it does not depend on the order of the additions: counts are bit-identical from run to run,
+  // for every chunking and every number of GPUs.
+  unsigned long long* acc;  // [V][3]
   // Hot tokens (small ids: vocabularies are score-sorted) would serialise every SM's atomics
   // on a handful of L2 addresses, so ids < hot_k accumulate into one of hot_r replicas
-  // (picked per block) that fold_hot_kernel sums into expected[] afterwards.
-  double* hot;        // [hot_r][hot_k]
+  // (picked per block) that fold_hot_acc_kernel sums into acc[] afterwards.
+  unsigned long long* hot_acc;  // [hot_r][hot_k][3]
   uint32_t hot_k, hot_r;
   // populate_nodes' dropout (src/model.rs:48-50; fb_*_kernel<G, .., true> only): the draw of the multi-byte match
   // (start byte, length) is keyed by the byte's offset in the call's text (+ drop_base, the shard's offset in a
@@ -89,6 +93,32 @@ struct FbParams {
   double dropout;
   unsigned long long drop_key, drop_base;
 };
+
+constexpr int ACC_LIMBS = 3;  // u64 words per accumulator
+__device__ __forceinline__ void acc_add(unsigned long long* slot, double c) {
+  unsigned long long ip = 0;
+  double fr = c;
+  if (c >= 1.0) {  // a probability: at most 1 up to rounding
+    ip = __double2ull_rz(c);
+    fr = c - (double)ip;
+  }
+  const double t = fr * 18446744073709551616.0;          // exact (a power of two)
+  unsigned long long v1 = __double2ull_rz(t);            // fraction bits 1..64
+  // t >= 2^53 is an integer, so the remainder is zero; below that the truncation and the difference are exact
+  const unsigned long long v0 = __double2ull_rz((t - (double)v1) * 18446744073709551616.0);  // fraction bits 65..128
+  if (v0) {
+    const unsigned long long old = atomicAdd(slot, v0);
+    if (old + v0 < old) v1++;  // (v1 <= 2^64 - 2^11: no overflow)
+  }
+  if (v1) {
+    const unsigned long long old = atomicAdd(slot + 1, v1);
+    if (old + v1 < old) ip++;
+  }
+  if (ip) atomicAdd(slot + 2, ip);
+}
+__device__ __forceinline__ unsigned long long* acc_slot(const FbParams& p, uint32_t bid, uint32_t id) {
+  return id < p.hot_k ? p.hot_acc + ((size_t)(bid % p.hot_r) * p.hot_k + id) * ACC_LIMBS : p.acc + (size_t)id * ACC_LIMBS;
+}
 
 __device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uint32_t& first, uint32_t& count) {
   if (!counts) return;
@@ -285,6 +315,9 @@ struct PairParams {
   uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
   uint32_t groups;     // consumer/producer groups per CTA
   uint32_t dbg;        // developer timing experiments (tools/probe.py): 1 = skip walks, 2 = skip the dp
+  // ROWS form (the default forward pass): the producers copy match rows instead of walking the trie
+  const uint32_t* rec;  // [N] match stream of match_kernel (tgx_match_kernels.cuh)
+  const double* rows;   // row table (trie_build.h)
 };
 // dropout in (0, 1): a second kernel parameter of viterbi_pair_drop_kernel only (see drop_draw) — the default
 // kernel's parameter block and code stay exactly what they were (its 64-register shape is sensitive to both)
@@ -366,6 +399,26 @@ __device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, con
   }
 }
 
+// Phase A in ROWS form: the matches of the start position come from its record of the match stream — (L - 1) << 28 |
+// row offset of the deepest token that starts there; its row lists the score of every token on the trie path down
+// to it, dense by length, -inf where a prefix is not a token (trie_build.h) — instead of a trie walk: one
+// independent load per length, no dependent probes.  The loads of a tile are issued a whole round before their values
+// are parked (rows_load / rows_store), the record another round earlier.
+__device__ __forceinline__ void rows_load(const double* __restrict__ rows, uint32_t rc, bool active, double (&v)[16]) {
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
+  const uint32_t L = active ? (rc >> 28) + 1u : 0u;
+  const double* base = rows + (size_t)(rc & 0x0FFFFFFFu) * 2 + 1;  // (the row's header comes first)
+#pragma unroll
+  for (int d = 0; d < 16; d++) v[d] = ((uint32_t)d < L) ? __ldg(base + d) : ninf;
+}
+__device__ __forceinline__ void rows_store(const double (&v)[16], double* row, int lane) {
+  unsigned char* rb = reinterpret_cast<unsigned char*>(row);
+  const uint32_t l18 = (uint32_t)(lane + 1) * 8u;
+#pragma unroll
+  for (int d = 0; d < 16; d++)  // target cell (start + len) % 16 = (lane + d + 1) % 16
+    *reinterpret_cast<double*>(rb + ((l18 + 8u * d) & 120u)) = v[d];
+}
+
 // Phase B over one 32-position tile for both halves of the consumer warp.  tb = this half's
 // table + g, so the operand of step j is tb[j * PT_ROW].  "Unreached" is best == -inf: scores
 // are finite, so a candidate built on an unreached position is -inf and can never win, and the
@@ -399,7 +452,7 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
 
 // Body shared by viterbi_pair_kernel and the hybrid kernel; called by every thread of the CTA
 // (warps beyond p.groups * WG only help staging the hot trie prefix).
-template <int R, int HOT, bool DROP = false>
+template <int R, int HOT, bool DROP = false, bool ROWS = false>
 __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem, const DropInfo* di = nullptr) {
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
@@ -425,6 +478,11 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
   unsigned long long pw[3] = {0, 0, 0};
   uint32_t psh = 0, pf_tile = 0;
   int32_t pf_unit = -1;
+  // ROWS: the row values in flight for the next round (tile pv_tile of pv_unit), the record for the round after
+  // (tile pf_tile of pf_unit)
+  uint32_t pf_rec = 0, pv_tile = 0;
+  int32_t pv_unit = -1;
+  double pv[16];
   // scheduler state (half-warp leaders of the consumer warp)
   PairInfo cur;
   cur.unit = -1; cur.start = 0; cur.n = 0; cur.tile0 = 0; cur.ntiles = 0; cur.pad[0] = cur.pad[1] = 0;
@@ -488,6 +546,30 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
       if (pi.unit >= 0 && t < pi.ntiles) {
         const uint32_t pos = t * 32 + lane;
         double* row = tab + ((size_t)((r & 1) * 2 + ph) * R + k) * PT_TILE + lane * PT_ROW;
+        if constexpr (ROWS) {
+          const uint32_t* rp = p.rec + pi.start + pos;
+          if (!(pv_unit == pi.unit && pv_tile == t))  // first tile of a sample: nothing was requested ahead
+            rows_load(p.rows, pos < pi.n ? __ldg(rp) : 0u, pos < pi.n, pv);
+          rows_store(pv, row, lane);
+          if (t + R < pi.ntiles) {  // the next tile's values: requested now, parked a round from now
+            const uint32_t q1 = pos + 32 * R;
+            uint32_t rc = pf_rec;
+            if (!(pf_unit == pi.unit && pf_tile == t + R)) rc = q1 < pi.n ? __ldg(rp + 32 * R) : 0u;
+            rows_load(p.rows, rc, q1 < pi.n, pv);
+            pv_unit = pi.unit;
+            pv_tile = t + R;
+            if (t + 2 * R < pi.ntiles) {
+              pf_rec = q1 + 32 * R < pi.n ? __ldg(rp + 64 * R) : 0u;
+              pf_unit = pi.unit;
+              pf_tile = t + 2 * R;
+            } else {
+              pf_unit = -1;
+            }
+          } else {
+            pv_unit = -1;
+            pf_unit = -1;
+          }
+        } else {
         const uint8_t* ptr = u.text + pi.start + pos;
         // the text of this tile was requested a round ago (HBM latency off the round's critical path)
         if (!(pf_unit == pi.unit && pf_tile == t)) load_window(ptr, p.blob_end, pw, psh);
@@ -505,6 +587,7 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
                                   drop_unit_key(di->seed, di->unit_base + (uint32_t)pi.unit), pos);
         else
           pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane);
+        }
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie
@@ -521,6 +604,13 @@ template <int R, int HOT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   pair_body<R, HOT>(p, smem);
+}
+
+// The default forward pass: the same consumer over the match stream (ROWS producers; no trie, no text).
+template <int R, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) viterbi_pair_rows_kernel(PairParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pair_body<R, 0, false, true>(p, smem);
 }
 
 // The same kernel with the keyed dropout draw in its producers (src/model.rs:100).
@@ -1070,8 +1160,7 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, doubl
         // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), wB[ts]), -z);
         const uint32_t id = mp & ID_MASK;
-        double* dst = id < p.hot_k ? p.hot + (size_t)(blockIdx.x % p.hot_r) * p.hot_k + id : p.expected + id;
-        atomicAdd(dst, tgx_exp(total, lt));
+        acc_add(acc_slot(p, blockIdx.x, id), tgx_exp(total, lt));
       }
       __syncwarp();
       if (pp < n && lig == 0) {
@@ -1082,302 +1171,6 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, doubl
       sl = sl == 0 ? W - 1 : sl - 1;
     }
   }
-}
-
-// -----------------------------------------------------------------------------------------
-// K4L / K5L  forward-backward, one LANE per snippet (snippets below the lane threshold, max_token_len <= 16).
-//
-// The lane-group kernels above advance 32 / G chains per warp instruction (ncu, G = 4: 11 of 32 threads active,
-// 194 warp instructions per position); here every lane of a warp is its own snippet, so one warp instruction
-// advances up to 32 chains.  The folds are the same operations in the same order (forward: ascending start per end
-// position; backward: ascending length per start position), so A, B and every contribution are bit-identical to
-// the lane-group kernels'.  The trie walk is fused with the fold: a terminal met at depth d is folded at once.
-// Per lane: a 16-slot window of accumulators in shared memory ([slot][lane]: conflict-free), the "seen" flags in
-// a register, the next 16 text bytes in two registers refilled one aligned 8-byte word per 8 positions.
-// -----------------------------------------------------------------------------------------
-constexpr int FL_WARPS = 4;
-
-struct FbLaneParams {
-  FbParams f;
-  const uint8_t* blob_end;
-  double* B;  // [N + U] backward log-probabilities (split form only)
-};
-
-__device__ __forceinline__ unsigned long long fl_word(const uint8_t* a, const uint8_t* blob_end) {
-  return a < blob_end ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : 0ull;
-}
-
-// Both kernels run a FLATTENED walk: one loop iteration = one trie probe of the lane's own (position, depth) state,
-// whatever position the other lanes are at, so a lane never waits for the deepest walk of its warp and the fold
-// below runs with most lanes active (ncu on the position-synchronous version: 8 of 32 threads per instruction).
-// The next probe is issued before the fold of the current terminal, which hides its latency.
-__device__ __forceinline__ uint32_t fl_byte(unsigned long long lo, unsigned long long hi, uint32_t d) {
-  return (uint32_t)((d < 8 ? lo : hi) >> (8 * (d & 7u))) & 0xFFu;
-}
-
-__device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
-                                                     const LibmTabs& lt) {
-  const FbParams& p = q.f;
-  const UnitParams& u = p.u;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = s_win + warp * (16 * 32) + lane;  // slot s at acc[s * 32]
-  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
-  const bool has = gidx < u.count;
-  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
-  const uint32_t n = has ? u.unit_len[unit] : 0;
-  const uint64_t start = has ? u.unit_start[unit] : 0;
-  double* A = p.A + start + unit;
-  if (has) A[0] = 0.0;
-  if (has && n == 0) p.status[unit] = 7;  // z = 0.0 is not normal (Q11)
-  bool active = has && n != 0;
-  const uint8_t* tp = u.text + start;
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<unsigned long long>(tp) & ~7ull);
-  uint32_t sh = (uint32_t)(tp - base);
-  unsigned long long w0 = 0, w1 = 0, w2 = 0;
-  if (active) {
-    w0 = fl_word(base, q.blob_end);
-    w1 = fl_word(base + 8, q.blob_end);
-    w2 = fl_word(base + 16, q.blob_end);
-  }
-  unsigned long long lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
-  unsigned long long hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
-  uint32_t seen = 0, pos = 0, d = 0, limit = min(16u, n), xb = u.root_base;
-  double a = 0.0;  // alpha of the nodes that start at pos; 0.0 when nothing ends there (src/lattice.rs:255, Q7)
-  uint32_t cw = 0x100u | fl_byte(lo, hi, 0);
-  uint4 e = __ldg(u.trie + (xb ^ cw));
-  // The vote makes every iteration a convergence point: without it the lanes of a warp drift into separate
-  // instruction streams (ncu: 7 of 32 threads active per instruction).
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    if (active) {
-      const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
-      const bool term = hit && (e.y & F_TERM);
-      const double y = __dadd_rn(__hiloint2double((int)e.w, (int)e.z), a);  // nodes[lid].score + alpha[lid]
-      const uint32_t ts = (pos + d + 1u) & 15u;
-      const bool cont = hit && (e.y & F_HASCH) && (d + 1u < limit);
-      if (cont) {
-        d++;
-        xb = e.x >> 9;
-      } else {
-        pos++;
-        d = 0;
-        xb = u.root_base;
-        if (pos < n) {
-          if (++sh == 8) {
-            sh = 0;
-            base += 8;
-            w0 = w1;
-            w1 = w2;
-            w2 = fl_word(base + 16, q.blob_end);
-          }
-          lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
-          hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
-          limit = min(16u, n - pos);
-        }
-      }
-      cw = 0x100u | fl_byte(lo, hi, d);
-      e = __ldg(u.trie + (xb ^ cw));  // the next probe flies while the terminal below is folded
-      if (term) {
-        if ((seen >> ts) & 1u) {
-          acc[ts * 32] = log_sum_exp(acc[ts * 32], y, lt);
-        } else {  // lid == end_nodes[pos][0] -> init_mode
-          acc[ts * 32] = y;
-          seen |= 1u << ts;
-        }
-      }
-      if (!cont) {  // pos is the NEXT position now: everything that ends there has been folded
-        const uint32_t sl = pos & 15u;
-        a = ((seen >> sl) & 1u) ? acc[sl * 32] : 0.0;
-        seen &= ~(1u << sl);
-        A[pos] = a;
-        if (pos == n) {  // a = alpha[eos]
-          const double az = fabs(a);
-          const bool normal = (az >= 2.2250738585072014e-308) && (az <= 1.7976931348623157e308);  // f64::is_normal
-          p.status[unit] = normal ? 0 : 7;
-          active = false;
-        }
-      }
-    }
-  }
-}
-
-// STORE_B: only the beta chain, written to q.B (same layout as A) — it needs neither A nor z, so it runs BESIDE the
-// forward kernel and fb_contrib_kernel adds the expected counts afterwards; the longest snippet then costs
-// max(forward, backward) instead of their sum.  !STORE_B: the fused form (after the forward kernel).
-template <bool STORE_B>
-__device__ __forceinline__ void fb_backward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
-                                                      const LibmTabs& lt) {
-  const FbParams& p = q.f;
-  const UnitParams& u = p.u;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* wB = s_win + warp * (16 * 32) + lane;
-  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
-  const bool has = gidx < u.count;
-  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
-  const uint32_t n = has ? u.unit_len[unit] : 0;
-  // bad z: the reference panics; nothing is added
-  bool active = has && n != 0 && (STORE_B || p.status[unit] == 0);
-  const uint64_t start = has ? u.unit_start[unit] : 0;
-  const double* A = p.A + start + unit;
-  double* Bout = q.B + start + unit;
-  const double z = (active && !STORE_B) ? A[n] : 0.0;
-  double* hot = p.hot + (size_t)(bid % p.hot_r) * p.hot_k;
-  wB[(n & 15u) * 32] = 0.0;  // beta at the end of the sentence (EOS)
-  if (STORE_B && has) Bout[n] = 0.0;
-  uint32_t pos = active ? n - 1 : 0;
-  const uint8_t* tp = u.text + start + pos;
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<unsigned long long>(tp) & ~7ull);
-  uint32_t sh = (uint32_t)(tp - base);
-  unsigned long long w0 = 0, w1 = 0, w2 = 0;
-  if (active) {
-    w0 = fl_word(base, q.blob_end);
-    w1 = fl_word(base + 8, q.blob_end);
-    w2 = fl_word(base + 16, q.blob_end);
-  }
-  unsigned long long lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
-  unsigned long long hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
-  double a = (active && !STORE_B) ? A[pos] : 0.0, a_next = (active && !STORE_B && pos) ? A[pos - 1] : 0.0;
-  double b = 0.0;  // stays 0.0 when nothing begins at pos (Q7)
-  bool first = true;
-  uint32_t d = 0, limit = 1, xb = u.root_base;
-  uint32_t cw = 0x100u | fl_byte(lo, hi, 0);
-  uint4 e = __ldg(u.trie + (xb ^ cw));
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    if (active) {
-      const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
-      const bool term = hit && (e.y & F_TERM);
-      const double sc = __hiloint2double((int)e.w, (int)e.z);
-      const double bt = wB[((pos + d + 1u) & 15u) * 32];
-      const uint32_t id = e.y & ID_MASK;
-      const bool cont = hit && (e.y & F_HASCH) && (d + 1u < limit);
-      uint32_t nxb = u.root_base, nd = 0;
-      if (cont) {
-        nd = d + 1;
-        nxb = e.x >> 9;
-      } else if (pos != 0) {  // first probe of position pos - 1
-        if (sh != 0) {
-          sh--;
-        } else {
-          sh = 7;
-          base -= 8;
-          w2 = w1;
-          w1 = w0;
-          w0 = fl_word(base, q.blob_end);
-        }
-        lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
-        hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
-      }
-      cw = 0x100u | fl_byte(lo, hi, nd);
-      e = __ldg(u.trie + (nxb ^ cw));  // the next probe flies while the terminal below is folded
-      if (term) {  // ascending length = begin_nodes[pos] order
-        const double y = __dadd_rn(sc, bt);  // nodes[rid].score + beta[rid]
-        b = first ? y : log_sum_exp(b, y, lt);
-        first = false;
-        if (!STORE_B) {
-          // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
-          const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), bt), -z);
-          atomicAdd(id < p.hot_k ? hot + id : p.expected + id, tgx_exp(total, lt));
-        }
-      }
-      d = nd;
-      xb = nxb;
-      if (!cont) {
-        wB[(pos & 15u) * 32] = b;
-        if (STORE_B) Bout[pos] = b;
-        if (pos == 0) {
-          active = false;
-        } else {
-          pos--;
-          if (!STORE_B) {
-            a = a_next;
-            a_next = pos ? A[pos - 1] : 0.0;
-          }
-          b = 0.0;
-          first = true;
-          limit = min(16u, n - pos);
-        }
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLaneParams q) {
-  __shared__ double s_win[FL_WARPS * 16 * 32];
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  fb_forward_lane_body(q, blockIdx.x, s_win, lt);
-}
-
-__global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneParams q) {
-  __shared__ double s_win[FL_WARPS * 16 * 32];
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  fb_backward_lane_body<false>(q, blockIdx.x, s_win, lt);
-}
-
-// Split form: even blocks run the forward chains of 128 snippets, odd blocks the beta chains of the same snippets,
-// so the block scheduler starts the longest snippets of BOTH directions first (two kernels on two streams do not
-// interleave: the second kernel's blocks wait for the first kernel's to be dispatched).
-__global__ void __launch_bounds__(FL_WARPS * 32) fb_split_lane_kernel(FbLaneParams q) {
-  __shared__ double s_win[FL_WARPS * 16 * 32];
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  if (blockIdx.x & 1u) fb_backward_lane_body<true>(q, blockIdx.x >> 1, s_win, lt);
-  else fb_forward_lane_body(q, blockIdx.x >> 1, s_win, lt);
-}
-
-// Expected counts from stored alpha and beta (split form): one warp per snippet, a lane per start position.
-// exp(alpha[pos] + score + beta[pos + len] - z) per matched token, in the reference's operation order
-// (src/lattice.rs:295-309), so every contribution equals the fused kernels' bit for bit.
-constexpr int FC_WARPS = 8;
-
-__global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams q) {
-  __shared__ unsigned long long s_et[256];
-  __shared__ double s_lt[256];
-  const FbParams& p = q.f;
-  const UnitParams& u = p.u;
-  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t widx = (uint64_t)blockIdx.x * FC_WARPS + warp;
-  if (widx >= u.count) return;
-  const uint32_t unit = u.order[u.first + widx];
-  if (p.status[unit] != 0) return;  // bad z: the reference panics; nothing is added
-  const uint32_t n = u.unit_len[unit];
-  const uint64_t start = u.unit_start[unit];
-  const double* A = p.A + start + unit;
-  const double* B = q.B + start + unit;
-  const uint8_t* text = u.text + start;
-  const double z = A[n];
-  double* hot = p.hot + (size_t)(blockIdx.x % p.hot_r) * p.hot_k;
-  for (uint32_t pos = lane; pos < n; pos += 32) {
-    const double a = A[pos];
-    const uint32_t limit = min(16u, n - pos);
-    uint32_t xb = u.root_base;
-    for (uint32_t d = 0; d < limit; d++) {
-      const uint32_t cw = 0x100u | __ldg(text + pos + d);
-      const uint4 e = __ldg(u.trie + (xb ^ cw));
-      if ((e.x ^ cw) & 0x1FFu) break;
-      if (e.y & F_TERM) {
-        const double sc = __hiloint2double((int)e.w, (int)e.z);
-        const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), B[pos + d + 1]), -z);
-        const uint32_t id = e.y & ID_MASK;
-        atomicAdd(id < p.hot_k ? hot + id : p.expected + id, tgx_exp(total, lt));
-      }
-      if (!(e.y & F_HASCH)) break;
-      xb = e.x >> 9;
-    }
-  }
-}
-
-__global__ void fold_hot_kernel(const double* __restrict__ hot, uint32_t hot_k, uint32_t hot_r,
-                                double* __restrict__ expected) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hot_k) return;
-  double s = 0.0;
-  for (uint32_t r = 0; r < hot_r; r++) s += hot[(size_t)r * hot_k + i];
-  expected[i] += s;
 }
 
 }  // namespace tgxk

@@ -24,7 +24,7 @@
 
 namespace tgxk {
 
-constexpr uint32_t REC_NOMATCH = 15u << 28;  // row 0: 16 x -inf
+constexpr uint32_t REC_NOMATCH = 15u << 28;  // row 0: empty header, 16 x -inf
 constexpr uint32_t REC_OFF = 0x0FFFFFFFu;
 
 // -----------------------------------------------------------------------------------------
@@ -186,7 +186,7 @@ __device__ __forceinline__ void rows_consume(const double* __restrict__ rows, ui
   auto fetch = [&](int j) -> double {
     const uint32_t rs = __shfl_sync(0xFFFFFFFFu, j < 16 ? r0 : r1, j & 15, 16);  // record of position j
     const uint32_t li = (uint32_t)(g - j - 1) & 15u;                            // candidate length - 1
-    const uint32_t idx = (li <= (rs >> 28)) ? (rs & REC_OFF) * 2u + li : li;
+    const uint32_t idx = 1u + ((li <= (rs >> 28)) ? (rs & REC_OFF) * 2u + li : li);  // (a row starts with its header)
     return ld_row(idx, hot_dbl, s_base, rows);  // (element-wise: a row may straddle the staged prefix)
   };
   double sc[4];

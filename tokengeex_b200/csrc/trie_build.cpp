@@ -255,45 +255,49 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   out->rows.clear();
   out->row_ids.clear();
   if (max_len >= 1 && max_len <= 16) {
-    std::vector<uint32_t> terms;  // terminal nodes
-    terms.reserve(n_term);
+    // terminal nodes in id order (ids are unique per terminal: the last duplicate owns the node) ...
+    std::vector<uint32_t> node_of_id(V, 0);
     for (uint32_t i = 1; i < nodes.size(); i++)
-      if (nodes[i].term_id >= 0) terms.push_back(i);
-    auto hotter = [&](uint32_t a, uint32_t b) {
-      const double sa = scores[nodes[a].term_id], sb = scores[nodes[b].term_id];
-      if (sa != sb) return sa > sb;
-      return nodes[a].term_id < nodes[b].term_id;
-    };
-    // (node order is byte order; score-sorted vocabularies are the common case, so sort by id first: then the
-    //  second, stable sort by score finds its input already ordered)
-    std::sort(terms.begin(), terms.end(), [&](uint32_t a, uint32_t b) { return nodes[a].term_id < nodes[b].term_id; });
+      if (nodes[i].term_id >= 0) node_of_id[nodes[i].term_id] = i;
+    std::vector<uint32_t> terms;
+    terms.reserve(n_term);
+    for (uint64_t id = 0; id < V; id++)
+      if (node_of_id[id]) terms.push_back(node_of_id[id]);
+    // ... which is already hottest-first for a score-sorted vocabulary (the usual case); otherwise sort
+    auto hotter = [&](uint32_t a, uint32_t b) { return scores[nodes[a].term_id] > scores[nodes[b].term_id]; };
     if (!std::is_sorted(terms.begin(), terms.end(), hotter)) std::stable_sort(terms.begin(), terms.end(), hotter);
     const double ninf = -INFINITY;
     std::vector<uint32_t> row_of(nodes.size(), 0);
-    uint64_t units16 = 8;  // row 0: 16 x -inf
+    uint64_t units16 = 9;  // row 0: header + 16 x -inf (+ pad)
     for (uint32_t nd : terms) {
       row_of[nd] = (uint32_t)units16;
-      units16 += (depth[nd] + 1u) / 2u;
+      units16 += (depth[nd] + 2u) / 2u;  // header + depth scores, padded to 16 bytes
     }
     if (units16 > SLOT8_OFF_MASK) return "row table too large";
     out->rows.assign(units16 * 2, ninf);
     out->row_ids.assign(units16 * 2, 0xFFFFFFFFu);
+    const uint64_t zero_bits = 0;
+    std::memcpy(&out->rows[0], &zero_bits, 8);
     for (uint32_t nd : terms) {
       const size_t base = (size_t)row_of[nd] * 2;
+      uint64_t mask = 0;
       for (uint32_t a = nd; a; a = parent[a])
         if (nodes[a].term_id >= 0) {
-          out->rows[base + depth[a] - 1] = scores[nodes[a].term_id];
-          out->row_ids[base + depth[a] - 1] = (uint32_t)nodes[a].term_id;
+          out->rows[base + depth[a]] = scores[nodes[a].term_id];
+          out->row_ids[base + depth[a]] = (uint32_t)nodes[a].term_id;
+          mask |= 1ull << (depth[a] - 1);
         }
+      std::memcpy(&out->rows[base], &mask, 8);
+      out->row_ids[base] = (uint32_t)mask;
     }
     out->slots8.assign(n_slots, 0);
     for (size_t i = 0; i < nodes.size(); i++) {
       const Node& nd = nodes[i];
-      const Slot& s = out->slots[nd.slot];
+      const Slot& sl = out->slots[nd.slot];
       uint32_t y = 0;
       if (nd.first_child) y |= SLOT8_HASCH;
       if (nd.term_id >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
-      out->slots8[nd.slot] = (uint64_t)s.x | ((uint64_t)y << 32);
+      out->slots8[nd.slot] = (uint64_t)sl.x | ((uint64_t)y << 32);
     }
   }
   lap("rows");

@@ -52,11 +52,12 @@ struct DoubleArray {
   // slots8[t] = slots[t].x | y8 << 32 with y8 = TERM8 | HASCH8 | row offset: the 8-byte form of the same double-array
   // (transition check + flags + the ROW of the token that ends at this node), half the footprint of `slots`.
   // A row lists, dense by length, the score of every vocabulary token that is a prefix of the row's token
-  // (= everything common_prefix_search yields on the way down to it, src/trie.rs:51-63): rows[2 * off16 + l - 1] =
-  // score of the prefix of length l, or -inf when that prefix is not a token; padded with -inf to an even count
-  // (16-byte units).  row_ids has the same layout with the token ids (0xFFFFFFFF = no token).  Rows are laid out by
-  // descending score of their own token (frequent tokens first), so the first bytes of the table are the hot ones
-  // the kernels stage in shared memory.  Row 0 = 16 x -inf = "no token starts here".
+  // (= everything common_prefix_search yields on the way down to it, src/trie.rs:51-63).  With off = 2 * (row offset in
+  // 16-byte units): rows[off] = header (as integer bits: bit l - 1 set iff the prefix of length l is a token),
+  // rows[off + l] = score of the prefix of length l, or -inf when that prefix is not a token; padded with -inf to a
+  // multiple of 16 bytes.  row_ids has the same layout with the token ids (0xFFFFFFFF = no token; [off] = the mask).
+  // Rows are laid out by descending score of their own token (frequent tokens first), so the first bytes of the table
+  // are the hot ones.  Row 0 = empty mask + 16 x -inf = "no token starts here".
   std::vector<uint64_t> slots8;
   std::vector<double> rows;
   std::vector<uint32_t> row_ids;

@@ -49,6 +49,7 @@ class PruneReport:
     freq_s: List[float] = field(default_factory=list)
     select_s: List[float] = field(default_factory=list)
     rebuild_s: List[float] = field(default_factory=list)
+    allreduce_s: List[float] = field(default_factory=list)  # the collective of every E-step / frequency pass
     audits: List[np.ndarray] = field(default_factory=list)
 
 
@@ -93,14 +94,25 @@ class ModelVocabularyPruner:
         d_off = torch.from_numpy(off.astype(np.uint64).view(np.int64)).to(dev)
         return {"torch": torch, "dev": dev, "text": d_text, "off": d_off, "S": len(off) - 1, "N": int(off[-1])}
 
-    def _reduce_dev(self, t):
-        """Sum across ranks on the device when the collective runs there (NCCL), else via the host."""
+    def _reduce_dev(self, t, torch=None):
+        """Integer tensor summed across ranks — on the device when the collective runs there (NCCL), else via the
+        host.  Returns a tensor on t's device; the time of the collective goes to self.last_allreduce_s."""
         coll = self.allreduce
+        self.last_allreduce_s = 0.0
         if coll is None:
-            return t.cpu().numpy()
+            return t
+        if torch is not None:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
         if hasattr(coll, "allreduce_tensor") and str(getattr(coll, "device", "cpu")).startswith("cuda"):
-            return coll.allreduce_tensor(t).cpu().numpy()
-        return coll(t.cpu().numpy())
+            t = coll.allreduce_tensor(t)
+            if torch is not None:
+                torch.cuda.synchronize()
+        else:
+            dev = t.device
+            t = (torch or __import__("torch")).from_numpy(coll(t.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
+        self.last_allreduce_s = time.perf_counter() - t0
+        return t
 
     # -- steps --------------------------------------------------------------------------------
     def run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray, dev=None) -> np.ndarray:
@@ -119,13 +131,19 @@ class ModelVocabularyPruner:
 
     def _run_e_step(self, model: N.Model, blob: np.ndarray, off: np.ndarray, dev=None) -> np.ndarray:
         if dev is not None:
+            # Counts as exact integer limbs (tgx_expected_counts_fixed_dev): the all-reduce is an integer sum, so the
+            # result is bit-identical for every number of ranks and every sharding of the corpus.
             torch = dev["torch"]
-            d_ex = torch.zeros(max(model.V, 1), dtype=torch.float64, device=dev["dev"])
-            rc, bad, badz = model.expected_counts_dev(dev["text"].data_ptr(), dev["off"].data_ptr(), dev["S"],
-                                                      dev["N"], d_ex.data_ptr())
+            V = max(model.V, 1)
+            d_limbs = torch.zeros(5 * V, dtype=torch.int64, device=dev["dev"])
+            rc, bad, badz = model.expected_counts_fixed_dev(dev["text"].data_ptr(), dev["off"].data_ptr(), dev["S"],
+                                                            dev["N"], d_limbs.data_ptr())
             if rc == N.TGX_ERR_BAD_Z:
                 raise FloatingPointError(f"normalization constant is f64::NaN (z={badz}, sample={bad})")
-            return self._reduce_dev(d_ex)[:model.V]
+            d_limbs = self._reduce_dev(d_limbs, torch)
+            d_ex = torch.empty(V, dtype=torch.float64, device=dev["dev"])
+            model.counts_from_limbs_dev(d_limbs.data_ptr(), model.V, d_ex.data_ptr())
+            return d_ex.cpu().numpy()[:model.V]
         ex, rc, bad, badz = model.expected_counts(blob, off)
         if rc == N.TGX_ERR_BAD_Z:  # the reference panics (src/prune.rs:90-96)
             raise FloatingPointError(f"normalization constant is f64::NaN (z={badz}, sample={bad})")
@@ -148,7 +166,7 @@ class ModelVocabularyPruner:
                                                         dev["N"], False, d_fr.data_ptr())
             if rc == N.TGX_ERR_NO_PATH:
                 raise RuntimeError(f"no path to position {blen}/{blen}")
-            fr = self._reduce_dev(d_fr)[:model.V].view(np.uint64)
+            fr = self._reduce_dev(d_fr, torch).cpu().numpy()[:model.V].view(np.uint64)
         else:
             fr, rc, bad, blen = model.token_frequencies(blob, off)
             if rc == N.TGX_ERR_NO_PATH:
@@ -156,6 +174,7 @@ class ModelVocabularyPruner:
             if self.allreduce is not None:
                 fr = self.allreduce(fr)
         report.freq_s.append(time.perf_counter() - t)
+        report.allreduce_s.append(getattr(self, "last_allreduce_s", 0.0))
         t = time.perf_counter()
         n_samples = self.n_samples_global if self.n_samples_global is not None else len(off) - 1
         # the model was rebuilt from `vocab` just before (src/prune.rs:48): its trie serves the n-best alternatives
@@ -182,6 +201,7 @@ class ModelVocabularyPruner:
                 t = time.perf_counter()
                 expected = self.run_e_step(model, blob, off, dev)
                 report.e_step_s.append(time.perf_counter() - t)
+                report.allreduce_s.append(getattr(self, "last_allreduce_s", 0.0))
                 log.info("E-step completed subiter=%d vocab_size=%d", subiter, len(vocab))
                 t = time.perf_counter()
                 new_vocab = self.run_m_step(vocab, expected)

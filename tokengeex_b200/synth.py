@@ -31,6 +31,7 @@ def lib() -> C.CDLL:
         L.tgx_synth_sample_lengths.restype = C.c_uint64
         L.tgx_synth_sample_lengths.argtypes = [C.c_uint64, C.c_uint64, _u64p, C.c_uint64]
         L.tgx_synth_corpus.argtypes = [C.c_int, C.c_uint64, _u64p, C.c_uint64, _u8p, C.c_int]
+        L.tgx_synth_corpus_range.argtypes = [C.c_int, C.c_uint64, _u64p, C.c_uint64, C.c_uint64, _u8p, C.c_int]
         L.tgx_synth_allow_exact.restype = C.c_int
         L.tgx_synth_allow_exact.argtypes = [_u8p, C.c_uint64]
         L.tgx_synth_vocab.restype = C.c_int64
@@ -60,6 +61,32 @@ def corpus(kind: int, seed: int, total_bytes: int, threads: int = 0, out: np.nda
     blob = np.empty(n, np.uint8) if out is None else out[:n]
     L.tgx_synth_corpus(kind, seed, off.ctypes.data_as(_u64p), S, blob.ctypes.data_as(_u8p), threads or n_threads())
     return blob, off
+
+
+def corpus_offsets(seed: int, total_bytes: int) -> np.ndarray:
+    """Offsets u64[S+1] of the corpus `corpus(kind, seed, total_bytes)` would generate (no text)."""
+    L = lib()
+    cap = total_bytes // 16 + 2
+    lens = np.zeros(cap, np.uint64)
+    S = int(L.tgx_synth_sample_lengths(seed, total_bytes, lens.ctypes.data_as(_u64p), cap))
+    off = np.zeros(S + 1, np.uint64)
+    np.cumsum(lens[:S], out=off[1:])
+    return off
+
+
+def corpus_shard(kind: int, seed: int, total_bytes: int, rank: int, world_size: int, threads: int = 0,
+                 out: np.ndarray | None = None) -> Tuple[np.ndarray, np.ndarray, int, int]:
+    """Rank `rank`'s byte-balanced shard (dist.shard_ranges) of ONE corpus, generated without the rest of it.
+    → (blob, offsets rebased to 0, index of the shard's first sample, samples in the whole corpus)."""
+    from .dist import shard_ranges
+    L = lib()
+    off = corpus_offsets(seed, total_bytes)
+    lo, hi = shard_ranges(off, world_size)[rank]
+    n = int(off[hi] - off[lo])
+    blob = np.empty(max(n, 1), np.uint8) if out is None else out[:max(n, 1)]
+    L.tgx_synth_corpus_range(kind, seed, off.ctypes.data_as(_u64p), lo, hi - lo, blob.ctypes.data_as(_u8p),
+                             threads or n_threads())
+    return blob[:n] if n else blob[:1], (off[lo:hi + 1] - off[lo]).astype(np.uint64), lo, len(off) - 1
 
 
 def vocab(blob: np.ndarray, off: np.ndarray, seed: int, vocab_size: int, max_token_length: int = 24,

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--estep-cfgs", default="", help="comma list of G:threshold pairs for the E-step")
     ap.add_argument("--snippet", type=int, default=81920, help="E-step snippet length (throughput experiments)")
     ap.add_argument("--algos", default="", help="comma list of forward algos to time (default all)")
+    ap.add_argument("--opts", default=None, help="encode: ONE configuration instead of the sweep: algo:key=value,key=value")
     args = ap.parse_args()
     import torch
     from tokengeex_b200 import _native as N, synth
@@ -44,10 +45,12 @@ def main():
     what = args.what.split(",")
     if "encode" in what:
         K = 1024
-        cfgs = [(2, {14: 0}), (0, {}), (0, {27: 1}), (0, {27: 2}), (0, {27: 8, 23: 768}), (0, {27: 8, 23: 512}), (0, {27: 4, 23: 1024, 24: 32 * K}),
-                (0, {24: 128 * K}), (0, {24: 0}), (0, {24: 64 * K, 23: 768}), (0, {23: 512})]
+        cfgs = [(2, {14: 0}), (0, {}), (0, {6: 8}), (0, {6: 6}), (0, {28: 1}), (0, {28: 0, 6: 0, 27: 1})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
+        if args.opts is not None:
+            a, _, kv = args.opts.partition(":")
+            cfgs = [(int(a), {int(x.split("=")[0]): int(x.split("=")[1]) for x in kv.split(",") if x})]
         for algo, opts in cfgs:
             m.set_option(3, algo)
             for k, v in opts.items():
