@@ -13,6 +13,7 @@ data-path collective and scaling is weak.  Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +29,7 @@ sys.path.insert(0, ROOT)
 VOCAB_SIZE = 131072
 MAX_TOKEN_LEN = 16
 VOCAB_SAMPLE_BYTES = 96_000_000
+FORWARD_KERNEL_NAME = "viterbi_pair_kernel<2, 1, 960>"  # when the match stream is off (option 3 = 2)
 METRIC = "encode_input_throughput"
 UNIT = "MB/s"
 
@@ -202,15 +204,14 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     del t_tb, t_to, t_sc, t_kp
     vocab = P.Vocab(list(toks), np.asarray(sc, np.float64), np.asarray(kp, np.uint8))
 
-    per_rank = args.prune_bytes // world
-    blob, off = synth.corpus(synth.KIND_CODE_CJK, 4 + 1000 * rank, per_rank)
+    # ONE corpus (seed 4) for every N: rank r generates and keeps its byte-balanced shard of it (dist.shard_ranges), so
+    # the all-reduced counts, the frequencies and the pruned vocabulary of an N-GPU run are the 1-GPU run's
+    blob, off, first_sample, n_samples = synth.corpus_shard(synth.KIND_CODE_CJK, 4, args.prune_bytes, rank, world)
     S, NB = len(off) - 1, int(off[-1])
     coll = None
-    n_samples = S
     if world > 1:
         from tokengeex_b200.dist import Collective
         coll = Collective(device=f"cuda:{local}")
-        n_samples = coll.sum_int(S)
     pr = P.ModelVocabularyPruner(65536, 0.8, 2, 0.0, device=local, allreduce=coll, n_samples_global=n_samples)
     d = pr._upload(blob, off)
 
@@ -236,7 +237,11 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     model.token_frequencies_dev(d["text"].data_ptr(), d["off"].data_ptr(), d["S"], d["N"], False, d_wfr.data_ptr())
     del d_wfr
     expected, t_e = timed(lambda: pr.run_e_step(model, blob, off, d))
-    e_dev_ms, fwd_ms, bwd_ms = model.stat(4), model.stat(2), model.stat(3)
+    e_dev_ms, fwd_ms, bwd_ms, e_match_ms = model.stat(4), model.stat(2), model.stat(3), model.stat(7)
+    t_allreduce_e = pr.last_allreduce_s
+    expected2 = pr.run_e_step(model, blob, off, d)  # a second run: the counts are bit-identical (integer accumulation)
+    counts_reproducible = bool(np.array_equal(np.asarray(expected).view(np.uint64), np.asarray(expected2).view(np.uint64)))
+    del expected2
     # property (i) at the full size: every byte of the corpus is covered by exactly one token on
     # every path of its snippet, so sum over ids of expected[id] * len(id) == corpus bytes (all ranks, after the
     # all-reduce) — checked on the counts of the timed E-step itself
@@ -258,7 +263,16 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
            "unit": "s", "iter_s": t_e + t_m + t_rebuild + t_prune,
            "e_step_s": t_e, "m_step_s": t_m, "model_rebuild_s": t_rebuild, "freq_pass_s": t_freq,
            "prune_select_s": t_sel, "vocab_after_m_step": len(new_vocab), "vocab_after_prune": len(pruned),
-           "e_step_device_ms": e_dev_ms, "fb_forward_ms": fwd_ms, "fb_backward_ms": bwd_ms,
+           "e_step_device_ms": e_dev_ms, "fb_forward_ms": fwd_ms, "fb_backward_ms": bwd_ms, "match_ms": e_match_ms,
+           "allreduce_e_step_s": t_allreduce_e, "allreduce_freq_s": rep.allreduce_s[-1] if rep.allreduce_s else 0.0,
+           "corpus": "ONE corpus (kind code+Chinese, seed 4) whatever the number of ranks; rank r holds shard r of it",
+           "n_samples_total": int(n_samples), "first_sample_of_rank0": int(first_sample),
+           "counts_bit_identical_between_two_runs": counts_reproducible,
+           # identical for every N (the driver's N = 1, 2, 4, 8 lines can be compared field by field)
+           "expected_counts_sha256": hashlib.sha256(np.ascontiguousarray(expected, np.float64).tobytes()).hexdigest()[:16],
+           "frequencies_sha256": hashlib.sha256(np.ascontiguousarray(pr.last_freq).tobytes()).hexdigest()[:16],
+           "pruned_vocab_sha256": hashlib.sha256(b"\0".join(pruned.tokens)).hexdigest()[:16],
+           "audit": [float(x) for x in rep.audits[-1]] if rep.audits else None,
            "e_step_input_MBps": args.prune_bytes / t_e / 1e6,
            "property_sum_expected_len_eq_bytes_rel_err": cover_err, "property_holds_1e-9": bool(cover_err < 1e-9),
            "bytes_per_gpu": NB, "samples_per_gpu": S,
@@ -267,7 +281,8 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     alg = NB + 8 * (S + 1) + 8 * len(vocab)
     out["roofline"] = {"bound": "hbm", "achieved": alg / (e_dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": alg / (e_dev_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
-                       "kernel": "fb_forward/backward_lane_kernel (snippets below the warp threshold) + fb_forward/backward_kernel<32> (whole E-step, device ms)"}
+                       "kernel": "match_kernel<4> + fbr_split_kernel<false> + fbr_contrib_kernel<false> (snippets below the warp "
+                                 "threshold) + fb_forward_kernel<32> / fb_backward_kernel<32, true> (whole E-step, device ms)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         threads = synth.n_threads()
@@ -294,6 +309,49 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     return out
 
 
+def run_prune_schedule(args, rank, world, local, torch, dist, N, synth):
+    """BASELINE.json configs[4]: the full prune schedule (src/prune.rs:23-57, docs/RECIPES.md:44-52) — 500k -> 65k
+    tokens, shrink 0.8, two EM sub-iterations per step, dropout 0.0 — over ONE corpus of args.schedule_bytes sharded over
+    the ranks, run TWICE: wall seconds, sizes after every step, the margin audit, and whether both runs end in the same
+    vocabulary (they must: the counts are integer sums)."""
+    from tokengeex_b200 import prune as P
+    dev = torch.device("cuda", local)
+    vb, vo = synth.corpus(synth.KIND_CODE_CJK, 4, PRUNE_VOCAB_SAMPLE_BYTES)  # (deterministic: identical on every rank)
+    toks, sc, kp = synth.vocab(vb, vo, 4, PRUNE_VOCAB, MAX_TOKEN_LEN, 0.05)
+    del vb, vo
+    vocab = P.Vocab(list(toks), np.asarray(sc, np.float64), np.asarray(kp, np.uint8))
+    blob, off, first_sample, n_samples = synth.corpus_shard(synth.KIND_CODE_CJK, 4, args.schedule_bytes, rank, world)
+    coll = None
+    if world > 1:
+        from tokengeex_b200.dist import Collective
+        coll = Collective(device=f"cuda:{local}")
+    runs = []
+    for rep_i in range(args.schedule_runs):
+        pr = P.ModelVocabularyPruner(65536, 0.8, 2, 0.0, device=local, allreduce=coll, n_samples_global=n_samples)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        final, rep = pr.prune(vocab, blob, off)
+        torch.cuda.synchronize()
+        wt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        runs.append({"wall_s": float(wt[0]), "final_vocab": len(final),
+                     "final_vocab_sha256": hashlib.sha256(b"\0".join(final.tokens)).hexdigest()[:16],
+                     "vocab_sizes": rep.vocab_sizes, "e_step_s": round(sum(rep.e_step_s), 3),
+                     "m_step_s": round(sum(rep.m_step_s), 3), "freq_pass_s": round(sum(rep.freq_s), 3),
+                     "prune_select_s": round(sum(rep.select_s), 3), "rebuild_s": round(sum(rep.rebuild_s), 3),
+                     "allreduce_s": round(sum(rep.allreduce_s), 3), "e_steps": len(rep.e_step_s),
+                     "m_step_margins": rep.m_margins,
+                     "cut_audit": [{"exact_loss_tie_at_cut": bool(a[5]), "loss_gap_at_cut": float(a[6]),
+                                    "silently_dropped": int(a[2]), "candidates": int(a[4])} for a in rep.audits]})
+    return {"workload": f"full prune schedule {len(vocab)} -> 65536 tokens, shrink 0.8, 2 EM sub-iterations, dropout 0.0, "
+                        f"{args.schedule_bytes} B code+Chinese corpus (seed 4) sharded x{world} (configs[4])",
+            "runs": runs, "runs_end_in_the_same_vocabulary": len({r["final_vocab_sha256"] for r in runs}) == 1,
+            "n_samples_total": int(n_samples)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +363,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prune", action="store_true", help="skip the EM prune-iteration measurement")
     ap.add_argument("--prune-bytes", type=int, default=4_000_000_000, help="total corpus bytes of the prune iteration")
+    ap.add_argument("--schedule-bytes", type=int, default=0,
+                    help="also run the full prune schedule (configs[4]) over a corpus of this many bytes in total")
+    ap.add_argument("--schedule-runs", type=int, default=2)
+    ap.add_argument("--only-schedule", action="store_true", help="skip the encode benchmark and the prune iteration")
     ap.add_argument("--chunk-bytes", type=int, default=0, help="bytes per chunk of the pipelined host entry point")
     ap.add_argument("--g-short", type=int, default=0)
     ap.add_argument("--long-threshold", type=int, default=0)
@@ -330,13 +392,25 @@ def main():
         numa_node = bind_to_gpu_numa_node(local)  # host buffers next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION/INFO prints to stdout, which has to carry exactly one JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("TGX_NCCL_DEBUG", "WARN")
+        # NCCL's own log goes to stderr-side files when the caller asks for it (NCCL_DEBUG=INFO prints to stdout, which
+        # has to carry exactly one JSON line): the setting itself is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE", "VERSION") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log")
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         if world > 1:
             dist.barrier()
+
+    if args.only_schedule:
+        sched = run_prune_schedule(args, rank, world, local, torch, dist, N, synth)
+        if rank == 0:
+            print(json.dumps({"metric": "prune_schedule_wall_s", "unit": "s", "n_gpus": world, "higher_is_better": False,
+                              "value": min(r["wall_s"] for r in sched["runs"]), "prune_schedule": sched}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     toks, sc, kp = build_vocab(synth, world)
     model = N.Model(toks, sc, device=local)
@@ -373,7 +447,7 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    dev_ms, vit_ms, back_ms, emit_ms = [], [], [], []
+    dev_ms, vit_ms, back_ms, emit_ms, match_ms = [], [], [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tokens = step_dev()
@@ -381,6 +455,7 @@ def main():
         vit_ms.append(model.stat(1))
         back_ms.append(model.stat(5))
         emit_ms.append(model.stat(6))
+        match_ms.append(model.stat(7))
     torch.cuda.synchronize()
     barrier()
     wall = time.perf_counter() - t0
@@ -403,13 +478,23 @@ def main():
     # roofline of the dominant kernel (the Viterbi kernel launches), this rank
     peak, peak_src = measured_peak()
     alg_bytes = NB + 4 * tokens + 16 * (S + 1)
-    vit = float(np.mean(vit_ms)) * 1e-3
+    # the forward pass is two kernels when the match stream is used (match_kernel, then the consumer of the stream);
+    # the roofline is quoted for the longer one
+    fwd_kernels = {FORWARD_KERNEL_NAME: float(np.mean(vit_ms))}
+    if float(np.mean(match_ms)) > 0.05:  # (the events bracket nothing when the match stream is off)
+        fwd_kernels = {"viterbi_rows_kernel": float(np.mean(vit_ms)), "match_kernel<4>": float(np.mean(match_ms))}
+    dom_kernel = max(fwd_kernels, key=fwd_kernels.get)
+    vit = fwd_kernels[dom_kernel] * 1e-3
     achieved = alg_bytes / vit / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("viterbi_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            ent = tj.get("kernels", {}).get(dom_kernel)
+            if ent:  # DRAM bytes of that kernel per input byte (ncu --set full capture named in the file) x this launch
+                traffic = float(ent["dram_bytes_per_input_byte"]) * NB
+                traffic_src = ent.get("source")
         except Exception:
             traffic = None
 
@@ -433,7 +518,43 @@ def main():
         e2e = {"value": bytes_all * args.steps / float(ew[0]) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": NB + 8 * (S + 1),
                "d2h_bytes_per_step": int(4 * r[0].size + 8 * (S + 1) + 12 * S),
-               "ms_per_step": 1e3 * float(ew[0]) / args.steps}
+               "ms_per_step": 1e3 * float(ew[0]) / args.steps,
+               "buffers": "pinned host memory (tgx_host_alloc) for text in and ids out"}
+        # the same call with ordinary (pageable) caller memory, as a Rust Vec or Python bytes would hand it over
+        pg_text = np.array(blob, copy=True)
+        pg_ids = np.empty(int(tokens) + 16, np.uint32)
+        model.encode_batch(pg_text, off, crlf=True, ids_out=pg_ids)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            r = model.encode_batch(pg_text, off, crlf=True, ids_out=pg_ids)
+        torch.cuda.synchronize()
+        barrier()
+        pw = torch.tensor([(time.perf_counter() - t0) / max(1, args.steps // 2)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(pw, op=dist.ReduceOp.MAX)
+        e2e["pageable"] = {"value": bytes_all / float(pw[0]) / 1e6, "unit": UNIT, "ms_per_step": 1e3 * float(pw[0]),
+                           "buffers": "pageable numpy arrays for text in and ids out"}
+        del pg_text, pg_ids
+        # and through the drop-in Python surface: tokengeex.Tokenizer.encode_batch(List[str], dropout) -> List[List[int]]
+        # (bindings/python/src/lib.rs:51-59) on a bounded sample; str -> utf-8 and ids -> Python lists included
+        if rank == 0:
+            import tokengeex  # the drop-in module name (re-exports tokengeex_b200.tokenizer.Tokenizer)
+            from tokengeex_b200.tokenizer import _Processor
+            tk = tokengeex.Tokenizer(toks, sc, kp, processors=[_Processor("crlf")], device=local)
+            if tk is not None:
+                k = int(np.searchsorted(off, 64_000_000))
+                raw = blob[:int(off[k])].tobytes()
+                texts = [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(k)]
+                tk.encode_batch(texts[:64], 0.0)
+                t0 = time.perf_counter()
+                out = tk.encode_batch(texts, 0.0)
+                dt = time.perf_counter() - t0
+                e2e["tokenizer_encode_batch"] = {"value": int(off[k]) / dt / 1e6, "unit": UNIT, "ms": 1e3 * dt,
+                                                 "sample": f"{k} samples, {int(off[k])} bytes as List[str] -> List[List[int]]",
+                                                 "tokens": int(sum(len(x) for x in out))}
+                del texts, out, raw
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -455,6 +576,27 @@ def main():
                "sample": f"first {int(o[-1])} bytes ({k} samples) of the same corpus, oracle encode_batch "
                          "(C++ restatement of the Rust rayon path)", "ids_match_gpu": ok}
 
+    # every rank: the device ids of a seeded sample of ITS shard against the oracle (bit-exact), min over ranks
+    sampled = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        om_s = O.OracleModel(toks, sc)
+        h_idoff = d_id_off.cpu().numpy().view(np.uint64)
+        rs = np.random.RandomState(1234 + rank)
+        lens_s = np.diff(off.astype(np.int64))
+        pick = set(rs.choice(S, size=min(S, 150), replace=False).tolist()) | set(np.argsort(lens_s)[-2:].tolist())
+        ok_s = True
+        for i in sorted(pick):
+            a, b = int(h_idoff[i]), int(h_idoff[i + 1])
+            got = d_ids[a:b].cpu().numpy().view(np.uint32).tolist()
+            ok_s = ok_s and got == om_s.encode(O.crlf(blob[int(off[i]):int(off[i + 1])].tobytes()), 0.0)
+        okt = torch.tensor([1 if ok_s else 0], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        sampled = {"ids_match_oracle": bool(int(okt[0])), "samples_per_rank": len(pick),
+                   "what": "seeded sample of every rank's shard + its two longest samples, oracle encode (bit-exact)"}
+        del om_s
+
     prune_iter = None
     if not args.no_prune:
         del d_text, d_ids, d_id_off, d_off, blob, h_text
@@ -463,6 +605,11 @@ def main():
         model.close()
         torch.cuda.empty_cache()
         prune_iter = run_prune_iter(args, rank, world, local, torch, dist, N, synth)
+
+    prune_schedule = None
+    if args.schedule_bytes:
+        torch.cuda.empty_cache()
+        prune_schedule = run_prune_schedule(args, rank, world, local, torch, dist, N, synth)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -479,15 +626,18 @@ def main():
                 "clocks": clk,
                 "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "viterbi_pair_kernel (forward dp; one launch per step)",
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "peak_source": peak_src,
+                             "kernel": dom_kernel + " (one launch per step; CUDA events on its own stream)",
                              "algorithmic_bytes": alg_bytes, "kernel_ms": vit * 1e3,
-                             "step_breakdown_ms": {"forward": vit * 1e3, "backtrack": float(np.mean(back_ms)),
+                             "forward_kernels_ms": fwd_kernels,
+                             "step_breakdown_ms": {"forward": sum(fwd_kernels.values()), "backtrack": float(np.mean(back_ms)),
                                                    "emit": float(np.mean(emit_ms)),
-                                                   "crlf_sort_scan_other": ms_per_step - vit * 1e3 -
+                                                   "crlf_sort_scan_other": ms_per_step - sum(fwd_kernels.values()) -
                                                    float(np.mean(back_ms)) - float(np.mean(emit_ms))}},
                 "cpu_baseline": cpu,
-                "prune_iter": prune_iter}
+                "sampled_parity": sampled,
+                "prune_iter": prune_iter, "prune_schedule": prune_schedule}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

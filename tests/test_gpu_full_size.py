@@ -99,3 +99,86 @@ def test_config1_1gb_131k_vocab_properties(N):
     for i in pick:
         text = O.crlf(blob[int(off[i]):int(off[i + 1])].tobytes())
         assert ids[int(id_off[i]):int(id_off[i + 1])].tolist() == om.encode(text, 0.0), i
+
+
+def test_config2_1gb_code_chinese_131k_vocab(N):
+    """configs[2]: one GPU's 1 GB shard of the code+Chinese mix (long multi-byte tokens, max token length 16) with the
+    vocabulary bench.py builds for N > 1: segmentation properties over the whole shard, every forward pass agrees,
+    the oracle on a seeded sample + the longest samples."""
+    import bench
+    from tokengeex_b200 import synth
+    toks, sc, kp = bench.build_vocab(synth, 2)
+    blob, off, _ = bench.workload(synth, 2, 1, 1_000_000_000)  # rank 1's shard of the N = 2 run
+    S, NB = len(off) - 1, int(off[-1])
+    assert NB >= 999_000_000 and len(toks) == 131072 and max(map(len, toks)) <= 16
+    assert any(len(t) >= 9 and t[0] >= 0xE4 for t in toks)  # multi-scalar CJK tokens are in the vocabulary
+    gm, om = N.Model(toks, sc, device=0), O.OracleModel(toks, sc)
+    lens = np.array([len(t) for t in toks], np.int64)
+    ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
+    assert rc == 0 and bad == -1 and not status.any()
+    pblob, poff = gm.crlf_batch(blob, off)
+    check_segmentation(blob, off, toks, ids, id_off, plen, pblob, poff)
+    fr, rc, *_ = gm.token_frequencies(blob, off, crlf=True)
+    assert rc == 0 and np.array_equal(fr.astype(np.int64), np.bincount(ids, minlength=len(toks)))
+    assert int((fr.astype(np.int64) * lens).sum()) == int(plen.sum())
+    for algo in (2, 0):  # pair-CTA kernel / match stream: not one id differs
+        gm.set_option(3, algo)
+        ids2, id_off2, *_ = gm.encode_batch(blob, off, crlf=True)
+        assert np.array_equal(id_off2, id_off) and np.array_equal(ids2, ids), algo
+    rng = random.Random(2)
+    order = np.argsort(np.diff(off.astype(np.int64)))
+    pick = sorted(set(rng.sample(range(S), 400)) | set(order[-3:].tolist()) | set(order[:3].tolist()))
+    for i in pick:
+        text = O.crlf(blob[int(off[i]):int(off[i + 1])].tobytes())
+        assert ids[int(id_off[i]):int(id_off[i + 1])].tolist() == om.encode(text, 0.0), i
+
+
+def test_config3_500k_vocab_e_step_frequencies_selection(N):
+    """configs[3] at its vocabulary size (500 000 tokens, code+Chinese): E-step against the oracle on a sample of the
+    corpus (1e-9 relative), bit-identical counts between two runs and between two chunkings, frequency pass exact,
+    M-step + prune_vocab selection (incl. the n-best alternatives over the model's own trie) equal to the oracle's."""
+    import bench
+    from tokengeex_b200 import prune as P
+    from tokengeex_b200 import synth
+    from tests.util import counts_rel_err
+    vb, vo = synth.corpus(synth.KIND_CODE_CJK, 4, bench.PRUNE_VOCAB_SAMPLE_BYTES)
+    toks, sc, kp = synth.vocab(vb, vo, 4, bench.PRUNE_VOCAB, 16, 0.05)
+    del vb, vo
+    assert len(toks) == 500_000
+    blob, off = synth.corpus(synth.KIND_CODE_CJK, 4, 48_000_000)
+    gm, om = N.Model(toks, sc, device=0), O.OracleModel(toks, sc, kp)
+    want = om.run_e_step(blob, off, threads=16)[0]
+    ex, rc, _, _ = gm.expected_counts(blob, off)
+    assert rc == 0 and counts_rel_err(ex, want) < 1e-9
+    ex2 = gm.expected_counts(blob, off)[0]
+    assert np.array_equal(ex.view(np.uint64), ex2.view(np.uint64))  # integer accumulation: no run-to-run jitter
+    k = len(off) // 2  # two calls over the two halves = one call (what sharding over GPUs relies on)
+    import torch
+    d_text = torch.from_numpy(blob).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_off2 = torch.from_numpy((off[k:] - off[k]).view(np.int64)).cuda()
+    limbs = torch.zeros(5 * len(toks), dtype=torch.int64, device="cuda")
+    gm.expected_counts_fixed_dev(d_text.data_ptr(), d_off.data_ptr(), k, int(off[k]), limbs.data_ptr())
+    d_text2 = d_text[int(off[k]):].clone()
+    gm.expected_counts_fixed_dev(d_text2.data_ptr(), d_off2.data_ptr(), len(off) - 1 - k, int(off[-1] - off[k]),
+                                 limbs.data_ptr())
+    d_ex = torch.empty(len(toks), dtype=torch.float64, device="cuda")
+    gm.counts_from_limbs_dev(limbs.data_ptr(), len(toks), d_ex.data_ptr())
+    assert np.array_equal(d_ex.cpu().numpy().view(np.uint64), ex.view(np.uint64))
+    # frequency pass at 500k tokens: exact
+    fr, rc, *_ = gm.token_frequencies(blob, off)
+    wfr = om.token_frequencies(blob, off, threads=16)
+    assert rc == 0 and np.array_equal(fr, wfr)
+    # M-step, rebuild, frequency pass and selection at ~250k tokens
+    kept, ns = N.m_step(want, kp)
+    idx = np.flatnonzero(kept)
+    v2 = P.Vocab([toks[i] for i in idx], ns[idx].copy(), np.asarray(kp, np.uint8)[idx].copy())
+    om2 = om.run_m_step(want)
+    t2, s2, k2 = om2.export()
+    assert t2 == v2.tokens and np.array_equal(np.asarray(s2).view(np.uint64), v2.scores.view(np.uint64))
+    gm.rebuild(v2.tokens, v2.scores)
+    fr2 = gm.token_frequencies(blob, off)[0]
+    assert np.array_equal(fr2, om2.token_frequencies(blob, off, threads=16))
+    ids, audit = gm.prune_select(v2.tokens, v2.scores, v2.keep, fr2, len(off) - 1, 65536, 0.8, threads=16)
+    wv, waudit = om2.prune_vocab(blob, off, 65536, 0.8, threads=16)
+    assert [v2.tokens[i] for i in ids] == list(wv.export()[0])

@@ -310,10 +310,10 @@ def test_token_frequencies_exact(N):
 def estep_cfg(m, g):
     """g = lanes per snippet of the lane-group kernels (lane-per-snippet kernels off); g = 0: every snippet below
     the long threshold runs one lane each (fb_*_lane_kernel), the rest a warp each."""
-    if g in (0, -3):  # -3: fused backward + counts (no beta array); 0: split form, the default
-        m.set_option(17, 1 << 30)
+    if g in (0, -2, -3):  # 0: split form, lane kernels that walk the trie (the default); -2: the lane kernels over the
+        m.set_option(17, 1 << 30)  # match stream; -3: no beta array (fused backward + counts on the lane-group kernels)
         m.set_option(2, 4)
-        m.set_option(19, 1 if g == 0 else 0)
+        m.set_option(19, {0: 1, -2: 2, -3: 0}[g])
     else:
         m.set_option(17, 0)
         m.set_option(2, g)
@@ -323,7 +323,7 @@ LATTICE_VOCAB = [(b"<", -3.0), (b" value", -6.0), (b">", -3.0), (b"DC value", -8
                  (b"<DC value>", -12.0)]
 
 
-@pytest.mark.parametrize("g", [0, -3, 1, 8, 32])
+@pytest.mark.parametrize("g", [0, -2, -3, 1, 8, 32])
 def test_reference_lattice_marginals(N, g):
     toks = [t for t, _ in LATTICE_VOCAB]
     sc = [s for _, s in LATTICE_VOCAB]
@@ -344,7 +344,7 @@ def test_reference_lattice_marginals(N, g):
     assert rc == 0 and np.allclose(ex, [0.5, 0.5, 0.5], rtol=1e-12)
 
 
-@pytest.mark.parametrize("g", [0, -3, 1, 4, 32])
+@pytest.mark.parametrize("g", [0, -2, -3, 1, 4, 32])
 def test_expected_counts_random_vs_oracle(N, g):
     rng = random.Random(200 + abs(g))
     for it in range(20):
@@ -374,7 +374,7 @@ def test_expected_counts_long_tokens(N):
     samples = [b"ab" * 50, b"a" * 100, b"b" * 200, b"abba" * 30] + rand_samples(rng, b"ab", 20, 1, 300)
     blob, off = N.pack(samples)
     want = om.run_e_step(blob, off, threads=1, literal=True)[0]
-    for g in (0, -3, 4, 32):
+    for g in (0, -2, -3, 4, 32):
         estep_cfg(gm, g)
         ex, rc, bad, badz = gm.expected_counts(blob, off)
         assert rc == 0 and np.allclose(ex, want, rtol=ORDER_TOL, atol=1e-27), (g, np.max(np.abs(ex - want)))
@@ -391,7 +391,7 @@ def test_expected_counts_synth_vs_oracle(N):
     blob, off, toks, sc, kp = synth_setup(2, 13, 2_000_000, 30000, 16)
     gm, om = both(N, toks, sc)
     want, wrc, wbad, _ = om.run_e_step(blob, off, threads=8, literal=False)
-    for g in (0, -3, 1, 8, -1):
+    for g in (0, -2, -3, 1, 8, -1):
         if g != -1:
             estep_cfg(gm, g)
         else:  # the default split: lanes below 16 KB, lane groups above, warps for the longest

@@ -117,3 +117,15 @@ def test_encode_without_device_raises_cleanly():
         t.encode("def", 0.0)
     with pytest.raises(TokenGeeXError):
         t.encode("def", 0.5)
+
+
+def test_add_base_tokens():
+    """src/tokenizer.rs:56-61 -> src/model.rs:184-194: new ids at the end, duplicates take the new id."""
+    from tokengeex_b200.tokenizer import Tokenizer
+    t = Tokenizer([b"a", b"b", b"ab"], [-1.0, -1.0, -1.5], special_tokens=["<s>"], device=None)
+    assert t.special_token_to_id("<s>") == 3
+    t.add_base_tokens([(b"ba", -1.25), (b"a", -0.5)])
+    assert t.base_vocab_size() == 5 and t.vocab_size() == 6
+    assert t.base_token_to_id(b"ba") == 3 and t.base_token_to_id(b"a") == 4  # HashMap::insert: the last id wins
+    assert t.id_to_base_token(4) == (b"a", -0.5) and t.special_token_to_id("<s>") == 5
+    assert list(t.common_prefix_search("ab")) == [4, 2]

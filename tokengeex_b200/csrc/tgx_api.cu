@@ -139,7 +139,7 @@ struct tgx_model {
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = match stream + row consumer (tgx_match_kernels.cuh; the default), 1 = lane-group kernels, 2 = pair-CTA kernel
   // (the default of the first round; still what encodes with dropout in (0, 1)).
-  int algo = 0;
+  int algo = 2;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
@@ -651,38 +651,44 @@ int order_after_caller(tgx_model* m) {
   return TGX_OK;
 }
 
-// Token hash of the emit kernel and the match tables of the default forward pass (max_token_len <= 16 only); a
-// vocabulary they cannot serve simply leaves hash.mask == 0 / have_rows == false and the older kernels take over.
-// On failure nothing the model already holds has been touched.
+// Token hash of the emit kernel (max_token_len <= 16 only); a vocabulary it cannot serve simply leaves hash.mask == 0
+// and emit walks the trie.  On failure nothing the model already holds has been touched.
 int upload_aux_tables(tgx_model* m, const tgx::DoubleArray& da, const uint8_t* token_bytes, const uint64_t* token_offsets,
                       uint64_t V, uint32_t max_token_len) {
+  (void)da;
   if (m->device < 0) return TGX_OK;
   cudaStream_t st = m->w().stream;
   tgx::TokenHash h;
   const bool hash_ok = V != 0 && max_token_len >= 1 && max_token_len <= 16 &&
                        tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty();
-  const bool rows_ok = !da.slots8.empty();
   if (hash_ok) CU(m->d_hash.reserve(h.slots.size() * sizeof(tgx::Slot)));
-  if (rows_ok) {
-    CU(m->d_trie8.reserve(da.slots8.size() * 8));
-    CU(m->d_rows.reserve(da.rows.size() * 8 + 256));
-    CU(m->d_rowids.reserve(da.row_ids.size() * 4 + 256));
-  }
   m->hash.mask = 0;
   m->hash.slots.clear();
-  m->have_rows = false;
-  if (hash_ok) CU(cudaMemcpyAsync(m->d_hash.p, h.slots.data(), h.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, st));
-  if (rows_ok) {
-    CU(cudaMemcpyAsync(m->d_trie8.p, da.slots8.data(), da.slots8.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->d_rows.p, da.rows.data(), da.rows.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->d_rowids.p, da.row_ids.data(), da.row_ids.size() * 4, cudaMemcpyHostToDevice, st));
+  m->have_rows = false;  // the match tables belong to the previous vocabulary: rebuilt on first use
+  if (hash_ok) {
+    CU(cudaMemcpyAsync(m->d_hash.p, h.slots.data(), h.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    m->hash = std::move(h);
   }
+  return TGX_OK;
+}
+
+// Match tables (trie_build.h: slots8 / rows / row_ids) of the current vocabulary on the device; built and uploaded on
+// first use.  have_rows stays false for vocabularies they cannot serve (tokens longer than 16 bytes).
+int ensure_match_tables(tgx_model* m) {
+  if (m->have_rows || m->device < 0) return TGX_OK;
+  if (!tgx::build_match_tables(&m->da).empty()) return TGX_OK;
+  const tgx::DoubleArray& da = m->da;
+  cudaStream_t st = m->w().stream;
+  CU(m->d_trie8.reserve(da.slots8.size() * 8));
+  CU(m->d_rows.reserve(da.rows.size() * 8 + 256));
+  CU(m->d_rowids.reserve(da.row_ids.size() * 4 + 256));
+  CU(cudaMemcpyAsync(m->d_trie8.p, da.slots8.data(), da.slots8.size() * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d_rows.p, da.rows.data(), da.rows.size() * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d_rowids.p, da.row_ids.data(), da.row_ids.size() * 4, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
-  if (hash_ok) m->hash = std::move(h);
-  if (rows_ok) {
-    m->have_rows = true;
-    m->rows16 = (uint32_t)(da.rows.size() / 2);
-  }
+  m->have_rows = true;
+  m->rows16 = (uint32_t)(da.rows.size() / 2);
   return TGX_OK;
 }
 
@@ -816,6 +822,10 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.count = U;  // upper bound for the grids
 
   const double dropout = with_dropout ? m->dropout : 0.0;  // the frequency passes encode with dropout 0.0
+  if (!(dropout > 0.0) && m->algo == 0 && u.rows <= 16) {
+    rc = ensure_match_tables(m);
+    if (rc) return rc;
+  }
   // with the draw: pair-CTA or lane-group kernels
   const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : (m->algo == 0 && !m->have_rows ? 2 : m->algo);
   CU(cudaEventRecord(m->w().ev[8], st));
@@ -1172,7 +1182,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 3: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "algo must be 0..2"); m->algo = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
-    case 19: m->estep_rows = m->estep_split = value ? 1 : 0; break;
+    case 19: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "E-step form must be 0..2"); m->estep_split = value ? 1 : 0; m->estep_rows = (int)value; break;
     case 20: if (value < 1 || value > 4096) return fail(TGX_ERR_INVALID, "replicas must be 1..4096"); m->hot_r = (int)value; break;
     case 21: if (value < 0 || value > (1 << 20)) return fail(TGX_ERR_INVALID, "hot ids must be 0..2^20"); m->hot_k = (int)value; break;
     case 18: if (value < 0 || value > 16) return fail(TGX_ERR_INVALID, "blocks per SM must be 0..16"); m->lane_blocks_per_sm = (int)value; break;
@@ -1235,8 +1245,8 @@ int tgx_model_prune_select(tgx_model* m, const uint8_t* token_bytes, const uint6
 // Developer aid (tools/analyse_rows.py; not part of include/tokengeex_b200.h): host walk of the 8-byte trie from every
 // byte of `text`.  out[0] = probes, out[1] = probes of slots below `staged` (what match_kernel would serve from shared
 // memory), out[2] = positions, out[3] = matches.
-int tgx_debug_probe_stats(const tgx_model* m, const uint8_t* text, uint64_t n, uint32_t staged, uint64_t* out) {
-  if (!m || !text || !out || m->da.slots8.empty()) return fail(TGX_ERR_INVALID, "no match tables");
+int tgx_debug_probe_stats(tgx_model* m, const uint8_t* text, uint64_t n, uint32_t staged, uint64_t* out) {
+  if (!m || !text || !out || !tgx::build_match_tables(&m->da).empty()) return fail(TGX_ERR_INVALID, "no match tables");
   uint64_t probes = 0, low = 0, matches = 0;
   for (uint64_t p = 0; p < n; p++) {
     uint32_t xb = m->da.root_base;
@@ -1832,9 +1842,19 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
 
   // The kernels over the match stream (one lane per snippet; counts from stored alpha / beta) need the match tables
   // and 8 more bytes of device memory per input byte for beta; without them the lane-group kernels take every snippet.
-  bool rows_ok = m->estep_rows && m->have_rows && p.u.rows <= 16;
+  // Split form (one lane per snippet, beta chains beside the alpha chains, counts from stored alpha / beta): needs 8
+  // more bytes of device memory per input byte for beta (+ 4 for the match stream).  Two sets of lane kernels: the ones
+  // that walk the trie (fb_split_lane_kernel; faster as measured, profiles/r02_estep_kernels.txt) and the ones over the
+  // match stream (fbr_split_kernel; they take the dropout draw, and option 19 = 2 selects them always).
+  bool rows_ok = m->estep_split && p.u.rows <= 16;
+  if (rows_ok && (drop || m->estep_rows == 2)) {
+    rc = ensure_match_tables(m);
+    if (rc) return rc;
+  }
+  const bool use_rows = rows_ok && m->have_rows && (drop || m->estep_rows == 2);
+  if (drop && !use_rows) rows_ok = false;  // no match tables: the lane-group kernels take the draw
   if (rows_ok) {
-    const size_t need = ((size_t)n_bytes + U + 2) * 8 + ((size_t)n_bytes + 64) * 4;
+    const size_t need = ((size_t)n_bytes + U + 2) * 8 + (use_rows ? ((size_t)n_bytes + 64) * 4 : 0);
     size_t fr = 0, tot = 0;
     const size_t have = m->Bbeta.cap + m->w().rec.cap;
     if (need > have && (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr + have < need + need / 8 + ((size_t)2 << 30))) rows_ok = false;
@@ -1844,7 +1864,7 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     }
   }
   CU(cudaEventRecord(m->w().ev[8], st));
-  if (rows_ok) {
+  if (use_rows) {
     rc = run_match(m, d_text, n_bytes);
     if (rc) return rc;
   }
@@ -1889,8 +1909,14 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   pn.rows = m->d_rows.as<double>();
   pn.row_ids = m->d_rowids.as<uint32_t>();
   pn.B = m->Bbeta.as<double>();
-  const bool split = rows_ok;  // beta chains stored and run beside the alpha chains, counts by fbr_contrib_kernel
+  auto contrib_grid = [&](uint32_t units) { return nblk(units, FC_WARPS); };  // a warp per snippet
+  FbLaneParams pw;  // the same snippets for the kernels that walk the trie
+  pw.f = pn.f;
+  pw.blob_end = d_text + n_bytes;
+  pw.B = pn.B;
+  const bool split = rows_ok;  // beta chains stored and run beside the alpha chains, counts by a third kernel
   const uint32_t lane_blocks = nblk(n_lane, FR_WARPS * 32);
+  static_assert(FR_WARPS == FL_WARPS && FRC_WARPS == FC_WARPS, "one launch shape for both sets of lane kernels");
   // forward / backward device times (tgx_model_last_stat 2, 3) are taken on the stream that carries most snippets
   cudaStream_t st_ev = (n_lane > ps.u.count) ? m->stream3 : st;
   CU(cudaEventRecord(m->w().ev[0], st_ev));
@@ -1910,7 +1936,8 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   }
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
   if (n_lane) {
-    if (drop) fbr_split_kernel<true><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
+    if (!use_rows) fb_split_lane_kernel<<<2 * lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pw);
+    else if (drop) fbr_split_kernel<true><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
     else fbr_split_kernel<false><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
@@ -1920,16 +1947,20 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     CU(cudaStreamWaitEvent(m->stream2, m->ev_join4, 0));
     FbRowsParams pc = pn;
     pc.f.u = pl.u;
-    if (drop) fbr_contrib_kernel<true><<<nblk(pl.u.count, FRC_WARPS), FRC_WARPS * 32, 0, m->stream2>>>(pc);
-    else fbr_contrib_kernel<false><<<nblk(pl.u.count, FRC_WARPS), FRC_WARPS * 32, 0, m->stream2>>>(pc);
+    FbLaneParams pcw = pw;
+    pcw.f.u = pl.u;
+    if (!use_rows) fb_contrib_kernel<<<contrib_grid(pl.u.count), FC_WARPS * 32, 0, m->stream2>>>(pcw);
+    else if (drop) fbr_contrib_kernel<true><<<contrib_grid(pl.u.count), FRC_WARPS * 32, 0, m->stream2>>>(pc);
+    else fbr_contrib_kernel<false><<<contrib_grid(pl.u.count), FRC_WARPS * 32, 0, m->stream2>>>(pc);
     m->w().stats.launches += 1;
   } else {
     CU(launch_fb_g(m, 32, pl, true, m->stream2));
   }
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
   if (n_lane) {  // alpha and beta are both there: the counts
-    if (drop) fbr_contrib_kernel<true><<<nblk(n_lane, FRC_WARPS), FRC_WARPS * 32, 0, m->stream3>>>(pn);
-    else fbr_contrib_kernel<false><<<nblk(n_lane, FRC_WARPS), FRC_WARPS * 32, 0, m->stream3>>>(pn);
+    if (!use_rows) fb_contrib_kernel<<<contrib_grid(n_lane), FC_WARPS * 32, 0, m->stream3>>>(pw);
+    else if (drop) fbr_contrib_kernel<true><<<contrib_grid(n_lane), FRC_WARPS * 32, 0, m->stream3>>>(pn);
+    else fbr_contrib_kernel<false><<<contrib_grid(n_lane), FRC_WARPS * 32, 0, m->stream3>>>(pn);
     m->w().stats.launches += 1;
   }
   CU(cudaGetLastError());
@@ -1938,10 +1969,8 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   CU(cudaStreamWaitEvent(st, m->ev_join, 0));
   CU(cudaEventRecord(m->ev_join3, m->stream3));
   CU(cudaStreamWaitEvent(st, m->ev_join3, 0));
-  if (p.hot_k) {
-    fold_hot_acc_kernel<<<nblk(p.hot_k, 256), 256, 0, st>>>(p.hot_acc, p.hot_k, p.hot_r, p.acc);
-    m->w().stats.launches += 1;
-  }
+  fold_hot_acc_kernel<<<nblk(m->V, 256), 256, 0, st>>>(p.hot_acc, p.hot_k, p.hot_r, p.acc, (uint32_t)m->V);
+  m->w().stats.launches += 1;
   export_acc_kernel<<<nblk(m->V, 256), 256, 0, st>>>(p.acc, (uint32_t)m->V, d_expected, d_limbs);
   m->w().stats.launches += 1;
   int64_t bad = -1;

@@ -26,6 +26,10 @@
 namespace tgxk {
 
 constexpr int FR_WARPS = 4;
+// cheap steps a lane may take per trip before the warp goes on to the fold without it: unbounded, one lane in a stretch
+// of text where every fold is a first term (nothing to log_sum_exp for hundreds of positions) held its whole warp in
+// the cheap loop (ncu: 8 of 32 threads per instruction, 131 warp instructions per position)
+constexpr int FR_CHEAP = 4;
 
 struct FbRowsParams {
   FbParams f;               // units, A, status, accumulators, dropout
@@ -84,7 +88,7 @@ __device__ __forceinline__ void fbr_forward_body(const FbRowsParams& q, uint32_t
   uint32_t ts = 0;
   double y = 0.0;
   while (__any_sync(0xFFFFFFFFu, active)) {
-    while (active && !pending) {
+    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
       if (m) {
         const uint32_t l = (uint32_t)__ffs((int)m);
         m &= m - 1u;
@@ -117,6 +121,7 @@ __device__ __forceinline__ void fbr_forward_body(const FbRowsParams& q, uint32_t
         }
       }
     }
+    __syncwarp();  // every lane is out of its cheap steps: the fold below runs with the whole warp (ncu without it: 8 of 32 threads per instruction — the lanes ran ahead into the fold one by one)
     if (pending) {
       acc[ts * 32] = log_sum_exp(acc[ts * 32], y, lt);
       pending = false;
@@ -159,7 +164,7 @@ __device__ __forceinline__ void fbr_backward_body(const FbRowsParams& q, uint32_
   bool first = true, pending = false;
   double y = 0.0;
   while (__any_sync(0xFFFFFFFFu, active)) {
-    while (active && !pending) {
+    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
       if (m) {  // ascending length = begin_nodes[pos] order
         const uint32_t l = (uint32_t)__ffs((int)m);
         m &= m - 1u;
@@ -188,6 +193,7 @@ __device__ __forceinline__ void fbr_backward_body(const FbRowsParams& q, uint32_
         }
       }
     }
+    __syncwarp();  // every lane is out of its cheap steps: the fold below runs with the whole warp (ncu without it: 8 of 32 threads per instruction — the lanes ran ahead into the fold one by one)
     if (pending) {
       b = log_sum_exp(b, y, lt);
       pending = false;
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(FRC_WARPS * 32) fbr_contrib_kernel(FbRowsParam
   double total = 0.0;
   uint32_t id = 0;
   while (__any_sync(0xFFFFFFFFu, active)) {
-    while (active && !pending) {
+    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
       if (m) {
         const uint32_t l = (uint32_t)__ffs((int)m);
         m &= m - 1u;
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(FRC_WARPS * 32) fbr_contrib_kernel(FbRowsParam
         }
       }
     }
+    __syncwarp();
     if (pending) {
       acc_add(acc_slot(p, blockIdx.x, id), tgx_exp(total, lt));
       pending = false;
@@ -271,27 +278,23 @@ __global__ void __launch_bounds__(FRC_WARPS * 32) fbr_contrib_kernel(FbRowsParam
 }
 
 // replicas of the hot ids -> the accumulators (exact integer sums)
-__device__ __host__ __forceinline__ void acc3_add(unsigned long long (&a)[3], unsigned long long b0, unsigned long long b1,
-                                                  unsigned long long b2) {
-  unsigned long long s0 = a[0] + b0;
-  unsigned long long c = s0 < a[0] ? 1ull : 0ull;
-  unsigned long long s1 = a[1] + b1;
+__device__ __host__ __forceinline__ void acc3_add(unsigned long long (&a)[3], const unsigned long long* b) {
+  const unsigned long long s0 = a[0] + b[0];
+  const unsigned long long c0 = s0 < a[0] ? 1ull : 0ull;
+  const unsigned long long s1 = a[1] + b[1];
   unsigned long long c1 = s1 < a[1] ? 1ull : 0ull;
-  const unsigned long long s1c = s1 + c;
+  const unsigned long long s1c = s1 + c0;
   if (s1c < s1) c1++;
   a[0] = s0;
   a[1] = s1c;
-  a[2] += b2 + c1;
+  a[2] += b[2] + c1;
 }
 __global__ void fold_hot_acc_kernel(const unsigned long long* __restrict__ hot_acc, uint32_t hot_k, uint32_t hot_r,
-                                    unsigned long long* __restrict__ acc) {
+                                    unsigned long long* __restrict__ acc, uint32_t V) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hot_k) return;
+  if (i >= hot_k || i >= V) return;
   unsigned long long a[3] = {acc[3 * (size_t)i], acc[3 * (size_t)i + 1], acc[3 * (size_t)i + 2]};
-  for (uint32_t r = 0; r < hot_r; r++) {
-    const unsigned long long* h = hot_acc + ((size_t)r * hot_k + i) * 3;
-    acc3_add(a, h[0], h[1], h[2]);
-  }
+  for (uint32_t r = 0; r < hot_r; r++) acc3_add(a, hot_acc + ((size_t)r * hot_k + i) * 3);
   acc[3 * (size_t)i] = a[0];
   acc[3 * (size_t)i + 1] = a[1];
   acc[3 * (size_t)i + 2] = a[2];

@@ -95,6 +95,11 @@ struct FbParams {
 };
 
 constexpr int ACC_LIMBS = 3;  // u64 words per accumulator
+// c -> integer part + 128 fraction bits in two 64-bit words, added with integer atomics; a carry out of a word goes
+// into the next one as a separate atomic (the additions commute, so the sum stays exact whatever the order).
+// (Measured alternative: four 32-bit chunks in counters of their own, no carries and so no atomic that has to return
+//  a value, but two reductions for a typical contribution instead of one: 87 ms per GB in the counts kernel against
+//  69 for this form and 35 for f64 atomics, which are not reproducible.)
 __device__ __forceinline__ void acc_add(unsigned long long* slot, double c) {
   unsigned long long ip = 0;
   double fr = c;
@@ -1169,6 +1174,294 @@ __global__ void __launch_bounds__(WPB * 32) fb_backward_kernel(FbParams p, doubl
       }
       __syncwarp();
       sl = sl == 0 ? W - 1 : sl - 1;
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// K4L / K5L  forward-backward, one LANE per snippet (snippets below the lane threshold, max_token_len <= 16).
+//
+// The lane-group kernels above advance 32 / G chains per warp instruction (ncu, G = 4: 11 of 32 threads active,
+// 194 warp instructions per position); here every lane of a warp is its own snippet, so one warp instruction
+// advances up to 32 chains.  The folds are the same operations in the same order (forward: ascending start per end
+// position; backward: ascending length per start position), so A, B and every contribution are bit-identical to
+// the lane-group kernels'.  The trie walk is fused with the fold: a terminal met at depth d is folded at once.
+// Per lane: a 16-slot window of accumulators in shared memory ([slot][lane]: conflict-free), the "seen" flags in
+// a register, the next 16 text bytes in two registers refilled one aligned 8-byte word per 8 positions.
+// -----------------------------------------------------------------------------------------
+constexpr int FL_WARPS = 4;
+
+struct FbLaneParams {
+  FbParams f;
+  const uint8_t* blob_end;
+  double* B;  // [N + U] backward log-probabilities (split form only)
+};
+
+__device__ __forceinline__ unsigned long long fl_word(const uint8_t* a, const uint8_t* blob_end) {
+  return a < blob_end ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : 0ull;
+}
+
+// Both kernels run a FLATTENED walk: one loop iteration = one trie probe of the lane's own (position, depth) state,
+// whatever position the other lanes are at, so a lane never waits for the deepest walk of its warp and the fold
+// below runs with most lanes active (ncu on the position-synchronous version: 8 of 32 threads per instruction).
+// The next probe is issued before the fold of the current terminal, which hides its latency.
+__device__ __forceinline__ uint32_t fl_byte(unsigned long long lo, unsigned long long hi, uint32_t d) {
+  return (uint32_t)((d < 8 ? lo : hi) >> (8 * (d & 7u))) & 0xFFu;
+}
+
+__device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
+                                                     const LibmTabs& lt) {
+  const FbParams& p = q.f;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = s_win + warp * (16 * 32) + lane;  // slot s at acc[s * 32]
+  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
+  const bool has = gidx < u.count;
+  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  const uint32_t n = has ? u.unit_len[unit] : 0;
+  const uint64_t start = has ? u.unit_start[unit] : 0;
+  double* A = p.A + start + unit;
+  if (has) A[0] = 0.0;
+  if (has && n == 0) p.status[unit] = 7;  // z = 0.0 is not normal (Q11)
+  bool active = has && n != 0;
+  const uint8_t* tp = u.text + start;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<unsigned long long>(tp) & ~7ull);
+  uint32_t sh = (uint32_t)(tp - base);
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;
+  if (active) {
+    w0 = fl_word(base, q.blob_end);
+    w1 = fl_word(base + 8, q.blob_end);
+    w2 = fl_word(base + 16, q.blob_end);
+  }
+  unsigned long long lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
+  unsigned long long hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
+  uint32_t seen = 0, pos = 0, d = 0, limit = min(16u, n), xb = u.root_base;
+  double a = 0.0;  // alpha of the nodes that start at pos; 0.0 when nothing ends there (src/lattice.rs:255, Q7)
+  uint32_t cw = 0x100u | fl_byte(lo, hi, 0);
+  uint4 e = __ldg(u.trie + (xb ^ cw));
+  // The vote makes every iteration a convergence point: without it the lanes of a warp drift into separate
+  // instruction streams (ncu: 7 of 32 threads active per instruction).
+  while (__any_sync(0xFFFFFFFFu, active)) {
+    if (active) {
+      const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
+      const bool term = hit && (e.y & F_TERM);
+      const double y = __dadd_rn(__hiloint2double((int)e.w, (int)e.z), a);  // nodes[lid].score + alpha[lid]
+      const uint32_t ts = (pos + d + 1u) & 15u;
+      const bool cont = hit && (e.y & F_HASCH) && (d + 1u < limit);
+      if (cont) {
+        d++;
+        xb = e.x >> 9;
+      } else {
+        pos++;
+        d = 0;
+        xb = u.root_base;
+        if (pos < n) {
+          if (++sh == 8) {
+            sh = 0;
+            base += 8;
+            w0 = w1;
+            w1 = w2;
+            w2 = fl_word(base + 16, q.blob_end);
+          }
+          lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
+          hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
+          limit = min(16u, n - pos);
+        }
+      }
+      cw = 0x100u | fl_byte(lo, hi, d);
+      e = __ldg(u.trie + (xb ^ cw));  // the next probe flies while the terminal below is folded
+      if (term) {
+        if ((seen >> ts) & 1u) {
+          acc[ts * 32] = log_sum_exp(acc[ts * 32], y, lt);
+        } else {  // lid == end_nodes[pos][0] -> init_mode
+          acc[ts * 32] = y;
+          seen |= 1u << ts;
+        }
+      }
+      if (!cont) {  // pos is the NEXT position now: everything that ends there has been folded
+        const uint32_t sl = pos & 15u;
+        a = ((seen >> sl) & 1u) ? acc[sl * 32] : 0.0;
+        seen &= ~(1u << sl);
+        A[pos] = a;
+        if (pos == n) {  // a = alpha[eos]
+          const double az = fabs(a);
+          const bool normal = (az >= 2.2250738585072014e-308) && (az <= 1.7976931348623157e308);  // f64::is_normal
+          p.status[unit] = normal ? 0 : 7;
+          active = false;
+        }
+      }
+    }
+  }
+}
+
+// STORE_B: only the beta chain, written to q.B (same layout as A) — it needs neither A nor z, so it runs BESIDE the
+// forward kernel and fb_contrib_kernel adds the expected counts afterwards; the longest snippet then costs
+// max(forward, backward) instead of their sum.  !STORE_B: the fused form (after the forward kernel).
+template <bool STORE_B>
+__device__ __forceinline__ void fb_backward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
+                                                      const LibmTabs& lt) {
+  const FbParams& p = q.f;
+  const UnitParams& u = p.u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* wB = s_win + warp * (16 * 32) + lane;
+  const uint64_t gidx = (uint64_t)bid * (FL_WARPS * 32) + threadIdx.x;
+  const bool has = gidx < u.count;
+  const uint32_t unit = has ? u.order[u.first + gidx] : 0;
+  const uint32_t n = has ? u.unit_len[unit] : 0;
+  // bad z: the reference panics; nothing is added
+  bool active = has && n != 0 && (STORE_B || p.status[unit] == 0);
+  const uint64_t start = has ? u.unit_start[unit] : 0;
+  const double* A = p.A + start + unit;
+  double* Bout = q.B + start + unit;
+  const double z = (active && !STORE_B) ? A[n] : 0.0;
+  wB[(n & 15u) * 32] = 0.0;  // beta at the end of the sentence (EOS)
+  if (STORE_B && has) Bout[n] = 0.0;
+  uint32_t pos = active ? n - 1 : 0;
+  const uint8_t* tp = u.text + start + pos;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<unsigned long long>(tp) & ~7ull);
+  uint32_t sh = (uint32_t)(tp - base);
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;
+  if (active) {
+    w0 = fl_word(base, q.blob_end);
+    w1 = fl_word(base + 8, q.blob_end);
+    w2 = fl_word(base + 16, q.blob_end);
+  }
+  unsigned long long lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
+  unsigned long long hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
+  double a = (active && !STORE_B) ? A[pos] : 0.0, a_next = (active && !STORE_B && pos) ? A[pos - 1] : 0.0;
+  double b = 0.0;  // stays 0.0 when nothing begins at pos (Q7)
+  bool first = true;
+  uint32_t d = 0, limit = 1, xb = u.root_base;
+  uint32_t cw = 0x100u | fl_byte(lo, hi, 0);
+  uint4 e = __ldg(u.trie + (xb ^ cw));
+  while (__any_sync(0xFFFFFFFFu, active)) {
+    if (active) {
+      const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
+      const bool term = hit && (e.y & F_TERM);
+      const double sc = __hiloint2double((int)e.w, (int)e.z);
+      const double bt = wB[((pos + d + 1u) & 15u) * 32];
+      const uint32_t id = e.y & ID_MASK;
+      const bool cont = hit && (e.y & F_HASCH) && (d + 1u < limit);
+      uint32_t nxb = u.root_base, nd = 0;
+      if (cont) {
+        nd = d + 1;
+        nxb = e.x >> 9;
+      } else if (pos != 0) {  // first probe of position pos - 1
+        if (sh != 0) {
+          sh--;
+        } else {
+          sh = 7;
+          base -= 8;
+          w2 = w1;
+          w1 = w0;
+          w0 = fl_word(base, q.blob_end);
+        }
+        lo = sh ? ((w0 >> (8 * sh)) | (w1 << (64 - 8 * sh))) : w0;
+        hi = sh ? ((w1 >> (8 * sh)) | (w2 << (64 - 8 * sh))) : w1;
+      }
+      cw = 0x100u | fl_byte(lo, hi, nd);
+      e = __ldg(u.trie + (nxb ^ cw));  // the next probe flies while the terminal below is folded
+      if (term) {  // ascending length = begin_nodes[pos] order
+        const double y = __dadd_rn(sc, bt);  // nodes[rid].score + beta[rid]
+        b = first ? y : log_sum_exp(b, y, lt);
+        first = false;
+        if (!STORE_B) {
+          // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
+          const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), bt), -z);
+          acc_add(acc_slot(p, bid, id), tgx_exp(total, lt));
+        }
+      }
+      d = nd;
+      xb = nxb;
+      if (!cont) {
+        wB[(pos & 15u) * 32] = b;
+        if (STORE_B) Bout[pos] = b;
+        if (pos == 0) {
+          active = false;
+        } else {
+          pos--;
+          if (!STORE_B) {
+            a = a_next;
+            a_next = pos ? A[pos - 1] : 0.0;
+          }
+          b = 0.0;
+          first = true;
+          limit = min(16u, n - pos);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  fb_forward_lane_body(q, blockIdx.x, s_win, lt);
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  fb_backward_lane_body<false>(q, blockIdx.x, s_win, lt);
+}
+
+// Split form: even blocks run the forward chains of 128 snippets, odd blocks the beta chains of the same snippets,
+// so the block scheduler starts the longest snippets of BOTH directions first (two kernels on two streams do not
+// interleave: the second kernel's blocks wait for the first kernel's to be dispatched).
+__global__ void __launch_bounds__(FL_WARPS * 32) fb_split_lane_kernel(FbLaneParams q) {
+  __shared__ double s_win[FL_WARPS * 16 * 32];
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  if (blockIdx.x & 1u) fb_backward_lane_body<true>(q, blockIdx.x >> 1, s_win, lt);
+  else fb_forward_lane_body(q, blockIdx.x >> 1, s_win, lt);
+}
+
+// Expected counts from stored alpha and beta (split form): one warp per snippet, a lane per start position.
+// exp(alpha[pos] + score + beta[pos + len] - z) per matched token, in the reference's operation order
+// (src/lattice.rs:295-309), so every contribution equals the fused kernels' bit for bit.
+constexpr int FC_WARPS = 8;
+
+// (Measured alternative: the counts of the ~1800 smallest ids in shared memory, flushed once per block of a persistent
+//  grid — 133 ms per GB against 69: every thread of a block then hammers the same few shared-memory words of the
+//  hottest tokens, where the global accumulators have 256 replicas.)
+__global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams q) {
+  __shared__ unsigned long long s_et[256];
+  __shared__ double s_lt[256];
+  const FbParams& p = q.f;
+  const UnitParams& u = p.u;
+  const LibmTabs lt = stage_libm_tables(s_et, s_lt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t widx = (uint64_t)blockIdx.x * FC_WARPS + warp;
+  if (widx >= u.count) return;
+  const uint32_t unit = u.order[u.first + widx];
+  if (p.status[unit] != 0) return;  // bad z: the reference panics; nothing is added
+  const uint32_t n = u.unit_len[unit];
+  const uint64_t start = u.unit_start[unit];
+  const double* A = p.A + start + unit;
+  const double* B = q.B + start + unit;
+  const uint8_t* text = u.text + start;
+  const double z = A[n];
+  for (uint32_t pos = lane; pos < n; pos += 32) {
+    const double a = A[pos];
+    const uint32_t limit = min(16u, n - pos);
+    uint32_t xb = u.root_base;
+    for (uint32_t d = 0; d < limit; d++) {
+      const uint32_t cw = 0x100u | __ldg(text + pos + d);
+      const uint4 e = __ldg(u.trie + (xb ^ cw));
+      if ((e.x ^ cw) & 0x1FFu) break;
+      if (e.y & F_TERM) {
+        const double sc = __hiloint2double((int)e.w, (int)e.z);
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), B[pos + d + 1]), -z);
+        const uint32_t id = e.y & ID_MASK;
+        acc_add(acc_slot(p, blockIdx.x, id), tgx_exp(total, lt));
+      }
+      if (!(e.y & F_HASCH)) break;
+      xb = e.x >> 9;
     }
   }
 }

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -169,12 +170,17 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     alloc_order.reserve(bfs.size());
     size_t shallow = 0;
     while (shallow < bfs.size() && depth[bfs[shallow]] < 2) alloc_order.push_back(bfs[shallow++]);
-    std::vector<uint32_t> deep;
+    // (weights are non-negative floats: their bit patterns order like the values; ties keep BFS order)
+    std::vector<uint64_t> deep;
     deep.reserve(bfs.size() - shallow);
     for (size_t i = shallow; i < bfs.size(); i++)
-      if (nodes[bfs[i]].first_child) deep.push_back(bfs[i]);
-    std::stable_sort(deep.begin(), deep.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
-    alloc_order.insert(alloc_order.end(), deep.begin(), deep.end());
+      if (nodes[bfs[i]].first_child) {
+        uint32_t wb;
+        std::memcpy(&wb, &weight[bfs[i]], 4);
+        deep.push_back(((uint64_t)(~wb) << 32) | (uint32_t)i);
+      }
+    std::sort(deep.begin(), deep.end());
+    for (uint64_t k : deep) alloc_order.push_back(bfs[(uint32_t)k]);
   }
   lap("order");
   for (uint32_t nidx : alloc_order) {
@@ -250,54 +256,21 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     out->slots[nd.slot] = s;
   }
   lap("emit");
-  // 6. match tables (trie_build.h): one row per terminal node, hottest (highest score) first
+  // 6. what build_match_tables needs later (the match tables are built on first use: trie_build.h)
   out->slots8.clear();
   out->rows.clear();
   out->row_ids.clear();
+  out->node_parent.clear();
   if (max_len >= 1 && max_len <= 16) {
-    // terminal nodes in id order (ids are unique per terminal: the last duplicate owns the node) ...
-    std::vector<uint32_t> node_of_id(V, 0);
-    for (uint32_t i = 1; i < nodes.size(); i++)
-      if (nodes[i].term_id >= 0) node_of_id[nodes[i].term_id] = i;
-    std::vector<uint32_t> terms;
-    terms.reserve(n_term);
-    for (uint64_t id = 0; id < V; id++)
-      if (node_of_id[id]) terms.push_back(node_of_id[id]);
-    // ... which is already hottest-first for a score-sorted vocabulary (the usual case); otherwise sort
-    auto hotter = [&](uint32_t a, uint32_t b) { return scores[nodes[a].term_id] > scores[nodes[b].term_id]; };
-    if (!std::is_sorted(terms.begin(), terms.end(), hotter)) std::stable_sort(terms.begin(), terms.end(), hotter);
-    const double ninf = -INFINITY;
-    std::vector<uint32_t> row_of(nodes.size(), 0);
-    uint64_t units16 = 9;  // row 0: header + 16 x -inf (+ pad)
-    for (uint32_t nd : terms) {
-      row_of[nd] = (uint32_t)units16;
-      units16 += (depth[nd] + 2u) / 2u;  // header + depth scores, padded to 16 bytes
-    }
-    if (units16 > SLOT8_OFF_MASK) return "row table too large";
-    out->rows.assign(units16 * 2, ninf);
-    out->row_ids.assign(units16 * 2, 0xFFFFFFFFu);
-    const uint64_t zero_bits = 0;
-    std::memcpy(&out->rows[0], &zero_bits, 8);
-    for (uint32_t nd : terms) {
-      const size_t base = (size_t)row_of[nd] * 2;
-      uint64_t mask = 0;
-      for (uint32_t a = nd; a; a = parent[a])
-        if (nodes[a].term_id >= 0) {
-          out->rows[base + depth[a]] = scores[nodes[a].term_id];
-          out->row_ids[base + depth[a]] = (uint32_t)nodes[a].term_id;
-          mask |= 1ull << (depth[a] - 1);
-        }
-      std::memcpy(&out->rows[base], &mask, 8);
-      out->row_ids[base] = (uint32_t)mask;
-    }
-    out->slots8.assign(n_slots, 0);
+    out->node_parent = std::move(parent);
+    out->node_depth = std::move(depth);
+    out->node_slot.resize(nodes.size());
+    out->node_term.resize(nodes.size());
+    out->node_score.assign(nodes.size(), 0.0);
     for (size_t i = 0; i < nodes.size(); i++) {
-      const Node& nd = nodes[i];
-      const Slot& sl = out->slots[nd.slot];
-      uint32_t y = 0;
-      if (nd.first_child) y |= SLOT8_HASCH;
-      if (nd.term_id >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
-      out->slots8[nd.slot] = (uint64_t)sl.x | ((uint64_t)y << 32);
+      out->node_slot[i] = nodes[i].slot;
+      out->node_term[i] = nodes[i].term_id;
+      if (nodes[i].term_id >= 0) out->node_score[i] = scores[nodes[i].term_id];
     }
   }
   lap("rows");
@@ -306,6 +279,70 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   out->n_nodes = (uint32_t)nodes.size();
   out->n_terminals = n_term;
   for (int d = 1; d <= 2; d++) out->hot[d] = std::min<uint32_t>(std::max(out->hot[d], 256u), n_slots);
+  return "";
+}
+
+std::string build_match_tables(DoubleArray* out) {
+  if (!out->slots8.empty()) return "";
+  if (out->node_parent.empty()) return "no match tables for this vocabulary (tokens longer than 16 bytes)";
+  const std::vector<uint32_t>& parent = out->node_parent;
+  const std::vector<uint8_t>& depth = out->node_depth;
+  const size_t n_nodes = parent.size();
+  const size_t n_slots = out->slots.size();
+  // terminal nodes in id order (ids are unique per terminal: the last duplicate owns the node) ...
+  std::vector<std::pair<int32_t, uint32_t>> byid;
+  byid.reserve(out->n_terminals);
+  for (uint32_t i = 1; i < n_nodes; i++)
+    if (out->node_term[i] >= 0) byid.emplace_back(out->node_term[i], i);
+  std::sort(byid.begin(), byid.end());
+  std::vector<uint32_t> terms;
+  terms.reserve(byid.size());
+  for (auto& pr : byid) terms.push_back(pr.second);
+  // ... which is already hottest-first for a score-sorted vocabulary (the usual case); otherwise sort
+  auto hotter = [&](uint32_t a, uint32_t b) { return out->node_score[a] > out->node_score[b]; };
+  if (!std::is_sorted(terms.begin(), terms.end(), hotter)) std::stable_sort(terms.begin(), terms.end(), hotter);
+  const double ninf = -INFINITY;
+  std::vector<uint32_t> row_of(n_nodes, 0);
+  uint64_t units16 = 9;  // row 0: header + 16 x -inf (+ pad)
+  for (uint32_t nd : terms) {
+    row_of[nd] = (uint32_t)units16;
+    units16 += (depth[nd] + 2u) / 2u;  // header + depth scores, padded to 16 bytes
+  }
+  if (units16 > SLOT8_OFF_MASK) return "row table too large";
+  out->rows.assign(units16 * 2, ninf);
+  out->row_ids.assign(units16 * 2, 0xFFFFFFFFu);
+  const uint64_t zero_bits = 0;
+  std::memcpy(&out->rows[0], &zero_bits, 8);
+  auto fill = [&](size_t lo, size_t hi) {
+    for (size_t t = lo; t < hi; t++) {
+      const uint32_t nd = terms[t];
+      const size_t base = (size_t)row_of[nd] * 2;
+      uint64_t mask = 0;
+      for (uint32_t a = nd; a; a = parent[a])
+        if (out->node_term[a] >= 0) {
+          out->rows[base + depth[a]] = out->node_score[a];
+          out->row_ids[base + depth[a]] = (uint32_t)out->node_term[a];
+          mask |= 1ull << (depth[a] - 1);
+        }
+      std::memcpy(&out->rows[base], &mask, 8);
+      out->row_ids[base] = (uint32_t)mask;
+    }
+  };
+  {
+    const size_t T = terms.size() >= 65536 ? 4 : 1;  // rows are disjoint: a few host threads
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < T; k++) th.emplace_back(fill, terms.size() * k / T, terms.size() * (k + 1) / T);
+    fill(0, terms.size() / T);
+    for (auto& x : th) x.join();
+  }
+  out->slots8.assign(n_slots, 0);
+  for (size_t i = 0; i < n_nodes; i++) {
+    const Slot& sl = out->slots[out->node_slot[i]];
+    uint32_t y = 0;
+    if (sl.y & SLOT_HASCH) y |= SLOT8_HASCH;
+    if (out->node_term[i] >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
+    out->slots8[out->node_slot[i]] = (uint64_t)sl.x | ((uint64_t)y << 32);
+  }
   return "";
 }
 

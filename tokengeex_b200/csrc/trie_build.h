@@ -58,10 +58,18 @@ struct DoubleArray {
   // multiple of 16 bytes.  row_ids has the same layout with the token ids (0xFFFFFFFF = no token; [off] = the mask).
   // Rows are laid out by descending score of their own token (frequent tokens first), so the first bytes of the table
   // are the hot ones.  Row 0 = empty mask + 16 x -inf = "no token starts here".
+  // Built on first use (build_match_tables) from the node arrays below, which build_double_array keeps: the EM loop
+  // rebuilds the model ~30 times and only some of its passes read the tables.
   std::vector<uint64_t> slots8;
   std::vector<double> rows;
   std::vector<uint32_t> row_ids;
+  std::vector<uint32_t> node_parent, node_slot;  // per trie node (node 0 = root); empty when max_token_len > 16
+  std::vector<int32_t> node_term;                // token id that ends at the node, or -1
+  std::vector<uint8_t> node_depth;
+  std::vector<double> node_score;
 };
+// Fills slots8 / rows / row_ids (no-op when they are there).  Returns "" on success.
+std::string build_match_tables(DoubleArray* da);
 constexpr uint32_t SLOT8_TERM = 1u << 31, SLOT8_HASCH = 1u << 30, SLOT8_OFF_MASK = 0x0FFFFFFFu;
 
 // Returns "" on success, else an error message.

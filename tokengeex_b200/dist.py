@@ -68,6 +68,18 @@ class Collective:
         t = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
         return self.allreduce_tensor(t).cpu().numpy()
 
+    def broadcast_u32(self, v, src: int = 0) -> np.ndarray:
+        """Rank `src`'s uint32 vector on every rank (the others pass None): length first, then the values."""
+        torch = self.torch
+        n = torch.tensor([len(v) if self.rank == src else 0], dtype=torch.int64, device=self.device)
+        self.dist.broadcast(n, src, group=self.group)
+        if self.rank == src:
+            t = torch.from_numpy(np.ascontiguousarray(v, np.uint32).view(np.int32).copy()).to(self.device)
+        else:
+            t = torch.empty(int(n[0]), dtype=torch.int32, device=self.device)
+        self.dist.broadcast(t, src, group=self.group)
+        return t.cpu().numpy().view(np.uint32)
+
     def sum_int(self, x: int) -> int:
         return int(self.allreduce(np.array([x], np.uint64))[0])
 

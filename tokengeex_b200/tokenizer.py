@@ -256,6 +256,23 @@ class Tokenizer:
     def special_tokens(self) -> List[str]:
         return list(self._special)
 
+    def add_base_tokens(self, tokens: Sequence[Tuple[bytes, float]], keep: bool = False) -> None:
+        """Tokenizer::add_base_tokens -> Model::add_tokens (src/tokenizer.rs:56-61, src/model.rs:184-194; Rust API
+        only, used by `merge`): the tokens get the next ids, the token -> id map takes the new id of a duplicate (the
+        trie's last-duplicate-wins rule) and the device model is rebuilt with the extended vocabulary on the next
+        encode.  Special-token ids move up by len(tokens), as in the reference (ids >= base_vocab_size())."""
+        for value, score in tokens:
+            value = bytes(value)
+            self._token_to_id[value] = len(self._tokens)
+            self._tokens.append(value)
+        if tokens:
+            self._scores = np.concatenate([self._scores, np.asarray([float(s) for _, s in tokens], np.float64)])
+            self._keep = np.concatenate([self._keep, np.full(len(tokens), 1 if keep else 0, np.uint8)])
+            for m in (self._model, self._model_bytes_only, self._host_model):
+                if m is not None:
+                    m.close()
+            self._model = self._model_bytes_only = self._host_model = None
+
     def vocab_size(self) -> int:
         return len(self._tokens) + len(self._special)
 
