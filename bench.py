@@ -34,6 +34,15 @@ METRIC = "encode_input_throughput"
 UNIT = "MB/s"
 
 
+_JSON_OUT = None  # see main(): the original stdout when NCCL may write to descriptor 1
+
+
+def emit_json(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def env_int(k, d):
     return int(os.environ.get(k, d))
 
@@ -392,11 +401,13 @@ def main():
         numa_node = bind_to_gpu_numa_node(local)  # host buffers next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own log goes to stderr-side files when the caller asks for it (NCCL_DEBUG=INFO prints to stdout, which
-        # has to carry exactly one JSON line): the setting itself is left alone
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE", "VERSION") and "NCCL_DEBUG_FILE" not in os.environ:
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log")
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        # NCCL_DEBUG is left as the caller set it.  NCCL writes its log to file descriptor 1, which has to carry exactly
+        # one JSON line: from here on descriptor 1 IS stderr (so the communicator lines stay visible to whoever captures
+        # the run) and the JSON line goes out through a private copy of the original stdout.
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -406,8 +417,8 @@ def main():
     if args.only_schedule:
         sched = run_prune_schedule(args, rank, world, local, torch, dist, N, synth)
         if rank == 0:
-            print(json.dumps({"metric": "prune_schedule_wall_s", "unit": "s", "n_gpus": world, "higher_is_better": False,
-                              "value": min(r["wall_s"] for r in sched["runs"]), "prune_schedule": sched}), flush=True)
+            emit_json({"metric": "prune_schedule_wall_s", "unit": "s", "n_gpus": world, "higher_is_better": False,
+                       "value": min(r["wall_s"] for r in sched["runs"]), "prune_schedule": sched})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -638,7 +649,7 @@ def main():
                 "cpu_baseline": cpu,
                 "sampled_parity": sampled,
                 "prune_iter": prune_iter, "prune_schedule": prune_schedule}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 

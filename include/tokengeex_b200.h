@@ -99,7 +99,8 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
                      uint32_t* ids, uint64_t ids_cap, uint64_t* id_off, int32_t* status, uint64_t* proc_len,
                      int64_t* first_bad);
 /* Same with device-resident inputs and outputs.  n_bytes = off[S].  *total_ids (host)
- * receives id_off[S]. */
+ * receives id_off[S].  d_off must be non-decreasing with samples shorter than 2^32 bytes (the host variants check it
+ * and return TGX_ERR_INVALID / TGX_ERR_UNSUPPORTED; the device variants do not read the offsets on the host). */
 int tgx_encode_batch_dev(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint64_t S,
                          uint64_t n_bytes, uint32_t flags, uint32_t* d_ids, uint64_t ids_cap,
                          uint64_t* d_id_off, int32_t* d_status, uint64_t* d_proc_len, uint64_t* total_ids,

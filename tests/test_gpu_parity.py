@@ -423,3 +423,17 @@ def test_very_long_samples(N):
     assert rc == 0 and counts_rel_err(ex, want) < REL_TOL
     fr = gm.token_frequencies(blob, off)[0]
     assert np.array_equal(fr, om.token_frequencies(blob, off, threads=8))
+
+
+def test_host_entry_point_rejects_bad_offsets(N):
+    """Offsets that decrease are an argument error (nothing is encoded, nothing is truncated silently)."""
+    import ctypes as C
+    m = N.Model([b"a", b"b"], [-1.0, -1.0])
+    blob = np.frombuffer(b"abab", np.uint8).copy()
+    off = np.array([0, 3, 2, 4], np.uint64)
+    ids, id_off = np.zeros(8, np.uint32), np.zeros(4, np.uint64)
+    rc = N.lib().tgx_encode_batch(m._h, blob.ctypes.data_as(N.u8p), off.ctypes.data_as(N.u64p), 3, 0,
+                                  ids.ctypes.data_as(N.u32p), 8, id_off.ctypes.data_as(N.u64p), None, None, None)
+    assert rc == N.TGX_ERR_INVALID and b"decrease" in N.lib().tgx_last_error()
+    ids2, id_off2, status, plen, rc, bad = m.encode_batch(blob, np.array([0, 2, 2, 4], np.uint64))
+    assert rc == 0 and ids2.tolist() == [0, 1, 0, 1] and id_off2.tolist() == [0, 2, 2, 4]

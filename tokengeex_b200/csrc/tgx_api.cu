@@ -105,6 +105,9 @@ struct tgx_model {
   cudaStream_t stream2 = nullptr;  // long units run beside the short ones (E-step)
   cudaStream_t stream3 = nullptr;  // lane-per-snippet kernels (E-step)
   cudaStream_t stream4 = nullptr;  // beta chains of the warp-per-snippet kernels in split form
+  cudaStream_t stream5 = nullptr, stream6 = nullptr;  // second / third group of lane snippets (E-step)
+  cudaEvent_t ev_grp[4] = {}, ev_join5 = nullptr, ev_join6 = nullptr;
+  int estep_cut1 = 150, estep_cut2 = 1000;  // per mille of the lane snippets (longest first) where the groups end
   cudaEvent_t ev_join3 = nullptr, ev_join4 = nullptr;
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // copy engines of the chunked host entry points
   cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
@@ -536,8 +539,9 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p, DropInfo di = DropIn
 }
 
 // ROWS form: one producer warp per chain is plenty (a row copy, not a walk), so R = 1 and as many groups as fit.
-cudaError_t launch_viterbi_pair_rows(tgx_model* m, PairParams p) {
-  constexpr int R = 1, WG = 2 * R + 1, MAXT = 960;
+template <int R, int MAXT>
+cudaError_t launch_viterbi_pair_rows_r(tgx_model* m, PairParams p) {
+  constexpr int WG = 2 * R + 1;
   auto kernel = viterbi_pair_rows_kernel<R, MAXT>;
   uint32_t groups = (uint32_t)std::min<size_t>({(size_t)m->smem_optin / pair_group_bytes(R), (size_t)(MAXT / (32 * WG)), (size_t)15});
   if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
@@ -553,6 +557,12 @@ cudaError_t launch_viterbi_pair_rows(tgx_model* m, PairParams p) {
   kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
   m->w().stats.launches += 1;
   return cudaGetLastError();
+}
+// ROWS form: option 4 = 2 -> R = 1 (one producer warp per chain, up to 10 groups); 4 (default) -> R = 2 (rounds of 64
+// positions, 5 groups of 5 warps, 800 threads: the latency shape)
+cudaError_t launch_viterbi_pair_rows(tgx_model* m, PairParams p) {
+  if (m->producers >= 4) return launch_viterbi_pair_rows_r<2, 800>(m, p);
+  return launch_viterbi_pair_rows_r<1, 960>(m, p);
 }
 
 // Two shapes (measured on B200, tools/probe.py, 1 GB / the 16 longest samples alone):
@@ -1047,6 +1057,11 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
     CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->stream4, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream5, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->stream6, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->ev_join6, cudaEventDisableTiming));
+    for (auto& e : m->ev_grp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&m->ev_join5, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&m->ev_join3, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&m->ev_join4, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
@@ -1127,6 +1142,12 @@ void tgx_model_destroy(tgx_model* m) {
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream3) cudaStreamDestroy(m->stream3);
     if (m->stream4) cudaStreamDestroy(m->stream4);
+    if (m->stream5) cudaStreamDestroy(m->stream5);
+    if (m->stream6) cudaStreamDestroy(m->stream6);
+    if (m->ev_join6) cudaEventDestroy(m->ev_join6);
+    for (auto& e : m->ev_grp)
+      if (e) cudaEventDestroy(e);
+    if (m->ev_join5) cudaEventDestroy(m->ev_join5);
     if (m->ev_join3) cudaEventDestroy(m->ev_join3);
     if (m->ev_join4) cudaEventDestroy(m->ev_join4);
     if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
@@ -1198,6 +1219,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
     case 27: if (value != 1 && value != 2 && value != 4 && value != 8) return fail(TGX_ERR_INVALID, "positions per thread must be 1, 2, 4 or 8"); m->match_ilp = (int)value; break;
     case 28: m->rows_consumer = value ? 1 : 0; break;
+    case 30: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut1 = (int)value; break;
+    case 31: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut2 = (int)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;
     default: return fail(TGX_ERR_INVALID, "unknown option");
   }
@@ -1398,8 +1421,16 @@ int tgx_encode_batch(tgx_model* m, const uint8_t* text, const uint64_t* off, uin
   int rc = check_model(m);
   if (rc) return rc;
   if (!off || !id_off || off[0] != 0) return fail(TGX_ERR_INVALID, "offsets must start at 0");
+  for (uint64_t i = 0; i < S; i++) {  // (the reference has no limit on a sample; the kernels index positions with 32 bits)
+    if (off[i + 1] < off[i]) return fail(TGX_ERR_INVALID, "offsets must not decrease");
+    if (off[i + 1] - off[i] >= (1ull << 32)) return fail(TGX_ERR_UNSUPPORTED, "a sample of 4 GiB or more is not supported");
+  }
   const uint64_t N = off[S];
   std::lock_guard<std::recursive_mutex> g(m->mu);
+  struct WiGuard {  // whatever path leaves this function, the next call starts on workspace 0
+    tgx_model* m;
+    ~WiGuard() { m->wi = 0; }
+  } wi_guard{m};
   if (first_bad_out) *first_bad_out = -1;
   if (S == 0) {
     id_off[0] = 0;
@@ -1919,7 +1950,8 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   static_assert(FR_WARPS == FL_WARPS && FRC_WARPS == FC_WARPS, "one launch shape for both sets of lane kernels");
   // forward / backward device times (tgx_model_last_stat 2, 3) are taken on the stream that carries most snippets
   cudaStream_t st_ev = (n_lane > ps.u.count) ? m->stream3 : st;
-  CU(cudaEventRecord(m->w().ev[0], st_ev));
+  (void)st_ev;
+  CU(cudaEventRecord(m->w().ev[0], st));  // (tgx_model_last_stat 2 = all chains and counts kernels, 3 = 0)
   CU(launch_fb_g(m, 32, pl, false, m->stream2));
   if (split && pl.u.count) {  // the beta chains of the longest snippets run beside their forward chains
     CU(cudaStreamWaitEvent(m->stream4, m->ev_fork, 0));
@@ -1935,14 +1967,38 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     CU(cudaEventRecord(m->ev_join4, m->stream4));
   }
   CU(launch_fb_g(m, m->g_estep, ps, false, st));
+  // The lane snippets go in two groups — the longest ones, then the rest — each on a stream of its own: chains, then
+  // counts.  The counts kernel is bound by L2 atomics, the chains by instruction issue, so the counts of the first
+  // group run beside the chains of the second.  (Measured alternative: four groups whose chain kernels share a stream,
+  // the counts on another — 0.90 s against 0.71 s for the 4 GB E-step: every group then waits for the longest chain of
+  // the group before it.)
+  constexpr int NGRP = 3;
+  const double c1 = m->estep_cut1 / 1000.0, c2 = m->estep_cut2 / 1000.0;
+  const double grp_cut[NGRP + 1] = {0.0, std::min(c1, c2), c2, 1.0};
   if (n_lane) {
-    if (!use_rows) fb_split_lane_kernel<<<2 * lane_blocks, FL_WARPS * 32, 0, m->stream3>>>(pw);
-    else if (drop) fbr_split_kernel<true><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
-    else fbr_split_kernel<false><<<2 * lane_blocks, FR_WARPS * 32, 0, m->stream3>>>(pn);
-    m->w().stats.launches += 1;
+    (void)lane_blocks;
+    CU(cudaStreamWaitEvent(m->stream5, m->ev_fork, 0));
+    CU(cudaStreamWaitEvent(m->stream6, m->ev_fork, 0));
+    for (int gi = 0; gi < NGRP; gi++) {
+      const uint32_t g0 = (uint32_t)(n_lane * grp_cut[gi]), g1 = (uint32_t)(n_lane * grp_cut[gi + 1]);
+      if (g1 <= g0) continue;
+      cudaStream_t gs = gi == 0 ? m->stream3 : (gi == 1 ? m->stream5 : m->stream6);
+      FbLaneParams gw = pw;
+      gw.f.u.first = pw.f.u.first + g0;
+      gw.f.u.count = g1 - g0;
+      FbRowsParams gn = pn;
+      gn.f.u = gw.f.u;
+      const uint32_t blocks = nblk(g1 - g0, FR_WARPS * 32);
+      if (!use_rows) fb_split_lane_kernel<<<2 * blocks, FL_WARPS * 32, 0, gs>>>(gw);
+      else if (drop) fbr_split_kernel<true><<<2 * blocks, FR_WARPS * 32, 0, gs>>>(gn);
+      else fbr_split_kernel<false><<<2 * blocks, FR_WARPS * 32, 0, gs>>>(gn);
+      if (!use_rows) fb_contrib_kernel<<<contrib_grid(g1 - g0), FC_WARPS * 32, 0, gs>>>(gw);
+      else if (drop) fbr_contrib_kernel<true><<<contrib_grid(g1 - g0), FRC_WARPS * 32, 0, gs>>>(gn);
+      else fbr_contrib_kernel<false><<<contrib_grid(g1 - g0), FRC_WARPS * 32, 0, gs>>>(gn);
+      m->w().stats.launches += 2;
+    }
   }
-  CU(cudaEventRecord(m->w().ev[1], st_ev));
-  CU(cudaEventRecord(m->w().ev[2], st_ev));
+
   if (split && pl.u.count) {
     CU(cudaStreamWaitEvent(m->stream2, m->ev_join4, 0));
     FbRowsParams pc = pn;
@@ -1957,14 +2013,18 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     CU(launch_fb_g(m, 32, pl, true, m->stream2));
   }
   CU(launch_fb_g(m, m->g_estep, ps, true, st));
-  if (n_lane) {  // alpha and beta are both there: the counts
-    if (!use_rows) fb_contrib_kernel<<<contrib_grid(n_lane), FC_WARPS * 32, 0, m->stream3>>>(pw);
-    else if (drop) fbr_contrib_kernel<true><<<contrib_grid(n_lane), FRC_WARPS * 32, 0, m->stream3>>>(pn);
-    else fbr_contrib_kernel<false><<<contrib_grid(n_lane), FRC_WARPS * 32, 0, m->stream3>>>(pn);
-    m->w().stats.launches += 1;
-  }
   CU(cudaGetLastError());
-  CU(cudaEventRecord(m->w().ev[3], st_ev));
+  CU(cudaEventRecord(m->ev_join5, m->stream5));
+  CU(cudaStreamWaitEvent(st, m->ev_join5, 0));
+  CU(cudaEventRecord(m->ev_join6, m->stream6));
+  CU(cudaStreamWaitEvent(st, m->ev_join6, 0));
+  CU(cudaEventRecord(m->ev_join, m->stream2));
+  CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+  CU(cudaEventRecord(m->ev_join3, m->stream3));
+  CU(cudaStreamWaitEvent(st, m->ev_join3, 0));
+  CU(cudaEventRecord(m->w().ev[1], st));
+  CU(cudaEventRecord(m->w().ev[2], st));
+  CU(cudaEventRecord(m->w().ev[3], st));
   CU(cudaEventRecord(m->ev_join, m->stream2));
   CU(cudaStreamWaitEvent(st, m->ev_join, 0));
   CU(cudaEventRecord(m->ev_join3, m->stream3));

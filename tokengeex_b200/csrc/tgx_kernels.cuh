@@ -887,8 +887,17 @@ __global__ void __launch_bounds__(EM_BLOCK) emit_kernel(EmitParams p) {
     const uint4 v = p.mark[tile * EM_BLOCK + threadIdx.x];
     if (staged) {  // (text is padded like mark: reading the whole last tile stays inside the allocation)
       const uint4* t16 = reinterpret_cast<const uint4*>(p.text) + tile * EM_BLOCK;
-      reinterpret_cast<uint4*>(s_text)[threadIdx.x + 1] =
-          (tile * EM_TILE + 16ull * threadIdx.x < p.text_bytes) ? __ldg(t16 + threadIdx.x) : make_uint4(0, 0, 0, 0);
+      // (the last vector of a caller-owned blob is read byte by byte: nothing beyond text_bytes is touched)
+      const unsigned long long vb = tile * EM_TILE + 16ull * threadIdx.x;
+      uint4 tv = make_uint4(0, 0, 0, 0);
+      if (vb + 16 <= p.text_bytes) {
+        tv = __ldg(t16 + threadIdx.x);
+      } else if (vb < p.text_bytes) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (uint32_t k = 0; vb + k < p.text_bytes; k++) w[k >> 2] |= (uint32_t)__ldg(p.text + vb + k) << (8 * (k & 3));
+        tv = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      reinterpret_cast<uint4*>(s_text)[threadIdx.x + 1] = tv;
       if (threadIdx.x == 0) reinterpret_cast<uint4*>(s_text)[0] = tile ? __ldg(t16 - 1) : make_uint4(0, 0, 0, 0);
     }
     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};

@@ -82,6 +82,10 @@ def main():
             m.set_option(19, cfg[4] if len(cfg) > 4 else 1)
             m.set_option(20, cfg[5] if len(cfg) > 5 else 64)
             m.set_option(21, cfg[6] if len(cfg) > 6 else 4096)
+            if os.environ.get("TGX_CUT"):
+                c1, c2 = (int(x) for x in os.environ["TGX_CUT"].split(","))
+                m.set_option(30, c1)
+                m.set_option(31, c2)
             m.set_option(2, g)
             m.set_option(5, thr)
             m.set_option(17, lane)
