@@ -196,9 +196,11 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        draw, see tgx_model_set_dropout).
  * The rest select between tested kernel variants and their launch shapes (bench / tests / tools/probe.py; not a stable
  * interface — defaults are what the measurements in profiles/ picked):
- *    3 = Viterbi forward pass when max_token_len <= 16: 0 = match stream + row consumer (tgx_match_kernels.cuh, the
- *        default), 1 = lane-group kernels (always used for longer tokens), 2 = pair-CTA kernel;
- *   23 / 24 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory;
+ *    3 = Viterbi forward pass when max_token_len <= 16: 2 = pair-CTA kernel (the default: the fastest as measured,
+ *        profiles/r02_*), 0 = match stream + row consumer (tgx_match_kernels.cuh), 1 = lane-group kernels (always used
+ *        for longer tokens);
+ *   23 / 24 / 27 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory, start positions
+ *        a thread walks side by side (1, 2, 4, 8);
  *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;
  *    0 / 1 = lane-group kernels: lanes per short sample (1,2,4,8,16,32), byte threshold from which a sample gets a
  *        full warp (also: warp-cooperative backtrack);
@@ -206,11 +208,14 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        levels staged in shared memory (0..2), shape (0 = by batch size, 1 = 5 groups, 2 = 6 groups);
  *   11 = chunked host entry point queues the next chunk's kernels before the current chunk has finished (default 0);
  *   16 = emit looks token ids up in the token hash (1, default when max_token_len <= 16) or re-walks the trie (0);
- *    2 / 5 / 17 / 18 / 19 / 20 / 21 = E-step: lanes per snippet of the lane-group kernels; byte threshold from which a
- *        snippet gets a full warp (0 = automatic); byte threshold below which a snippet runs on ONE lane (< 0 =
- *        automatic, 0 = never); resident blocks per SM of the lane kernels; split form (beta chains stored and run
- *        beside the alpha chains, default 1); replicas (default 256) of the count vector for the hottest ids (default:
- *        ids below 4096). */
+ *    2 / 5 / 17 / 18 / 19 / 20 / 21 / 30 / 31 = E-step: lanes per snippet of the lane-group kernels; byte threshold from
+ *        which a snippet gets a full warp (0 = automatic); byte threshold below which a snippet runs on ONE lane (< 0 =
+ *        automatic, 0 = never); resident blocks per SM of the lane kernels; form (1, the default: beta chains stored and
+ *        run beside the alpha chains, lane kernels that walk the trie — the ones over the match stream with dropout;
+ *        2: the lane kernels over the match stream always; 0: no beta array, lane-group kernels only); replicas
+ *        (default 256) of the accumulators of the hottest ids (default: ids below 4096); per mille of the lane
+ *        snippets, longest first, at which the first / second group of lane snippets ends (groups run on streams of
+ *        their own: the counts of one beside the chains of the next). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);
 
 /* The `dropout` argument of Model::encode (src/model.rs:59,100) for the encode entry points
@@ -232,8 +237,8 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value);
  * The setting belongs to the model handle and applies to the calls that follow it: threads that encode through one
  * handle with different dropout values serialise set + call themselves (tokengeex_b200/tokenizer.py holds a lock).
  * With dropout > 0 the forward pass runs on the pair kernel with the draw in its producers
- * (viterbi_pair_kernel<2, HOT, 800, true>; lane-group viterbi_kernel<G, true> for tokens > 16 bytes) and the E-step on the
- * lane-group kernels in fused form (fb_{forward,backward}_kernel<G, .., true>). */
+ * (viterbi_pair_drop_kernel; lane-group viterbi_kernel<G, true> for tokens > 16 bytes) and the E-step on the lane kernels
+ * over the match stream (fbr_split_kernel<true> / fbr_contrib_kernel<true>; lane-group kernels for tokens > 16 bytes). */
 int tgx_model_set_dropout(tgx_model* m, double dropout, uint64_t seed);
 
 #ifdef __cplusplus

@@ -146,7 +146,6 @@ struct tgx_model {
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
-  int rows_consumer = 1;          // 0 = pair-CTA consumer with ROWS producers, 1 = viterbi_rows_kernel
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
@@ -538,33 +537,6 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p, DropInfo di = DropIn
   return cudaGetLastError();
 }
 
-// ROWS form: one producer warp per chain is plenty (a row copy, not a walk), so R = 1 and as many groups as fit.
-template <int R, int MAXT>
-cudaError_t launch_viterbi_pair_rows_r(tgx_model* m, PairParams p) {
-  constexpr int WG = 2 * R + 1;
-  auto kernel = viterbi_pair_rows_kernel<R, MAXT>;
-  uint32_t groups = (uint32_t)std::min<size_t>({(size_t)m->smem_optin / pair_group_bytes(R), (size_t)(MAXT / (32 * WG)), (size_t)15});
-  if (m->groups > 0) groups = std::min<uint32_t>(groups, (uint32_t)m->groups);
-  groups = std::max<uint32_t>(1, std::min<uint32_t>(groups, (p.u.count + 1) / 2));
-  p.groups = groups;
-  const size_t smem = pair_smem_bytes(R, groups, 0);
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const uint32_t grid =
-      (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
-  e = dev_fill(p.counter, 0, 4, m->w().stream);
-  if (e != cudaSuccess) return e;
-  kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
-  m->w().stats.launches += 1;
-  return cudaGetLastError();
-}
-// ROWS form: option 4 = 2 -> R = 1 (one producer warp per chain, up to 10 groups); 4 (default) -> R = 2 (rounds of 64
-// positions, 5 groups of 5 warps, 800 threads: the latency shape)
-cudaError_t launch_viterbi_pair_rows(tgx_model* m, PairParams p) {
-  if (m->producers >= 4) return launch_viterbi_pair_rows_r<2, 800>(m, p);
-  return launch_viterbi_pair_rows_r<1, 960>(m, p);
-}
-
 // Two shapes (measured on B200, tools/probe.py, 1 GB / the 16 longest samples alone):
 //   latency   5 groups, two trie levels in shared memory, 72 registers: 35.8 ms / 13.5 ms
 //   throughput  6 groups (R = 2) with one staged level, 64 registers:    33.5 ms / 16.0 ms
@@ -845,21 +817,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   }
   CU(cudaEventRecord(m->w().ev[9], st));
   CU(cudaEventRecord(m->w().ev[0], st));
-  if (algo == 0 && u.rows <= 16 && m->rows_consumer == 0) {
-    if (N && U) {  // the pair-CTA consumer over the match stream
-      PairParams p;
-      p.u = u;
-      p.u.part = 0;
-      p.blob_end = d_text + N;
-      p.bp = m->w().bp.as<uint8_t>();
-      p.counter = m->w().small.as<unsigned int>() + 8;
-      p.dbg = 0;
-      p.hot_slots = 0;
-      p.rec = m->w().rec.as<uint32_t>();
-      p.rows = m->d_rows.as<double>();
-      CU(launch_viterbi_pair_rows(m, p));
-    }
-  } else if (algo == 0 && u.rows <= 16) {
+  if (algo == 0 && u.rows <= 16) {
     if (N && U) {
       RowsParams rp;
       rp.u = u;
@@ -887,8 +845,6 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     p.bp = m->w().bp.as<uint8_t>();
     p.counter = m->w().small.as<unsigned int>() + 8;
     p.dbg = 0;
-    p.rec = nullptr;
-    p.rows = nullptr;
     DropInfo di;
     di.dropout = dropout;
     di.seed = m->drop_seed;
@@ -1218,7 +1174,6 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 25: if (value < 1 || value > 32) return fail(TGX_ERR_INVALID, "warps must be 1..32"); m->rows_warps = (int)value; break;
     case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
     case 27: if (value != 1 && value != 2 && value != 4 && value != 8) return fail(TGX_ERR_INVALID, "positions per thread must be 1, 2, 4 or 8"); m->match_ilp = (int)value; break;
-    case 28: m->rows_consumer = value ? 1 : 0; break;
     case 30: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut1 = (int)value; break;
     case 31: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut2 = (int)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;

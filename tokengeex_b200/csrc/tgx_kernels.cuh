@@ -320,9 +320,6 @@ struct PairParams {
   uint32_t hot_slots;  // leading trie slots staged in shared memory (covers HOT levels)
   uint32_t groups;     // consumer/producer groups per CTA
   uint32_t dbg;        // developer timing experiments (tools/probe.py): 1 = skip walks, 2 = skip the dp
-  // ROWS form (the default forward pass): the producers copy match rows instead of walking the trie
-  const uint32_t* rec;  // [N] match stream of match_kernel (tgx_match_kernels.cuh)
-  const double* rows;   // row table (trie_build.h)
 };
 // dropout in (0, 1): a second kernel parameter of viterbi_pair_drop_kernel only (see drop_draw) — the default
 // kernel's parameter block and code stay exactly what they were (its 64-register shape is sensitive to both)
@@ -404,26 +401,6 @@ __device__ __forceinline__ void pair_produce(const uint4* __restrict__ trie, con
   }
 }
 
-// Phase A in ROWS form: the matches of the start position come from its record of the match stream — (L - 1) << 28 |
-// row offset of the deepest token that starts there; its row lists the score of every token on the trie path down
-// to it, dense by length, -inf where a prefix is not a token (trie_build.h) — instead of a trie walk: one
-// independent load per length, no dependent probes.  The loads of a tile are issued a whole round before their values
-// are parked (rows_load / rows_store), the record another round earlier.
-__device__ __forceinline__ void rows_load(const double* __restrict__ rows, uint32_t rc, bool active, double (&v)[16]) {
-  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
-  const uint32_t L = active ? (rc >> 28) + 1u : 0u;
-  const double* base = rows + (size_t)(rc & 0x0FFFFFFFu) * 2 + 1;  // (the row's header comes first)
-#pragma unroll
-  for (int d = 0; d < 16; d++) v[d] = ((uint32_t)d < L) ? __ldg(base + d) : ninf;
-}
-__device__ __forceinline__ void rows_store(const double (&v)[16], double* row, int lane) {
-  unsigned char* rb = reinterpret_cast<unsigned char*>(row);
-  const uint32_t l18 = (uint32_t)(lane + 1) * 8u;
-#pragma unroll
-  for (int d = 0; d < 16; d++)  // target cell (start + len) % 16 = (lane + d + 1) % 16
-    *reinterpret_cast<double*>(rb + ((l18 + 8u * d) & 120u)) = v[d];
-}
-
 // Phase B over one 32-position tile for both halves of the consumer warp.  tb = this half's
 // table + g, so the operand of step j is tb[j * PT_ROW].  "Unreached" is best == -inf: scores
 // are finite, so a candidate built on an unreached position is -inf and can never win, and the
@@ -457,7 +434,7 @@ __device__ __forceinline__ void pair_consume(const double* __restrict__ tb, int 
 
 // Body shared by viterbi_pair_kernel and the hybrid kernel; called by every thread of the CTA
 // (warps beyond p.groups * WG only help staging the hot trie prefix).
-template <int R, int HOT, bool DROP = false, bool ROWS = false>
+template <int R, int HOT, bool DROP = false>
 __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* smem, const DropInfo* di = nullptr) {
   constexpr int WG = 2 * R + 1;  // warps per group: consumer + 2R producers
   const UnitParams& u = p.u;
@@ -483,11 +460,6 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
   unsigned long long pw[3] = {0, 0, 0};
   uint32_t psh = 0, pf_tile = 0;
   int32_t pf_unit = -1;
-  // ROWS: the row values in flight for the next round (tile pv_tile of pv_unit), the record for the round after
-  // (tile pf_tile of pf_unit)
-  uint32_t pf_rec = 0, pv_tile = 0;
-  int32_t pv_unit = -1;
-  double pv[16];
   // scheduler state (half-warp leaders of the consumer warp)
   PairInfo cur;
   cur.unit = -1; cur.start = 0; cur.n = 0; cur.tile0 = 0; cur.ntiles = 0; cur.pad[0] = cur.pad[1] = 0;
@@ -551,30 +523,6 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
       if (pi.unit >= 0 && t < pi.ntiles) {
         const uint32_t pos = t * 32 + lane;
         double* row = tab + ((size_t)((r & 1) * 2 + ph) * R + k) * PT_TILE + lane * PT_ROW;
-        if constexpr (ROWS) {
-          const uint32_t* rp = p.rec + pi.start + pos;
-          if (!(pv_unit == pi.unit && pv_tile == t))  // first tile of a sample: nothing was requested ahead
-            rows_load(p.rows, pos < pi.n ? __ldg(rp) : 0u, pos < pi.n, pv);
-          rows_store(pv, row, lane);
-          if (t + R < pi.ntiles) {  // the next tile's values: requested now, parked a round from now
-            const uint32_t q1 = pos + 32 * R;
-            uint32_t rc = pf_rec;
-            if (!(pf_unit == pi.unit && pf_tile == t + R)) rc = q1 < pi.n ? __ldg(rp + 32 * R) : 0u;
-            rows_load(p.rows, rc, q1 < pi.n, pv);
-            pv_unit = pi.unit;
-            pv_tile = t + R;
-            if (t + 2 * R < pi.ntiles) {
-              pf_rec = q1 + 32 * R < pi.n ? __ldg(rp + 64 * R) : 0u;
-              pf_unit = pi.unit;
-              pf_tile = t + 2 * R;
-            } else {
-              pf_unit = -1;
-            }
-          } else {
-            pv_unit = -1;
-            pf_unit = -1;
-          }
-        } else {
         const uint8_t* ptr = u.text + pi.start + pos;
         // the text of this tile was requested a round ago (HBM latency off the round's critical path)
         if (!(pf_unit == pi.unit && pf_tile == t)) load_window(ptr, p.blob_end, pw, psh);
@@ -592,7 +540,6 @@ __device__ __forceinline__ void pair_body(const PairParams& p, unsigned char* sm
                                   drop_unit_key(di->seed, di->unit_base + (uint32_t)pi.unit), pos);
         else
           pair_produce<HOT>(u.trie, hot, u.root_base, w3, sh, pos < pi.n && !(p.dbg & 1u), row, lane);
-        }
       }
     }
     // group barrier: the groups of a CTA only share the read-only hot trie
@@ -609,13 +556,6 @@ template <int R, int HOT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) viterbi_pair_kernel(PairParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   pair_body<R, HOT>(p, smem);
-}
-
-// The default forward pass: the same consumer over the match stream (ROWS producers; no trie, no text).
-template <int R, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) viterbi_pair_rows_kernel(PairParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  pair_body<R, 0, false, true>(p, smem);
 }
 
 // The same kernel with the keyed dropout draw in its producers (src/model.rs:100).

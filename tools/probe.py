@@ -45,7 +45,7 @@ def main():
     what = args.what.split(",")
     if "encode" in what:
         K = 1024
-        cfgs = [(2, {14: 0}), (0, {}), (0, {6: 8}), (0, {6: 6}), (0, {28: 1}), (0, {28: 0, 6: 0, 27: 1})]
+        cfgs = [(2, {14: 0}), (2, {14: 1}), (0, {}), (0, {25: 12}), (0, {27: 1}), (1, {})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
         if args.opts is not None:
