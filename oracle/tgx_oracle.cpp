@@ -21,7 +21,7 @@
 // tests/test_oracle_goldens.py checks all of them.  run_e_step / run_m_step /
 // prune_vocab / nbest have NO golden in the reference ("parity unpinned" by the
 // reference's tests); they are pinned here by line-by-line restatement plus an
-// independent brute-force path enumerator (tests/test_oracle_bruteforce.py).
+// independent brute-force path enumerator (tests/bruteforce.py (used by tests/test_oracle_goldens.py)).
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference).

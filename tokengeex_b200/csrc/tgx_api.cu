@@ -1047,7 +1047,7 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
     return fail(TGX_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> g(m->mu);
   tgx::DoubleArray da;
-  std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da);
+  std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da, /*hot_order=*/false);
   if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);  // the model is unchanged
   if (m->device >= 0) {
     CU(cudaSetDevice(m->device));

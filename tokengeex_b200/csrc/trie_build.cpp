@@ -47,7 +47,7 @@ inline void xor_permute(const uint64_t (&in)[4], uint32_t L, uint64_t (&out)[4])
 }  // namespace
 
 std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const double* scores,
-                               uint64_t V, DoubleArray* out) {
+                               uint64_t V, DoubleArray* out, bool hot_order) {
   if (V >= MAX_VOCAB) return "vocabulary too large (ids must fit 24 bits)";
   uint32_t max_len = 0;
   for (uint64_t i = 0; i < V; i++) {
@@ -158,7 +158,9 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   // a parent's children land in the lowest block that has room when the parent is processed, so the nodes walks
   // visit most sit at the front of the array — the part match_kernel stages in shared memory.
   std::vector<uint32_t> alloc_order;
-  {
+  if (!hot_order) {
+    alloc_order = bfs;
+  } else {
     double smax = -INFINITY;
     for (uint64_t i = 0; i < V; i++) smax = std::max(smax, scores[i]);
     std::vector<float> weight(nodes.size(), 0.f);

@@ -73,8 +73,11 @@ std::string build_match_tables(DoubleArray* da);
 constexpr uint32_t SLOT8_TERM = 1u << 31, SLOT8_HASCH = 1u << 30, SLOT8_OFF_MASK = 0x0FFFFFFFu;
 
 // Returns "" on success, else an error message.
+// hot_order: slots beyond the first two levels are handed out by descending walk frequency instead of BFS order (a
+// few per cent fewer L1 misses in the kernels, ~30 ms more per 250k tokens here: on for models that are built once,
+// off for the rebuilds of the EM loop).
 std::string build_double_array(const uint8_t* token_bytes, const uint64_t* token_offsets,
-                               const double* scores, uint64_t vocab_size, DoubleArray* out);
+                               const double* scores, uint64_t vocab_size, DoubleArray* out, bool hot_order = true);
 
 // ---- token hash: bytes of a vocabulary token (1..16 bytes) -> id, ONE probe instead of one trie probe per byte.
 // Used by the emit kernel, which only ever looks up strings that ARE vocabulary tokens (the marked tokens of the
