@@ -10,6 +10,8 @@ from tokengeex_b200 import _native as N
 
 def main():
     kind, seed, nbytes, v0, target, subiters = 2, 21, 1_500_000, 4000, 2000, 2
+    if len(sys.argv) > 1:  # kind seed bytes vocab target subiters
+        kind, seed, nbytes, v0, target, subiters = (int(x) for x in sys.argv[1:7])
     blob, off, toks, sc, kp = synth_setup(kind, seed, nbytes, v0, 16)
     toks = list(toks); sc = np.array(sc); kp = np.array(kp)
     om = O.OracleModel(toks, sc, kp)
