@@ -176,6 +176,51 @@ def test_match_rows_random_vs_oracle(N, stage, hot, warps, threads):
         check_against_oracle(N, gm, om, samples, it)
 
 
+@pytest.mark.parametrize("lanes,shape", [(4, 0), (1, 0), (4, 2), (1, 2), (2, 0), (2, 1), (2, 2), (4, 1)])
+@pytest.mark.parametrize("thr,ctas", [(1 << 30, 1), (2000, 8), (1, 64), (300, 3)])
+def test_thread_kernel_random_vs_oracle(N, thr, ctas, lanes, shape):
+    """match_kernel + viterbi_team_kernel (four lanes per sample, a dp cell travels through them: tgx_team_kernel.cuh)
+    or viterbi_thread_kernel (one LANE per sample, the 16 open dp cells in registers; tgx_thread_kernel.cuh; option 36),
+    in every launch shape (option 34), with the samples of at least `thr` bytes on the pair-CTA kernel beside it (option 32; 2^30 =
+    everything on lanes, 1 = everything on the pair kernel): random vocabularies incl. incomplete ones (NoPath, positions
+    where no token starts, unreachable stretches), integer scores (exact ties), tokens of every length up to 16, sample
+    starts at every alignment of the record stream, empty samples, more samples than lanes."""
+    rng = random.Random(3100 + ctas)
+    for it in range(30):
+        alphabet = [b"ab", b"abcd", b"abc"][it % 3]
+        toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(4, 300), max_len=rng.randrange(1, 17),
+                                  complete=(it % 4 != 0), int_scores=(it % 2 == 0))
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 3)
+        gm.set_option(32, thr)
+        gm.set_option(33, ctas)
+        gm.set_option(34, shape)
+        gm.set_option(36, lanes)
+        gm.set_option(35, [160 << 10, 0, 4096, 300][it % 4])
+        samples = rand_samples(rng, alphabet, rng.randrange(1, 400), 0, 700) + rand_samples(rng, alphabet, 4, 1000, 9000)
+        samples += [alphabet[:1] * k for k in (1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
+        rng.shuffle(samples)
+        check_against_oracle(N, gm, om, samples, it)
+
+
+def test_thread_kernel_full_window(N):
+    """Tokens of every length 1..16 (length 16 lands on the ring cell that was just recycled), overlapping tokens
+    everywhere, long samples next to short ones in one warp."""
+    rng = random.Random(3201)
+    for it in range(8):
+        toks = [b"a", b"b"] + [bytes(rng.choice(b"ab") for _ in range(rng.randrange(2, 17))) for _ in range(600)]
+        toks = sorted(set(toks)) + [b"a" * 16, b"b" * 16, b"ab" * 8]
+        scores = [-(rng.random() * 6 + 0.5) if it % 2 else -float(rng.randrange(2, 6)) for _ in toks]
+        gm, om = both(N, toks, scores)
+        gm.set_option(3, 3)
+        gm.set_option(32, [1 << 30, 50000, 1000, 1 << 30][it % 4])
+        gm.set_option(36, [4, 2, 1, 1, 4, 2, 2, 1][it])
+        gm.set_option(34, it % 3)
+        samples = rand_samples(rng, b"ab", 30, 0, 3000) + [b"ab" * 4000, b"a" * 70000, b"aab" * 1000, b"b" * 333]
+        samples += [b"a" * k for k in range(1, 20)]
+        check_against_oracle(N, gm, om, samples, it)
+
+
 def test_match_rows_full_window(N):
     """Tokens of every length 1..16 (length 16 lands on the cell that was just recycled), vocabularies whose tokens
     overlap everywhere, long samples, rows deeper than the staged prefix."""
@@ -212,8 +257,9 @@ def test_match_rows_synth_corpus(N):
     blob, off, toks, sc, kp = synth_setup(2, 12, 3_000_000, 20000, 16)
     gm = N.Model(toks, sc, device=0)
     res = []
-    for algo in (0, 1, 2):
+    for algo in (0, 1, 2, 3):
         gm.set_option(3, algo)
+        gm.set_option(32, 20000)
         res.append(gm.encode_batch(blob, off, crlf=True))
     for r in res[1:]:
         assert r[4] == 0 and np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1])
@@ -413,9 +459,11 @@ def test_very_long_samples(N):
     toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=150, max_len=10)
     gm, om = both(N, toks, scores)
     samples = [bytes(rng.choice(b"abcd") for _ in range(n)) for n in (400_000, 2 * 81920, 81921, 7, 0, 81920)]
-    for algo in (0, 1, 2):
+    for algo in (0, 1, 2, 3):
         gm.set_option(3, algo)
         check_against_oracle(N, gm, om, samples, algo)
+    gm.set_option(32, 1 << 30)
+    check_against_oracle(N, gm, om, samples, "lanes only")
     gm.set_option(3, 0)
     blob, off = N.pack(samples)
     ex, rc, bad, badz = gm.expected_counts(blob, off)

@@ -21,6 +21,8 @@
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
 #include "tgx_match_kernels.cuh"
+#include "tgx_thread_kernel.cuh"
+#include "tgx_team_kernel.cuh"
 #include "tgx_fb_rows_kernels.cuh"
 #include "trie_build.h"
 
@@ -62,7 +64,8 @@ struct DevBuf {
 };
 
 struct Stats {
-  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0, match_ms = 0;
+  double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0, match_ms = 0,
+         side_ms = 0, forward_ms = 0;
 };
 
 }  // namespace
@@ -77,8 +80,13 @@ struct Workspace {
   // doing — here the bulk D2H of the previous chunk.  Control words are read through this stream.
   cudaStream_t stream_ctl = nullptr;
   cudaEvent_t ev_ctl = nullptr;
+  // algo 3: the pair-CTA kernel of the batch's longest samples runs here, beside match + teams on `stream`
+  cudaStream_t stream_side = nullptr;
+  cudaStream_t stream_low = nullptr;  // lowest priority: the team CTAs that take over the SMs the pair-CTA kernel frees
+  cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr, ev_low_join = nullptr;
+  bool side_used = false;  // ev[10..11] were recorded by the call in flight
   unsigned long long* h_words = nullptr;  // pinned, 8 words
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[14] = {};  // [10..11] pair-CTA kernel on the side stream, [12] forward pass complete (algo 3)
   Stats stats;
   DevBuf text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt, ntok, status,
       small, rec;
@@ -145,12 +153,20 @@ struct tgx_model {
   int algo = 2;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
+  int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
+  // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
+  // position) on a stream of its own, the rest one LANE each on viterbi_thread_kernel over the match stream
+  int64_t thread_long_threshold = 131072;
+  int thread_lanes = 4;  // algo 3: lanes per sample of the consumer over the match stream: 4 (viterbi_team_kernel) or 1 (viterbi_thread_kernel)
+  int thread_shape = 0;  // viterbi_team_kernel: 0 / 1 / 2 = 32 / 24 / 16 warps per SM; viterbi_thread_kernel: 0 = 16 warps per SM (128 registers), 1 = 12 warps (168), 2 = 8 warps
+  int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_thread_kernel stages in shared memory
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
   int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
   int num_sms = 148;
   int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
+  uint32_t pair_grid_cap = 0;  // CTAs the next pair-kernel launch may use (0 = one per SM); set and cleared by algo 3
   int smem_optin = 232448;
   // Chunked host entry point: queue chunk k+1's kernels (second workspace) before chunk k has finished.  Off by
   // default: measured on B200 (tools/e2e_trace.py, 1 GB) it LOSES, 75.4 vs 67.6 ms with two chunks — the next
@@ -528,9 +544,13 @@ cudaError_t launch_viterbi_pair(tgx_model* m, PairParams p, DropInfo di = DropIn
                            (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1));
   if (e != cudaSuccess) return e;
   const uint32_t grid =
-      (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups), (uint64_t)m->num_sms);
-  e = dev_fill(p.counter, 0, 4, m->w().stream);
-  if (e != cudaSuccess) return e;
+      (uint32_t)std::min<uint64_t>(((uint64_t)p.u.count + 2 * groups - 1) / (2 * groups),
+                                   (uint64_t)(m->pair_grid_cap ? m->pair_grid_cap : (uint32_t)m->num_sms));
+  if (!m->pair_grid_cap) {  // (algo 3 clears the counter before it forks: nothing may sit in front of this kernel on
+                            //  its stream, or the spare team CTAs take the SMs that were left free for it)
+    e = dev_fill(p.counter, 0, 4, m->w().stream);
+    if (e != cudaSuccess) return e;
+  }
   if constexpr (DROP) kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p, di);
   else kernel<<<grid, groups * WG * 32, smem, m->w().stream>>>(p);
   m->w().stats.launches += 1;
@@ -726,6 +746,8 @@ int sort_units(tgx_model* m, uint32_t U) {
   return TGX_OK;
 }
 
+int read_words(tgx_model* m, const void* d0, const void* d1, unsigned long long* o0, unsigned long long* o1);
+
 // match_kernel over the whole blob: m->w().rec[p] = record of start position p (tgx_match_kernels.cuh)
 int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
   cudaStream_t st = m->w().stream;
@@ -745,7 +767,10 @@ int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t per_cta = (uint64_t)threads * ilp;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((N + per_cta - 1) / per_cta, (uint64_t)m->num_sms);
+    const uint64_t want = (uint64_t)m->num_sms * (uint64_t)std::max(1, m->match_ctas_per_sm);
+    const uint64_t rounds = std::max<uint64_t>(1, (N + per_cta * want - 1) / (per_cta * want));
+    mp.slice = rounds * per_cta;
+    const uint32_t grid = (uint32_t)((N + mp.slice - 1) / mp.slice);
     kernel<<<grid, threads, smem, st>>>(mp);
     return cudaGetLastError();
   };
@@ -783,7 +808,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   if (rc) return rc;
   uint32_t* counts = m->w().small.as<uint32_t>();
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
-  split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr, counts);
+  const uint32_t thr2 = (uint32_t)std::min<int64_t>(m->thread_long_threshold, 0x7FFFFFFF);
+  split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr2, counts);
   m->w().stats.launches += 1;
   CU(dev_fill(m->w().ntok.p, 0, ((size_t)U + 1) * 8, st));
   CU(dev_fill(m->w().status.p, 0, (size_t)U * 4 + 4, st));
@@ -804,20 +830,124 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.count = U;  // upper bound for the grids
 
   const double dropout = with_dropout ? m->dropout : 0.0;  // the frequency passes encode with dropout 0.0
-  if (!(dropout > 0.0) && m->algo == 0 && u.rows <= 16) {
+  if (!(dropout > 0.0) && (m->algo == 0 || m->algo == 3) && u.rows <= 16) {
     rc = ensure_match_tables(m);
     if (rc) return rc;
   }
   // with the draw: pair-CTA or lane-group kernels
-  const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : (m->algo == 0 && !m->have_rows ? 2 : m->algo);
+  const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : ((m->algo == 0 || m->algo == 3) && !m->have_rows ? 2 : m->algo);
+  m->w().side_used = false;
+  uint32_t n_long = 0;  // algo 3: samples of at least thread_long_threshold bytes (the one host wait in the middle of a call)
+  if (algo == 3 && u.rows <= 16 && N && U) {
+    unsigned long long w01 = 0, w23 = 0;
+    rc = read_words(m, counts, counts + 2, &w01, &w23);
+    if (rc) return rc;
+    n_long = std::min<uint32_t>((uint32_t)w23, (uint32_t)(w01 >> 32));  // min(counts[2], counts[1])
+  }
   CU(cudaEventRecord(m->w().ev[8], st));
-  if (algo == 0 && u.rows <= 16 && N) {
+  if ((algo == 0 || algo == 3) && u.rows <= 16 && N) {
     rc = run_match(m, d_text, N);
     if (rc) return rc;
   }
   CU(cudaEventRecord(m->w().ev[9], st));
-  CU(cudaEventRecord(m->w().ev[0], st));
-  if (algo == 0 && u.rows <= 16) {
+  CU(cudaEventRecord(m->w().ev[0], st));  // [0]..[1]: the consumer of the match stream / the forward kernel
+  if (algo == 3 && u.rows <= 16) {
+    if (N && U) {
+      // The samples of at least thread_long_threshold bytes run on the pair-CTA kernel (16 lanes per sample: the shortest
+      // chain per position) BESIDE the teams, on P SMs of their own: forked when match_kernel — which fills every SM —
+      // has finished.  Measured: a side kernel that runs beside match_kernel only adds its time to it, and persistent
+      // team CTAs on every SM keep the pair CTAs waiting until they exit; so the team kernel gets num_sms - P CTAs,
+      // the pair kernel P (highest stream priority), and P more team CTAs wait on a lowest-priority stream for the SMs
+      // the pair CTAs free.  P needs the number of long samples on the host: n_long was read above.
+      const uint32_t per_cta = 10;  // chains of the pair kernel's latency shape (5 groups of two samples)
+      const uint32_t P = n_long ? std::min<uint32_t>((n_long + per_cta - 1) / per_cta, (uint32_t)m->num_sms * 2u / 3u) : 0u;
+      unsigned int* ctr = m->w().small.as<unsigned int>() + 8;
+      CU(dev_fill(ctr, 0, 8, st));
+      CU(cudaEventRecord(m->w().ev_side_fork, st));
+      if (P) {
+        CU(cudaStreamWaitEvent(m->w().stream_side, m->w().ev_side_fork, 0));
+        PairParams pp;
+        pp.u = u;
+        pp.u.part = 3;
+        pp.u.count = n_long;
+        pp.blob_end = d_text + N;
+        pp.bp = m->w().bp.as<uint8_t>();
+        pp.counter = ctr;
+        pp.dbg = 0;
+        m->w().side_used = true;
+        CU(cudaEventRecord(m->w().ev[10], m->w().stream_side));
+        {
+          cudaStream_t keep = m->w().stream;
+          m->w().stream = m->w().stream_side;
+          m->pair_grid_cap = P;
+          cudaError_t e = launch_viterbi_pair_r<2>(m, pp, 0);
+          m->pair_grid_cap = 0;
+          m->w().stream = keep;
+          CU(e);
+        }
+        CU(cudaEventRecord(m->w().ev[11], m->w().stream_side));
+        CU(cudaEventRecord(m->w().ev_side_join, m->w().stream_side));
+        CU(cudaStreamWaitEvent(m->w().stream_low, m->w().ev_side_fork, 0));
+      }
+      ThreadParams tp;
+      tp.u = u;
+      tp.u.part = 4;
+      tp.u.count = U - std::min(U, n_long);
+      tp.rec = m->w().rec.as<uint32_t>();
+      tp.rows = m->d_rows.as<double>();
+      tp.bp = m->w().bp.as<uint8_t>();
+      tp.counter = m->w().small.as<unsigned int>() + 9;
+      const size_t budget = (size_t)std::min<int64_t>(m->thread_hot_bytes, (int64_t)m->smem_optin - 1024);
+      tp.hot16 = (uint32_t)std::max<size_t>(std::min<size_t>(m->rows16, budget / 16), std::min<size_t>(m->rows16, 9));  // (row 0 is always staged)
+      const size_t smem = (size_t)tp.hot16 * 16;
+      TeamParams tm;
+      tm.u = tp.u;
+      tm.rec = tp.rec;
+      tm.rows = tp.rows;
+      tm.hot16 = tp.hot16;
+      tm.bp = tp.bp;
+      tm.counter = tp.counter;
+      const uint32_t n_short = tp.u.count;
+      // one launch on the compute stream (num_sms - P CTAs) and, when the pair kernel holds P SMs, one of P CTAs behind it
+      auto launch2 = [&](auto kernel, const auto& prm, uint32_t warps, uint32_t per_warp) -> cudaError_t {
+        if (!n_short) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const uint32_t ctas = ((n_short + per_warp - 1) / per_warp + warps - 1) / warps;
+        const uint32_t g1 = std::max<uint32_t>(1, std::min<uint32_t>(ctas, (uint32_t)m->num_sms - P));
+        kernel<<<g1, warps * 32, smem, st>>>(prm);
+        m->w().stats.launches += 1;
+        if (P && ctas > g1) {
+          kernel<<<std::min<uint32_t>(ctas - g1, P), warps * 32, smem, m->w().stream_low>>>(prm);
+          m->w().stats.launches += 1;
+        }
+        return cudaGetLastError();
+      };
+      if (m->thread_lanes == 2) {
+        switch (m->thread_shape) {
+          case 1: CU(launch2(viterbi_team_kernel<2, 16>, tm, 16, 16)); break;
+          case 2: CU(launch2(viterbi_team_kernel<2, 12>, tm, 12, 16)); break;
+          default: CU(launch2(viterbi_team_kernel<2, 20>, tm, 20, 16)); break;
+        }
+      } else if (m->thread_lanes == 4) {
+        switch (m->thread_shape) {
+          case 1: CU(launch2(viterbi_team_kernel<4, 20>, tm, 20, 8)); break;
+          case 2: CU(launch2(viterbi_team_kernel<4, 16>, tm, 16, 8)); break;
+          default: CU(launch2(viterbi_team_kernel<4, 24>, tm, 24, 8)); break;
+        }
+      } else {
+        switch (m->thread_shape) {
+          case 1: CU(launch2(viterbi_thread_kernel<12, 1>, tp, 12, 32)); break;
+          case 2: CU(launch2(viterbi_thread_kernel<8, 1>, tp, 8, 32)); break;
+          default: CU(launch2(viterbi_thread_kernel<16, 1>, tp, 16, 32)); break;
+        }
+      }
+      if (P) {
+        CU(cudaEventRecord(m->w().ev_low_join, m->w().stream_low));
+        CU(cudaStreamWaitEvent(st, m->w().ev_low_join, 0));
+      }
+    }
+  } else if (algo == 0 && u.rows <= 16) {
     if (N && U) {
       RowsParams rp;
       rp.u = u;
@@ -868,6 +998,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     CU(launch_viterbi_g(m, m->g_short, p));
   }
   CU(cudaEventRecord(m->w().ev[1], st));
+  if (m->w().side_used) CU(cudaStreamWaitEvent(st, m->w().ev_side_join, 0));
+  CU(cudaEventRecord(m->w().ev[12], st));
   CU(cudaEventRecord(m->w().ev[2], st));
   if (U) {
     BacktrackParams b;
@@ -970,6 +1102,8 @@ void finish_stats(tgx_model* m, int which) {
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[2], m->w().ev[3]) == cudaSuccess) m->w().stats.back_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[4], m->w().ev[5]) == cudaSuccess) m->w().stats.emit_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[8], m->w().ev[9]) == cudaSuccess) m->w().stats.match_ms = ms;
+  if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[8], m->w().ev[12]) == cudaSuccess) m->w().stats.forward_ms = ms;
+  if (which == 1 && m->w().side_used && cudaEventElapsedTime(&ms, m->w().ev[10], m->w().ev[11]) == cudaSuccess) m->w().stats.side_ms = ms;
   if (cudaEventElapsedTime(&ms, m->w().ev[6], m->w().ev[7]) == cudaSuccess) m->w().stats.total_ms = ms;
   m->last_stats = m->w().stats;
 }
@@ -1007,6 +1141,15 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
       CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&w.stream_ctl, cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&w.ev_ctl, cudaEventDisableTiming));
+      {  // forked when match_kernel has finished: pair CTAs first, then the teams, then the spare team CTAs
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&w.stream_side, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&w.stream_low, cudaStreamNonBlocking, lo));
+      }
+      CU(cudaEventCreateWithFlags(&w.ev_low_join, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&w.ev_side_fork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&w.ev_side_join, cudaEventDisableTiming));
       CU(cudaHostAlloc(reinterpret_cast<void**>(&w.h_words), 64, cudaHostAllocDefault));
       for (auto& e : w.ev) CU(cudaEventCreate(&e));
     }
@@ -1088,6 +1231,11 @@ void tgx_model_destroy(tgx_model* m) {
       if (w.stream) cudaStreamDestroy(w.stream);
       if (w.stream_ctl) cudaStreamDestroy(w.stream_ctl);
       if (w.ev_ctl) cudaEventDestroy(w.ev_ctl);
+      if (w.stream_side) cudaStreamDestroy(w.stream_side);
+      if (w.stream_low) cudaStreamDestroy(w.stream_low);
+      if (w.ev_low_join) cudaEventDestroy(w.ev_low_join);
+      if (w.ev_side_fork) cudaEventDestroy(w.ev_side_fork);
+      if (w.ev_side_join) cudaEventDestroy(w.ev_side_join);
       if (w.h_words) cudaFreeHost(w.h_words);
     }
     if (m->d_trie) cudaFree(m->d_trie);
@@ -1156,7 +1304,12 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
-    case 3: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "algo must be 0..2"); m->algo = (int)value; break;
+    case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
+    case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 36: if (value != 1 && value != 2 && value != 4) return fail(TGX_ERR_INVALID, "lanes per sample must be 1, 2 or 4"); m->thread_lanes = (int)value; break;
+    case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->thread_hot_bytes = value; break;
+    case 34: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "shape must be 0..2"); m->thread_shape = (int)value; break;
+    case 33: if (value < 1 || value > 64) return fail(TGX_ERR_INVALID, "CTAs per SM must be 1..64"); m->match_ctas_per_sm = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
     case 19: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "E-step form must be 0..2"); m->estep_split = value ? 1 : 0; m->estep_rows = (int)value; break;
@@ -1203,6 +1356,8 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
     case 5: return m->last_stats.back_ms;
     case 6: return m->last_stats.emit_ms;
     case 7: return m->last_stats.match_ms;
+    case 8: return m->last_stats.forward_ms;  // match + consumers (+ the wait for the side stream)
+    case 9: return m->last_stats.side_ms;     // pair-CTA kernel of the longest samples on the side stream (algo 3)
   }
   return 0;
 }

@@ -130,6 +130,8 @@ __device__ __forceinline__ void unit_range(const uint32_t* counts, int part, uin
   const uint32_t nl = counts[0], nn = counts[1];
   if (part == 1) { first = 0; count = nl; }
   else if (part == 2) { first = nl; count = nn - nl; }
+  else if (part == 3) { first = 0; count = min(counts[2], nn); }
+  else if (part == 4) { const uint32_t n2 = min(counts[2], nn); first = n2; count = nn - n2; }
   else { first = 0; count = nn; }
 }
 

@@ -37,7 +37,8 @@ struct MatchParams {
   const uint2* trie8;       // tgx::DoubleArray::slots8
   uint32_t root_base;
   uint32_t staged;          // leading slots staged in shared memory
-  uint32_t* rec;            // [N]
+  uint32_t* rec;            // [N + 64]
+  unsigned long long slice; // positions per CTA (a multiple of blockDim.x * ILP)
 };
 
 // A thread owns ILP consecutive start positions and walks them side by side, one trie level per step: ILP independent
@@ -77,18 +78,22 @@ __global__ void __launch_bounds__(mk_max_threads(ILP), 1) match_kernel(MatchPara
   }
   __syncthreads();
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * ILP;
-  unsigned long long pos = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * ILP;
+  // CTA b owns the positions [b * slice, (b + 1) * slice): more CTAs than SMs, handed out as SMs come free (the
+  // forward pass of the longest samples may hold some of them for the whole of this kernel)
+  const unsigned long long stride = (unsigned long long)blockDim.x * ILP;
+  unsigned long long pos = (unsigned long long)blockIdx.x * p.slice + (unsigned long long)threadIdx.x * ILP;
+  const unsigned long long lim = min(p.N, ((unsigned long long)blockIdx.x + 1) * p.slice);
+  if (blockIdx.x == 0 && threadIdx.x < 64) p.rec[p.N + threadIdx.x] = 0u;  // padding the consumers may read: row 0
   unsigned long long w[3] = {0, 0, 0};
   uint32_t sh = 0;
-  if (pos < p.N) load_window(p.text + pos, p.blob_end, w, sh);
-  while (pos < p.N) {
+  if (pos < lim) load_window(p.text + pos, p.blob_end, w, sh);
+  while (pos < lim) {
     // 24 bytes from `pos` on (the last sh of them read as zero: the walks need 16 + ILP - 1 <= 23)
     const unsigned long long a0 = sh ? ((w[0] >> (8 * sh)) | (w[1] << (64 - 8 * sh))) : w[0];
     const unsigned long long a1 = sh ? ((w[1] >> (8 * sh)) | (w[2] << (64 - 8 * sh))) : w[1];
     const unsigned long long a2 = sh ? (w[2] >> (8 * sh)) : w[2];
     const unsigned long long npos = pos + stride;
-    if (npos < p.N) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during these walks
+    if (npos < lim) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during these walks
     uint32_t xb[ILP], best[ILP];
     bool go[ILP];
 #pragma unroll

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--what", default="encode,estep")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--single", type=int, default=0, help="encode only the N longest samples")
+    ap.add_argument("--maxlen", type=int, default=0, help="drop the samples of at least this many bytes")
+    ap.add_argument("--minlen", type=int, default=0, help="drop the samples shorter than this")
     ap.add_argument("--estep-cfgs", default="", help="comma list of G:threshold pairs for the E-step")
     ap.add_argument("--snippet", type=int, default=81920, help="E-step snippet length (throughput experiments)")
     ap.add_argument("--algos", default="", help="comma list of forward algos to time (default all)")
@@ -34,6 +36,11 @@ def main():
         idx = np.argsort(-lens)[:args.single]
         parts = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in idx]
         blob, off = N.pack(parts)
+    if args.maxlen or args.minlen:
+        lens = np.diff(off.astype(np.int64))
+        keep = np.flatnonzero((lens >= args.minlen) & ((lens < args.maxlen) if args.maxlen else True))
+        parts = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in keep]
+        blob, off = N.pack(parts)
     S, NB = len(off) - 1, int(off[-1])
     d_text = torch.from_numpy(blob).cuda()
     d_off = torch.from_numpy(off.view(np.int64)).cuda()
@@ -45,12 +52,14 @@ def main():
     what = args.what.split(",")
     if "encode" in what:
         K = 1024
-        cfgs = [(2, {14: 0}), (2, {14: 1}), (0, {}), (0, {25: 12}), (0, {27: 1}), (1, {})]
+        cfgs = [(2, {14: 0}), (0, {}), (3, {32: 131072}), (3, {32: 65536}), (3, {32: 32768}), (3, {32: 200000}), (3, {32: 1 << 30})]
         if args.algos:
             cfgs = [c for c in cfgs if str(c[0]) in args.algos.split(",")]
-        if args.opts is not None:
-            a, _, kv = args.opts.partition(":")
-            cfgs = [(int(a), {int(x.split("=")[0]): int(x.split("=")[1]) for x in kv.split(",") if x})]
+        if args.opts is not None:  # "algo:key=value,key=value;algo:..."
+            cfgs = []
+            for one in args.opts.split(";"):
+                a, _, kv = one.partition(":")
+                cfgs.append((int(a), {int(x.split("=")[0]): int(x.split("=")[1]) for x in kv.split(",") if x}))
         for algo, opts in cfgs:
             m.set_option(3, algo)
             for k, v in opts.items():
@@ -62,7 +71,7 @@ def main():
                 best = min(best, m.stat(4))
             chk = int(d_ids[:tot].to(torch.int64).sum()) if tot else 0
             print(f"encode algo={algo} opts={opts}: {best:.2f} ms  {NB / best / 1e6:.2f} GB/s  forward {m.stat(1):.2f} ms "
-                  f"match {m.stat(7):.2f} ms backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot} idsum={chk} rc={rc}", flush=True)
+                  f"match {m.stat(7):.2f} ms all-forward {m.stat(8):.2f} ms side {m.stat(9):.2f} ms backtrack {m.stat(5):.2f} ms emit {m.stat(6):.2f} ms tokens={tot} idsum={chk} rc={rc}", flush=True)
         m.set_option(3, 0)
     if "freq" in what:
       for eh in (0, 1):
