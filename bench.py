@@ -29,7 +29,9 @@ sys.path.insert(0, ROOT)
 VOCAB_SIZE = 131072
 MAX_TOKEN_LEN = 16
 VOCAB_SAMPLE_BYTES = 96_000_000
-FORWARD_KERNEL_NAME = "viterbi_pair_kernel<2, 1, 960>"  # when the match stream is off (option 3 = 2)
+FORWARD_KERNEL_NAME = "viterbi_pair_kernel<2, 1, 960>"  # forward pass 2 (batches below 600 MiB)
+TEAM_KERNEL_NAME = "viterbi_team_kernel<4, 16>"  # forward pass 3: the consumer of the match stream
+SIDE_KERNEL_NAME = "viterbi_pair_kernel<2, 2, 800> (samples >= 64 KiB, side stream, beside the teams)"
 METRIC = "encode_input_throughput"
 UNIT = "MB/s"
 
@@ -458,7 +460,7 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    dev_ms, vit_ms, back_ms, emit_ms, match_ms = [], [], [], [], []
+    dev_ms, vit_ms, back_ms, emit_ms, match_ms, allfwd_ms, side_ms = [], [], [], [], [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tokens = step_dev()
@@ -467,6 +469,9 @@ def main():
         back_ms.append(model.stat(5))
         emit_ms.append(model.stat(6))
         match_ms.append(model.stat(7))
+        allfwd_ms.append(model.stat(8))
+        side_ms.append(model.stat(9))
+    fwd_algo = int(model.stat(10))
     torch.cuda.synchronize()
     barrier()
     wall = time.perf_counter() - t0
@@ -489,11 +494,19 @@ def main():
     # roofline of the dominant kernel (the Viterbi kernel launches), this rank
     peak, peak_src = measured_peak()
     alg_bytes = NB + 4 * tokens + 16 * (S + 1)
-    # the forward pass is two kernels when the match stream is used (match_kernel, then the consumer of the stream);
-    # the roofline is quoted for the longer one
-    fwd_kernels = {FORWARD_KERNEL_NAME: float(np.mean(vit_ms))}
-    if float(np.mean(match_ms)) > 0.05:  # (the events bracket nothing when the match stream is off)
+    # The forward pass by the algorithm the library picked for this batch (tgx_model_last_stat 10): the pair-CTA kernel
+    # alone (2), or match_kernel, then the lane teams over the match stream with the pair-CTA kernel of the longest
+    # samples beside them on a stream of its own (3; 0 = the row consumer).  The roofline is quoted for the longest one.
+    if fwd_algo == 3:
+        fwd_kernels = {"match_kernel<4>": float(np.mean(match_ms)), TEAM_KERNEL_NAME: float(np.mean(vit_ms)),
+                       SIDE_KERNEL_NAME: float(np.mean(side_ms))}
+        forward_ms = float(np.mean(allfwd_ms))
+    elif fwd_algo == 0:
         fwd_kernels = {"viterbi_rows_kernel": float(np.mean(vit_ms)), "match_kernel<4>": float(np.mean(match_ms))}
+        forward_ms = sum(fwd_kernels.values())
+    else:
+        fwd_kernels = {FORWARD_KERNEL_NAME: float(np.mean(vit_ms))}
+        forward_ms = float(np.mean(vit_ms))
     dom_kernel = max(fwd_kernels, key=fwd_kernels.get)
     vit = fwd_kernels[dom_kernel] * 1e-3
     achieved = alg_bytes / vit / 1e9
@@ -639,12 +652,16 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "peak_source": peak_src,
-                             "kernel": dom_kernel + " (one launch per step; CUDA events on its own stream)",
+                             "kernel": dom_kernel + " (the longest kernel of the forward pass; CUDA events on its own stream)",
                              "algorithmic_bytes": alg_bytes, "kernel_ms": vit * 1e3,
+                             "forward_algo": fwd_algo,
                              "forward_kernels_ms": fwd_kernels,
-                             "step_breakdown_ms": {"forward": sum(fwd_kernels.values()), "backtrack": float(np.mean(back_ms)),
+                             "forward_pass_ms": forward_ms,
+                             "frac_of_whole_forward_pass": alg_bytes / (forward_ms * 1e-3) / 1e9 / peak,
+                             "frac_of_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                             "step_breakdown_ms": {"forward": forward_ms, "backtrack": float(np.mean(back_ms)),
                                                    "emit": float(np.mean(emit_ms)),
-                                                   "crlf_sort_scan_other": ms_per_step - sum(fwd_kernels.values()) -
+                                                   "crlf_sort_scan_other": ms_per_step - forward_ms -
                                                    float(np.mean(back_ms)) - float(np.mean(emit_ms))}},
                 "cpu_baseline": cpu,
                 "sampled_parity": sampled,

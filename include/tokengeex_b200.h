@@ -185,9 +185,11 @@ int tgx_host_free(void* p);
 /* Counters of the last compute call on this model (for bench.py): number of kernels
  * launched and device milliseconds of the dominant kernel(s), measured with CUDA events
  * on the model's stream.  what: 0 = kernels launched, 1 = Viterbi forward ms, 2 = fb-forward ms,
- * 3 = fb-backward ms, 4 = whole call device ms, 5 = backtrack ms, 6 = emit ms, 7 = match_kernel ms (forward algo 0;
- * then 1 = viterbi_rows_kernel alone).  (For the chunked
- * host entry point these describe the LAST chunk.) */
+ * 3 = fb-backward ms, 4 = whole call device ms, 5 = backtrack ms, 6 = emit ms, 7 = match_kernel ms (forward passes over
+ * the match stream; then 1 = the consumer of the stream alone: viterbi_rows_kernel / viterbi_team_kernel), 8 = the whole
+ * forward pass (match + consumers + the wait for the side stream), 9 = the pair-CTA kernel of the longest samples on its
+ * side stream (forward pass 3), 10 = the forward pass the call used (option 3; automatic resolves to 2 or 3).  (For the
+ * chunked host entry point these describe the LAST chunk.) */
 double tgx_model_last_stat(const tgx_model* m, int what);
 
 /* Options.  Two of them are for callers:
@@ -196,9 +198,15 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        draw, see tgx_model_set_dropout).
  * The rest select between tested kernel variants and their launch shapes (bench / tests / tools/probe.py; not a stable
  * interface — defaults are what the measurements in profiles/ picked):
- *    3 = Viterbi forward pass when max_token_len <= 16: 2 = pair-CTA kernel (the default: the fastest as measured,
- *        profiles/r02_*), 0 = match stream + row consumer (tgx_match_kernels.cuh), 1 = lane-group kernels (always used
- *        for longer tokens);
+ *    3 = Viterbi forward pass when max_token_len <= 16: 4 = automatic (the default): 3 for a batch of at least 600 MiB,
+ *        else 2; 2 = pair-CTA kernel; 3 = match stream + lane teams (tgx_team_kernel.cuh), the longest samples on the
+ *        pair-CTA kernel beside them; 0 = match stream + row consumer (tgx_match_kernels.cuh); 1 = lane-group kernels
+ *        (always used for longer tokens).  The forward pass 3 waits once, in the middle of the call, for the number of
+ *        long samples (it sizes the grids);
+ *   32 / 33 / 34 / 35 / 36 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default
+ *        65536); match_kernel CTAs (slices of the blob) per SM; launch shape of the consumer (0..2: warps per SM, most to
+ *        fewest); bytes of leading match rows staged in shared memory; lanes per sample (4, the default; 2; 1 =
+ *        viterbi_thread_kernel);
  *   23 / 24 / 27 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory, start positions
  *        a thread walks side by side (1, 2, 4, 8);
  *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;

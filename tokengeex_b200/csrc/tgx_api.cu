@@ -65,7 +65,7 @@ struct DevBuf {
 
 struct Stats {
   double launches = 0, viterbi_ms = 0, fwd_ms = 0, bwd_ms = 0, total_ms = 0, back_ms = 0, emit_ms = 0, match_ms = 0,
-         side_ms = 0, forward_ms = 0;
+         side_ms = 0, forward_ms = 0, algo = 0;
 };
 
 }  // namespace
@@ -84,6 +84,7 @@ struct Workspace {
   cudaStream_t stream_side = nullptr;
   cudaStream_t stream_low = nullptr;  // lowest priority: the team CTAs that take over the SMs the pair-CTA kernel frees
   cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr, ev_low_join = nullptr;
+  int algo_used = 2;       // forward algorithm of the call in flight (tgx_model_last_stat 10)
   bool side_used = false;  // ev[10..11] were recorded by the call in flight
   unsigned long long* h_words = nullptr;  // pinned, 8 words
   cudaEvent_t ev[14] = {};  // [10..11] pair-CTA kernel on the side stream, [12] forward pass complete (algo 3)
@@ -148,17 +149,20 @@ struct tgx_model {
   int hot_k = 4096, hot_r = 256;  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids
   int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
-  // 0 = match stream + row consumer (tgx_match_kernels.cuh; the default), 1 = lane-group kernels, 2 = pair-CTA kernel
-  // (the default of the first round; still what encodes with dropout in (0, 1)).
-  int algo = 2;
+  // 0 = match stream + row consumer (tgx_match_kernels.cuh), 1 = lane-group kernels, 2 = pair-CTA kernel (the default
+  // of the first round; still what encodes with dropout in (0, 1)), 3 = match stream + lane teams with the longest
+  // samples on the pair-CTA kernel beside them (tgx_team_kernel.cuh), 4 = automatic (the default): 3 for a batch of at
+  // least `wide_bytes` bytes, else 2 — below that a batch is bound by its longest sample's chain, which the pair-CTA
+  // kernel runs fastest (measured on B200: 1 GB 29.5 against 32.3 ms, 352 MB chunks 18 against 13.5 ms).
+  int algo = 4;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
   // position) on a stream of its own, the rest one LANE each on viterbi_thread_kernel over the match stream
-  int64_t thread_long_threshold = 131072;
+  int64_t thread_long_threshold = 65536;
   int thread_lanes = 4;  // algo 3: lanes per sample of the consumer over the match stream: 4 (viterbi_team_kernel) or 1 (viterbi_thread_kernel)
-  int thread_shape = 0;  // viterbi_team_kernel: 0 / 1 / 2 = 32 / 24 / 16 warps per SM; viterbi_thread_kernel: 0 = 16 warps per SM (128 registers), 1 = 12 warps (168), 2 = 8 warps
+  int thread_shape = 2;  // viterbi_team_kernel<4>: 0 / 1 / 2 = 24 / 20 / 16 warps per SM (<2>: 20 / 16 / 12); viterbi_thread_kernel: 0 = 16 warps per SM (128 registers), 1 = 12 warps (168), 2 = 8 warps
   int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_thread_kernel stages in shared memory
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
@@ -830,12 +834,17 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   u.count = U;  // upper bound for the grids
 
   const double dropout = with_dropout ? m->dropout : 0.0;  // the frequency passes encode with dropout 0.0
-  if (!(dropout > 0.0) && (m->algo == 0 || m->algo == 3) && u.rows <= 16) {
+  // with the draw: pair-CTA or lane-group kernels
+  // automatic: the teams for the encode entry points only (`with_dropout` marks them) — the frequency passes of the EM
+  // loop run once per rebuilt model, where building the match tables costs more than the teams save (measured at
+  // 4 GB / 250k tokens: 0.204 against 0.148 s)
+  const int algo_req = m->algo == 4 ? (with_dropout && N >= m->wide_bytes && u.rows <= 16 ? 3 : 2) : m->algo;
+  if (!(dropout > 0.0) && (algo_req == 0 || algo_req == 3) && u.rows <= 16) {
     rc = ensure_match_tables(m);
     if (rc) return rc;
   }
-  // with the draw: pair-CTA or lane-group kernels
-  const int algo = dropout > 0.0 ? (m->algo == 1 ? 1 : 2) : ((m->algo == 0 || m->algo == 3) && !m->have_rows ? 2 : m->algo);
+  const int algo = dropout > 0.0 ? (algo_req == 1 ? 1 : 2) : ((algo_req == 0 || algo_req == 3) && !m->have_rows ? 2 : algo_req);
+  m->w().algo_used = algo;
   m->w().side_used = false;
   uint32_t n_long = 0;  // algo 3: samples of at least thread_long_threshold bytes (the one host wait in the middle of a call)
   if (algo == 3 && u.rows <= 16 && N && U) {
@@ -1103,6 +1112,7 @@ void finish_stats(tgx_model* m, int which) {
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[4], m->w().ev[5]) == cudaSuccess) m->w().stats.emit_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[8], m->w().ev[9]) == cudaSuccess) m->w().stats.match_ms = ms;
   if (which == 1 && cudaEventElapsedTime(&ms, m->w().ev[8], m->w().ev[12]) == cudaSuccess) m->w().stats.forward_ms = ms;
+  if (which == 1) m->w().stats.algo = m->w().algo_used;
   if (which == 1 && m->w().side_used && cudaEventElapsedTime(&ms, m->w().ev[10], m->w().ev[11]) == cudaSuccess) m->w().stats.side_ms = ms;
   if (cudaEventElapsedTime(&ms, m->w().ev[6], m->w().ev[7]) == cudaSuccess) m->w().stats.total_ms = ms;
   m->last_stats = m->w().stats;
@@ -1304,7 +1314,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 1: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->long_threshold = value; break;
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
-    case 3: if (value < 0 || value > 3) return fail(TGX_ERR_INVALID, "algo must be 0..3"); m->algo = (int)value; break;
+    case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
     case 36: if (value != 1 && value != 2 && value != 4) return fail(TGX_ERR_INVALID, "lanes per sample must be 1, 2 or 4"); m->thread_lanes = (int)value; break;
     case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->thread_hot_bytes = value; break;
@@ -1357,6 +1367,7 @@ double tgx_model_last_stat(const tgx_model* m, int what) {
     case 6: return m->last_stats.emit_ms;
     case 7: return m->last_stats.match_ms;
     case 8: return m->last_stats.forward_ms;  // match + consumers (+ the wait for the side stream)
+    case 10: return m->last_stats.algo;       // forward algorithm the call used (option 3; 4 = automatic resolves to 2 or 3)
     case 9: return m->last_stats.side_ms;     // pair-CTA kernel of the longest samples on the side stream (algo 3)
   }
   return 0;
