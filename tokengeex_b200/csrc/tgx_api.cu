@@ -157,10 +157,12 @@ struct tgx_model {
   int algo = 4;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
+  int match_compact = 1;          // match2_kernel (walks compacted inside their warp) instead of match_kernel
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
   // position) on a stream of its own, the rest one LANE each on viterbi_thread_kernel over the match stream
   int64_t thread_long_threshold = 65536;
+  int side_load = 20;    // algo 3: long samples per pair CTA on the side stream (10 chains each)
   int thread_lanes = 4;  // algo 3: lanes per sample of the consumer over the match stream: 4 (viterbi_team_kernel) or 1 (viterbi_thread_kernel)
   int thread_shape = 2;  // viterbi_team_kernel<4>: 0 / 1 / 2 = 24 / 20 / 16 warps per SM (<2>: 20 / 16 / 12); viterbi_thread_kernel: 0 = 16 warps per SM (128 registers), 1 = 12 warps (168), 2 = 8 warps
   int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_thread_kernel stages in shared memory
@@ -778,6 +780,22 @@ int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
     kernel<<<grid, threads, smem, st>>>(mp);
     return cudaGetLastError();
   };
+  if (m->match_compact) {  // walks compacted inside their warp: 1024 threads, four starts per lane, the queues behind the trie
+    const uint32_t threads = MK2_THREADS;
+    const size_t qbytes = (size_t)(threads / 32) * 2 * MK2_Q * 8;
+    const size_t budget2 = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024 - (int64_t)qbytes);
+    mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget2 / 8);
+    const size_t smem2 = (size_t)mp.staged * 8 + qbytes;
+    CU(cudaFuncSetAttribute(match2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const uint64_t per_cta = (uint64_t)threads * 4;
+    const uint64_t want = (uint64_t)m->num_sms * (uint64_t)std::max(1, m->match_ctas_per_sm);
+    const uint64_t rounds = std::max<uint64_t>(1, (N + per_cta * want - 1) / (per_cta * want));
+    mp.slice = rounds * per_cta;
+    match2_kernel<<<(uint32_t)((N + mp.slice - 1) / mp.slice), threads, smem2, st>>>(mp);
+    CU(cudaGetLastError());
+    m->w().stats.launches += 1;
+    return TGX_OK;
+  }
   switch (m->match_ilp) {
     case 1: CU(launch(match_kernel<1>, 1)); break;
     case 2: CU(launch(match_kernel<2>, 2)); break;
@@ -868,7 +886,10 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
       // team CTAs on every SM keep the pair CTAs waiting until they exit; so the team kernel gets num_sms - P CTAs,
       // the pair kernel P (highest stream priority), and P more team CTAs wait on a lowest-priority stream for the SMs
       // the pair CTAs free.  P needs the number of long samples on the host: n_long was read above.
-      const uint32_t per_cta = 10;  // chains of the pair kernel's latency shape (5 groups of two samples)
+      // A pair CTA runs 10 chains (5 groups of two samples) and a chain takes its samples longest first, so P is sized
+      // for `side_load` / 10 samples per chain: the batch's longest sample bounds the side kernel anyway (12.6 ms for
+      // 262144 bytes), and the shorter long ones fit behind each other inside that time on fewer SMs.
+      const uint32_t per_cta = (uint32_t)std::max(1, m->side_load);
       const uint32_t P = n_long ? std::min<uint32_t>((n_long + per_cta - 1) / per_cta, (uint32_t)m->num_sms * 2u / 3u) : 0u;
       unsigned int* ctr = m->w().small.as<unsigned int>() + 8;
       CU(dev_fill(ctr, 0, 8, st));
@@ -942,6 +963,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
         switch (m->thread_shape) {
           case 1: CU(launch2(viterbi_team_kernel<4, 20>, tm, 20, 8)); break;
           case 2: CU(launch2(viterbi_team_kernel<4, 16>, tm, 16, 8)); break;
+          case 3: CU(launch2(viterbi_team_kernel<4, 12>, tm, 12, 8)); break;
+          case 4: CU(launch2(viterbi_team_kernel<4, 14>, tm, 14, 8)); break;
           default: CU(launch2(viterbi_team_kernel<4, 24>, tm, 24, 8)); break;
         }
       } else {
@@ -1316,9 +1339,11 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;
+    case 37: m->match_compact = value ? 1 : 0; break;
     case 36: if (value != 1 && value != 2 && value != 4) return fail(TGX_ERR_INVALID, "lanes per sample must be 1, 2 or 4"); m->thread_lanes = (int)value; break;
     case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->thread_hot_bytes = value; break;
-    case 34: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "shape must be 0..2"); m->thread_shape = (int)value; break;
+    case 34: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "shape must be 0..4"); m->thread_shape = (int)value; break;
     case 33: if (value < 1 || value > 64) return fail(TGX_ERR_INVALID, "CTAs per SM must be 1..64"); m->match_ctas_per_sm = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off

@@ -144,6 +144,145 @@ __global__ void __launch_bounds__(mk_max_threads(ILP), 1) match_kernel(MatchPara
   }
 }
 
+// match2_kernel: the same records, with the walks COMPACTED twice inside their warp.
+//
+// match_kernel keeps a warp in its walk loop until the deepest of its 128 walks is done: 13 trips on average (of 16)
+// for walks that need 5 probes on average (tools/analyse_walk_depth.py: 43 % of the starts are alive after four probes,
+// 15 % after eight) — ncu: 16 of 32 threads per instruction.  Here a warp walks its 128 starts four levels deep (four
+// per lane, side by side, no exit test), writes the survivors' states (start, base, deepest token so far) to a queue in
+// shared memory, and walks those four levels further with ONE walk per lane (two trips of the queue on average), queues
+// the survivors again and finishes them (a single trip, exit when the last one is done).  No barrier: the queues are
+// the warp's own.
+constexpr int MK2_THREADS = 768;
+constexpr int MK2_Q = 128;  // entries per queue: the warp's starts of one trip
+
+__device__ __forceinline__ uint32_t mk_byte_cw(unsigned long long a, int j) {  // 0x100 | byte j of a (0 <= j < 8)
+  return __byte_perm(j < 4 ? (uint32_t)a : (uint32_t)(a >> 32), 1u, 0x5540 + (j & 3));
+}
+
+__global__ void __launch_bounds__(MK2_THREADS, 1) match2_kernel(MatchParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  {
+    uint2* s_trie = reinterpret_cast<uint2*>(smem);
+    for (uint32_t i = threadIdx.x; i < p.staged; i += blockDim.x) s_trie[i] = __ldg(p.trie8 + i);
+  }
+  __syncthreads();
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* q1 = reinterpret_cast<uint2*>(smem + (size_t)p.staged * 8) + (size_t)warp * 2 * MK2_Q;
+  uint2* q2 = q1 + MK2_Q;
+  const uint32_t lt = (1u << lane) - 1u;
+  const unsigned long long stride = (unsigned long long)blockDim.x * 4;
+  unsigned long long pos = (unsigned long long)blockIdx.x * p.slice + (unsigned long long)threadIdx.x * 4;
+  const unsigned long long lim = min(p.N, ((unsigned long long)blockIdx.x + 1) * p.slice);
+  if (blockIdx.x == 0 && threadIdx.x < 64) p.rec[p.N + threadIdx.x] = 0u;  // padding the consumers may read: row 0
+  const bool aligned = (reinterpret_cast<unsigned long long>(p.rec) & 15ull) == 0;
+  unsigned long long w[3] = {0, 0, 0};
+  uint32_t sh = 0;
+  if (pos < lim) load_window(p.text + pos, p.blob_end, w, sh);
+  // (a warp's 128 starts lie in one slice: the slice is a multiple of blockDim.x * 4)
+  while (pos - (unsigned long long)lane * 4 < lim) {
+    const unsigned long long wpos = pos - (unsigned long long)lane * 4;  // the warp's first start
+    const unsigned long long a0 = window_bytes(w, sh, 0);               // 8 bytes from `pos` on (zero beyond the blob)
+    const unsigned long long npos = pos + stride;
+    if (npos < lim) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during these walks
+    // ---- levels 1..4: four walks per lane, side by side
+    uint32_t xb[4], best[4];
+    bool go[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      xb[i] = p.root_base;
+      best[i] = REC_NOMATCH;
+      go[i] = pos + i < lim;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      uint2 e[4];
+      uint32_t cw[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        cw[i] = mk_byte_cw(a0, i + d);
+        e[i] = mk_probe(go[i] ? (xb[i] ^ cw[i]) : 0u, p.staged, s_base, p.trie8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool hit = go[i] && ((e[i].x ^ cw[i]) & 0x1FFu) == 0u;
+        if (hit && (e[i].y & tgx::SLOT8_TERM)) best[i] = ((uint32_t)d << 28) | (e[i].y & tgx::SLOT8_OFF_MASK);
+        go[i] = hit && (e[i].y & tgx::SLOT8_HASCH);
+        xb[i] = e[i].x >> 9;
+      }
+    }
+    if (pos + 4 <= p.N && aligned) {
+      *reinterpret_cast<uint4*>(p.rec + pos) = make_uint4(best[0], best[1], best[2], best[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (pos + i < p.N) p.rec[pos + i] = best[i];
+    }
+    // ---- the walks that go on: into the warp's queue (their records are written again when they end)
+    uint32_t c1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, go[i]);
+      if (go[i]) q1[c1 + __popc(b & lt)] = make_uint2(xb[i] | (uint32_t)(lane * 4 + i) << 24, best[i]);
+      c1 += __popc(b);
+    }
+    __syncwarp();
+    // ---- levels 5..8: one walk per lane
+    uint32_t c2 = 0;
+    for (uint32_t e0 = 0; e0 < c1; e0 += 32) {
+      const bool has = e0 + lane < c1;
+      const uint2 ent = has ? q1[e0 + lane] : make_uint2(0u, 0u);
+      const uint32_t rel = ent.x >> 24;
+      uint32_t x = ent.x & 0xFFFFFFu, bst = ent.y;
+      unsigned long long v[3] = {0, 0, 0};
+      uint32_t vs = 0;
+      if (has) load_window(p.text + wpos + rel + 4, p.blob_end, v, vs);
+      const unsigned long long a = window_bytes(v, vs, 0);
+      bool g = has;
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        const uint32_t cw = mk_byte_cw(a, d);
+        const uint2 e = mk_probe(g ? (x ^ cw) : 0u, p.staged, s_base, p.trie8);
+        const bool hit = g && ((e.x ^ cw) & 0x1FFu) == 0u;
+        if (hit && (e.y & tgx::SLOT8_TERM)) bst = ((uint32_t)(d + 4) << 28) | (e.y & tgx::SLOT8_OFF_MASK);
+        g = hit && (e.y & tgx::SLOT8_HASCH);
+        x = e.x >> 9;
+      }
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, g);
+      if (g) q2[c2 + __popc(b & lt)] = make_uint2(x | rel << 24, bst);
+      else if (has) p.rec[wpos + rel] = bst;
+      c2 += __popc(b);
+    }
+    __syncwarp();
+    // ---- levels 9..16
+    for (uint32_t e0 = 0; e0 < c2; e0 += 32) {
+      const bool has = e0 + lane < c2;
+      const uint2 ent = has ? q2[e0 + lane] : make_uint2(0u, 0u);
+      const uint32_t rel = ent.x >> 24;
+      uint32_t x = ent.x & 0xFFFFFFu, bst = ent.y;
+      unsigned long long v[3] = {0, 0, 0};
+      uint32_t vs = 0;
+      if (has) load_window(p.text + wpos + rel + 8, p.blob_end, v, vs);
+      const unsigned long long a = window_bytes(v, vs, 0);
+      bool g = has;
+#pragma unroll 1
+      for (int d = 0; d < 8; d++) {
+        const uint32_t cw = 0x100u | (uint32_t)((a >> (8 * d)) & 0xFFull);
+        const uint2 e = mk_probe(g ? (x ^ cw) : 0u, p.staged, s_base, p.trie8);
+        const bool hit = g && ((e.x ^ cw) & 0x1FFu) == 0u;
+        if (hit && (e.y & tgx::SLOT8_TERM)) bst = ((uint32_t)(d + 8) << 28) | (e.y & tgx::SLOT8_OFF_MASK);
+        g = hit && (e.y & tgx::SLOT8_HASCH);
+        x = e.x >> 9;
+        if (!__any_sync(0xFFFFFFFFu, g)) break;
+      }
+      if (has) p.rec[wpos + rel] = bst;
+    }
+    __syncwarp();  // (the queues are written again in the next trip)
+    pos = npos;
+  }
+}
+
 // -----------------------------------------------------------------------------------------
 // K2b  viterbi_rows_kernel: the relax chain of Model::encode (src/model.rs:83-110) over the match stream.
 // -----------------------------------------------------------------------------------------
