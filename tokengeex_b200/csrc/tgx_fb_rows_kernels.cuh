@@ -6,11 +6,12 @@
 //   * match_kernel (tgx_match_kernels.cuh) has written, once, the record of every start position; its row
 //     (trie_build.h) has a header mask and the scores / ids of the matches dense by length.  The three kernels here
 //     read that instead of walking the trie three times.
-//   * a trip of the main loop is ONE log_sum_exp (or one exp in the counts kernel) for every lane of the warp: each
-//     lane first runs its cheap steps — next match, first term of a fold (which only assigns), next position — until
-//     it has a fold pending, then the warp does the ~220-instruction exp/log together.  In the kernels that probe the
-//     trie a trip was one probe and the fold ran only in the lanes whose probe hit a terminal that was not the first
-//     of its fold (ncu: 13 of 32 threads active per instruction).
+//   * a trip of the main loop is ONE match per lane: [step to the next position when this one has none left], take the
+//     match, log_sum_exp (or exp + accumulate in the counts kernel) — the first term of a fold included, as
+//     log_sum_exp(-inf, y), which returns y bit for bit.  (First form of these kernels: a loop of up to four cheap
+//     steps per lane in front of the fold; its branches serialised: 10.7 of 32 threads per instruction, 50 ms for the
+//     300 MB of profiles/r02_ncu_estep_rows_kernels.txt against 35 ms now.)  In the kernels that probe the trie a
+//     trip is one probe and the fold runs only in the lanes whose probe hit a terminal that is not the first of its fold.
 //   * populate_nodes' dropout (src/model.rs:48-50) is a keyed draw per (byte offset, length) as in the other E-step
 //     kernels, so the three kernels see one lattice.
 // Expected counts are accumulated in 128-bit fixed point (64 fraction bits) with integer atomics: the sum does not
@@ -26,10 +27,6 @@
 namespace tgxk {
 
 constexpr int FR_WARPS = 4;
-// cheap steps a lane may take per trip before the warp goes on to the fold without it: unbounded, one lane in a stretch
-// of text where every fold is a first term (nothing to log_sum_exp for hundreds of positions) held its whole warp in
-// the cheap loop (ncu: 8 of 32 threads per instruction, 131 warp instructions per position)
-constexpr int FR_CHEAP = 4;
 
 struct FbRowsParams {
   FbParams f;               // units, A, status, accumulators, dropout
@@ -84,48 +81,51 @@ __device__ __forceinline__ void fbr_forward_body(const FbRowsParams& q, uint32_t
     if (n > 2) rc2 = __ldg(recs + 2);
   }
   double a = 0.0;  // alpha of the nodes that start at pos
-  bool pending = false;
-  uint32_t ts = 0;
-  double y = 0.0;
+  // A trip = one candidate per lane, and EVERY candidate is a log_sum_exp: the first term of a fold (init_mode,
+  // src/lattice.rs:322-323: "return y") goes through the same code with x = -inf — vmax = y > -inf + 50 returns y, the
+  // same bits — so a trip has no cheap/expensive lanes: [step to the next position if this one has no match left],
+  // take the next match, fold.  (The form with a loop of cheap steps in front of the fold ran 10.7 of 32 threads per
+  // instruction: the two branches of that loop serialised, four times per trip.)
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
   while (__any_sync(0xFFFFFFFFu, active)) {
-    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
-      if (m) {
-        const uint32_t l = (uint32_t)__ffs((int)m);
-        m &= m - 1u;
-        if (fr_dropped<DROP>(p, start + pos, l)) continue;
-        y = __dadd_rn(__ldg(q.rows + off + l), a);  // nodes[lid].score + alpha[lid]
-        ts = (pos + l) & 15u;
-        if ((seen >> ts) & 1u) {
-          pending = true;
-        } else {  // lid == end_nodes[pos][0] -> init_mode
-          acc[ts * 32] = y;
-          seen |= 1u << ts;
-        }
-      } else {  // everything that ends at pos + 1 has been folded
-        pos++;
-        const uint32_t sl = pos & 15u;
-        a = ((seen >> sl) & 1u) ? acc[sl * 32] : 0.0;
-        seen &= ~(1u << sl);
-        A[pos] = a;
-        if (pos == n) {  // a = alpha[eos]
-          const double az = fabs(a);
-          const bool normal = (az >= 2.2250738585072014e-308) && (az <= 1.7976931348623157e308);  // f64::is_normal
-          p.status[unit] = normal ? 0 : 7;
-          active = false;
-        } else {
-          off = noff;
-          m = fr_mask(nhdr, n - pos);
-          noff = (rc2 & REC_OFF) * 2u;
-          if (pos + 1 < n) nhdr = __ldg(q.rows + noff);
-          if (pos + 2 < n) rc2 = __ldg(recs + pos + 2);
-        }
+    // (a position where no token starts — or all of them dropped — takes another trip: rare)
+    if (active && !m) {  // everything that ends at pos + 1 has been folded
+      pos++;
+      const uint32_t sl = pos & 15u;
+      a = ((seen >> sl) & 1u) ? acc[sl * 32] : 0.0;
+      seen &= ~(1u << sl);
+      A[pos] = a;
+      if (pos == n) {  // a = alpha[eos]
+        const double az = fabs(a);
+        const bool normal = (az >= 2.2250738585072014e-308) && (az <= 1.7976931348623157e308);  // f64::is_normal
+        p.status[unit] = normal ? 0 : 7;
+        active = false;
+      } else {
+        off = noff;
+        m = fr_mask(nhdr, n - pos);
+        noff = (rc2 & REC_OFF) * 2u;
+        if (pos + 1 < n) nhdr = __ldg(q.rows + noff);
+        if (pos + 2 < n) rc2 = __ldg(recs + pos + 2);
       }
     }
-    __syncwarp();  // every lane is out of its cheap steps: the fold below runs with the whole warp (ncu without it: 8 of 32 threads per instruction — the lanes ran ahead into the fold one by one)
-    if (pending) {
-      acc[ts * 32] = log_sum_exp(acc[ts * 32], y, lt);
-      pending = false;
+    // (measured: letting a lane that met a first term assign it and take a second match in the same trip is slower,
+    //  334 against 321 ms per GB: the second take serialises like the old cheap loop)
+    bool fold = false;
+    uint32_t ts = 0;
+    double x = ninf, y = 0.0;
+    if (active && m) {
+      const uint32_t l = (uint32_t)__ffs((int)m);
+      m &= m - 1u;
+      if (!fr_dropped<DROP>(p, start + pos, l)) {
+        y = __dadd_rn(__ldg(q.rows + off + l), a);  // nodes[lid].score + alpha[lid]
+        ts = (pos + l) & 15u;
+        if ((seen >> ts) & 1u) x = acc[ts * 32];  // else lid == end_nodes[pos][0]: init_mode
+        seen |= 1u << ts;
+        fold = true;
+      }
     }
+    __syncwarp();
+    if (fold) acc[ts * 32] = log_sum_exp(x, y, lt);
   }
 }
 
@@ -161,43 +161,39 @@ __device__ __forceinline__ void fbr_backward_body(const FbRowsParams& q, uint32_
     if (pos >= 2) rc2 = __ldg(recs + pos - 2);
   }
   double b = 0.0;  // stays 0.0 when nothing begins at pos (Q7)
-  bool first = true, pending = false;
-  double y = 0.0;
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
-      if (m) {  // ascending length = begin_nodes[pos] order
-        const uint32_t l = (uint32_t)__ffs((int)m);
-        m &= m - 1u;
-        if (fr_dropped<DROP>(p, start + pos, l)) continue;
-        y = __dadd_rn(__ldg(q.rows + off + l), wB[((pos + l) & 15u) * 32]);  // nodes[rid].score + beta[rid]
-        if (first) {
-          b = y;
-          first = false;
-        } else {
-          pending = true;
-        }
+  bool first = true;
+  const double ninf = __longlong_as_double(0xFFF0000000000000ll);
+  while (__any_sync(0xFFFFFFFFu, active)) {  // (trips as in fbr_forward_body)
+    if (active && !m) {
+      wB[(pos & 15u) * 32] = b;
+      Bout[pos] = b;
+      if (pos == 0) {
+        active = false;
       } else {
-        wB[(pos & 15u) * 32] = b;
-        Bout[pos] = b;
-        if (pos == 0) {
-          active = false;
-        } else {
-          pos--;
-          b = 0.0;
-          first = true;
-          off = noff;
-          m = fr_mask(nhdr, n - pos);
-          noff = (rc2 & REC_OFF) * 2u;
-          if (pos >= 1) nhdr = __ldg(q.rows + noff);
-          if (pos >= 2) rc2 = __ldg(recs + pos - 2);
-        }
+        pos--;
+        b = 0.0;
+        first = true;
+        off = noff;
+        m = fr_mask(nhdr, n - pos);
+        noff = (rc2 & REC_OFF) * 2u;
+        if (pos >= 1) nhdr = __ldg(q.rows + noff);
+        if (pos >= 2) rc2 = __ldg(recs + pos - 2);
       }
     }
-    __syncwarp();  // every lane is out of its cheap steps: the fold below runs with the whole warp (ncu without it: 8 of 32 threads per instruction — the lanes ran ahead into the fold one by one)
-    if (pending) {
-      b = log_sum_exp(b, y, lt);
-      pending = false;
+    bool fold = false;
+    double x = ninf, y = 0.0;
+    if (active && m) {  // ascending length = begin_nodes[pos] order
+      const uint32_t l = (uint32_t)__ffs((int)m);
+      m &= m - 1u;
+      if (!fr_dropped<DROP>(p, start + pos, l)) {
+        y = __dadd_rn(__ldg(q.rows + off + l), wB[((pos + l) & 15u) * 32]);  // nodes[rid].score + beta[rid]
+        if (!first) x = b;  // else init_mode
+        first = false;
+        fold = true;
+      }
     }
+    __syncwarp();
+    if (fold) b = log_sum_exp(x, y, lt);
   }
 }
 
@@ -245,35 +241,32 @@ __global__ void __launch_bounds__(FRC_WARPS * 32) fbr_contrib_kernel(FbRowsParam
     m = fr_mask(__ldg(q.rows + off), n - pos);
     a = A[pos];
   }
-  bool pending = false;
-  double total = 0.0;
-  uint32_t id = 0;
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    for (int it = 0; it < FR_CHEAP && active && !pending; it++) {
-      if (m) {
-        const uint32_t l = (uint32_t)__ffs((int)m);
-        m &= m - 1u;
-        if (fr_dropped<DROP>(p, start + pos, l)) continue;
+  while (__any_sync(0xFFFFFFFFu, active)) {  // a trip = [next position], one match, one exp + one accumulation per lane
+    if (active && !m) {
+      pos += 32;
+      if (pos >= n) {
+        active = false;
+      } else {
+        off = (__ldg(recs + pos) & REC_OFF) * 2u;
+        m = fr_mask(__ldg(q.rows + off), n - pos);
+        a = A[pos];
+      }
+    }
+    bool add = false;
+    double total = 0.0;
+    uint32_t id = 0;
+    if (active && m) {
+      const uint32_t l = (uint32_t)__ffs((int)m);
+      m &= m - 1u;
+      if (!fr_dropped<DROP>(p, start + pos, l)) {
         // total = a + score + b - z ; update = total.exp()   (src/lattice.rs:305-307)
         total = __dadd_rn(__dadd_rn(__dadd_rn(a, __ldg(q.rows + off + l)), B[pos + l]), -z);
         id = __ldg(q.row_ids + off + l);
-        pending = true;
-      } else {
-        pos += 32;
-        if (pos >= n) {
-          active = false;
-        } else {
-          off = (__ldg(recs + pos) & REC_OFF) * 2u;
-          m = fr_mask(__ldg(q.rows + off), n - pos);
-          a = A[pos];
-        }
+        add = true;
       }
     }
     __syncwarp();
-    if (pending) {
-      acc_add(acc_slot(p, blockIdx.x, id), tgx_exp(total, lt));
-      pending = false;
-    }
+    if (add) acc_add(acc_slot(p, blockIdx.x, id), tgx_exp(total, lt));
   }
 }
 
