@@ -90,7 +90,7 @@ struct Workspace {
   cudaEvent_t ev[14] = {};  // [10..11] pair-CTA kernel on the side stream, [12] forward pass complete (algo 3)
   Stats stats;
   DevBuf text2, off2, bitmap, blk, ustart, ulen, keys_out, vals_in, vals_out, cubtmp, bp, mark, tilecnt, ntok, status,
-      small, rec;
+      small, rec, skip;
 };
 
 struct tgx_model {
@@ -157,6 +157,7 @@ struct tgx_model {
   int algo = 4;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
   int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
+  int match_skip = 1;             // forward pass 3: no walks inside the samples the pair-CTA kernel takes
   int match_compact = 1;          // match2_kernel (walks compacted inside their warp) instead of match_kernel
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
@@ -755,7 +756,7 @@ int sort_units(tgx_model* m, uint32_t U) {
 int read_words(tgx_model* m, const void* d0, const void* d1, unsigned long long* o0, unsigned long long* o1);
 
 // match_kernel over the whole blob: m->w().rec[p] = record of start position p (tgx_match_kernels.cuh)
-int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
+int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N, const uint8_t* d_skip = nullptr) {
   cudaStream_t st = m->w().stream;
   CU(m->w().rec.reserve((N + 64) * 4));
   MatchParams mp;
@@ -765,6 +766,8 @@ int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N) {
   mp.trie8 = m->d_trie8.as<uint2>();
   mp.root_base = m->da.root_base;
   mp.rec = m->w().rec.as<uint32_t>();
+  mp.skip = d_skip;
+  mp.slice = 0;
   const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
   mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
   const size_t smem = (size_t)mp.staged * 8;
@@ -873,7 +876,18 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   }
   CU(cudaEventRecord(m->w().ev[8], st));
   if ((algo == 0 || algo == 3) && u.rows <= 16 && N) {
-    rc = run_match(m, d_text, N);
+    const uint8_t* d_skip = nullptr;
+    if (algo == 3 && n_long && m->match_compact && m->match_skip) {
+      // nobody reads the records inside the samples the pair-CTA kernel takes: match2_kernel writes row 0 there
+      const size_t nb = (size_t)((N + 127) >> 7);
+      CU(m->w().skip.reserve(nb + 64));
+      CU(dev_fill(m->w().skip.p, 0, nb, st));
+      mark_skip_kernel<<<nblk((uint64_t)n_long * 32, 256), 256, 0, st>>>(u.unit_start, u.unit_len, u.order, n_long,
+                                                                        m->w().skip.as<uint8_t>());
+      m->w().stats.launches += 1;
+      d_skip = m->w().skip.as<uint8_t>();
+    }
+    rc = run_match(m, d_text, N, d_skip);
     if (rc) return rc;
   }
   CU(cudaEventRecord(m->w().ev[9], st));
@@ -1339,6 +1353,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 39: m->match_skip = value ? 1 : 0; break;
     case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;
     case 37: m->match_compact = value ? 1 : 0; break;
     case 36: if (value != 1 && value != 2 && value != 4) return fail(TGX_ERR_INVALID, "lanes per sample must be 1, 2 or 4"); m->thread_lanes = (int)value; break;

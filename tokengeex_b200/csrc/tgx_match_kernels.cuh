@@ -39,7 +39,21 @@ struct MatchParams {
   uint32_t staged;          // leading slots staged in shared memory
   uint32_t* rec;            // [N + 64]
   unsigned long long slice; // positions per CTA (a multiple of blockDim.x * ILP)
+  const uint8_t* skip;      // match2_kernel: [ceil(N / 128)] != 0 = nobody reads the records of these 128 positions
+                            // (they lie inside a sample that the pair-CTA kernel takes): write row 0, do not walk
 };
+
+// skip[t] = 1 for every 128-position block that lies wholly inside one of the first n_long units of the
+// length-descending order (the samples the pair-CTA kernel takes in forward pass 3): one warp per unit
+__global__ void mark_skip_kernel(const uint64_t* __restrict__ unit_start, const uint32_t* __restrict__ unit_len,
+                                 const uint32_t* __restrict__ order, uint32_t n_long, uint8_t* __restrict__ skip) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_long) return;
+  const uint32_t unit = order[w];
+  const unsigned long long a = unit_start[unit], b = a + unit_len[unit];
+  const unsigned long long t0 = (a + 127) >> 7, t1 = b >> 7;  // blocks [t0, t1) are inside [a, b)
+  for (unsigned long long t = t0 + lane; t < t1; t += 32) skip[t] = 1;
+}
 
 // A thread owns ILP consecutive start positions and walks them side by side, one trie level per step: ILP independent
 // probes in flight per thread.  Every probe is two predicated loads — shared memory for the staged prefix of the
@@ -182,10 +196,21 @@ __global__ void __launch_bounds__(MK2_THREADS, 1) match2_kernel(MatchParams p) {
   if (pos < lim) load_window(p.text + pos, p.blob_end, w, sh);
   // (a warp's 128 starts lie in one slice: the slice is a multiple of blockDim.x * 4)
   while (pos - (unsigned long long)lane * 4 < lim) {
-    const unsigned long long wpos = pos - (unsigned long long)lane * 4;  // the warp's first start
+    const unsigned long long wpos = pos - (unsigned long long)lane * 4;  // the warp's first start (a multiple of 128)
     const unsigned long long a0 = window_bytes(w, sh, 0);               // 8 bytes from `pos` on (zero beyond the blob)
     const unsigned long long npos = pos + stride;
     if (npos < lim) load_window(p.text + npos, p.blob_end, w, sh);  // the next window flies during these walks
+    if (p.skip && __ldg(p.skip + (wpos >> 7))) {  // (warp-uniform)
+      if (pos + 4 <= p.N && aligned) {
+        *reinterpret_cast<uint4*>(p.rec + pos) = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (pos + i < p.N) p.rec[pos + i] = 0u;
+      }
+      pos = npos;
+      continue;
+    }
     // ---- levels 1..4: four walks per lane, side by side
     uint32_t xb[4], best[4];
     bool go[4];
