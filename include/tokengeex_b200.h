@@ -204,9 +204,11 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        (always used for longer tokens).  The forward pass 3 waits once, in the middle of the call, for the number of
  *        long samples (it sizes the grids);
  *   32 / 33 / 34 / 35 / 36 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default
- *        65536); match_kernel CTAs (slices of the blob) per SM; launch shape of the consumer (0..2: warps per SM, most to
- *        fewest); bytes of leading match rows staged in shared memory; lanes per sample (4, the default; 2; 1 =
+ *        65536); match_kernel CTAs (slices of the blob) per SM; launch shape of the consumer (0..4: warps per SM; 2 = 16,
+ *        the default); bytes of leading match rows staged in shared memory; lanes per sample (4, the default; 2; 1 =
  *        viterbi_thread_kernel);
+ *   37 / 38 / 39 = match2_kernel (walks compacted inside their warp; 0 = match_kernel<ILP>); long samples per pair CTA
+ *        on the side stream of forward pass 3 (default 20); match2_kernel skips the positions inside those samples;
  *   23 / 24 / 27 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory, start positions
  *        a thread walks side by side (1, 2, 4, 8);
  *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;
