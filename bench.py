@@ -507,7 +507,9 @@ def main():
     else:
         fwd_kernels = {FORWARD_KERNEL_NAME: float(np.mean(vit_ms))}
         forward_ms = float(np.mean(vit_ms))
-    dom_kernel = max(fwd_kernels, key=fwd_kernels.get)
+    # (the pair-CTA kernel of the longest samples runs BESIDE the teams on a few SMs and sees 8 % of the bytes: it is
+    # listed, but the roofline of the whole batch's bytes is quoted for the longer of the two kernels that see them all)
+    dom_kernel = max((k for k in fwd_kernels if k != SIDE_KERNEL_NAME), key=fwd_kernels.get)
     vit = fwd_kernels[dom_kernel] * 1e-3
     achieved = alg_bytes / vit / 1e9
     traffic, traffic_src = None, None
