@@ -203,10 +203,8 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        pair-CTA kernel beside them; 0 = match stream + row consumer (tgx_match_kernels.cuh); 1 = lane-group kernels
  *        (always used for longer tokens).  The forward pass 3 waits once, in the middle of the call, for the number of
  *        long samples (it sizes the grids);
- *   32 / 33 / 34 / 35 / 36 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default
- *        65536); match_kernel CTAs (slices of the blob) per SM; launch shape of the consumer (0..4: warps per SM; 2 = 16,
- *        the default); bytes of leading match rows staged in shared memory; lanes per sample (4, the default; 2; 1 =
- *        viterbi_thread_kernel);
+ *   32 / 33 / 35 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default 65536);
+ *        match_kernel CTAs (slices of the blob) per SM; bytes of leading match rows staged in shared memory;
  *   37 / 38 / 39 = match2_kernel (walks compacted inside their warp; 0 = match_kernel<ILP>); long samples per pair CTA
  *        on the side stream of forward pass 3 (default 20); match2_kernel skips the positions inside those samples;
  *   23 / 24 / 27 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory, start positions

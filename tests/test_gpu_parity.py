@@ -176,13 +176,12 @@ def test_match_rows_random_vs_oracle(N, stage, hot, warps, threads):
         check_against_oracle(N, gm, om, samples, it)
 
 
-@pytest.mark.parametrize("lanes,shape", [(4, 0), (1, 0), (4, 2), (1, 2), (2, 0), (2, 1), (2, 2), (4, 1)])
+@pytest.mark.parametrize("match2", [1, 0])
 @pytest.mark.parametrize("thr,ctas", [(1 << 30, 1), (2000, 8), (1, 64), (300, 3)])
-def test_thread_kernel_random_vs_oracle(N, thr, ctas, lanes, shape):
-    """match_kernel + viterbi_team_kernel (four lanes per sample, a dp cell travels through them: tgx_team_kernel.cuh)
-    or viterbi_thread_kernel (one LANE per sample, the 16 open dp cells in registers; tgx_thread_kernel.cuh; option 36),
-    in every launch shape (option 34), with the samples of at least `thr` bytes on the pair-CTA kernel beside it (option 32; 2^30 =
-    everything on lanes, 1 = everything on the pair kernel): random vocabularies incl. incomplete ones (NoPath, positions
+def test_team_kernel_random_vs_oracle(N, thr, ctas, match2):
+    """match2_kernel (or match_kernel, option 37) + viterbi_team_kernel (four lanes per sample, a dp cell travels through
+    them: tgx_team_kernel.cuh) with the samples of at least `thr` bytes on the pair-CTA kernel beside it (option 32; 2^30 =
+    everything on teams, 1 = everything on the pair kernel): random vocabularies incl. incomplete ones (NoPath, positions
     where no token starts, unreachable stretches), integer scores (exact ties), tokens of every length up to 16, sample
     starts at every alignment of the record stream, empty samples, more samples than lanes."""
     rng = random.Random(3100 + ctas)
@@ -194,8 +193,9 @@ def test_thread_kernel_random_vs_oracle(N, thr, ctas, lanes, shape):
         gm.set_option(3, 3)
         gm.set_option(32, thr)
         gm.set_option(33, ctas)
-        gm.set_option(34, shape)
-        gm.set_option(36, lanes)
+        gm.set_option(37, match2)
+        gm.set_option(39, it % 2)
+        gm.set_option(38, [20, 1, 3][it % 3])
         gm.set_option(35, [160 << 10, 0, 4096, 300][it % 4])
         samples = rand_samples(rng, alphabet, rng.randrange(1, 400), 0, 700) + rand_samples(rng, alphabet, 4, 1000, 9000)
         samples += [alphabet[:1] * k for k in (1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
@@ -203,7 +203,7 @@ def test_thread_kernel_random_vs_oracle(N, thr, ctas, lanes, shape):
         check_against_oracle(N, gm, om, samples, it)
 
 
-def test_thread_kernel_full_window(N):
+def test_team_kernel_full_window(N):
     """Tokens of every length 1..16 (length 16 lands on the ring cell that was just recycled), overlapping tokens
     everywhere, long samples next to short ones in one warp."""
     rng = random.Random(3201)
@@ -214,8 +214,7 @@ def test_thread_kernel_full_window(N):
         gm, om = both(N, toks, scores)
         gm.set_option(3, 3)
         gm.set_option(32, [1 << 30, 50000, 1000, 1 << 30][it % 4])
-        gm.set_option(36, [4, 2, 1, 1, 4, 2, 2, 1][it])
-        gm.set_option(34, it % 3)
+        gm.set_option(37, it % 2)
         samples = rand_samples(rng, b"ab", 30, 0, 3000) + [b"ab" * 4000, b"a" * 70000, b"aab" * 1000, b"b" * 333]
         samples += [b"a" * k for k in range(1, 20)]
         check_against_oracle(N, gm, om, samples, it)
@@ -463,7 +462,7 @@ def test_very_long_samples(N):
         gm.set_option(3, algo)
         check_against_oracle(N, gm, om, samples, algo)
     gm.set_option(32, 1 << 30)
-    check_against_oracle(N, gm, om, samples, "lanes only")
+    check_against_oracle(N, gm, om, samples, "teams only")
     gm.set_option(3, 0)
     blob, off = N.pack(samples)
     ex, rc, bad, badz = gm.expected_counts(blob, off)

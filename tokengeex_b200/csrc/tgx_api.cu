@@ -21,7 +21,6 @@
 #include "../../include/tokengeex_b200.h"
 #include "tgx_kernels.cuh"
 #include "tgx_match_kernels.cuh"
-#include "tgx_thread_kernel.cuh"
 #include "tgx_team_kernel.cuh"
 #include "tgx_fb_rows_kernels.cuh"
 #include "trie_build.h"
@@ -161,12 +160,10 @@ struct tgx_model {
   int match_compact = 1;          // match2_kernel (walks compacted inside their warp) instead of match_kernel
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
-  // position) on a stream of its own, the rest one LANE each on viterbi_thread_kernel over the match stream
+  // position) on a stream of its own, the rest four lanes each on viterbi_team_kernel over the match stream
   int64_t thread_long_threshold = 65536;
   int side_load = 20;    // algo 3: long samples per pair CTA on the side stream (10 chains each)
-  int thread_lanes = 4;  // algo 3: lanes per sample of the consumer over the match stream: 4 (viterbi_team_kernel) or 1 (viterbi_thread_kernel)
-  int thread_shape = 2;  // viterbi_team_kernel<4>: 0 / 1 / 2 = 24 / 20 / 16 warps per SM (<2>: 20 / 16 / 12); viterbi_thread_kernel: 0 = 16 warps per SM (128 registers), 1 = 12 warps (168), 2 = 8 warps
-  int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_thread_kernel stages in shared memory
+  int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_team_kernel stages in shared memory
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
@@ -933,60 +930,30 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
         CU(cudaEventRecord(m->w().ev_side_join, m->w().stream_side));
         CU(cudaStreamWaitEvent(m->w().stream_low, m->w().ev_side_fork, 0));
       }
-      ThreadParams tp;
-      tp.u = u;
-      tp.u.part = 4;
-      tp.u.count = U - std::min(U, n_long);
-      tp.rec = m->w().rec.as<uint32_t>();
-      tp.rows = m->d_rows.as<double>();
-      tp.bp = m->w().bp.as<uint8_t>();
-      tp.counter = m->w().small.as<unsigned int>() + 9;
-      const size_t budget = (size_t)std::min<int64_t>(m->thread_hot_bytes, (int64_t)m->smem_optin - 1024);
-      tp.hot16 = (uint32_t)std::max<size_t>(std::min<size_t>(m->rows16, budget / 16), std::min<size_t>(m->rows16, 9));  // (row 0 is always staged)
-      const size_t smem = (size_t)tp.hot16 * 16;
       TeamParams tm;
-      tm.u = tp.u;
-      tm.rec = tp.rec;
-      tm.rows = tp.rows;
-      tm.hot16 = tp.hot16;
-      tm.bp = tp.bp;
-      tm.counter = tp.counter;
-      const uint32_t n_short = tp.u.count;
-      // one launch on the compute stream (num_sms - P CTAs) and, when the pair kernel holds P SMs, one of P CTAs behind it
-      auto launch2 = [&](auto kernel, const auto& prm, uint32_t warps, uint32_t per_warp) -> cudaError_t {
-        if (!n_short) return cudaSuccess;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+      tm.u = u;
+      tm.u.part = 4;
+      tm.u.count = U - std::min(U, n_long);
+      tm.rec = m->w().rec.as<uint32_t>();
+      tm.rows = m->d_rows.as<double>();
+      tm.bp = m->w().bp.as<uint8_t>();
+      tm.counter = m->w().small.as<unsigned int>() + 9;
+      const size_t budget = (size_t)std::min<int64_t>(m->thread_hot_bytes, (int64_t)m->smem_optin - 1024);
+      tm.hot16 = (uint32_t)std::max<size_t>(std::min<size_t>(m->rows16, budget / 16), std::min<size_t>(m->rows16, 9));  // (row 0 is always staged)
+      const size_t smem = (size_t)tm.hot16 * 16;
+      const uint32_t n_short = tm.u.count;
+      if (n_short) {  // one launch on the compute stream (num_sms - P CTAs) and, when the pair kernel holds P SMs, one of P CTAs behind it
+        constexpr uint32_t warps = TM_WARPS, per_warp = 8;
+        CU(cudaFuncSetAttribute(viterbi_team_kernel<warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const uint32_t ctas = ((n_short + per_warp - 1) / per_warp + warps - 1) / warps;
         const uint32_t g1 = std::max<uint32_t>(1, std::min<uint32_t>(ctas, (uint32_t)m->num_sms - P));
-        kernel<<<g1, warps * 32, smem, st>>>(prm);
+        viterbi_team_kernel<warps><<<g1, warps * 32, smem, st>>>(tm);
         m->w().stats.launches += 1;
         if (P && ctas > g1) {
-          kernel<<<std::min<uint32_t>(ctas - g1, P), warps * 32, smem, m->w().stream_low>>>(prm);
+          viterbi_team_kernel<warps><<<std::min<uint32_t>(ctas - g1, P), warps * 32, smem, m->w().stream_low>>>(tm);
           m->w().stats.launches += 1;
         }
-        return cudaGetLastError();
-      };
-      if (m->thread_lanes == 2) {
-        switch (m->thread_shape) {
-          case 1: CU(launch2(viterbi_team_kernel<2, 16>, tm, 16, 16)); break;
-          case 2: CU(launch2(viterbi_team_kernel<2, 12>, tm, 12, 16)); break;
-          default: CU(launch2(viterbi_team_kernel<2, 20>, tm, 20, 16)); break;
-        }
-      } else if (m->thread_lanes == 4) {
-        switch (m->thread_shape) {
-          case 1: CU(launch2(viterbi_team_kernel<4, 20>, tm, 20, 8)); break;
-          case 2: CU(launch2(viterbi_team_kernel<4, 16>, tm, 16, 8)); break;
-          case 3: CU(launch2(viterbi_team_kernel<4, 12>, tm, 12, 8)); break;
-          case 4: CU(launch2(viterbi_team_kernel<4, 14>, tm, 14, 8)); break;
-          default: CU(launch2(viterbi_team_kernel<4, 24>, tm, 24, 8)); break;
-        }
-      } else {
-        switch (m->thread_shape) {
-          case 1: CU(launch2(viterbi_thread_kernel<12, 1>, tp, 12, 32)); break;
-          case 2: CU(launch2(viterbi_thread_kernel<8, 1>, tp, 8, 32)); break;
-          default: CU(launch2(viterbi_thread_kernel<16, 1>, tp, 16, 32)); break;
-        }
+        CU(cudaGetLastError());
       }
       if (P) {
         CU(cudaEventRecord(m->w().ev_low_join, m->w().stream_low));
@@ -1356,9 +1323,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 39: m->match_skip = value ? 1 : 0; break;
     case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;
     case 37: m->match_compact = value ? 1 : 0; break;
-    case 36: if (value != 1 && value != 2 && value != 4) return fail(TGX_ERR_INVALID, "lanes per sample must be 1, 2 or 4"); m->thread_lanes = (int)value; break;
     case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->thread_hot_bytes = value; break;
-    case 34: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "shape must be 0..4"); m->thread_shape = (int)value; break;
     case 33: if (value < 1 || value > 64) return fail(TGX_ERR_INVALID, "CTAs per SM must be 1..64"); m->match_ctas_per_sm = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off

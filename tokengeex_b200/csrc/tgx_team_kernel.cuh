@@ -2,9 +2,9 @@
 // SAMPLE, eight samples per warp.
 //
 // Between the two extremes measured in round 2 — 16 lanes per sample (pair_consume / rows_consume: the shortest chain,
-// ~95-120 cycles per position, but 15 warp instructions per position) and one lane per sample (viterbi_thread_kernel:
-// 4.6 warp instructions per position, but ~150 instructions in a lane's stream per position: a warp that is left alone
-// advances a position per ~800 cycles) — a team of four: lane t of a team owns the candidate lengths 4t .. 4t + 3
+// ~95-120 cycles per position, but 15 warp instructions per position) and one lane per sample (the 16 open cells in a
+// register ring: 4.6 warp instructions per position, but ~150 instructions in a lane's stream per position: a warp that
+// is left alone advances a position per ~800 cycles) — a team of four: lane t of a team owns the candidate lengths 4t .. 4t + 3
 // (lane 0: 1, 2, 3 and 16), i.e. two 16-byte pairs of the start's row, and keeps the dp cells those candidates land on
 // in a four-slot register ring.  A cell is born in lane 0 (its first candidate is the token of length 16 from the
 // earliest start), travels to lane 3, 2, 1 and back to lane 0 — one shuffle per step, always towards the lanes that own
@@ -37,11 +37,14 @@ struct TeamParams {
 
 constexpr int TM_PF = 0;  // steps between the L1 prefetch of a cold row and its use (<= 8: the record ring holds 12 ahead)
 
-// G = lanes per sample (2 or 4): a lane owns LPL = 16 / G consecutive entries of the start's row.  G = 2 halves the warp
-// instructions per position (16 chains per warp), G = 4 halves the instructions per step of a chain.
-template <int G, int WARPS>
+// 16 warps per SM: measured against 12 / 14 / 20 / 24 (fewer lose throughput, more lengthen every chain and spill below
+// 96 registers).  Measured and removed: two lanes per sample (twice the chains per warp, but 400 cycles
+// per step for a warp alone: slower), one lane per sample (viterbi_thread_kernel: 146 instructions per position in a
+// lane's stream, only samples below 16 KB fit).
+constexpr int TM_WARPS = 16;
+template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams p) {
-  static_assert(G == 2 || G == 4, "lanes per sample");
+  constexpr int G = 4;         // lanes per sample
   constexpr int LPL = 16 / G;  // entries (candidate lengths) per lane = slots of its ring
   constexpr int NP = LPL / 2;  // 16-byte pairs per lane
   extern __shared__ __align__(16) unsigned char smem[];
