@@ -219,7 +219,7 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *    2 / 5 / 17 / 18 / 19 / 20 / 21 / 30 / 31 = E-step: lanes per snippet of the lane-group kernels; byte threshold from
  *        which a snippet gets a full warp (0 = automatic); byte threshold below which a snippet runs on ONE lane (< 0 =
  *        automatic, 0 = never); resident blocks per SM of the lane kernels; form (1, the default: beta chains stored and
- *        run beside the alpha chains, lane kernels that walk the trie — the ones over the match stream with dropout;
+ *        run beside the alpha chains, lane kernels that walk the trie, with or without the dropout draw;
  *        2: the lane kernels over the match stream always; 0: no beta array, lane-group kernels only); replicas
  *        (default 256) of the accumulators of the hottest ids (default: ids below 4096); per mille of the lane
  *        snippets, longest first, at which the first / second group of lane snippets ends (groups run on streams of

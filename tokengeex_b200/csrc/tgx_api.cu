@@ -2002,14 +2002,14 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
   // Split form (one lane per snippet, beta chains beside the alpha chains, counts from stored alpha / beta): needs 8
   // more bytes of device memory per input byte for beta (+ 4 for the match stream).  Two sets of lane kernels: the ones
   // that walk the trie (fb_split_lane_kernel; faster as measured, profiles/r02_estep_kernels.txt) and the ones over the
-  // match stream (fbr_split_kernel; they take the dropout draw, and option 19 = 2 selects them always).
+  // match stream (fbr_split_kernel; option 19 = 2 selects them).
+  // Both take the dropout draw (the walking ones since the end of round 2: 335 against 430 ms per GB at dropout 0.01).
   bool rows_ok = m->estep_split && p.u.rows <= 16;
-  if (rows_ok && (drop || m->estep_rows == 2)) {
+  if (rows_ok && m->estep_rows == 2) {
     rc = ensure_match_tables(m);
     if (rc) return rc;
   }
-  const bool use_rows = rows_ok && m->have_rows && (drop || m->estep_rows == 2);
-  if (drop && !use_rows) rows_ok = false;  // no match tables: the lane-group kernels take the draw
+  const bool use_rows = rows_ok && m->have_rows && m->estep_rows == 2;
   if (rows_ok) {
     const size_t need = ((size_t)n_bytes + U + 2) * 8 + (use_rows ? ((size_t)n_bytes + 64) * 4 : 0);
     size_t fr = 0, tot = 0;
@@ -2115,10 +2115,12 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
       FbRowsParams gn = pn;
       gn.f.u = gw.f.u;
       const uint32_t blocks = nblk(g1 - g0, FR_WARPS * 32);
-      if (!use_rows) fb_split_lane_kernel<<<2 * blocks, FL_WARPS * 32, 0, gs>>>(gw);
+      if (!use_rows && drop) fb_split_lane_kernel<true><<<2 * blocks, FL_WARPS * 32, 0, gs>>>(gw);
+      else if (!use_rows) fb_split_lane_kernel<false><<<2 * blocks, FL_WARPS * 32, 0, gs>>>(gw);
       else if (drop) fbr_split_kernel<true><<<2 * blocks, FR_WARPS * 32, 0, gs>>>(gn);
       else fbr_split_kernel<false><<<2 * blocks, FR_WARPS * 32, 0, gs>>>(gn);
-      if (!use_rows) fb_contrib_kernel<<<contrib_grid(g1 - g0), FC_WARPS * 32, 0, gs>>>(gw);
+      if (!use_rows && drop) fb_contrib_kernel<true><<<contrib_grid(g1 - g0), FC_WARPS * 32, 0, gs>>>(gw);
+      else if (!use_rows) fb_contrib_kernel<false><<<contrib_grid(g1 - g0), FC_WARPS * 32, 0, gs>>>(gw);
       else if (drop) fbr_contrib_kernel<true><<<contrib_grid(g1 - g0), FRC_WARPS * 32, 0, gs>>>(gn);
       else fbr_contrib_kernel<false><<<contrib_grid(g1 - g0), FRC_WARPS * 32, 0, gs>>>(gn);
       m->w().stats.launches += 2;
@@ -2131,7 +2133,8 @@ int expected_counts_impl(tgx_model* m, const uint8_t* d_text, const uint64_t* d_
     pc.f.u = pl.u;
     FbLaneParams pcw = pw;
     pcw.f.u = pl.u;
-    if (!use_rows) fb_contrib_kernel<<<contrib_grid(pl.u.count), FC_WARPS * 32, 0, m->stream2>>>(pcw);
+    if (!use_rows && drop) fb_contrib_kernel<true><<<contrib_grid(pl.u.count), FC_WARPS * 32, 0, m->stream2>>>(pcw);
+    else if (!use_rows) fb_contrib_kernel<false><<<contrib_grid(pl.u.count), FC_WARPS * 32, 0, m->stream2>>>(pcw);
     else if (drop) fbr_contrib_kernel<true><<<contrib_grid(pl.u.count), FRC_WARPS * 32, 0, m->stream2>>>(pc);
     else fbr_contrib_kernel<false><<<contrib_grid(pl.u.count), FRC_WARPS * 32, 0, m->stream2>>>(pc);
     m->w().stats.launches += 1;

@@ -1160,6 +1160,14 @@ __device__ __forceinline__ uint32_t fl_byte(unsigned long long lo, unsigned long
   return (uint32_t)((d < 8 ? lo : hi) >> (8 * (d & 7u))) & 0xFFu;
 }
 
+// populate_nodes' dropout (src/model.rs:48-50): the keyed draw of the multi-byte match (start byte, length)
+template <bool DROP>
+__device__ __forceinline__ bool fb_dropped(const FbParams& p, unsigned long long byte_off, uint32_t l) {
+  if (!DROP) return false;
+  return l > 1u && !(p.dropout < drop_draw(p.drop_key, p.drop_base + byte_off, l));
+}
+
+template <bool DROP>
 __device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
                                                      const LibmTabs& lt) {
   const FbParams& p = q.f;
@@ -1195,7 +1203,7 @@ __device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint
   while (__any_sync(0xFFFFFFFFu, active)) {
     if (active) {
       const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
-      const bool term = hit && (e.y & F_TERM);
+      const bool term = hit && (e.y & F_TERM) && !fb_dropped<DROP>(p, start + pos, d + 1u);
       const double y = __dadd_rn(__hiloint2double((int)e.w, (int)e.z), a);  // nodes[lid].score + alpha[lid]
       const uint32_t ts = (pos + d + 1u) & 15u;
       const bool cont = hit && (e.y & F_HASCH) && (d + 1u < limit);
@@ -1248,7 +1256,7 @@ __device__ __forceinline__ void fb_forward_lane_body(const FbLaneParams& q, uint
 // STORE_B: only the beta chain, written to q.B (same layout as A) — it needs neither A nor z, so it runs BESIDE the
 // forward kernel and fb_contrib_kernel adds the expected counts afterwards; the longest snippet then costs
 // max(forward, backward) instead of their sum.  !STORE_B: the fused form (after the forward kernel).
-template <bool STORE_B>
+template <bool STORE_B, bool DROP>
 __device__ __forceinline__ void fb_backward_lane_body(const FbLaneParams& q, uint32_t bid, double* s_win,
                                                       const LibmTabs& lt) {
   const FbParams& p = q.f;
@@ -1288,7 +1296,7 @@ __device__ __forceinline__ void fb_backward_lane_body(const FbLaneParams& q, uin
   while (__any_sync(0xFFFFFFFFu, active)) {
     if (active) {
       const bool hit = ((e.x ^ cw) & 0x1FFu) == 0;
-      const bool term = hit && (e.y & F_TERM);
+      const bool term = hit && (e.y & F_TERM) && !fb_dropped<DROP>(p, start + pos, d + 1u);
       const double sc = __hiloint2double((int)e.w, (int)e.z);
       const double bt = wB[((pos + d + 1u) & 15u) * 32];
       const uint32_t id = e.y & ID_MASK;
@@ -1349,7 +1357,7 @@ __global__ void __launch_bounds__(FL_WARPS * 32) fb_forward_lane_kernel(FbLanePa
   __shared__ unsigned long long s_et[256];
   __shared__ double s_lt[256];
   const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  fb_forward_lane_body(q, blockIdx.x, s_win, lt);
+  fb_forward_lane_body<false>(q, blockIdx.x, s_win, lt);
 }
 
 __global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneParams q) {
@@ -1357,19 +1365,22 @@ __global__ void __launch_bounds__(FL_WARPS * 32) fb_backward_lane_kernel(FbLaneP
   __shared__ unsigned long long s_et[256];
   __shared__ double s_lt[256];
   const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  fb_backward_lane_body<false>(q, blockIdx.x, s_win, lt);
+  fb_backward_lane_body<false, false>(q, blockIdx.x, s_win, lt);
 }
 
 // Split form: even blocks run the forward chains of 128 snippets, odd blocks the beta chains of the same snippets,
 // so the block scheduler starts the longest snippets of BOTH directions first (two kernels on two streams do not
 // interleave: the second kernel's blocks wait for the first kernel's to be dispatched).
+// DROP: with the keyed dropout draw (the reference's default `--dropout 0.01`, src/prune.rs:87): a terminal that is
+// dropped is simply not a terminal for the folds; the walk goes on through it.
+template <bool DROP>
 __global__ void __launch_bounds__(FL_WARPS * 32) fb_split_lane_kernel(FbLaneParams q) {
   __shared__ double s_win[FL_WARPS * 16 * 32];
   __shared__ unsigned long long s_et[256];
   __shared__ double s_lt[256];
   const LibmTabs lt = stage_libm_tables(s_et, s_lt);
-  if (blockIdx.x & 1u) fb_backward_lane_body<true>(q, blockIdx.x >> 1, s_win, lt);
-  else fb_forward_lane_body(q, blockIdx.x >> 1, s_win, lt);
+  if (blockIdx.x & 1u) fb_backward_lane_body<true, DROP>(q, blockIdx.x >> 1, s_win, lt);
+  else fb_forward_lane_body<DROP>(q, blockIdx.x >> 1, s_win, lt);
 }
 
 // Expected counts from stored alpha and beta (split form): one warp per snippet, a lane per start position.
@@ -1380,6 +1391,7 @@ constexpr int FC_WARPS = 8;
 // (Measured alternative: the counts of the ~1800 smallest ids in shared memory, flushed once per block of a persistent
 //  grid — 133 ms per GB against 69: every thread of a block then hammers the same few shared-memory words of the
 //  hottest tokens, where the global accumulators have 256 replicas.)
+template <bool DROP>
 __global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams q) {
   __shared__ unsigned long long s_et[256];
   __shared__ double s_lt[256];
@@ -1405,7 +1417,7 @@ __global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams 
       const uint32_t cw = 0x100u | __ldg(text + pos + d);
       const uint4 e = __ldg(u.trie + (xb ^ cw));
       if ((e.x ^ cw) & 0x1FFu) break;
-      if (e.y & F_TERM) {
+      if ((e.y & F_TERM) && !fb_dropped<DROP>(p, start + pos, d + 1u)) {
         const double sc = __hiloint2double((int)e.w, (int)e.z);
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(a, sc), B[pos + d + 1]), -z);
         const uint32_t id = e.y & ID_MASK;
