@@ -30,7 +30,7 @@ VOCAB_SIZE = 131072
 MAX_TOKEN_LEN = 16
 VOCAB_SAMPLE_BYTES = 96_000_000
 FORWARD_KERNEL_NAME = "viterbi_pair_kernel<2, 1, 960>"  # forward pass 2 (batches below 600 MiB)
-TEAM_KERNEL_NAME = "viterbi_team_kernel<4, 16>"  # forward pass 3: the consumer of the match stream
+TEAM_KERNEL_NAME = "viterbi_team_kernel<16>"  # forward pass 3: the consumer of the match stream
 SIDE_KERNEL_NAME = "viterbi_pair_kernel<2, 2, 800> (samples >= 64 KiB, side stream, beside the teams)"
 METRIC = "encode_input_throughput"
 UNIT = "MB/s"

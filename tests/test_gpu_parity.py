@@ -262,6 +262,11 @@ def test_match_rows_synth_corpus(N):
         res.append(gm.encode_batch(blob, off, crlf=True))
     for r in res[1:]:
         assert r[4] == 0 and np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1])
+    # the frequency pass through the lane teams (forced: the automatic choice keeps it on the pair-CTA kernel)
+    gm.set_option(3, 3)
+    gm.set_option(32, 20000)
+    fr, rc, bad, blen = gm.token_frequencies(blob, off)
+    assert rc == 0 and np.array_equal(fr, O.OracleModel(toks, sc).token_frequencies(blob, off, threads=8))
 
 
 @pytest.mark.parametrize("algo", [0, 1, 2])
