@@ -104,6 +104,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """The timed region starts here: stop() reports the samples taken from now on (nvidia-smi needs a few hundred
+        milliseconds to deliver its first line, so it is started during the warm-up)."""
+        self.n0 = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -115,7 +120,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[getattr(self, "n0", 0):]
+        during = bool(rows)
+        if not rows:  # a timed region shorter than the sampling period: the warm-up steps ran the same kernels
+            rows = self.rows[-3:]
+        self.samples_from = "timed region" if during else "warm-up steps of the same workload (timed region shorter than the sampling period)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -128,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_from": self.samples_from}
 
 
 def run_reference(args, rank, world):
@@ -292,8 +302,8 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     alg = NB + 8 * (S + 1) + 8 * len(vocab)
     out["roofline"] = {"bound": "hbm", "achieved": alg / (e_dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": alg / (e_dev_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
-                       "kernel": "match_kernel<4> + fbr_split_kernel<false> + fbr_contrib_kernel<false> (snippets below the warp "
-                                 "threshold) + fb_forward_kernel<32> / fb_backward_kernel<32, true> (whole E-step, device ms)"}
+                       "kernel": "fb_split_lane_kernel<false> + fb_contrib_kernel<false> (snippets below the warp threshold) + "
+                                 "fb_forward_kernel<32> / fb_backward_kernel<32, true> (whole E-step, device ms)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         threads = synth.n_threads()
@@ -452,14 +462,19 @@ def main():
         assert rc == 0, "NoPath in benchmark corpus"
         return tot
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # (nvidia-smi delivers its first line after a few hundred milliseconds: started with the warm-up)
     for _ in range(max(args.warmup, 3)):
         tokens = step_dev()
+    if rank == 0:  # a few more untimed steps until the sampler is alive (the timed region may be shorter than its period)
+        t_w = time.perf_counter()
+        while clocks.proc and not clocks.rows and time.perf_counter() - t_w < 2.0:
+            tokens = step_dev()
     launches = int(model.stat(0))
     torch.cuda.synchronize()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.mark()
     dev_ms, vit_ms, back_ms, emit_ms, match_ms, allfwd_ms, side_ms = [], [], [], [], [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -498,11 +513,11 @@ def main():
     # alone (2), or match_kernel, then the lane teams over the match stream with the pair-CTA kernel of the longest
     # samples beside them on a stream of its own (3; 0 = the row consumer).  The roofline is quoted for the longest one.
     if fwd_algo == 3:
-        fwd_kernels = {"match_kernel<4>": float(np.mean(match_ms)), TEAM_KERNEL_NAME: float(np.mean(vit_ms)),
+        fwd_kernels = {"match2_kernel": float(np.mean(match_ms)), TEAM_KERNEL_NAME: float(np.mean(vit_ms)),
                        SIDE_KERNEL_NAME: float(np.mean(side_ms))}
         forward_ms = float(np.mean(allfwd_ms))
     elif fwd_algo == 0:
-        fwd_kernels = {"viterbi_rows_kernel": float(np.mean(vit_ms)), "match_kernel<4>": float(np.mean(match_ms))}
+        fwd_kernels = {"viterbi_rows_kernel": float(np.mean(vit_ms)), "match2_kernel": float(np.mean(match_ms))}
         forward_ms = sum(fwd_kernels.values())
     else:
         fwd_kernels = {FORWARD_KERNEL_NAME: float(np.mean(vit_ms))}
