@@ -207,12 +207,11 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        match_kernel CTAs (slices of the blob) per SM; bytes of leading match rows staged in shared memory;
  *   37 / 38 / 39 = match2_kernel (walks compacted inside their warp; 0 = match_kernel<ILP>); long samples per pair CTA
  *        on the side stream of forward pass 3 (default 20); match2_kernel skips the positions inside those samples;
- *   23 / 24 / 27 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory, start positions
- *        a thread walks side by side (1, 2, 4, 8);
+ *   23 / 24 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory;
  *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;
  *    0 / 1 = lane-group kernels: lanes per short sample (1,2,4,8,16,32), byte threshold from which a sample gets a
  *        full warp (also: warp-cooperative backtrack);
- *    4 / 6 / 13 / 14 = pair-CTA kernel: producer warps per consumer (2, 4), groups per CTA (0 = as many as fit), trie
+ *    6 / 13 / 14 = pair-CTA kernel: groups per CTA (0 = as many as fit), trie
  *        levels staged in shared memory (0..2), shape (0 = by batch size, 1 = 5 groups, 2 = 6 groups);
  *   11 = chunked host entry point queues the next chunk's kernels before the current chunk has finished (default 0);
  *   16 = emit looks token ids up in the token hash (1, default when max_token_len <= 16) or re-walks the trie (0);

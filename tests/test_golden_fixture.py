@@ -64,9 +64,8 @@ def test_cuda_reproduces_fixture(fx):
     from tokengeex_b200 import _native as N
     gm = N.Model(fx["toks"], fx["sc"], device=0)
     blob, off = N.pack(fx["samples"])
-    for algo, producers in ((0, 4), (2, 2), (2, 4), (1, 4)):  # match rows (default) / pair-CTA kernel / lane groups
+    for algo in (0, 2, 3, 1):  # match rows / pair-CTA kernel / lane teams / lane groups
         gm.set_option(3, algo)
-        gm.set_option(4, producers)
         ids, id_off, status, plen, rc, bad = gm.encode_batch(blob, off, crlf=True)
         assert ids.tolist() == fx["encode_crlf"]["ids"] and id_off.tolist() == fx["encode_crlf"]["id_off"]
         assert status.tolist() == fx["encode_crlf"]["status"] and plen.tolist() == fx["encode_crlf"]["proc_len"]

@@ -90,16 +90,15 @@ def test_random_small_vs_oracle(N, g, thr):
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
 
 
-@pytest.mark.parametrize("producers,shape", [(2, 1), (4, 1), (2, 2), (4, 2)])
-def test_random_small_vs_oracle_cta(N, producers, shape):
+@pytest.mark.parametrize("seed,shape", [(2, 1), (4, 1), (2, 2), (4, 2)])
+def test_random_small_vs_oracle_cta(N, seed, shape):
     """CTA-cooperative producer/consumer kernel (the default path), both shapes (option 14: 5 / 6 groups per CTA)."""
-    rng = random.Random(300 + producers)
+    rng = random.Random(300 + seed)
     for it in range(25):
         toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=rng.randrange(4, 60), max_len=rng.randrange(1, 12),
                                   complete=(it % 4 != 0), int_scores=(it % 2 == 0))
         gm, om = both(N, toks, scores)
         gm.set_option(3, 2)  # pair-CTA kernel
-        gm.set_option(4, producers)
         gm.set_option(14, shape)
         samples = rand_samples(rng, b"abcd", rng.randrange(1, 70), 0, 400)
         got, status, plen, rc, bad = gpu_encode(N, gm, samples)
@@ -111,11 +110,11 @@ def test_random_small_vs_oracle_cta(N, producers, shape):
                 assert status[i] == N.TGX_ERR_NO_PATH and got[i] == [] and plen[i] == e.length
 
 
-@pytest.mark.parametrize("producers,shape,hot", [(2, 1, 2), (4, 1, 2), (4, 2, 1), (2, 2, 0), (4, 1, 0)])
-def test_pair_kernel_full_window(N, producers, shape, hot):
+@pytest.mark.parametrize("seed,shape,hot", [(2, 1, 2), (4, 1, 2), (4, 2, 1), (2, 2, 0), (4, 1, 0)])
+def test_pair_kernel_full_window(N, seed, shape, hot):
     """Tokens of every length 1..16 (length 16 re-uses the dp cell that is being finalised), samples that span many
     32-position tiles and rounds, sample switches inside a CTA, unreachable stretches, exact ties."""
-    rng = random.Random(900 + producers)
+    rng = random.Random(900 + seed)
     for it in range(12):
         alphabet = b"ab" if it % 2 == 0 else b"abc"
         toks, scores = rand_vocab(rng, alphabet=alphabet, n_tok=rng.randrange(30, 400), max_len=16,
@@ -124,7 +123,6 @@ def test_pair_kernel_full_window(N, producers, shape, hot):
         scores = list(scores) + [-2.5, -30.0, -4.0]
         gm, om = both(N, toks, scores)
         gm.set_option(3, 2)  # pair-CTA kernel
-        gm.set_option(4, producers)
         gm.set_option(14, shape)
         gm.set_option(13, hot)  # trie levels staged in shared memory
         samples = rand_samples(rng, alphabet, rng.randrange(3, 40), 0, 5000)

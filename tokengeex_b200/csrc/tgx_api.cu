@@ -155,7 +155,6 @@ struct tgx_model {
   // kernel runs fastest (measured on B200: 1 GB 29.5 against 32.3 ms, 352 MB chunks 18 against 13.5 ms).
   int algo = 4;
   int match_threads = 1024;       // threads per CTA of match_kernel (one CTA per SM)
-  int match_ilp = 4;              // start positions a thread of match_kernel walks side by side (1, 2, 4, 8)
   int match_skip = 1;             // forward pass 3: no walks inside the samples the pair-CTA kernel takes
   int match_compact = 1;          // match2_kernel (walks compacted inside their warp) instead of match_kernel
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
@@ -167,7 +166,6 @@ struct tgx_model {
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
-  int producers = 4;   // producer warps per consumer warp of the pair kernel (2 or 4)
   int num_sms = 148;
   int groups = 0;       // consumer/producer groups per CTA of the pair kernel; 0 = as many as fit
   uint32_t pair_grid_cap = 0;  // CTAs the next pair-kernel launch may use (0 = one per SM); set and cleared by algo 3
@@ -796,12 +794,7 @@ int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N, const uint8_t* d_
     m->w().stats.launches += 1;
     return TGX_OK;
   }
-  switch (m->match_ilp) {
-    case 1: CU(launch(match_kernel<1>, 1)); break;
-    case 2: CU(launch(match_kernel<2>, 2)); break;
-    case 8: CU(launch(match_kernel<8>, 8)); break;
-    default: CU(launch(match_kernel<4>, 4)); break;
-  }
+  CU(launch(match_kernel<4>, 4));
   m->w().stats.launches += 1;
   return TGX_OK;
 }
@@ -993,10 +986,8 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
     di.seed = m->drop_seed;
     di.unit_base = m->drop_unit_base;
     if (!p.u.count) {
-    } else if (m->producers >= 4 || dropout > 0.0) {
-      CU(launch_viterbi_pair_r<2>(m, p, N, di));
     } else {
-      CU(launch_viterbi_pair_r<1>(m, p, N));
+      CU(launch_viterbi_pair_r<2>(m, p, N, di));
     }
   } else {
     ViterbiParams p;
@@ -1334,14 +1325,12 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 11: m->overlap_chunks = value ? 1 : 0; break;
     case 14: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "pair shape must be 0..2"); m->pair_shape = (int)value; break;
     case 13: if (value < 0 || value > 2) return fail(TGX_ERR_INVALID, "hot levels must be 0..2"); m->hot_levels = (int)value; break;
-    case 4: if (value != 2 && value != 4) return fail(TGX_ERR_INVALID, "producers must be 2 or 4"); m->producers = (int)value; break;
     case 7: if (value < 4096) return fail(TGX_ERR_INVALID, "chunk bytes must be >= 4096"); m->chunk_bytes = (uint64_t)value; break;
     case 22: if (value < 0) return fail(TGX_ERR_INVALID, "byte base must be >= 0"); m->drop_byte_base = (uint64_t)value; break;
     case 23: if (value < 32 || value > 1024 || value % 32) return fail(TGX_ERR_INVALID, "match threads must be 32..1024, a multiple of 32"); m->match_threads = (int)value; break;
     case 24: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->match_stage_bytes = value; break;
     case 25: if (value < 1 || value > 32) return fail(TGX_ERR_INVALID, "warps must be 1..32"); m->rows_warps = (int)value; break;
     case 26: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->rows_hot_bytes = value; break;
-    case 27: if (value != 1 && value != 2 && value != 4 && value != 8) return fail(TGX_ERR_INVALID, "positions per thread must be 1, 2, 4 or 8"); m->match_ilp = (int)value; break;
     case 30: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut1 = (int)value; break;
     case 31: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->estep_cut2 = (int)value; break;
     case 6: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->groups = (int)value; break;

@@ -84,7 +84,7 @@ constexpr int mk_max_threads(int ilp) { return ilp <= 4 ? 1024 : 768; }  // regi
 
 template <int ILP>
 __global__ void __launch_bounds__(mk_max_threads(ILP), 1) match_kernel(MatchParams p) {
-  static_assert(ILP == 1 || ILP == 2 || ILP == 4 || ILP == 8, "positions per thread");
+  static_assert(ILP == 4, "positions per thread (1, 2 and 8 were measured: the time does not move)");
   extern __shared__ __align__(16) unsigned char smem[];
   {
     uint2* s_trie = reinterpret_cast<uint2*>(smem);
