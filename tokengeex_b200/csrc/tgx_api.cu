@@ -102,7 +102,7 @@ struct tgx_model {
   tgx::TokenHash hash;
   DevBuf d_hash;
   // match tables (trie_build.h: slots8 / rows / row_ids; max_token_len <= 16 only): have_rows == false = not available
-  DevBuf d_trie8, d_rows, d_rowids;
+  DevBuf d_trie8, d_rows, d_rowids, d_pair2;
   bool have_rows = false;
   uint32_t rows16 = 0;  // 16-byte units in the row table
   Workspace ws[2];
@@ -690,6 +690,8 @@ int ensure_match_tables(tgx_model* m) {
   CU(cudaMemcpyAsync(m->d_trie8.p, da.slots8.data(), da.slots8.size() * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->d_rows.p, da.rows.data(), da.rows.size() * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->d_rowids.p, da.row_ids.data(), da.row_ids.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(m->d_pair2.reserve(da.pair2.size() * 8));
+  CU(cudaMemcpyAsync(m->d_pair2.p, da.pair2.data(), da.pair2.size() * 8, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   m->have_rows = true;
   m->rows16 = (uint32_t)(da.rows.size() / 2);
@@ -762,6 +764,7 @@ int run_match(tgx_model* m, const uint8_t* d_text, uint64_t N, const uint8_t* d_
   mp.root_base = m->da.root_base;
   mp.rec = m->w().rec.as<uint32_t>();
   mp.skip = d_skip;
+  mp.pair2 = m->d_pair2.as<uint2>();
   mp.slice = 0;
   const size_t budget = (size_t)std::min<int64_t>(m->match_stage_bytes, (int64_t)m->smem_optin - 1024);
   mp.staged = (uint32_t)std::min<size_t>(m->da.slots8.size(), budget / 8);
@@ -1247,6 +1250,7 @@ void tgx_model_destroy(tgx_model* m) {
     m->d_hash.release();
     m->d_trie8.release();
     m->d_rows.release();
+    m->d_pair2.release();
     m->d_rowids.release();
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream3) cudaStreamDestroy(m->stream3);

@@ -39,6 +39,7 @@ struct MatchParams {
   uint32_t staged;          // leading slots staged in shared memory
   uint32_t* rec;            // [N + 64]
   unsigned long long slice; // positions per CTA (a multiple of blockDim.x * ILP)
+  const uint2* pair2;       // match2_kernel: tgx::DoubleArray::pair2 (the state of a walk after its two first bytes)
   const uint8_t* skip;      // match2_kernel: [ceil(N / 128)] != 0 = nobody reads the records of these 128 positions
                             // (they lie inside a sample that the pair-CTA kernel takes): write row 0, do not walk
 };
@@ -211,17 +212,18 @@ __global__ void __launch_bounds__(MK2_THREADS, 1) match2_kernel(MatchParams p) {
       pos = npos;
       continue;
     }
-    // ---- levels 1..4: four walks per lane, side by side
+    // ---- levels 1..4: four walks per lane, side by side; the two first levels come from the pair table
     uint32_t xb[4], best[4];
     bool go[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      xb[i] = p.root_base;
-      best[i] = REC_NOMATCH;
-      go[i] = pos + i < lim;
+      const uint2 t2 = __ldg(p.pair2 + (uint32_t)((a0 >> (8 * i)) & 0xFFFFull));
+      xb[i] = t2.x & 0x7FFFFFFFu;
+      best[i] = t2.y;
+      go[i] = (t2.x >> 31) != 0u && pos + i < lim;
     }
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
+    for (int d = 2; d < 4; d++) {
       uint2 e[4];
       uint32_t cw[4];
 #pragma unroll

@@ -260,6 +260,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   lap("emit");
   // 6. what build_match_tables needs later (the match tables are built on first use: trie_build.h)
   out->slots8.clear();
+  out->pair2.clear();
   out->rows.clear();
   out->row_ids.clear();
   out->node_parent.clear();
@@ -344,6 +345,38 @@ std::string build_match_tables(DoubleArray* out) {
     if (sl.y & SLOT_HASCH) y |= SLOT8_HASCH;
     if (out->node_term[i] >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
     out->slots8[out->node_slot[i]] = (uint64_t)sl.x | ((uint64_t)y << 32);
+  }
+  // the two first levels of every walk, tabulated (the probes of match_kernel, restated)
+  out->pair2.assign(65536, 0);
+  for (uint32_t b0 = 0; b0 < 256; b0++) {
+    uint32_t xb1 = 0, best1 = 15u << 28;
+    bool go1 = false;
+    {
+      const uint32_t cw = 0x100u | b0, t = out->root_base ^ cw;
+      if (t < n_slots) {
+        const uint32_t ex = (uint32_t)out->slots8[t], ey = (uint32_t)(out->slots8[t] >> 32);
+        const bool hit = ((ex ^ cw) & 0x1FFu) == 0;
+        if (hit && (ey & SLOT8_TERM)) best1 = (0u << 28) | (ey & SLOT8_OFF_MASK);
+        go1 = hit && (ey & SLOT8_HASCH);
+        xb1 = ex >> 9;
+      }
+    }
+    for (uint32_t b1 = 0; b1 < 256; b1++) {
+      uint32_t xb = xb1, best = best1;
+      bool go = go1;
+      if (go) {
+        const uint32_t cw = 0x100u | b1, t = xb ^ cw;
+        go = false;
+        if (t < n_slots) {
+          const uint32_t ex = (uint32_t)out->slots8[t], ey = (uint32_t)(out->slots8[t] >> 32);
+          const bool hit = ((ex ^ cw) & 0x1FFu) == 0;
+          if (hit && (ey & SLOT8_TERM)) best = (1u << 28) | (ey & SLOT8_OFF_MASK);
+          go = hit && (ey & SLOT8_HASCH);
+          xb = ex >> 9;
+        }
+      }
+      out->pair2[b0 | (b1 << 8)] = (uint64_t)(go ? (xb | (1u << 31)) : 0u) | ((uint64_t)best << 32);
+    }
   }
   return "";
 }

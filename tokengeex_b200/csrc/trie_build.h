@@ -61,6 +61,10 @@ struct DoubleArray {
   // Built on first use (build_match_tables) from the node arrays below, which build_double_array keeps: the EM loop
   // rebuilds the model ~30 times and only some of its passes read the tables.
   std::vector<uint64_t> slots8;
+  // pair2[b0 | b1 << 8]: the walk's state after the two bytes b0 b1 — low word = base of the depth-2 node | 1 << 31 when
+  // the walk goes on, 0 when it has ended; high word = the record (match_kernel's format) of the deepest token so far.
+  // match2_kernel starts its walks here: one 8-byte load instead of the two first probes.
+  std::vector<uint64_t> pair2;
   std::vector<double> rows;
   std::vector<uint32_t> row_ids;
   std::vector<uint32_t> node_parent, node_slot;  // per trie node (node 0 = root); empty when max_token_len > 16
