@@ -106,11 +106,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
     // Only the lanes whose pair lies inside the row load it (a team's row is short most of the time: the lanes of the
     // long lengths stay out of the load — the shared-memory / L1 data pipe is what bounds this kernel, ncu: 70 % busy);
     // a register that is not loaded keeps an older score, and the relax of an entry beyond the row is predicated off.
-    double sc[LPL];
-    double s16 = ninf;
+    // Two sets, loaded TWO steps ahead (set k & 1 serves step k): a step of a warp sees 8 rows, one of them cold (L2)
+    // most of the time, and one step of lead (~70 instructions) does not cover an L2 access.
+    double sc[2][LPL];
+    double s16[2] = {ninf, ninf};
 #pragma unroll
-    for (int i = 0; i < LPL; i++) sc[i] = ninf;
-    auto load_scores = [&](uint32_t r) {
+    for (int i = 0; i < LPL; i++) sc[0][i] = sc[1][i] = ninf;
+    auto load_scores = [&](uint32_t r, int w) {
       const double2* b = row_of(r) + (uint32_t)NP * t;
       const uint32_t L1n = (r >> 28) + 1u;
 #pragma unroll
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
             "setp.ne.u32 q, %3, 0;\n\t"
             "@q ld.v2.f64 {%0, %1}, [%2];\n\t"
             "}"
-            : "+d"(sc[2 * j]), "+d"(sc[2 * j + 1])
+            : "+d"(sc[w][2 * j]), "+d"(sc[w][2 * j + 1])
             : "l"(b + j), "r"(need));
       }
       {  // entry 16: lane 0's candidate of length 16
@@ -131,11 +133,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
             "setp.ne.u32 q, %2, 0;\n\t"
             "@q ld.f64 %0, [%1];\n\t"
             "}"
-            : "+d"(s16)
+            : "+d"(s16[w])
             : "l"(reinterpret_cast<const double*>(b) + 16), "r"(need));
       }
     };
-    load_scores(gq[0].x);
+    load_scores(gq[0].x, 0);
+    load_scores(gq[0].y, 1);
     for (uint32_t sv0 = 0; sv0 < nsteps; sv0 += 16) {
 #pragma unroll
       for (int k = 0; k < 16; k++) {
@@ -153,8 +156,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
         }
         const uint4 r4 = gq[(k >> 2) & 3];
         const uint32_t rs = (k & 3) == 0 ? r4.x : (k & 3) == 1 ? r4.y : (k & 3) == 2 ? r4.z : r4.w;
-        const uint4 q4 = gq[((k + 1) >> 2) & 3];
-        const uint32_t rn = ((k + 1) & 3) == 0 ? q4.x : ((k + 1) & 3) == 1 ? q4.y : ((k + 1) & 3) == 2 ? q4.z : q4.w;
+        const uint4 q4 = gq[((k + 2) >> 2) & 3];  // the record of the step after next
+        const uint32_t rn = ((k + 2) & 3) == 0 ? q4.x : ((k + 2) & 3) == 1 ? q4.y : ((k + 2) & 3) == 2 ? q4.z : q4.w;
         if (TM_PF > 0) {  // a cold row of the step TM_PF ahead: into L1
           const int kp = k + TM_PF;
           const uint4 p4 = gq[(kp >> 2) & 3];
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
         const uint32_t L1 = (rs >> 28) + 1u;  // entries 1 .. L1 of the row are real (scores or -inf), the rest is not this row
         // candidate: dp[pos].score + vocab[id].score (src/model.rs:98), kept if strictly greater (:100-101)
         {
-          const double cand = __dadd_rn(cur, t == 0u ? s16 : sc[0]);
+          const double cand = __dadd_rn(cur, t == 0u ? s16[k & 1] : sc[k & 1][0]);
           if (len[0] <= L1 && cand > x) {
             x = cand;
             xb = len[0];
@@ -199,13 +202,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) viterbi_team_kernel(TeamParams 
         }
 #pragma unroll
         for (int i = 1; i < LPL; i++) {
-          const double cand = __dadd_rn(cur, sc[i]);
+          const double cand = __dadd_rn(cur, sc[k & 1][i]);
           if (len[i] <= L1 && cand > c[(k + i) % LPL]) {
             c[(k + i) % LPL] = cand;
             bl[(k + i) % LPL] = len[i];
           }
         }
-        load_scores(rn);  // the next step's scores
+        load_scores(rn, k & 1);  // the scores of the step after next, into the set that was just used
         // the cell moves on to the lane that owns the later starts (lane 0's newborn to the last lane): it is the
         // newest cell of that lane's window from the next step on, in the slot this step's oldest one just left
         c[k0] = __shfl_sync(0xFFFFFFFFu, x, (int)((t + 1u) & (uint32_t)(G - 1)), G);
