@@ -161,6 +161,7 @@ struct tgx_model {
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
   // position) on a stream of its own, the rest four lanes each on viterbi_team_kernel over the match stream
   int64_t thread_long_threshold = 65536;
+  int side_groups = 4;   // ... and groups per CTA of that kernel: four (8 chains) run a chain in ~90 cycles per position, five in ~100
   int side_load = 20;    // algo 3: long samples per pair CTA on the side stream (10 chains each)
   int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_team_kernel stages in shared memory
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
@@ -917,7 +918,10 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
           cudaStream_t keep = m->w().stream;
           m->w().stream = m->w().stream_side;
           m->pair_grid_cap = P;
+          const int keep_groups = m->groups;
+          if (m->side_groups > 0) m->groups = m->groups > 0 ? std::min(m->groups, m->side_groups) : m->side_groups;
           cudaError_t e = launch_viterbi_pair_r<2>(m, pp, 0);
+          m->groups = keep_groups;
           m->pair_grid_cap = 0;
           m->w().stream = keep;
           CU(e);
@@ -1315,6 +1319,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 43: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->side_groups = (int)value; break;
     case 39: m->match_skip = value ? 1 : 0; break;
     case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;
     case 37: m->match_compact = value ? 1 : 0; break;
