@@ -205,8 +205,9 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        long samples (it sizes the grids);
  *   32 / 33 / 35 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default 65536);
  *        match_kernel CTAs (slices of the blob) per SM; bytes of leading match rows staged in shared memory;
- *   37 / 38 / 39 = match2_kernel (walks compacted inside their warp; 0 = match_kernel<ILP>); long samples per pair CTA
+ *   37 / 38 / 39 / 43 = match2_kernel (walks compacted inside their warp; 0 = match_kernel); long samples per pair CTA
  *        on the side stream of forward pass 3 (default 20); match2_kernel skips the positions inside those samples;
+ *        groups per CTA of that side kernel (default 4);
  *   23 / 24 = match_kernel: threads per CTA, bytes of leading trie slots staged in shared memory;
  *   25 / 26 = viterbi_rows_kernel: warps per CTA, bytes of leading match rows staged in shared memory;
  *    0 / 1 = lane-group kernels: lanes per short sample (1,2,4,8,16,32), byte threshold from which a sample gets a

@@ -194,6 +194,7 @@ def test_team_kernel_random_vs_oracle(N, thr, ctas, match2):
         gm.set_option(37, match2)
         gm.set_option(39, it % 2)
         gm.set_option(38, [20, 1, 3][it % 3])
+        gm.set_option(43, [4, 0, 2, 5][it % 4])
         gm.set_option(35, [160 << 10, 0, 4096, 300][it % 4])
         samples = rand_samples(rng, alphabet, rng.randrange(1, 400), 0, 700) + rand_samples(rng, alphabet, 4, 1000, 9000)
         samples += [alphabet[:1] * k for k in (1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 511, 512, 513, 1300)] + [b""]
