@@ -60,9 +60,10 @@ def main():
             for one in args.opts.split(";"):
                 a, _, kv = one.partition(":")
                 cfgs.append((int(a), {int(x.split("=")[0]): int(x.split("=")[1]) for x in kv.split(",") if x}))
+        defaults = {6: 0, 13: 2, 14: 0, 32: 65536, 33: 8, 35: 160 << 10, 37: 1, 38: 20, 39: 1, 43: 4}
         for algo, opts in cfgs:
             m.set_option(3, algo)
-            for k, v in opts.items():
+            for k, v in {**defaults, **opts}.items():  # (options are sticky: every configuration starts from the defaults)
                 m.set_option(k, v)
             best = 1e9
             for _ in range(args.reps + 1):
