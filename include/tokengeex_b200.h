@@ -205,6 +205,8 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        long samples (it sizes the grids);
  *   32 / 33 / 35 = forward pass 3: byte length from which a sample runs on the pair-CTA kernel (default 65536);
  *        match_kernel CTAs (slices of the blob) per SM; bytes of leading match rows staged in shared memory;
+ *   45 = tgx_model_rebuild keeps the double-array's layout when the new vocabulary is a subset of the one it was built
+ *        for and has at least this many per mille of its tokens (default 450; 0 = always build afresh);
  *   37 / 38 / 39 / 43 = match2_kernel (walks compacted inside their warp; 0 = match_kernel); long samples per pair CTA
  *        on the side stream of forward pass 3 (default 20); match2_kernel skips the positions inside those samples;
  *        groups per CTA of that side kernel (default 4);

@@ -46,3 +46,40 @@ def test_double_array_is_dense_and_byte_complete():
     ids, lens = hm.common_prefix_search(bytes([0xFF]))
     assert ids == [] and lens == []
     assert hm.common_prefix_search(b"\x00")[0] == [0]
+
+
+def test_rebuild_keeps_the_layout_for_a_subset_and_builds_afresh_otherwise():
+    """tgx_model_rebuild with a SUBSET of the vocabulary the array was built for (what the EM loop hands over after every
+    M-step and every prune step, src/prune.rs:48,53) rewrites terminals / ids / scores in place (retarget_double_array):
+    common_prefix_search equals the oracle's on the new vocabulary — new ids, new scores, the tokens that went never
+    yielded — for every share that is kept; below 45 % of the built size, with a token the array has no node for, or
+    with option 45 = 0 the array is built afresh."""
+    rng = random.Random(5)
+    alpha = b"abcdefgh"
+    toks = sorted({bytes(rng.choice(alpha) for _ in range(rng.randrange(1, 13))) for _ in range(6000)} | {bytes([c]) for c in alpha})
+    sc = [-(rng.random() * 8 + 0.1) for _ in toks]
+    hm = N.Model(toks, sc, device=None)
+    slots0, built = hm.info().trie_slots, len(toks)
+    for frac in (0.9, 0.7, 0.5, 0.3):
+        keep = [i for i in range(len(toks)) if rng.random() < frac or len(toks[i]) == 1]
+        t2, s2 = [toks[i] for i in keep], [sc[i] - 0.5 for i in keep]
+        hm.rebuild(t2, s2)
+        om = O.OracleModel(t2, s2)
+        for _ in range(1500):
+            q = rng.choice(toks) + bytes(rng.choice(alpha) for _ in range(rng.randrange(0, 6)))
+            assert hm.common_prefix_search(q) == om.common_prefix_search(q), (frac, q)
+        kept_layout = hm.info().trie_slots == slots0
+        assert kept_layout == (len(t2) * 1000 >= built * 450), (frac, len(t2), built)
+        if not kept_layout:
+            slots0, built = hm.info().trie_slots, len(t2)
+        toks, sc = t2, s2
+    t3, s3 = toks + [b"zzzz", toks[0]], sc + [-1.0, -0.25]  # a new token, and a duplicate (the last id wins)
+    hm.rebuild(t3, s3)
+    om = O.OracleModel(t3, s3)
+    for q in (b"zzzzab", toks[0] + b"a", toks[5]):
+        assert hm.common_prefix_search(q) == om.common_prefix_search(q)
+    hm.set_option(45, 0)
+    hm.rebuild(t3[:-3], s3[:-3])
+    om = O.OracleModel(t3[:-3], s3[:-3])
+    for q in (toks[0] + b"a", toks[7], b"zzzz"):
+        assert hm.common_prefix_search(q) == om.common_prefix_search(q)

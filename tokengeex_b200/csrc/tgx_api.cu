@@ -95,6 +95,8 @@ struct Workspace {
 struct tgx_model {
   tgx::DoubleArray da;
   uint64_t V = 0;
+  uint64_t V_built = 0;        // vocabulary size the double-array's layout was built for
+  int retarget_permille = 450; // tgx_model_rebuild keeps the layout for a subset of at least this share of V_built (0 = never)
   int device = -1;
   uint4* d_trie = nullptr;
   size_t trie_cap = 0;  // slots allocated at d_trie
@@ -1137,6 +1139,7 @@ int tgx_model_create(const uint8_t* token_bytes, const uint64_t* token_offsets, 
   std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &m->da);
   if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);
   m->V = vocab_size;
+  m->V_built = vocab_size;
   m->device = device;
   if (device >= 0) {
     int n = 0;
@@ -1202,7 +1205,14 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
     return fail(TGX_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> g(m->mu);
   tgx::DoubleArray da;
-  std::string err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da, /*hot_order=*/false);
+  std::string err = "miss";
+  // a subset of the vocabulary the array was built for, not much smaller than it: keep the layout (trie_build.h)
+  if (m->retarget_permille > 0 && m->V_built && vocab_size * 1000ull >= m->V_built * (uint64_t)m->retarget_permille)
+    err = tgx::retarget_double_array(m->da, token_bytes, token_offsets, scores, vocab_size, &da);
+  if (err == "miss") {
+    err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da, /*hot_order=*/false);
+    if (err.empty()) m->V_built = vocab_size;
+  }
   if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);  // the model is unchanged
   if (m->device >= 0) {
     CU(cudaSetDevice(m->device));
@@ -1319,6 +1329,7 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
     case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 45: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->retarget_permille = (int)value; break;
     case 43: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->side_groups = (int)value; break;
     case 39: m->match_skip = value ? 1 : 0; break;
     case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;

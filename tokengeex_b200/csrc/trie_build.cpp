@@ -285,6 +285,70 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   return "";
 }
 
+std::string retarget_double_array(const DoubleArray& old, const uint8_t* bytes, const uint64_t* off, const double* scores,
+                                  uint64_t V, DoubleArray* out) {
+  if (old.slots.empty() || V > MAX_VOCAB) return "miss";
+  const size_t n_slots = old.slots.size();
+  std::vector<uint32_t> slot_of(V, 0xFFFFFFFFu);
+  uint32_t max_len = 0;
+  for (uint64_t i = 0; i < V; i++) {
+    const uint64_t len = off[i + 1] - off[i];
+    if (!std::isfinite(scores[i])) return "non-finite token score";
+    if (len == 0) continue;  // the empty token never matches
+    if (len > old.max_token_len) return "miss";
+    const uint8_t* t = bytes + off[i];
+    uint32_t xbase = old.root_base, at = 0;
+    for (uint64_t d = 0; d < len; d++) {
+      const uint32_t cw = 0x100u | t[d];
+      at = xbase ^ cw;
+      if (at >= n_slots) return "miss";
+      const Slot& e = old.slots[at];
+      if ((e.x ^ cw) & 0x1FFu) return "miss";
+      if (d + 1 < len && !(e.y & SLOT_HASCH)) return "miss";
+      xbase = e.x >> 9;
+    }
+    slot_of[i] = at;
+    max_len = std::max<uint32_t>(max_len, (uint32_t)len);
+  }
+  *out = old;
+  out->slots8.clear();
+  out->pair2.clear();
+  out->rows.clear();
+  out->row_ids.clear();
+  for (Slot& s : out->slots) {
+    s.y &= ~(SLOT_TERM | SLOT_ID_MASK);
+    s.z = s.w = 0;
+  }
+  uint32_t n_term = 0;
+  for (uint64_t i = 0; i < V; i++) {  // in id order: the last of equal byte strings wins (src/trie.rs:19)
+    if (slot_of[i] == 0xFFFFFFFFu) continue;
+    Slot& s = out->slots[slot_of[i]];
+    if (!(s.y & SLOT_TERM)) n_term++;
+    s.y = (s.y & ~SLOT_ID_MASK) | SLOT_TERM | ((uint32_t)i & SLOT_ID_MASK);
+    uint64_t bits;
+    std::memcpy(&bits, &scores[i], 8);
+    s.z = (uint32_t)bits;
+    s.w = (uint32_t)(bits >> 32);
+  }
+  (void)max_len;  // max_token_len stays the depth of the ARRAY (the kernels size their windows by it)
+  out->n_terminals = n_term;
+  if (!out->node_parent.empty()) {  // what build_match_tables reads
+    {
+      std::vector<uint32_t> node_at(n_slots, 0);
+      for (size_t nd = 0; nd < out->node_slot.size(); nd++) node_at[out->node_slot[nd]] = (uint32_t)nd;
+      std::fill(out->node_term.begin(), out->node_term.end(), -1);
+      std::fill(out->node_score.begin(), out->node_score.end(), 0.0);
+      for (uint64_t i = 0; i < V; i++) {
+        if (slot_of[i] == 0xFFFFFFFFu) continue;
+        const uint32_t nd = node_at[slot_of[i]];
+        out->node_term[nd] = (int32_t)i;
+        out->node_score[nd] = scores[i];
+      }
+    }
+  }
+  return "";
+}
+
 std::string build_match_tables(DoubleArray* out) {
   if (!out->slots8.empty()) return "";
   if (out->node_parent.empty()) return "no match tables for this vocabulary (tokens longer than 16 bytes)";
