@@ -162,10 +162,10 @@ struct tgx_model {
   int match_ctas_per_sm = 8;      // match_kernel: CTAs (contiguous slices of the blob) per SM, handed out as SMs come free
   // algo 3: samples at least this long run on the pair-CTA kernel (16 lanes per sample: the shortest chain per
   // position) on a stream of its own, the rest four lanes each on viterbi_team_kernel over the match stream
-  int64_t thread_long_threshold = 65536;
+  int64_t team_long_threshold = 65536;
   int side_groups = 4;   // ... and groups per CTA of that kernel: four (8 chains) run a chain in ~90 cycles per position, five in ~100
   int side_load = 20;    // algo 3: long samples per pair CTA on the side stream (10 chains each)
-  int64_t thread_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_team_kernel stages in shared memory
+  int64_t team_hot_bytes = 160 << 10;  // leading bytes of the row table viterbi_team_kernel stages in shared memory
   int64_t match_stage_bytes = 64 << 10;  // leading trie slots (8 bytes each) match_kernel stages in shared memory
   int rows_warps = 16;            // warps per CTA of viterbi_rows_kernel (one CTA per SM; two samples per warp)
   int64_t rows_hot_bytes = 96 << 10;  // leading bytes of the row table viterbi_rows_kernel stages in shared memory
@@ -829,7 +829,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   if (rc) return rc;
   uint32_t* counts = m->w().small.as<uint32_t>();
   uint32_t thr = (uint32_t)std::min<int64_t>(m->long_threshold, 0x7FFFFFFF);
-  const uint32_t thr2 = (uint32_t)std::min<int64_t>(m->thread_long_threshold, 0x7FFFFFFF);
+  const uint32_t thr2 = (uint32_t)std::min<int64_t>(m->team_long_threshold, 0x7FFFFFFF);
   split_sorted<<<1, 32, 0, st>>>(m->w().keys_out.as<uint32_t>(), U, thr, thr2, counts);
   m->w().stats.launches += 1;
   CU(dev_fill(m->w().ntok.p, 0, ((size_t)U + 1) * 8, st));
@@ -863,7 +863,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   const int algo = dropout > 0.0 ? (algo_req == 1 ? 1 : 2) : ((algo_req == 0 || algo_req == 3) && !m->have_rows ? 2 : algo_req);
   m->w().algo_used = algo;
   m->w().side_used = false;
-  uint32_t n_long = 0;  // algo 3: samples of at least thread_long_threshold bytes (the one host wait in the middle of a call)
+  uint32_t n_long = 0;  // algo 3: samples of at least team_long_threshold bytes (the one host wait in the middle of a call)
   if (algo == 3 && u.rows <= 16 && N && U) {
     unsigned long long w01 = 0, w23 = 0;
     rc = read_words(m, counts, counts + 2, &w01, &w23);
@@ -890,7 +890,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
   CU(cudaEventRecord(m->w().ev[0], st));  // [0]..[1]: the consumer of the match stream / the forward kernel
   if (algo == 3 && u.rows <= 16) {
     if (N && U) {
-      // The samples of at least thread_long_threshold bytes run on the pair-CTA kernel (16 lanes per sample: the shortest
+      // The samples of at least team_long_threshold bytes run on the pair-CTA kernel (16 lanes per sample: the shortest
       // chain per position) BESIDE the teams, on P SMs of their own: forked when match_kernel — which fills every SM —
       // has finished.  Measured: a side kernel that runs beside match_kernel only adds its time to it, and persistent
       // team CTAs on every SM keep the pair CTAs waiting until they exit; so the team kernel gets num_sms - P CTAs,
@@ -940,7 +940,7 @@ int run_viterbi(tgx_model* m, const uint8_t* d_text, const uint64_t* d_off, uint
       tm.rows = m->d_rows.as<double>();
       tm.bp = m->w().bp.as<uint8_t>();
       tm.counter = m->w().small.as<unsigned int>() + 9;
-      const size_t budget = (size_t)std::min<int64_t>(m->thread_hot_bytes, (int64_t)m->smem_optin - 1024);
+      const size_t budget = (size_t)std::min<int64_t>(m->team_hot_bytes, (int64_t)m->smem_optin - 1024);
       tm.hot16 = (uint32_t)std::max<size_t>(std::min<size_t>(m->rows16, budget / 16), std::min<size_t>(m->rows16, 9));  // (row 0 is always staged)
       const size_t smem = (size_t)tm.hot16 * 16;
       const uint32_t n_short = tm.u.count;
@@ -1328,13 +1328,13 @@ int tgx_model_set_option(tgx_model* m, int key, int64_t value) {
     case 2: if (!okg(value)) return fail(TGX_ERR_INVALID, "lanes per snippet must be 1,2,4,8,16,32"); m->g_estep = (int)value; break;
     case 5: if (value < 0) return fail(TGX_ERR_INVALID, "threshold must be >= 0 (0 = automatic)"); m->estep_long_threshold = value; break;
     case 3: if (value < 0 || value > 4) return fail(TGX_ERR_INVALID, "algo must be 0..4"); m->algo = (int)value; break;
-    case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->thread_long_threshold = value; break;
+    case 32: if (value < 1) return fail(TGX_ERR_INVALID, "threshold must be >= 1"); m->team_long_threshold = value; break;
     case 45: if (value < 0 || value > 1000) return fail(TGX_ERR_INVALID, "per mille"); m->retarget_permille = (int)value; break;
     case 43: if (value < 0 || value > 15) return fail(TGX_ERR_INVALID, "groups per CTA must be 0..15"); m->side_groups = (int)value; break;
     case 39: m->match_skip = value ? 1 : 0; break;
     case 38: if (value < 1 || value > 1000) return fail(TGX_ERR_INVALID, "samples per CTA must be 1..1000"); m->side_load = (int)value; break;
     case 37: m->match_compact = value ? 1 : 0; break;
-    case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->thread_hot_bytes = value; break;
+    case 35: if (value < 0) return fail(TGX_ERR_INVALID, "bytes must be >= 0"); m->team_hot_bytes = value; break;
     case 33: if (value < 1 || value > 64) return fail(TGX_ERR_INVALID, "CTAs per SM must be 1..64"); m->match_ctas_per_sm = (int)value; break;
     case 16: m->emit_hash = value ? 1 : 0; break;
     case 17: m->estep_lane_threshold = value; break;  // < 0 = automatic, 0 = off
