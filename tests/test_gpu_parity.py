@@ -455,6 +455,23 @@ def test_expected_counts_synth_vs_oracle(N):
         assert abs(float((ex * lens).sum()) - int(off[-1])) < 1e-9 * int(off[-1])
 
 
+def test_expected_counts_replica_shapes_bit_identical(N):
+    """The replicas of the hot ids (options 20 / 21) are a placement of the fixed-point accumulators, not arithmetic:
+    every shape — none, one id, more ids than the vocabulary has — gives the same counts to the bit (the exact sum
+    that stands in for the f64 merge of src/prune.rs:104-112)."""
+    blob, off, toks, sc, kp = synth_setup(2, 17, 1_500_000, 20000, 16)
+    gm, om = both(N, toks, sc)
+    base = gm.expected_counts(blob, off)[0]
+    want = om.run_e_step(blob, off, threads=8, literal=False)[0]
+    assert counts_rel_err(base, want) < REL_TOL
+    for r, k in ((1, 4096), (64, 0), (7, 1), (4096, 16), (3, 1 << 20), (256, 4096)):
+        gm.set_option(20, r)
+        gm.set_option(21, k)
+        ex, rc, bad, badz = gm.expected_counts(blob, off)
+        assert rc == 0
+        assert np.array_equal(ex.view(np.uint64), base.view(np.uint64)), (r, k)
+
+
 def test_very_long_samples(N):
     """Samples far beyond the 64-position rounds, the 1024-position backtrack chunks and the 81920-byte snippet
     length of the E-step (src/prune.rs:75,83): one of 400 KB, one of exactly 2 * 81920 bytes, one of 81920 + 1."""

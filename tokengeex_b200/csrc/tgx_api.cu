@@ -147,7 +147,9 @@ struct tgx_model {
   // kernel adds the expected counts (needs 8 more bytes per input byte; falls back to the fused form without them).
   int estep_split = 1;
   int estep_rows = 1;  // E-step over the match stream (tgx_fb_rows_kernels.cuh) when the match tables exist
-  int hot_k = 4096, hot_r = 256;  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids
+  // E-step: replicas of the count vector for the hot_k hottest (smallest) ids.  (4 GB / 500k tokens, tools/probe.py: 636 ms
+  // with 32-128 replicas of 1024-4096 ids, 647 with 256 x 4096, 669 with 512 x 4096, 639 with 16 x 2048.)
+  int hot_k = 4096, hot_r = 64;
   int lane_blocks_per_sm = 0;  // lane E-step kernels: resident 128-thread blocks per SM (0 = as many as fit, 9)
   // Viterbi forward (max_token_len <= 16; longer vocabularies always use the lane-group kernels):
   // 0 = match stream + row consumer (tgx_match_kernels.cuh), 1 = lane-group kernels, 2 = pair-CTA kernel (the default

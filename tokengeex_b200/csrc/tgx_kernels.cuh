@@ -1390,7 +1390,7 @@ constexpr int FC_WARPS = 8;
 
 // (Measured alternative: the counts of the ~1800 smallest ids in shared memory, flushed once per block of a persistent
 //  grid — 133 ms per GB against 69: every thread of a block then hammers the same few shared-memory words of the
-//  hottest tokens, where the global accumulators have 256 replicas.)
+//  hottest tokens, where the global accumulators have 64 replicas.)
 template <bool DROP>
 __global__ void __launch_bounds__(FC_WARPS * 32) fb_contrib_kernel(FbLaneParams q) {
   __shared__ unsigned long long s_et[256];
