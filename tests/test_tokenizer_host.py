@@ -129,3 +129,20 @@ def test_add_base_tokens():
     assert t.base_token_to_id(b"ba") == 3 and t.base_token_to_id(b"a") == 4  # HashMap::insert: the last id wins
     assert t.id_to_base_token(4) == (b"a", -0.5) and t.special_token_to_id("<s>") == 5
     assert list(t.common_prefix_search("ab")) == [4, 2]
+
+
+def test_id_rows_both_forms():
+    """The rows of `encode_batch` (src/tokenizer.rs:93-123) are the same lists whether they are built per row (long
+    rows) or sliced from one conversion (short rows); empty rows stay empty."""
+    import numpy as np
+    from tokengeex_b200.tokenizer import id_rows
+    rng = np.random.default_rng(5)
+    for T, S in ((4000, 7), (50, 40), (0, 3), (9, 1), (64, 8)):
+        ids = rng.integers(0, 1 << 32, T, dtype=np.uint64).astype(np.uint32)
+        cut = np.sort(rng.integers(0, T + 1, S - 1)) if S > 1 else np.zeros(0, np.int64)
+        id_off = np.concatenate([[0], cut, [T]]).astype(np.uint64)
+        rows = id_rows(ids, id_off)
+        assert len(rows) == S and all(type(r) is list for r in rows)
+        assert [x for r in rows for x in r] == [int(x) for x in ids]
+        assert [len(r) for r in rows] == [int(b - a) for a, b in zip(id_off[:-1], id_off[1:])]
+        assert all(type(x) is int for r in rows for x in r)
