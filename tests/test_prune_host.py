@@ -51,3 +51,35 @@ def test_prune_select_matches_oracle():
         # alternatives / always_keep themselves
         ak, aoff, aids = om.token_alternatives()
         assert int(audit[0]) == int((ak == 0).sum())
+
+
+def test_prune_select_and_m_step_threaded_paths_match_oracle():
+    """Sizes at which the host threads engage (chunked stable sorts merged pairwise, scores of the M-step split over
+    threads): still the oracle's order, ties included (src/prune.rs:124-170,247-318)."""
+    rng = random.Random(11)
+    for it in range(3):
+        toks, scores = rand_vocab(rng, alphabet=b"abcd", n_tok=1500, max_len=6, int_scores=(it == 0))
+        keep = np.array([len(t) == 1 for t in toks], np.uint8)
+        samples = rand_samples(rng, b"abcd", 400, 20, 200)
+        blob, off = O.pack_samples(samples)
+        om = O.OracleModel(toks, scores, keep)
+        fr = om.token_frequencies(blob, off)
+        if it == 2:
+            fr = np.minimum(fr, 2)  # many equal losses
+        shrink = [0.6, 0.8, 0.9][it]
+        want, waudit = om.prune_vocab(blob, off, 100, shrink) if it != 2 else (None, None)
+        for th in (1, 4, 7):
+            ids, audit = N.prune_select(toks, scores, keep, fr, len(samples), 100, shrink, threads=th)
+            if th == 1:
+                ids1, audit1 = ids, audit
+            assert np.array_equal(ids, ids1) and np.array_equal(audit, audit1)
+        if want is not None:
+            wt, ws, wk = want.export()
+            assert [toks[i] for i in ids1] == wt
+            assert np.array_equal(np.asarray(scores)[ids1], ws)
+            assert np.array_equal(audit1[:7], waudit[:7])
+        ex = np.array([rng.choice([0.0, 0.1, 0.499999, 0.5, 0.5000001, 3.0, 1e6 * rng.random()]) for _ in toks])
+        want_t, want_s, want_k = om.run_m_step(ex).export()
+        kept, ns = N.m_step(ex, keep)
+        idx = np.flatnonzero(kept)
+        assert [toks[i] for i in idx] == want_t and np.array_equal(ns[idx], want_s)

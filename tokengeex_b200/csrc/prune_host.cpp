@@ -182,6 +182,41 @@ int nbest2(TokenLattice& lat, std::vector<Hyp>& arena, Heap& agenda, std::vector
   return found;
 }
 
+// std::stable_sort over `threads` contiguous chunks, then rounds of pairwise std::inplace_merge (stable: the left
+// chunk's elements stay in front of equal ones from the right) — the same order as one stable sort.
+template <class T, class Cmp>
+void stable_sort_threads(std::vector<T>& v, Cmp cmp, int threads) {
+  const size_t n = v.size();
+  size_t chunks = std::min<size_t>((size_t)std::max(1, threads), n / 64);
+  if (chunks < 2) {
+    std::stable_sort(v.begin(), v.end(), cmp);
+    return;
+  }
+  std::vector<size_t> cut(chunks + 1);
+  for (size_t c = 0; c <= chunks; c++) cut[c] = n * c / chunks;
+  {
+    std::vector<std::thread> ts;
+    for (size_t c = 1; c < chunks; c++)
+      ts.emplace_back([&, c] { std::stable_sort(v.begin() + cut[c], v.begin() + cut[c + 1], cmp); });
+    std::stable_sort(v.begin(), v.begin() + cut[1], cmp);
+    for (auto& t : ts) t.join();
+  }
+  while (cut.size() > 2) {  // merge neighbours: (0,1) (2,3) ..; an odd chunk at the end waits for the next round
+    std::vector<size_t> nc;
+    std::vector<std::thread> ts;
+    size_t c = 0;
+    for (; c + 2 < cut.size(); c += 2) {
+      const size_t a = cut[c], m = cut[c + 1], b = cut[c + 2];
+      ts.emplace_back([&v, cmp, a, m, b] { std::inplace_merge(v.begin() + a, v.begin() + m, v.begin() + b, cmp); });
+      nc.push_back(a);
+    }
+    for (; c + 1 < cut.size(); c++) nc.push_back(cut[c]);
+    nc.push_back(n);
+    for (auto& t : ts) t.join();
+    cut.swap(nc);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,15 +243,25 @@ int tgx_m_step(const double* expected, const uint8_t* keep, uint64_t V, uint8_t*
     k++;
   }
   const double logsum = digamma(sum);
-  int bad = 0;
-  for (uint64_t i = 0; i < V; i++) {
-    if (!kept[i]) continue;
-    const double s = digamma(new_scores[i]) - logsum;
-    if (std::isnan(s) || std::isinf(s)) bad = 1;
-    new_scores[i] = s;
-  }
+  // (the sum above is the reference's, left to right; the scores below are independent of each other: host threads)
+  std::atomic<int> bad{0};
+  auto scores_of = [&](uint64_t lo, uint64_t hi) {
+    int b = 0;
+    for (uint64_t i = lo; i < hi; i++) {
+      if (!kept[i]) continue;
+      const double s = digamma(new_scores[i]) - logsum;
+      if (std::isnan(s) || std::isinf(s)) b = 1;
+      new_scores[i] = s;
+    }
+    if (b) bad.store(1);
+  };
+  const uint64_t T = V < 256 ? 1 : std::min<uint64_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> ts;
+  for (uint64_t t = 1; t < T; t++) ts.emplace_back(scores_of, V * t / T, V * (t + 1) / T);
+  scores_of(0, V / T);
+  for (auto& t : ts) t.join();
   if (n_kept) *n_kept = k;
-  return bad ? TGX_ERR_INVALID : TGX_OK;
+  return bad.load() ? TGX_ERR_INVALID : TGX_OK;
 }
 
 // prune_vocab without its frequency pass.  Inputs: the vocabulary (blob/offsets/scores/keep),
@@ -251,9 +296,17 @@ int tgx::prune_select_with(const tgx::DoubleArray& da, const uint8_t* token_byte
   size_t pruned_size = (size_t)((double)V * shrink_factor);         // :174  (truncation)
   pruned_size = std::max<size_t>(pruned_size, target_vocab_size);   // :175
 
-  // ---- alternatives (:179-203), parallel over tokens
-  std::vector<uint8_t> always_keep(V, 1);
-  std::vector<std::vector<uint32_t>> alternatives(V);
+  // ---- alternatives (:179-203) and losses (:247-300), parallel over tokens: a token's loss reads only the input
+  // frequencies of its alternative's ids, so it is computed by the thread that found the alternative; the lists below
+  // are then filled serially in id order, as the reference's loop does.
+  uint64_t sum_u = 0;
+  for (uint64_t i = 0; i < V; i++) sum_u += freq[i];
+  const double sum_f = (double)sum_u;
+  const double logsum = std::log(sum_f);
+  enum : uint8_t { KEPT = 0, ZERO_DROP = 1, CANDIDATE = 2, SILENT = 3, BAD_LOSS = 4 };
+  std::vector<uint8_t> state(V, KEPT), flags(V, 0);  // flags: 1 = always_keep is false, 2 = has alternatives
+  std::vector<double> loss_of(V, 0.0);
+  const int T = std::max(1, threads);
   {
     std::atomic<uint64_t> next{0};
     auto work = [&]() {
@@ -268,61 +321,59 @@ int tgx::prune_select_with(const tgx::DoubleArray& da, const uint8_t* token_byte
         for (uint64_t id = lo; id < hi; id++) {
           lat.build(da, scores, token_bytes + token_offsets[id], (size_t)(token_offsets[id + 1] - token_offsets[id]));
           const int nb = nbest2(lat, arena, agenda, paths);
-          if (nb > 1 && paths[0].size() > 1) always_keep[id] = 0;   // :191-195
-          if (nb > 1 && paths[0].size() == 1) alternatives[id] = paths[1];  // :197-202
+          const bool always_keep = !(nb > 1 && paths[0].size() > 1);  // :191-195
+          const bool has_alt = nb > 1 && paths[0].size() == 1 && !paths[1].empty();  // :197-202
+          flags[id] = (uint8_t)((always_keep ? 0 : 1) | (has_alt ? 2 : 0));
+          if (keep && keep[id]) continue;  // KEPT
+          if (freq[id] == 0 && !always_keep) {
+            state[id] = ZERO_DROP;
+          } else if (!has_alt) {
+            // KEPT
+          } else if (freq[id] != 0) {
+            const double f = (double)freq[id];
+            const double logprob = std::log(f) - logsum;
+            // `alternatives.len()` is the OUTER Vec's length, i.e. V (:279)
+            const double alt_logsum = std::log(sum_f + f * (double)(V - 1));
+            double alt_logprob = 0.0;
+            for (uint32_t a : paths[1]) alt_logprob += std::log((double)freq[a] + f) - alt_logsum;
+            const double loss = (f / (double)n_samples) * (logprob - alt_logprob);
+            loss_of[id] = loss;
+            state[id] = std::isnormal(loss) ? CANDIDATE : BAD_LOSS;
+          } else {
+            state[id] = SILENT;  // freq == 0 && always_keep && has alternatives: falls through every branch
+          }
         }
       }
     };
-    const int T = std::max(1, threads);
     std::vector<std::thread> ts;
     for (int t = 1; t < T; t++) ts.emplace_back(work);
     work();
     for (auto& t : ts) t.join();
   }
 
-  // ---- losses (:247-300)
-  uint64_t sum_u = 0;
-  for (uint64_t i = 0; i < V; i++) sum_u += freq[i];
-  const double sum_f = (double)sum_u;
-  const double logsum = std::log(sum_f);
   std::vector<std::pair<uint32_t, double>> candidates;
-  std::vector<uint32_t> pruned;
+  std::vector<std::pair<uint32_t, double>> pruned;  // (id, score)
   uint64_t n_akf = 0, n_alt = 0, n_silent = 0, n_zero = 0;
   for (uint64_t id = 0; id < V; id++) {
-    if (!always_keep[id]) n_akf++;
-    if (!alternatives[id].empty()) n_alt++;
-    if (keep && keep[id]) {
-      pruned.push_back((uint32_t)id);
-      continue;
-    }
-    if (freq[id] == 0 && !always_keep[id]) {
-      n_zero++;
-      continue;
-    } else if (alternatives[id].empty()) {
-      pruned.push_back((uint32_t)id);
-    } else if (freq[id] != 0) {
-      const double f = (double)freq[id];
-      const double logprob = std::log(f) - logsum;
-      // `alternatives.len()` is the OUTER Vec's length, i.e. V (:279)
-      const double alt_logsum = std::log(sum_f + f * (double)(V - 1));
-      double alt_logprob = 0.0;
-      for (uint32_t a : alternatives[id]) alt_logprob += std::log((double)freq[a] + f) - alt_logsum;
-      const double loss = (f / (double)n_samples) * (logprob - alt_logprob);
-      if (!std::isnormal(loss)) return TGX_ERR_INVALID;
-      candidates.emplace_back((uint32_t)id, loss);
-    } else {
-      n_silent++;  // freq == 0 && always_keep && has alternatives: falls through every branch
+    if (flags[id] & 1) n_akf++;
+    if (flags[id] & 2) n_alt++;
+    switch (state[id]) {
+      case KEPT: pruned.emplace_back((uint32_t)id, scores[id]); break;
+      case ZERO_DROP: n_zero++; break;
+      case CANDIDATE: candidates.emplace_back((uint32_t)id, loss_of[id]); break;
+      case SILENT: n_silent++; break;
+      default: return TGX_ERR_INVALID;  // a loss that is not normal: the reference panics (:291-296)
     }
   }
   // :308 loss descending (exact ties: id ascending)
-  std::stable_sort(candidates.begin(), candidates.end(),
-                   [](const std::pair<uint32_t, double>& a, const std::pair<uint32_t, double>& b) {
-                     return a.second > b.second;
-                   });
+  const auto by_second_desc = [](const std::pair<uint32_t, double>& a, const std::pair<uint32_t, double>& b) {
+    return a.second > b.second;
+  };
+  stable_sort_threads(candidates, by_second_desc, T);
   size_t taken = 0;
   for (auto& c : candidates) {  // :309-314  (`==`, so an already over-full list takes every candidate)
     if (pruned.size() == pruned_size) break;
-    pruned.push_back(c.first);
+    pruned.emplace_back(c.first, scores[c.first]);
     taken++;
   }
   double gap = 0.0, tie = 0.0;
@@ -331,8 +382,8 @@ int tgx::prune_select_with(const tgx::DoubleArray& da, const uint8_t* token_byte
     tie = gap == 0.0 ? 1.0 : 0.0;
   }
   // :316 score descending (exact ties keep the order above)
-  std::stable_sort(pruned.begin(), pruned.end(), [&](uint32_t a, uint32_t b) { return scores[a] > scores[b]; });
-  std::memcpy(out_ids, pruned.data(), pruned.size() * 4);
+  stable_sort_threads(pruned, by_second_desc, T);
+  for (size_t i = 0; i < pruned.size(); i++) out_ids[i] = pruned[i].first;
   *out_n = pruned.size();
   if (audit) {
     audit[0] = (double)n_akf;
