@@ -226,7 +226,7 @@ double tgx_model_last_stat(const tgx_model* m, int what);
  *        automatic, 0 = never); resident blocks per SM of the lane kernels; form (1, the default: beta chains stored and
  *        run beside the alpha chains, lane kernels that walk the trie, with or without the dropout draw;
  *        2: the lane kernels over the match stream always; 0: no beta array, lane-group kernels only); replicas
- *        (default 256) of the accumulators of the hottest ids (default: ids below 4096); per mille of the lane
+ *        (default 64) of the accumulators of the hottest ids (default: ids below 4096); per mille of the lane
  *        snippets, longest first, at which the first / second group of lane snippets ends (groups run on streams of
  *        their own: the counts of one beside the chains of the next). */
 int tgx_model_set_option(tgx_model* m, int key, int64_t value);

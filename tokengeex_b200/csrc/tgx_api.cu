@@ -16,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tokengeex_b200.h"
@@ -662,14 +663,22 @@ int order_after_caller(tgx_model* m) {
 
 // Token hash of the emit kernel (max_token_len <= 16 only); a vocabulary it cannot serve simply leaves hash.mask == 0
 // and emit walks the trie.  On failure nothing the model already holds has been touched.
+// `built`: a token hash of this vocabulary that the caller has built already (beside the trie, on a thread of its own),
+// with the builder's message in `built_err`; null = build it here.
 int upload_aux_tables(tgx_model* m, const tgx::DoubleArray& da, const uint8_t* token_bytes, const uint64_t* token_offsets,
-                      uint64_t V, uint32_t max_token_len) {
+                      uint64_t V, uint32_t max_token_len, tgx::TokenHash* built = nullptr,
+                      const std::string* built_err = nullptr) {
   (void)da;
   if (m->device < 0) return TGX_OK;
   cudaStream_t st = m->w().stream;
   tgx::TokenHash h;
-  const bool hash_ok = V != 0 && max_token_len >= 1 && max_token_len <= 16 &&
-                       tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty();
+  bool hash_ok = V != 0 && max_token_len >= 1 && max_token_len <= 16;
+  if (hash_ok && built) {
+    hash_ok = built_err->empty();
+    if (hash_ok) h = std::move(*built);
+  } else if (hash_ok) {
+    hash_ok = tgx::build_token_hash(token_bytes, token_offsets, V, &h).empty();
+  }
   if (hash_ok) CU(m->d_hash.reserve(h.slots.size() * sizeof(tgx::Slot)));
   m->hash.mask = 0;
   m->hash.slots.clear();
@@ -1206,16 +1215,33 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
   if (!m || !token_offsets || (!token_bytes && vocab_size && token_offsets[vocab_size]) || (!scores && vocab_size))
     return fail(TGX_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> g(m->mu);
-  tgx::DoubleArray da;
+  // the token hash of the new vocabulary (what emit_kernel probes) only needs the bytes: built beside the trie
+  tgx::TokenHash hash;
+  std::string hash_err = "not built";
+  std::thread hash_thread;
+  if (m->device >= 0 && vocab_size)
+    hash_thread = std::thread([&] { hash_err = tgx::build_token_hash(token_bytes, token_offsets, vocab_size, &hash); });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } joiner{hash_thread};
+  tgx::DoubleArray fresh;
   std::string err = "miss";
-  // a subset of the vocabulary the array was built for, not much smaller than it: keep the layout (trie_build.h)
+  // a subset of the vocabulary the array was built for, not much smaller than it: keep the layout (trie_build.h);
+  // in place — a miss leaves the array untouched
   if (m->retarget_permille > 0 && m->V_built && vocab_size * 1000ull >= m->V_built * (uint64_t)m->retarget_permille)
-    err = tgx::retarget_double_array(m->da, token_bytes, token_offsets, scores, vocab_size, &da);
+    err = tgx::retarget_double_array(&m->da, token_bytes, token_offsets, scores, vocab_size);
+  const bool in_place = err.empty();
   if (err == "miss") {
-    err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &da, /*hot_order=*/false);
+    err = tgx::build_double_array(token_bytes, token_offsets, scores, vocab_size, &fresh, /*hot_order=*/false);
     if (err.empty()) m->V_built = vocab_size;
   }
   if (!err.empty()) return fail(TGX_ERR_UNSUPPORTED, err);  // the model is unchanged
+  if (!in_place) m->da = std::move(fresh);
+  m->V = vocab_size;
+  const tgx::DoubleArray& da = m->da;
   if (m->device >= 0) {
     CU(cudaSetDevice(m->device));
     CU(cudaStreamSynchronize(m->w().stream));
@@ -1228,11 +1254,10 @@ int tgx_model_rebuild(tgx_model* m, const uint8_t* token_bytes, const uint64_t* 
     }
     CU(cudaMemcpyAsync(m->d_trie, da.slots.data(), da.slots.size() * sizeof(tgx::Slot), cudaMemcpyHostToDevice, m->w().stream));
     CU(cudaStreamSynchronize(m->w().stream));
-    int rc = upload_aux_tables(m, da, token_bytes, token_offsets, vocab_size, da.max_token_len);
+    if (hash_thread.joinable()) hash_thread.join();
+    int rc = upload_aux_tables(m, da, token_bytes, token_offsets, vocab_size, da.max_token_len, &hash, &hash_err);
     if (rc) return rc;
   }
-  m->da = std::move(da);
-  m->V = vocab_size;
   return TGX_OK;
 }
 

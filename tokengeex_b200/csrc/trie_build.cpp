@@ -2,8 +2,10 @@
 #include "trie_build.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <thread>
 #include <chrono>
@@ -268,13 +270,7 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
     out->node_parent = std::move(parent);
     out->node_depth = std::move(depth);
     out->node_slot.resize(nodes.size());
-    out->node_term.resize(nodes.size());
-    out->node_score.assign(nodes.size(), 0.0);
-    for (size_t i = 0; i < nodes.size(); i++) {
-      out->node_slot[i] = nodes[i].slot;
-      out->node_term[i] = nodes[i].term_id;
-      if (nodes[i].term_id >= 0) out->node_score[i] = scores[nodes[i].term_id];
-    }
+    for (size_t i = 0; i < nodes.size(); i++) out->node_slot[i] = nodes[i].slot;
   }
   lap("rows");
   out->root_base = base_of[0] ^ 0x100u;
@@ -285,44 +281,81 @@ std::string build_double_array(const uint8_t* bytes, const uint64_t* off, const 
   return "";
 }
 
-std::string retarget_double_array(const DoubleArray& old, const uint8_t* bytes, const uint64_t* off, const double* scores,
-                                  uint64_t V, DoubleArray* out) {
-  if (old.slots.empty() || V > MAX_VOCAB) return "miss";
-  const size_t n_slots = old.slots.size();
+std::string retarget_double_array(DoubleArray* da, const uint8_t* bytes, const uint64_t* off, const double* scores,
+                                  uint64_t V) {
+  if (da->slots.empty() || V > MAX_VOCAB) return "miss";
+  const size_t n_slots = da->slots.size();
+  const uint32_t depth_max = da->max_token_len;
+  const size_t T = V < 2048 ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+  auto over_threads = [T](size_t n, const std::function<void(size_t, size_t, size_t)>& f) {
+    std::vector<std::thread> ts;
+    for (size_t t = 1; t < T; t++) ts.emplace_back(f, t, n * t / T, n * (t + 1) / T);
+    f(0, 0, n / T);
+    for (auto& x : ts) x.join();
+  };
+  // 1. every token walked to its slot (read-only: a failure leaves the array as it was).  Blocks of ids handed out to
+  //    host threads.  "miss" sends the caller to build_double_array, which reports a non-finite score itself, so which
+  //    of several failures is seen first does not matter.
   std::vector<uint32_t> slot_of(V, 0xFFFFFFFFu);
-  uint32_t max_len = 0;
-  for (uint64_t i = 0; i < V; i++) {
-    const uint64_t len = off[i + 1] - off[i];
-    if (!std::isfinite(scores[i])) return "non-finite token score";
-    if (len == 0) continue;  // the empty token never matches
-    if (len > old.max_token_len) return "miss";
-    const uint8_t* t = bytes + off[i];
-    uint32_t xbase = old.root_base, at = 0;
-    for (uint64_t d = 0; d < len; d++) {
-      const uint32_t cw = 0x100u | t[d];
-      at = xbase ^ cw;
-      if (at >= n_slots) return "miss";
-      const Slot& e = old.slots[at];
-      if ((e.x ^ cw) & 0x1FFu) return "miss";
-      if (d + 1 < len && !(e.y & SLOT_HASCH)) return "miss";
-      xbase = e.x >> 9;
+  std::atomic<uint64_t> next{0};
+  std::atomic<int> failed{0};  // 1 = miss, 2 = non-finite score
+  over_threads(T, [&](size_t, size_t, size_t) {
+    const Slot* slots = da->slots.data();
+    while (!failed.load(std::memory_order_relaxed)) {
+      const uint64_t lo = next.fetch_add(4096);
+      if (lo >= V) break;
+      const uint64_t hi = std::min<uint64_t>(V, lo + 4096);
+      for (uint64_t i = lo; i < hi; i++) {
+        const uint64_t len = off[i + 1] - off[i];
+        int kind = 0;
+        if (!std::isfinite(scores[i])) {
+          kind = 2;
+        } else if (len == 0) {
+          continue;  // the empty token never matches
+        } else if (len > depth_max) {
+          kind = 1;
+        } else {
+          const uint8_t* tk = bytes + off[i];
+          uint32_t xbase = da->root_base, at = 0;
+          for (uint64_t d = 0; d < len && !kind; d++) {
+            const uint32_t cw = 0x100u | tk[d];
+            at = xbase ^ cw;
+            if (at >= n_slots) {
+              kind = 1;
+              break;
+            }
+            const Slot& e = slots[at];
+            if (((e.x ^ cw) & 0x1FFu) || (d + 1 < len && !(e.y & SLOT_HASCH))) kind = 1;
+            xbase = e.x >> 9;
+          }
+          if (!kind) slot_of[i] = at;
+        }
+        if (kind) {
+          int none = 0;
+          if (kind == 2) failed.store(2);
+          else failed.compare_exchange_strong(none, 1);
+          return;
+        }
+      }
     }
-    slot_of[i] = at;
-    max_len = std::max<uint32_t>(max_len, (uint32_t)len);
-  }
-  *out = old;
-  out->slots8.clear();
-  out->pair2.clear();
-  out->rows.clear();
-  out->row_ids.clear();
-  for (Slot& s : out->slots) {
-    s.y &= ~(SLOT_TERM | SLOT_ID_MASK);
-    s.z = s.w = 0;
-  }
+  });
+  if (failed.load()) return failed.load() == 2 ? "non-finite token score" : "miss";
+  // 2. nothing can fail from here on: terminals / ids / scores rewritten in place
+  da->slots8.clear();
+  da->pair2.clear();
+  da->rows.clear();
+  da->row_ids.clear();
+  over_threads(n_slots, [&](size_t, size_t lo, size_t hi) {
+    Slot* slots = da->slots.data();
+    for (size_t k = lo; k < hi; k++) {
+      slots[k].y &= ~(SLOT_TERM | SLOT_ID_MASK);
+      slots[k].z = slots[k].w = 0;
+    }
+  });
   uint32_t n_term = 0;
   for (uint64_t i = 0; i < V; i++) {  // in id order: the last of equal byte strings wins (src/trie.rs:19)
     if (slot_of[i] == 0xFFFFFFFFu) continue;
-    Slot& s = out->slots[slot_of[i]];
+    Slot& s = da->slots[slot_of[i]];
     if (!(s.y & SLOT_TERM)) n_term++;
     s.y = (s.y & ~SLOT_ID_MASK) | SLOT_TERM | ((uint32_t)i & SLOT_ID_MASK);
     uint64_t bits;
@@ -330,22 +363,8 @@ std::string retarget_double_array(const DoubleArray& old, const uint8_t* bytes, 
     s.z = (uint32_t)bits;
     s.w = (uint32_t)(bits >> 32);
   }
-  (void)max_len;  // max_token_len stays the depth of the ARRAY (the kernels size their windows by it)
-  out->n_terminals = n_term;
-  if (!out->node_parent.empty()) {  // what build_match_tables reads
-    {
-      std::vector<uint32_t> node_at(n_slots, 0);
-      for (size_t nd = 0; nd < out->node_slot.size(); nd++) node_at[out->node_slot[nd]] = (uint32_t)nd;
-      std::fill(out->node_term.begin(), out->node_term.end(), -1);
-      std::fill(out->node_score.begin(), out->node_score.end(), 0.0);
-      for (uint64_t i = 0; i < V; i++) {
-        if (slot_of[i] == 0xFFFFFFFFu) continue;
-        const uint32_t nd = node_at[slot_of[i]];
-        out->node_term[nd] = (int32_t)i;
-        out->node_score[nd] = scores[i];
-      }
-    }
-  }
+  // (max_token_len stays the depth of the ARRAY: the kernels size their windows by it)
+  da->n_terminals = n_term;
   return "";
 }
 
@@ -356,17 +375,29 @@ std::string build_match_tables(DoubleArray* out) {
   const std::vector<uint8_t>& depth = out->node_depth;
   const size_t n_nodes = parent.size();
   const size_t n_slots = out->slots.size();
+  // the token that ends at a node and its score are what the node's slot says (node 0, the root, ends none)
+  auto term_of = [&](uint32_t nd) -> int32_t {
+    const Slot& sl = out->slots[out->node_slot[nd]];
+    return nd != 0 && (sl.y & SLOT_TERM) ? (int32_t)(sl.y & SLOT_ID_MASK) : -1;
+  };
+  auto score_of = [&](uint32_t nd) -> double {
+    const Slot& sl = out->slots[out->node_slot[nd]];
+    const uint64_t bits = (uint64_t)sl.z | ((uint64_t)sl.w << 32);
+    double v;
+    std::memcpy(&v, &bits, 8);
+    return v;
+  };
   // terminal nodes in id order (ids are unique per terminal: the last duplicate owns the node) ...
   std::vector<std::pair<int32_t, uint32_t>> byid;
   byid.reserve(out->n_terminals);
   for (uint32_t i = 1; i < n_nodes; i++)
-    if (out->node_term[i] >= 0) byid.emplace_back(out->node_term[i], i);
+    if (term_of(i) >= 0) byid.emplace_back(term_of(i), i);
   std::sort(byid.begin(), byid.end());
   std::vector<uint32_t> terms;
   terms.reserve(byid.size());
   for (auto& pr : byid) terms.push_back(pr.second);
   // ... which is already hottest-first for a score-sorted vocabulary (the usual case); otherwise sort
-  auto hotter = [&](uint32_t a, uint32_t b) { return out->node_score[a] > out->node_score[b]; };
+  auto hotter = [&](uint32_t a, uint32_t b) { return score_of(a) > score_of(b); };
   if (!std::is_sorted(terms.begin(), terms.end(), hotter)) std::stable_sort(terms.begin(), terms.end(), hotter);
   const double ninf = -INFINITY;
   std::vector<uint32_t> row_of(n_nodes, 0);
@@ -386,9 +417,9 @@ std::string build_match_tables(DoubleArray* out) {
       const size_t base = (size_t)row_of[nd] * 2;
       uint64_t mask = 0;
       for (uint32_t a = nd; a; a = parent[a])
-        if (out->node_term[a] >= 0) {
-          out->rows[base + depth[a]] = out->node_score[a];
-          out->row_ids[base + depth[a]] = (uint32_t)out->node_term[a];
+        if (term_of(a) >= 0) {
+          out->rows[base + depth[a]] = score_of(a);
+          out->row_ids[base + depth[a]] = (uint32_t)term_of(a);
           mask |= 1ull << (depth[a] - 1);
         }
       std::memcpy(&out->rows[base], &mask, 8);
@@ -407,7 +438,7 @@ std::string build_match_tables(DoubleArray* out) {
     const Slot& sl = out->slots[out->node_slot[i]];
     uint32_t y = 0;
     if (sl.y & SLOT_HASCH) y |= SLOT8_HASCH;
-    if (out->node_term[i] >= 0 && i != 0) y |= SLOT8_TERM | row_of[i];
+    if (term_of((uint32_t)i) >= 0) y |= SLOT8_TERM | row_of[i];
     out->slots8[out->node_slot[i]] = (uint64_t)sl.x | ((uint64_t)y << 32);
   }
   // the two first levels of every walk, tabulated (the probes of match_kernel, restated)

@@ -67,10 +67,10 @@ struct DoubleArray {
   std::vector<uint64_t> pair2;
   std::vector<double> rows;
   std::vector<uint32_t> row_ids;
-  std::vector<uint32_t> node_parent, node_slot;  // per trie node (node 0 = root); empty when max_token_len > 16
-  std::vector<int32_t> node_term;                // token id that ends at the node, or -1
+  // per trie node (node 0 = root); empty when max_token_len > 16.  (The token that ends at a node, and its score, are in
+  // the node's slot: a retargeted array needs no second copy of them.)
+  std::vector<uint32_t> node_parent, node_slot;
   std::vector<uint8_t> node_depth;
-  std::vector<double> node_score;
 };
 // Fills slots8 / rows / row_ids (no-op when they are there).  Returns "" on success.
 std::string build_match_tables(DoubleArray* da);
@@ -85,12 +85,13 @@ std::string build_double_array(const uint8_t* token_bytes, const uint64_t* token
 
 // The EM loop's rebuilds (src/prune.rs:48,53: `*model = Model::from(vocab)` after every M-step and every prune step)
 // hand over a SUBSET of the vocabulary the array was built for.  This keeps the array's layout — every token of the
-// new vocabulary is walked to its slot, terminal flags / ids / scores are rewritten, the nodes of the tokens that went
-// stay as non-terminal nodes — instead of sorting, building and packing again (0.02 against 0.11 s per 250k tokens).
+// new vocabulary is walked to its slot (host threads), terminal flags / ids / scores are rewritten IN PLACE, the nodes
+// of the tokens that went stay as non-terminal nodes — instead of sorting, building and packing again.
 // Same matches, ids and scores as a fresh build: the kernels only ever yield terminals.  Returns "" on success, "miss"
-// when some token has no node in `old` (not a subset: build afresh), else an error message.
-std::string retarget_double_array(const DoubleArray& old, const uint8_t* token_bytes, const uint64_t* token_offsets,
-                                  const double* scores, uint64_t vocab_size, DoubleArray* out);
+// when some token has no node in the array (not a subset: build afresh), else an error message; the array is
+// untouched unless "" is returned.
+std::string retarget_double_array(DoubleArray* da, const uint8_t* token_bytes, const uint64_t* token_offsets,
+                                  const double* scores, uint64_t vocab_size);
 
 // ---- token hash: bytes of a vocabulary token (1..16 bytes) -> id, ONE probe instead of one trie probe per byte.
 // Used by the emit kernel, which only ever looks up strings that ARE vocabulary tokens (the marked tokens of the
