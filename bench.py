@@ -273,7 +273,7 @@ def run_prune_iter(args, rank, world, local, torch, dist, N, synth):
     new_vocab, t_m = timed(lambda: pr.run_m_step(vocab, expected))
 
     def rebuild():  # *model = Model::from(vocab): new trie, same handle and workspaces
-        model.rebuild(new_vocab.tokens, new_vocab.scores)
+        model.rebuild(new_vocab.tokens, new_vocab.scores, packed=new_vocab.packed())  # (as ModelVocabularyPruner.prune does)
         return model
     model2, t_rebuild = timed(rebuild)
     rep = P.PruneReport()

@@ -83,3 +83,25 @@ def test_prune_select_and_m_step_threaded_paths_match_oracle():
         kept, ns = N.m_step(ex, keep)
         idx = np.flatnonzero(kept)
         assert [toks[i] for i in idx] == want_t and np.array_equal(ns[idx], want_s)
+
+
+def test_vocab_packed_once_and_accepted_by_rebuild_and_selection():
+    """The EM loop packs a vocabulary once (prune.Vocab.packed) and hands the pack to tgx_model_rebuild and
+    tgx_model_prune_select: the same results as packing inside each call."""
+    from tokengeex_b200.prune import Vocab
+    rng = random.Random(3)
+    toks, scores = rand_vocab(rng, alphabet=b"abc", n_tok=300, max_len=5)
+    keep = np.array([len(t) == 1 for t in toks], np.uint8)
+    v = Vocab(list(toks), np.asarray(scores, np.float64), keep)
+    pk = v.packed()
+    assert pk is v.packed()
+    blob, off = N.pack(toks)
+    assert np.array_equal(pk[0], blob) and np.array_equal(pk[1], off)
+    fr = np.array([rng.randrange(0, 50) for _ in toks], np.uint64)
+    a, b = N.Model(toks, scores, device=None), N.Model(toks[:5], scores[:5], device=None)
+    b.rebuild(v.tokens, v.scores, packed=pk)
+    for q in (b"abcabc", b"ccc", b"a"):
+        assert a.common_prefix_search(q) == b.common_prefix_search(q)
+    ids_a, aud_a = a.prune_select(v.tokens, v.scores, v.keep, fr, 100, 50, 0.8, threads=2)
+    ids_b, aud_b = b.prune_select(v.tokens, v.scores, v.keep, fr, 100, 50, 0.8, threads=2, packed=pk)
+    assert np.array_equal(ids_a, ids_b) and np.array_equal(aud_a, aud_b)

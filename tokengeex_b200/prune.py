@@ -36,9 +36,17 @@ class Vocab:
     tokens: List[bytes]
     scores: np.ndarray  # f64[V]
     keep: np.ndarray    # u8[V]
+    _packed: Optional[tuple] = field(default=None, repr=False, compare=False)
 
     def __len__(self):
         return len(self.tokens)
+
+    def packed(self):
+        """(blob u8[], offsets u64[V + 1]) of the tokens as the C ABI takes them, made once per vocabulary (a Vocab is
+        not modified after it is built: every step of the loop returns a new one)."""
+        if self._packed is None:
+            self._packed = N.pack(self.tokens)
+        return self._packed
 
 
 @dataclass
@@ -206,12 +214,13 @@ class ModelVocabularyPruner:
             ids, audit = None, np.zeros(8)
             if coll.rank == 0:
                 ids, audit = model.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
-                                                self.shrink_factor, threads=max(2, cores - coll.world_size + 1))
+                                                self.shrink_factor, threads=max(2, cores - coll.world_size + 1),
+                                                packed=vocab.packed())
             ids = coll.broadcast_u32(ids, 0)
             audit = coll.allreduce(np.ascontiguousarray(audit, np.float64))  # (zeros on the other ranks)
         else:
             ids, audit = model.prune_select(vocab.tokens, vocab.scores, vocab.keep, fr, n_samples, self.vocab_size,
-                                            self.shrink_factor, threads=max(2, cores))
+                                            self.shrink_factor, threads=max(2, cores), packed=vocab.packed())
         report.select_s.append(time.perf_counter() - t)
         report.audits.append(audit)
         return Vocab([vocab.tokens[i] for i in ids], vocab.scores[ids].copy(), vocab.keep[ids].copy())
@@ -238,14 +247,14 @@ class ModelVocabularyPruner:
                          len(new_vocab))
                 vocab = new_vocab
                 t = time.perf_counter()
-                model.rebuild(vocab.tokens, vocab.scores)  # *model = Model::from(vocab)  (src/prune.rs:48)
+                model.rebuild(vocab.tokens, vocab.scores, packed=vocab.packed())  # *model = Model::from(vocab)  (src/prune.rs:48)
                 report.rebuild_s.append(time.perf_counter() - t)
                 report.vocab_sizes.append(len(vocab))
             before = len(vocab)
             vocab = self.prune_vocab(model, vocab, blob, off, report, dev)
             log.info("Pruning vocabulary from=%d to=%d", before, len(vocab))
             t = time.perf_counter()
-            model.rebuild(vocab.tokens, vocab.scores)  # (src/prune.rs:53)
+            model.rebuild(vocab.tokens, vocab.scores, packed=vocab.packed())  # (src/prune.rs:53)
             report.rebuild_s.append(time.perf_counter() - t)
             report.vocab_sizes.append(len(vocab))
         model.close()
