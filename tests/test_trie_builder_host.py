@@ -83,3 +83,31 @@ def test_rebuild_keeps_the_layout_for_a_subset_and_builds_afresh_otherwise():
     om = O.OracleModel(t3[:-3], s3[:-3])
     for q in (toks[0] + b"a", toks[7], b"zzzz"):
         assert hm.common_prefix_search(q) == om.common_prefix_search(q)
+
+
+def test_failed_rebuild_leaves_the_model_as_it_was():
+    """tgx_model_rebuild rewrites the array in place for a subset, but only after every token has been walked to its
+    slot and every score checked: a vocabulary it refuses (a non-finite score; a token beyond 64 bytes after a miss)
+    leaves the old vocabulary answering (include/tokengeex_b200.h: "On failure the model is unchanged")."""
+    rng = random.Random(9)
+    alpha = b"abcdef"
+    toks = sorted({bytes(rng.choice(alpha) for _ in range(rng.randrange(1, 10))) for _ in range(4000)} | {bytes([c]) for c in alpha})
+    sc = [-(rng.random() * 8 + 0.1) for _ in toks]
+    hm = N.Model(toks, sc, device=None)
+    om = O.OracleModel(toks, sc)
+    queries = [rng.choice(toks) + bytes(rng.choice(alpha) for _ in range(rng.randrange(0, 5))) for _ in range(500)]
+    before = [hm.common_prefix_search(q) for q in queries]
+    assert before == [om.common_prefix_search(q) for q in queries]
+    sub = [i for i in range(len(toks)) if i % 5 or len(toks[i]) == 1]
+    bad_scores = [sc[i] for i in sub]
+    bad_scores[len(sub) // 2] = float("inf")  # in the middle of a subset that would otherwise keep the layout
+    with pytest.raises(N.TgxError):
+        hm.rebuild([toks[i] for i in sub], bad_scores)
+    assert [hm.common_prefix_search(q) for q in queries] == before
+    with pytest.raises(N.TgxError):
+        hm.rebuild([toks[i] for i in sub] + [b"x" * 65], [sc[i] for i in sub] + [-1.0])
+    assert [hm.common_prefix_search(q) for q in queries] == before
+    assert hm.info().vocab_size == len(toks)
+    hm.rebuild([toks[i] for i in sub], [sc[i] for i in sub])  # and the same subset with good scores goes through
+    om2 = O.OracleModel([toks[i] for i in sub], [sc[i] for i in sub])
+    assert [hm.common_prefix_search(q) for q in queries] == [om2.common_prefix_search(q) for q in queries]
