@@ -561,6 +561,37 @@ def main():
                "d2h_bytes_per_step": int(4 * r[0].size + 8 * (S + 1) + 12 * S),
                "ms_per_step": 1e3 * float(ew[0]) / args.steps,
                "buffers": "pinned host memory (tgx_host_alloc) for text in and ids out"}
+        # What the host side alone allows: the step's H2D and D2H bytes copied between the same pinned buffers and the
+        # device on two streams, no kernel at all — at N ranks every rank does this at once, so the figure is the
+        # ceiling the box's host memory / PCIe path sets for `e2e` whatever the kernels do.  (No collective inside:
+        # a failure here is recorded, never fatal.)
+        co_ms = float("nan")
+        try:
+            n_ids = int(r[0].size)
+            t_in, t_out = torch.from_numpy(blob), torch.from_numpy(h_ids.view(np.int32))[:n_ids]
+            d_out = d_ids[:n_ids]
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            reps = max(2, args.steps // 2)
+            for i in range(reps + 1):  # the first pass is a warm-up
+                if i == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                with torch.cuda.stream(s_in):
+                    d_text.copy_(t_in, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    t_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            co_ms = 1e3 * (time.perf_counter() - t0) / reps
+            e2e["copy_only"] = {"pinned_host_buffers": bool(t_in.is_pinned() and t_out.is_pinned())}
+        except Exception as ex:  # noqa: BLE001
+            e2e["copy_only"] = {"error": repr(ex)[:200]}
+        cw = torch.tensor([co_ms if co_ms == co_ms else -1.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(cw, op=dist.ReduceOp.MAX)
+        if float(cw[0]) > 0 and "error" not in e2e["copy_only"]:
+            e2e["copy_only"].update({"ms_per_step": float(cw[0]), "value": bytes_all / (float(cw[0]) * 1e-3) / 1e6,
+                                     "unit": UNIT, "what": "H2D of the text + D2H of the ids alone, both directions at "
+                                     "once, max over ranks: the ceiling of e2e on this host"})
         # the same call with ordinary (pageable) caller memory, as a Rust Vec or Python bytes would hand it over
         pg_text = np.array(blob, copy=True)
         pg_ids = np.empty(int(tokens) + 16, np.uint32)
