@@ -105,3 +105,30 @@ def test_vocab_packed_once_and_accepted_by_rebuild_and_selection():
     ids_a, aud_a = a.prune_select(v.tokens, v.scores, v.keep, fr, 100, 50, 0.8, threads=2)
     ids_b, aud_b = b.prune_select(v.tokens, v.scores, v.keep, fr, 100, 50, 0.8, threads=2, packed=pk)
     assert np.array_equal(ids_a, ids_b) and np.array_equal(aud_a, aud_b)
+
+
+def test_selection_and_m_step_at_200k_tokens_match_oracle():
+    """Row a10 at the size of the configurations (BASELINE configs[3] prunes a 250k-token vocabulary after its first
+    M-step): 200 000 tokens, a 24 MB corpus for the oracle's frequency pass — the surviving tokens IN ORDER, their
+    scores, the audit and the M-step's scores are the oracle's (src/prune.rs:124-170,173-319), with every host thread
+    path engaged.  No GPU needed: the frequency vector is the oracle's own."""
+    from tokengeex_b200 import synth
+    vb, vo = synth.corpus(synth.KIND_CODE_CJK, 2, 48_000_000)
+    toks, sc, kp = synth.vocab(vb, vo, 2, 200000, 16, 0.05)
+    blob, off = synth.corpus(synth.KIND_CODE_CJK, 7, 24_000_000)
+    keep = np.asarray(kp, np.uint8)
+    om = O.OracleModel(toks, sc, keep)
+    fr = om.token_frequencies(blob, off, threads=8)
+    want, waudit = om.prune_vocab(blob, off, 65536, 0.8)
+    wt, ws, wk = want.export()
+    ids, audit = N.prune_select(toks, sc, keep, fr, len(off) - 1, 65536, 0.8, threads=8)
+    assert [toks[i] for i in ids] == list(wt)
+    assert np.array_equal(np.asarray(sc)[ids].view(np.uint64), np.asarray(ws).view(np.uint64))
+    assert np.array_equal(audit[:7], waudit[:7])
+    assert audit[4] > 50000  # tens of thousands of candidates ranked by loss
+    ex = fr.astype(np.float64) * 0.37  # counts on both sides of the 0.5 threshold
+    want_t, want_s, want_k = om.run_m_step(ex).export()
+    kept, ns = N.m_step(ex, keep)
+    idx = np.flatnonzero(kept)
+    assert [toks[i] for i in idx] == list(want_t)
+    assert np.array_equal(ns[idx].view(np.uint64), np.asarray(want_s).view(np.uint64))
