@@ -287,10 +287,11 @@ std::string retarget_double_array(DoubleArray* da, const uint8_t* bytes, const u
   const size_t n_slots = da->slots.size();
   const uint32_t depth_max = da->max_token_len;
   const size_t T = V < 2048 ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
-  auto over_threads = [T](size_t n, const std::function<void(size_t, size_t, size_t)>& f) {
+  // f(lo, hi) over T equal ranges of [0, n), one per host thread (n = T: T workers that share work themselves)
+  auto over_threads = [T](size_t n, const std::function<void(size_t, size_t)>& f) {
     std::vector<std::thread> ts;
-    for (size_t t = 1; t < T; t++) ts.emplace_back(f, t, n * t / T, n * (t + 1) / T);
-    f(0, 0, n / T);
+    for (size_t t = 1; t < T; t++) ts.emplace_back(f, n * t / T, n * (t + 1) / T);
+    f(0, n / T);
     for (auto& x : ts) x.join();
   };
   // 1. every token walked to its slot (read-only: a failure leaves the array as it was).  Blocks of ids handed out to
@@ -299,7 +300,7 @@ std::string retarget_double_array(DoubleArray* da, const uint8_t* bytes, const u
   std::vector<uint32_t> slot_of(V, 0xFFFFFFFFu);
   std::atomic<uint64_t> next{0};
   std::atomic<int> failed{0};  // 1 = miss, 2 = non-finite score
-  over_threads(T, [&](size_t, size_t, size_t) {
+  over_threads(T, [&](size_t, size_t) {  // T workers; the blocks of ids come from `next`
     const Slot* slots = da->slots.data();
     while (!failed.load(std::memory_order_relaxed)) {
       const uint64_t lo = next.fetch_add(4096);
@@ -345,7 +346,7 @@ std::string retarget_double_array(DoubleArray* da, const uint8_t* bytes, const u
   da->pair2.clear();
   da->rows.clear();
   da->row_ids.clear();
-  over_threads(n_slots, [&](size_t, size_t lo, size_t hi) {
+  over_threads(n_slots, [&](size_t lo, size_t hi) {
     Slot* slots = da->slots.data();
     for (size_t k = lo; k < hi; k++) {
       slots[k].y &= ~(SLOT_TERM | SLOT_ID_MASK);
